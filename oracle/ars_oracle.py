@@ -1,0 +1,542 @@
+"""CPU oracle for the Audio-Raytracing-Studio render hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file.
+Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl
+reference` legs of `bench.py` may use it, and only as the checker / the timed
+CPU baseline -- never as a fallback for the CUDA path.
+
+It restates, stage by stage, what `/root/reference/raytracer_studio.py`
+(`rs.py` below) computes, using the same numerical back-ends the reference
+uses (numpy.fft, scipy.signal.fftconvolve) so float32 roundings line up.
+Each function cites the reference lines it follows.
+
+Parity status
+  * Every stage below is pinned against the *unmodified* reference executed in
+    the authoring container: `oracle/make_golden.py` imports rs.py under stub
+    modules and writes `tests/golden/*.npz`; `tests/test_oracle_golden.py`
+    replays them.  (The reference itself ships no tests or golden vectors.)
+  * Two third-party boundaries have no source under /root/reference and are
+    not installed here: pyloudnorm (integrated loudness) and libsndfile
+    (float -> PCM16).  `integrated_loudness()` and `pcm16()` restate their
+    published algorithms (ITU-R BS.1770-4 gating as implemented by pyloudnorm
+    0.1.x; libsndfile `f2s_array`: lrintf(x * 0x7FFF)).  PARITY UNPINNED for
+    these two functions.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy.signal import fftconvolve, lfilter
+
+F32 = np.float32
+
+# rs.py:29-32 -- material name -> absorption coefficient (German names are the
+# reference's keys); rs.py:33,253 -- unknown material falls back to "Holz".
+ABSORPTION = {"Stein": 0.15, "Holz": 0.35, "Teppich": 0.7, "Glas": 0.2,
+              "Beton": 0.1, "Vorhang (schwer)": 0.8}
+FALLBACK_MATERIAL = "Holz"
+
+# rs.py:37-42 -- output layouts (channel count, channel names in column order)
+LAYOUTS = {
+    "Stereo": (2, ["FL", "FR"]),
+    "5.1 (Standard)": (6, ["FL", "FR", "C", "LFE", "RL", "RR"]),
+    "7.1 (Surround)": (8, ["FL", "FR", "C", "LFE", "RL", "RR", "SL", "SR"]),
+    "5.1.2 (Atmos Light)": (8, ["FL", "FR", "C", "LFE", "RL", "RR", "TFL", "TFR"]),
+}
+FALLBACK_LAYOUT = "5.1 (Standard)"
+
+# rs.py:160-166 -- (duration s, reflections, max early delay s, early/late split s)
+_HALLS = {"Plate": (0.8, 25, 0.025, 0.03),
+          "Room": (1.5, 35, 0.06, 0.08),
+          "Cathedral": (4.0, 20, 0.10, 0.12)}
+
+
+# --------------------------------------------------------------------------
+# scalar prologue (a1-a4)
+# --------------------------------------------------------------------------
+def hall_base(hall: str):
+    """rs.py:157-166; unknown hall -> Room."""
+    return _HALLS.get(hall, _HALLS["Room"])
+
+
+def shape_params(hall: str, room_size: float, z: float):
+    """rs.py:211-233 -> (duration, reflection count, max delay, split time)."""
+    room_size = float(room_size)
+    z = float(z)
+    dur0, refl0, delay0, split0 = hall_base(hall)
+    rel = room_size / 100.0
+    k_dur = np.clip(rel ** 0.33, 0.5, 2.5)
+    k_delay = np.clip(rel ** 0.25, 0.7, 1.8)
+    k_refl = np.clip(1 + (room_size - 100) / 500.0, 0.8, 1.5)
+    duration = np.clip(dur0 * k_dur, 0.1, 10.0)
+    refl = np.clip(int(refl0 * k_refl), 5, 80)
+    k_z = 1.0 + (z - 0.5) * 0.1
+    max_delay = np.clip(delay0 * k_delay * k_z, 0.01, 0.3)
+    split = np.clip(split0 * k_delay, 0.02, 0.2)
+    return duration, refl, max_delay, split
+
+
+def directionality(x, y, z, hall: str, diffusion, dry_wet=0.5):
+    """rs.py:184-206."""
+    x, y, z = (np.clip(float(v), 0.0, 1.0) for v in (x, y, z))
+    diffusion = np.clip(float(diffusion), 0.0, 1.0)
+    dw = np.clip(float(dry_wet), 0.0, 1.0)
+    off_centre = np.sqrt(((x - 0.5) * 2) ** 2 + ((z - 0.5) * 1.0) ** 2) / np.sqrt(1 ** 2 + 0.5 ** 2)
+    off_depth = abs(y - 0.5) * 2
+    pos = np.clip((1.0 - off_centre * 0.3) * (1.0 - off_depth * 0.2), 0.5, 1.0)
+    base = {"Plate": 0.95, "Room": 0.65, "Cathedral": 0.25}.get(hall, 0.65)
+    core = base * pos * (1.0 - diffusion * 0.8)
+    lift = max(0.0, (dw - 0.6) * 0.4)
+    return np.clip(core + lift, 0.05, 0.95)
+
+
+def adapt_levels(dry_wet, early=0.8, late=0.6):
+    """rs.py:168-179 -- returns np.float64 scalars (matters downstream, App. A)."""
+    dw = np.clip(float(dry_wet), 0.0, 1.0)
+    early = float(early)
+    late = float(late)
+    e = np.clip(early * (1.0 - dw ** 1.5 * 0.7), 0.0, 2.0)
+    l = np.clip(late * (1.0 + dw ** 1.5 * 0.6), 0.0, 2.0)
+    return e, l
+
+
+# --------------------------------------------------------------------------
+# IR synthesis (a5)
+# --------------------------------------------------------------------------
+def ir_geometry(rate, duration, max_delay, split_time):
+    """Integer geometry of the IR, rs.py:249,254-255,259,271-272."""
+    length = max(1, int(float(duration) * int(rate)))
+    split = max(1, min(int(float(split_time) * int(rate)), length - 1))
+    max_delay_samples = max(2, int(float(max_delay) * int(rate)))
+    tap_hi = min(max_delay_samples, split)
+    return length, split, tap_hi, length - split
+
+
+def draw_ir_randoms(rate, duration, refl_count, max_delay, split_time, rng=np.random):
+    """Replays the reference's RNG call sequence (rs.py:262,264,285) on `rng`
+    (default: numpy's global legacy generator, as in the reference).
+
+    Returns (tap_delays int64[k], tap_base float64[k], noise float64[late_len]).
+    """
+    length, split, tap_hi, late_len = ir_geometry(rate, duration, max_delay, split_time)
+    delays, bases = [], []
+    if int(refl_count) > 0 and split > 1 and tap_hi > 1:
+        for _ in range(int(refl_count)):
+            d = rng.randint(1, max(2, tap_hi))
+            if 0 < d < split:
+                delays.append(d)
+                bases.append(rng.uniform(0.3, 0.8))
+    noise = rng.uniform(-1, 1, size=late_len) if late_len > 0 else np.zeros(0)
+    return np.asarray(delays, np.int64), np.asarray(bases, np.float64), np.asarray(noise, np.float64)
+
+
+def synth_ir(rate, duration, max_delay, absorption, direc, split_time, diffusion,
+             tap_delays, tap_base, noise):
+    """rs.py:249-305 with the random draws passed in.  -> (early f32[L], late f32[L])."""
+    rate = int(rate)
+    duration = float(duration)
+    direc = float(direc)
+    diffusion = float(diffusion)
+    length, split, tap_hi, late_len = ir_geometry(rate, duration, max_delay, split_time)
+    early = np.zeros(length, F32)
+    late = np.zeros(length, F32)
+
+    # early taps, rs.py:265-268 (accumulated one by one into the float32 array)
+    for d, b in zip(tap_delays, tap_base):
+        s = b * (1.0 - absorption)
+        s *= np.clip(direc, 0.1, 1.0)
+        s *= (1.0 - (d / tap_hi) ** 0.7)
+        early[d] += s
+
+    # diffuse tail, rs.py:273-296
+    if late_len > 0:
+        floor_ratio = 10 ** (-50 / 20)
+        decay = np.power(floor_ratio, 1.0 / late_len) if late_len > 1 else 0.1
+        decay = np.clip(decay * (1.0 - absorption * 0.1), 0.8, 0.99999)
+        amp = 0.6 * (1.0 - np.clip(direc, 0.0, 0.9))
+        amp *= np.clip(1.0 / (1 + duration * 0.5), 0.3, 1.0)
+        amp *= (1.0 - absorption ** 0.5)
+        width = int(np.clip(rate * 0.001 * (1.0 + diffusion * 2.0), 1, 10))
+        shaped = noise
+        if width > 1 and late_len >= width:
+            box = np.convolve(noise, np.ones(width) / width, mode="same")
+            s_raw, s_box = np.std(noise), np.std(box)
+            shaped = box / s_box * s_raw if s_box > 1e-6 else noise
+        amp *= (1.0 + diffusion * 0.2)
+        late[split:] = shaped * amp * np.power(decay, np.arange(late_len))
+
+    # separate peak normalisation of the two parts, rs.py:299-303
+    if length > 1:
+        pk = np.max(np.abs(early[1:]))
+        if pk > 1e-6:
+            early[1:] = (early[1:] / pk) * 0.9
+    pk = np.max(np.abs(late))
+    if pk > 1e-6:
+        late = (late / pk) * 0.7
+    return early, late
+
+
+def generate_ir(rate, duration, refl_count, max_delay, material, direc, split_time,
+                diffusion, rng=np.random):
+    """a5 end to end (rs.py:238-305): draws from `rng`, then synthesises."""
+    if int(rate) <= 0 or float(duration) <= 0:
+        return np.array([1.0], F32), np.zeros(1, F32)
+    absorption = ABSORPTION.get(material, ABSORPTION[FALLBACK_MATERIAL])
+    taps, bases, noise = draw_ir_randoms(rate, duration, refl_count, max_delay, split_time, rng)
+    return synth_ir(rate, duration, max_delay, absorption, direc, split_time, diffusion,
+                    taps, bases, noise)
+
+
+# --------------------------------------------------------------------------
+# spectral stages (a6, EQ part of a7/a9), mixing (a8)
+# --------------------------------------------------------------------------
+def air_filter(sig: np.ndarray, rate, air):
+    """rs.py:310-333: whole-signal rfft, linear gain ramp above 2 kHz, irfft."""
+    if air < 0.01 or not isinstance(sig, np.ndarray) or sig.ndim != 2 or sig.size == 0:
+        return sig
+    n = sig.shape[0]
+    if n < 2:
+        return sig
+    spec = np.fft.rfft(sig, axis=0)
+    f = np.fft.rfftfreq(n, d=1.0 / rate)
+    start = 2000
+    band = f >= start
+    gain = np.ones_like(f)
+    top = f[-1] if len(f) > 0 else start + 1
+    if np.any(band) and top > start:
+        depth = np.clip(air, 0.0, 1.0) * 0.8
+        ramp = np.clip((f[band] - start) / (top - start), 0, 1)
+        gain[band] = 1.0 - ramp * depth
+    spec *= gain[:, None]
+    return np.fft.irfft(spec, n=n, axis=0).astype(F32)
+
+
+def eq_needed(bass, treble) -> bool:
+    """rs.py:389/443 gate."""
+    return (not np.isclose(bass, 1.0)) or (not np.isclose(treble, 1.0))
+
+
+def eq_filter(sig: np.ndarray, rate, bass, treble):
+    """rs.py:389-397 / 443-451: brick-wall shelves on the exact N-point rfft."""
+    if sig is None or sig.size == 0 or not eq_needed(bass, treble):
+        return sig
+    n = sig.shape[0]
+    if n < 2:
+        return sig
+    spec = np.fft.rfft(sig, axis=0)
+    f = np.fft.rfftfreq(n, d=1.0 / rate)
+    spec[(f > 1e-6) & (f <= 250)] *= np.clip(bass, 0.1, 5.0)
+    spec[f >= 4000] *= np.clip(treble, 0.1, 5.0)
+    return np.fft.irfft(spec, n=n, axis=0).astype(F32)
+
+
+def dry_gain_factor(dry_wet, kill_start):
+    """rs.py:93-105 -> (dw, factor applied to the dry branch before (1-dw))."""
+    dw = np.clip(float(dry_wet), 0.0, 1.0)
+    ks = np.clip(float(kill_start), 0.0, 1.0)
+    g = 1.0
+    if ks < 1.0 and dw >= ks:
+        span = 1.0 - ks
+        g = 0.0 if span < 1e-6 else np.clip(1.0 - (dw - ks) / span, 0.0, 1.0)
+    return dw, g
+
+
+def dry_wet(dry, wet, dry_wet_amount, kill_start=0.5):
+    """rs.py:84-121."""
+    dry = np.asarray(dry, dtype=F32)
+    wet = np.asarray(wet, dtype=F32)
+    dw, g = dry_gain_factor(dry_wet_amount, kill_start)
+    m = min(dry.shape[0], wet.shape[0])
+    out = (g * (1.0 - dw) * dry[:m]) + (dw * wet[:m])
+    if dry.shape[0] > m:
+        out = np.concatenate((out, dry[m:] * g * (1.0 - dw)), axis=0)
+    elif wet.shape[0] > m:
+        out = np.concatenate((out, wet[m:] * dw), axis=0)
+    return out.astype(F32)
+
+
+def peak_guard(x: np.ndarray):
+    """rs.py:402-404 (also 456-458): divide by the peak only if it exceeds 1;
+    a non-zero signal below 1e-9 is flushed to zero."""
+    pk = np.max(np.abs(x))
+    if pk > 1.0:
+        return x / pk
+    if np.any(x) and pk < 1e-9:
+        return np.zeros_like(x)
+    return x
+
+
+def as_stereo_f32(data: np.ndarray):
+    """rs.py:343-346 / 417-420."""
+    if data.ndim == 1:
+        data = np.stack((data, data), axis=1)
+    elif data.shape[1] == 1:
+        data = np.repeat(data, 2, axis=1)
+    elif data.shape[1] > 2:
+        data = data[:, :2]
+    return data.astype(F32)
+
+
+def _pair_convolve(stereo, ir_l, ir_r, n_out):
+    a = fftconvolve(stereo[:, 0], ir_l, mode="full")
+    b = fftconvolve(stereo[:, 1], ir_r, mode="full")
+    return np.stack((a[:n_out], b[:n_out]), axis=1)
+
+
+def convolve_split(data, early_ir, late_ir, early_level, late_level, dry_wet_amount,
+                   bass=1.0, treble=1.0, rate=44100, kill_start=0.5, air=0.0):
+    """a7, rs.py:338-408."""
+    if data is None or data.size == 0:
+        return np.zeros((0, 2), F32)
+    x = as_stereo_f32(data)
+    e = np.asarray(early_ir, F32).flatten() if early_ir is not None else np.zeros(1)
+    l = np.asarray(late_ir, F32).flatten() if late_ir is not None else np.zeros(1)
+    n = x.shape[0]
+    n_e = n + len(e) - 1 if len(e) > 0 else n
+    n_l = n + len(l) - 1 if len(l) > 0 else n
+    n_out = max(n, n_e, n_l)
+    x_pad = np.pad(x, ((0, n_out - n), (0, 0))) if n_out > n else x
+
+    wet_e = np.zeros((n_out, 2), F32)
+    if e.size > 1 and np.any(e) and early_level > 1e-6:
+        wet_e = _pair_convolve(x, e, e, n_out)
+    wet_l = np.zeros((n_out, 2), F32)
+    if l.size > 1 and np.any(l) and late_level > 1e-6:
+        wet_l = _pair_convolve(x, l, l, n_out)
+    if air > 0.01 and wet_l.size > 0:
+        wet_l = air_filter(wet_l, rate, air)
+
+    wet = (wet_e * early_level) + (wet_l * late_level)
+    mixed = dry_wet(x_pad, wet, dry_wet_amount, kill_start)
+    mixed = eq_filter(mixed, rate, bass, treble)
+    if mixed is None or mixed.size == 0:
+        return np.zeros((0, 2), F32)
+    return peak_guard(mixed).astype(F32)
+
+
+def convolve_external(data, ir, dry_wet_amount, bass=1.0, treble=1.0, rate=44100, kill_start=0.5):
+    """a9, rs.py:410-462."""
+    if data is None or data.size == 0:
+        return np.zeros((0, 2), F32)
+    if ir is None or not isinstance(ir, np.ndarray) or ir.ndim != 2 or ir.shape[1] != 2:
+        return data.astype(F32)
+    x = as_stereo_f32(data)
+    ir = ir.astype(F32)
+    n = x.shape[0]
+    n_out = n + ir.shape[0] - 1 if ir.shape[0] > 0 else n
+    x_pad = np.pad(x, ((0, n_out - n), (0, 0))) if n_out > n else x
+    wet = _pair_convolve(x, ir[:, 0], ir[:, 1], n_out)
+    mixed = dry_wet(x_pad, wet, dry_wet_amount, kill_start)
+    mixed = eq_filter(mixed, rate, bass, treble)
+    if mixed is None or mixed.size == 0:
+        return np.zeros((0, 2), F32)
+    return peak_guard(mixed).astype(F32)
+
+
+# --------------------------------------------------------------------------
+# panner and channel mapper (a10-a12)
+# --------------------------------------------------------------------------
+def pan_gains(x, y, z):
+    """rs.py:468,475-485 -> dict of Python-float gains (weak scalars => float32 math)."""
+    x, y, z = (np.clip(float(v), 0.0, 1.0) for v in (x, y, z))
+    gl, gr = math.sqrt(1.0 - x), math.sqrt(x)
+    pull = (0.5 - z) * (abs(y - 0.5) * 0.3)
+    gf = max(0, math.sqrt(1.0 - y) + pull)
+    gb = max(0, math.sqrt(y) - pull)
+    return dict(fl=gl * gf, fr=gr * gf, rl=gl * gb, rr=gr * gb,
+                c=math.cos((x - 0.5) * math.pi) * gf, mono=0.707, lfe=0.15)
+
+
+def pan_5_1(stereo, x, y, z):
+    """a10, rs.py:464-501."""
+    if stereo is None or stereo.size == 0:
+        return np.zeros((0, 6), F32)
+    s = as_stereo_f32(stereo)
+    g = pan_gains(x, y, z)
+    mono = (s[:, 0] + s[:, 1]) * g["mono"]
+    out = np.zeros((s.shape[0], 6), F32)
+    out[:, 0] = s[:, 0] * g["fl"]
+    out[:, 1] = s[:, 1] * g["fr"]
+    out[:, 2] = mono * g["c"]
+    out[:, 3] = mono * g["lfe"]
+    out[:, 4] = s[:, 0] * g["rl"]
+    out[:, 5] = s[:, 1] * g["rr"]
+    pk = np.max(np.abs(out))
+    if pk > 1.0:
+        out /= pk
+    elif np.any(out) and pk < 1e-9:
+        out = np.zeros_like(out)
+    return out.astype(F32)
+
+
+def delay_rows(sig, d):
+    """a11, rs.py:507-515."""
+    d = int(d)
+    if not isinstance(sig, np.ndarray) or sig.ndim != 2 or d <= 0:
+        return sig
+    n = sig.shape[0]
+    return np.concatenate((np.zeros((d, sig.shape[1]), sig.dtype), sig), axis=0)[:n]
+
+
+def map_layout(six, layout: str, rate, z=0.5):
+    """a12, rs.py:517-563.  "5.1 (Standard)" hands back (and may scale) the input object."""
+    if layout not in LAYOUTS:
+        layout = FALLBACK_LAYOUT
+    ch, names = LAYOUTS[layout]
+    if six is None or not isinstance(six, np.ndarray) or six.ndim != 2 or six.shape[1] != 6:
+        return np.zeros((0, ch), F32), names
+    out = np.zeros((six.shape[0], ch), six.dtype)
+    if layout == "Stereo":
+        out[:, 0] = six[:, 0] + six[:, 2] * 0.707 + six[:, 4] * 0.5
+        out[:, 1] = six[:, 1] + six[:, 2] * 0.707 + six[:, 5] * 0.5
+    elif layout == "5.1 (Standard)":
+        out = six
+    elif layout == "7.1 (Surround)":
+        out[:, :6] = six
+        d = int(rate * 12 / 1000)
+        out[:, 6:7] = delay_rows(six[:, 4:5], d) * 0.7
+        out[:, 7:8] = delay_rows(six[:, 5:6], d) * 0.7
+    else:  # 5.1.2: height gain is an np.float64 => product formed in float64 (App. A)
+        out[:, :6] = six
+        d = int(rate * 18 / 1000)
+        hg = np.clip(float(z), 0.0, 1.0) * 0.6
+        out[:, 6:7] = delay_rows(six[:, 4:5], d) * hg
+        out[:, 7:8] = delay_rows(six[:, 5:6], d) * hg
+    pk = np.max(np.abs(out))
+    if pk > 1.0:
+        out /= pk
+    elif np.any(out) and pk < 1e-9:
+        out = np.zeros_like(out)
+    return out, names
+
+
+# --------------------------------------------------------------------------
+# metrics (a13) and PCM packing (a14)
+# --------------------------------------------------------------------------
+def k_weighting_coeffs(rate):
+    """pyloudnorm 0.1.x IIRfilter.generate_coefficients for the two K-weighting
+    stages (high shelf +4 dB/1500 Hz/Q 0.7071, high pass 38 Hz/Q 0.5).  PARITY UNPINNED."""
+    out = []
+    # stage 1: RBJ high shelf
+    G, Q, fc = 4.0, 1.0 / np.sqrt(2.0), 1500.0
+    A = 10 ** (G / 40.0)
+    w0 = 2.0 * np.pi * (fc / rate)
+    al = np.sin(w0) / (2.0 * Q)
+    b = np.array([A * ((A + 1) + (A - 1) * np.cos(w0) + 2 * np.sqrt(A) * al),
+                  -2 * A * ((A - 1) + (A + 1) * np.cos(w0)),
+                  A * ((A + 1) + (A - 1) * np.cos(w0) - 2 * np.sqrt(A) * al)])
+    a = np.array([(A + 1) - (A - 1) * np.cos(w0) + 2 * np.sqrt(A) * al,
+                  2 * ((A - 1) - (A + 1) * np.cos(w0)),
+                  (A + 1) - (A - 1) * np.cos(w0) - 2 * np.sqrt(A) * al])
+    out.append((b / a[0], a / a[0]))
+    # stage 2: RBJ high pass
+    Q, fc = 0.5, 38.0
+    w0 = 2.0 * np.pi * (fc / rate)
+    al = np.sin(w0) / (2.0 * Q)
+    b = np.array([(1 + np.cos(w0)) / 2, -(1 + np.cos(w0)), (1 + np.cos(w0)) / 2])
+    a = np.array([1 + al, -2 * np.cos(w0), 1 - al])
+    out.append((b / a[0], a / a[0]))
+    return out
+
+
+def loudness_blocks(n_samples, rate, block=0.400, overlap=0.75):
+    """Gating-block sample ranges exactly as pyloudnorm computes them (float64
+    products truncated by int()).  -> list of (lo, hi)."""
+    step = 1.0 - overlap
+    T = n_samples / rate
+    count = int(np.round(((T - block) / (block * step))) + 1)
+    return [(int(block * (j * step) * rate), int(block * (j * step + 1) * rate)) for j in range(count)]
+
+
+def integrated_loudness(mono: np.ndarray, rate):
+    """pyloudnorm.Meter(rate).integrated_loudness(mono) restated.
+    Raises ValueError for input shorter than one 400 ms block, as pyloudnorm does.
+    PARITY UNPINNED (pyloudnorm is not installed in the authoring container)."""
+    block = 0.400
+    if not np.issubdtype(mono.dtype, np.floating):
+        raise ValueError("Data must be floating point.")
+    if mono.shape[0] < block * rate:
+        raise ValueError("Audio must have length greater than the block size.")
+    y = mono.copy()                      # keeps the input dtype (float32 on the hot path)
+    for b, a in k_weighting_coeffs(rate):
+        y[:] = lfilter(b, a, y)          # float64 result rounded back into y's dtype
+    zs = np.array([(1.0 / (block * rate)) * np.sum(np.square(y[lo:hi]))
+                   for lo, hi in loudness_blocks(len(y), rate)], dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lj = -0.691 + 10.0 * np.log10(zs)
+        keep = lj >= -70.0
+        rel = -0.691 + 10.0 * np.log10(np.mean(zs[keep])) - 10.0 if np.any(keep) else np.nan
+        keep = (lj > rel) & (lj > -70.0)
+        z_avg = np.nan_to_num(np.mean(zs[keep])) if np.any(keep) else 0.0
+        return float(-0.691 + 10.0 * np.log10(z_avg))
+
+
+def lufs_input(data: np.ndarray):
+    """rs.py:687-688: mono signal the loudness meter sees."""
+    return data[:, 0] if min(data.shape[1], 2) == 1 else np.mean(data[:, :2], axis=1)
+
+
+def metrics(data, rate, with_lufs=True):
+    """a13, rs.py:674-698.  `with_lufs=False` skips the pyloudnorm part."""
+    out = {"lufs": None, "true_peak_dbfs": None, "rms_dbfs": None}
+    if data is None or not isinstance(data, np.ndarray) or data.size == 0 or rate <= 0:
+        return out
+    if data.ndim == 1:
+        data = data[:, None]
+    elif data.ndim != 2:
+        return out
+    if with_lufs:
+        mono = lufs_input(data)
+        if np.max(np.abs(mono)) < 1e-6:
+            out["lufs"] = -np.inf
+        else:
+            try:
+                out["lufs"] = integrated_loudness(mono, rate)
+            except Exception:
+                out["lufs"] = None
+    pk = np.max(np.abs(data))
+    rms = np.sqrt(np.mean(data ** 2))
+    out["true_peak_dbfs"] = 20 * math.log10(pk) if pk > 1e-15 else -np.inf
+    out["rms_dbfs"] = 20 * math.log10(rms) if rms > 1e-15 else -np.inf
+    return out
+
+
+def pcm16(data: np.ndarray):
+    """a14, rs.py:1082-1084: clip to +-0.9999 (float32), non-finite -> 0, then
+    libsndfile's float->short rule lrintf(x * 32767.0f) (round half to even).
+    PARITY UNPINNED for the libsndfile step."""
+    c = np.clip(data, -0.9999, 0.9999)
+    if not np.all(np.isfinite(c)):
+        c = np.nan_to_num(c, nan=0.0, posinf=0.0, neginf=0.0)
+    return np.rint(c.astype(F32) * F32(32767.0)).astype(np.int16)
+
+
+# --------------------------------------------------------------------------
+# whole render on arrays (compute part of rs.py:991-1084, no file I/O)
+# --------------------------------------------------------------------------
+def render(samples, rate, *, external_ir=None, hall="Room", room_size=100.0, diffusion=0.5,
+           air=0.1, early=0.8, late=0.6, dry_wet_amount=0.5, kill_start=0.5, bass=1.0,
+           treble=1.0, x=0.5, y=0.5, z=0.5, material="Holz", layout=FALLBACK_LAYOUT,
+           rng=np.random, with_lufs=True):
+    """-> dict(stereo, final, names, metrics, pcm).  rs.py:1020-1084."""
+    s = np.asarray(samples, F32)
+    if s.ndim == 1:
+        s = s[:, None]
+    if s.shape[1] == 1:
+        s = np.repeat(s, 2, axis=1)
+    elif s.shape[1] > 2:
+        s = s[:, :2]
+    if external_ir is not None:
+        stereo = convolve_external(s, external_ir, dry_wet_amount, bass, treble, rate, kill_start)
+    else:
+        dur, refl, mdel, split = shape_params(hall, room_size, z)
+        d = directionality(x, y, z, hall, diffusion, dry_wet_amount)
+        e_ir, l_ir = generate_ir(rate, dur, refl, mdel, material, d, split, diffusion, rng)
+        e_lvl, l_lvl = adapt_levels(dry_wet_amount, early, late)
+        stereo = convolve_split(s, e_ir, l_ir, e_lvl, l_lvl, dry_wet_amount, bass, treble,
+                                rate, kill_start, air)
+    six = pan_5_1(stereo, x, y, z)
+    final, names = map_layout(six, layout, rate, z)
+    m = metrics(final, rate, with_lufs=with_lufs)
+    return dict(stereo=stereo, final=final, names=names, metrics=m, pcm=pcm16(final))

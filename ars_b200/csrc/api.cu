@@ -1,0 +1,562 @@
+// extern "C" surface of libars_b200 (declared in include/ars_b200.h).
+#include "../../include/ars_b200.h"
+
+#include <cmath>
+#include <limits>
+
+#include "epilogue.cuh"
+#include "ir_synth.cuh"
+#include "metrics.cuh"
+
+namespace ars {
+const char* last_error_cstr();
+void fft_profile_begin();
+void fft_profile_end(long long* launches, double* ms, double* bytes);
+
+#define ARS_API_BEGIN                                                   \
+    try {                                                               \
+        std::lock_guard<std::recursive_mutex> _lk(ctx().mu);            \
+        ARS_CUDA(cudaSetDevice(ctx().device));
+#define ARS_API_END                                                     \
+        return ARS_OK;                                                  \
+    } catch (const Error& e) {                                          \
+        set_last_error(e.what());                                       \
+        return e.code;                                                  \
+    } catch (const std::exception& e) {                                 \
+        set_last_error(e.what());                                       \
+        return ARS_ERR_INTERNAL;                                        \
+    }
+
+static inline double clip(double v, double lo, double hi) { return std::min(hi, std::max(lo, v)); }
+
+template <class T> static T* upload(const char* name, const T* host, size_t count) {
+    Ctx& c = ctx();
+    T* d = c.buf(name, sizeof(T) * std::max<size_t>(count, 1)).as<T>();
+    if (count) ARS_CUDA(cudaMemcpyAsync(d, host, sizeof(T) * count, cudaMemcpyHostToDevice, c.stream));
+    return d;
+}
+template <class T> static void download(T* host, const T* dev, size_t count) {
+    if (count) ARS_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx().stream));
+}
+static void sync() { ARS_CUDA(cudaStreamSynchronize(ctx().stream)); }
+
+static RenderState* fresh_state() {
+    Ctx& c = ctx();
+    RenderState* st = c.buf("state", sizeof(RenderState)).as<RenderState>();
+    ARS_CUDA(cudaMemsetAsync(st, 0, sizeof(RenderState), c.stream));
+    return st;
+}
+
+// ---- scalar helpers that mirror the reference's Python float arithmetic (C doubles, libm) ----
+struct IrGeom { i64 length, split, tap_hi, late_len; };
+static IrGeom ir_geometry(double rate, double dur, double max_delay, double split_time) {
+    // rs.py:249,254-255,259,271-272 -- rate is int(rate) in the reference
+    const i64 r = (i64)rate;
+    IrGeom g;
+    g.length = std::max<i64>(1, (i64)(dur * (double)r));
+    g.split = std::max<i64>(1, std::min<i64>((i64)(split_time * (double)r), g.length - 1));
+    const i64 mds = std::max<i64>(2, (i64)(max_delay * (double)r));
+    g.tap_hi = std::min(mds, g.split);
+    g.late_len = g.length - g.split;
+    return g;
+}
+
+static IrSpec ir_spec(double rate, double dur, double absorption, double direc, double diffusion, const IrGeom& g,
+                      int ntaps) {
+    IrSpec sp;
+    sp.length = g.length;
+    sp.split = g.split;
+    sp.ntaps = ntaps;
+    const i64 r = (i64)rate;
+    if (g.late_len > 0) {
+        const double floor_ratio = std::pow(10.0, -50.0 / 20.0);                          // rs.py:273
+        double decay = g.late_len > 1 ? std::pow(floor_ratio, 1.0 / (double)g.late_len) : 0.1;
+        decay = clip(decay * (1.0 - absorption * 0.1), 0.8, 0.99999);                     // rs.py:277
+        double amp = 0.6 * (1.0 - clip(direc, 0.0, 0.9));                                 // rs.py:279
+        amp *= clip(1.0 / (1 + dur * 0.5), 0.3, 1.0);
+        amp *= (1.0 - std::pow(absorption, 0.5));
+        sp.width = (int)clip((double)r * 0.001 * (1.0 + diffusion * 2.0), 1, 10);         // rs.py:284
+        amp *= (1.0 + diffusion * 0.2);                                                   // rs.py:294
+        sp.amp = amp;
+        sp.decay = decay;
+    }
+    return sp;
+}
+
+static std::vector<double> tap_strengths(const ArsIrDraws* dr, double absorption, double direc, i64 tap_hi) {
+    std::vector<double> s((size_t)std::max(0, dr ? dr->ntaps : 0));
+    for (size_t j = 0; j < s.size(); ++j) {
+        double v = dr->tap_base[j] * (1.0 - absorption);                                   // rs.py:265
+        v *= clip(direc, 0.1, 1.0);                                                        // rs.py:266
+        v *= (1.0 - std::pow((double)dr->tap_delay[j] / (double)tap_hi, 0.7));             // rs.py:267
+        s[j] = v;
+    }
+    return s;
+}
+
+static void dry_gain_factor(double dry_wet, double kill_start, double* dw_out, double* dmf_out) {
+    // rs.py:93-105
+    const double dw = clip(dry_wet, 0.0, 1.0), ks = clip(kill_start, 0.0, 1.0);
+    double g = 1.0;
+    if (ks < 1.0 && dw >= ks) {
+        const double span = 1.0 - ks;
+        g = span < 1e-6 ? 0.0 : clip(1.0 - (dw - ks) / span, 0.0, 1.0);
+    }
+    *dw_out = dw;
+    *dmf_out = g;
+}
+
+static bool is_close_to_one(double a) {
+    // np.isclose(a, 1.0): |a - 1| <= atol + rtol * |1| with atol 1e-8, rtol 1e-5
+    return std::isfinite(a) && std::fabs(a - 1.0) <= (1e-8 + 1e-5 * 1.0);
+}
+
+static TailSpec make_tail(i64 N, int layout, double rate, double x_, double y_, double z_) {
+    // rs.py:468, 475-485 (gains), 542, 549-550 (delays, height gain)
+    TailSpec ts;
+    ts.N = N;
+    ts.layout = layout;
+    ts.C = layout_channels(layout);
+    const double x = clip(x_, 0.0, 1.0), y = clip(y_, 0.0, 1.0), z = clip(z_, 0.0, 1.0);
+    const double gl = std::sqrt(1.0 - x), gr = std::sqrt(x);
+    const double pull = (0.5 - z) * (std::fabs(y - 0.5) * 0.3);
+    const double gf = std::max(0.0, std::sqrt(1.0 - y) + pull), gb = std::max(0.0, std::sqrt(y) - pull);
+    const double PI = 3.141592653589793;       // math.pi
+    ts.g_fl = (float)(gl * gf);
+    ts.g_fr = (float)(gr * gf);
+    ts.g_rl = (float)(gl * gb);
+    ts.g_rr = (float)(gr * gb);
+    ts.g_c = (float)(std::cos((x - 0.5) * PI) * gf);
+    ts.g_lfe = 0.15f;
+    const i64 r = (i64)rate;
+    if (layout == LAYOUT_7_1) ts.delay = (i64)((double)(r * 12) / 1000.0);       // int(rate * 12 / 1000)
+    else if (layout == LAYOUT_5_1_2) ts.delay = (i64)((double)(r * 18) / 1000.0);
+    ts.height_gain = clip(z_, 0.0, 1.0) * 0.6;
+    return ts;
+}
+
+static void finish_metrics(const RenderState& st, i64 count, ArsMetrics* m) {
+    const float peak = [&] { float f; unsigned u = st.peak_final; memcpy(&f, &u, 4); return f; }();
+    const double inf = std::numeric_limits<double>::infinity();
+    m->peak_linear = (double)peak;
+    const float rms = count > 0 ? (float)std::sqrt(st.sumsq / (double)count) : 0.f;   // numpy keeps float32 here
+    m->rms_linear = (double)rms;
+    m->true_peak_dbfs = (double)peak > 1e-15 ? 20.0 * std::log10((double)peak) : -inf;
+    m->rms_dbfs = (double)rms > 1e-15 ? 20.0 * std::log10((double)rms) : -inf;
+}
+
+// loudness of the mono feed already on the device (rs.py:685-691)
+static void lufs_of(const float* d_mono, i64 N, double rate, RenderState* d_state, ArsMetrics* m) {
+    Ctx& c = ctx();
+    unsigned* mb = c.buf("lufs.max", sizeof(unsigned)).as<unsigned>();
+    ARS_CUDA(cudaMemsetAsync(mb, 0, sizeof(unsigned), c.stream));
+    absmax_f32(d_mono, N, mb);
+    unsigned bits = 0;
+    download(&bits, mb, 1);
+    sync();
+    float pk;
+    memcpy(&pk, &bits, 4);
+    if (pk < 1e-6f) {                      // rs.py:689
+        m->lufs = -std::numeric_limits<double>::infinity();
+        m->lufs_status = ARS_LUFS_OK;
+        return;
+    }
+    double l = 0.0;
+    const int s = integrated_loudness(d_mono, N, rate, &l);
+    m->lufs = s == 0 ? l : 0.0;
+    m->lufs_status = s == 0 ? ARS_LUFS_OK : ARS_LUFS_NONE;
+    (void)d_state;
+}
+
+static int layout_ok(int layout) { return layout >= LAYOUT_STEREO && layout <= LAYOUT_5_1_2; }
+
+// ---------------------------------------------------------------- render core ----
+static i64 render_out_len(const ArsRenderParams* p, i64 n, i64 ext_len) {
+    if (p->external_ir) return ext_len > 0 ? n + ext_len - 1 : n;                  // rs.py:423-424
+    const IrGeom g = ir_geometry(p->rate, p->ir_duration, p->ir_max_delay, p->ir_split_time);
+    return n + g.length - 1;                                                       // rs.py:352-355
+}
+
+static void common_filter_spec(FilterSpec& fs, i64 N, double rate, double dry_wet, double kill, double bass,
+                               double treble) {
+    double dw, dmf;
+    dry_gain_factor(dry_wet, kill, &dw, &dmf);
+    fs.N = N;
+    fs.dw = dw;
+    fs.dry_gain = dmf * (1.0 - dw);
+    if (N >= 2 && !(is_close_to_one(bass) && is_close_to_one(treble))) fill_eq(fs, N, rate, bass, treble);   // rs.py:389-391
+}
+
+// all pointers on the device except draws->tap_* (host); draws->noise on the device
+static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int cin, const float* d_ext_ir, i64 ext_len,
+                        const ArsIrDraws* draws, float* d_out_stereo, float* d_out_f32, short* d_out_pcm,
+                        ArsMetrics* metrics) {
+    Ctx& c = ctx();
+    ARS_CHECK(p && d_in && n > 0 && cin >= 1, "render: empty input");
+    ARS_CHECK(p->rate >= 1.0, "render: bad sample rate");
+    ARS_CHECK(layout_ok(p->layout), "render: unknown layout id");
+    RenderState* st = fresh_state();
+    const i64 N = render_out_len(p, n, ext_len);
+    float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
+    FilterSpec fs;
+    common_filter_spec(fs, N, p->rate, p->dry_wet, p->kill_start, p->bass_gain, p->treble_gain);
+    if (p->external_ir) {
+        ARS_CHECK(d_ext_ir && ext_len >= 1, "render: external IR missing");
+        fs.mode = FILT_EXT;
+        spectral_filter(d_in, n, cin, d_ext_ir, ext_len, nullptr, 0, fs, y, st);
+    } else {
+        ARS_CHECK(p->ir_duration > 0, "render: IR duration must be positive");
+        const IrGeom g = ir_geometry(p->rate, p->ir_duration, p->ir_max_delay, p->ir_split_time);
+        const int ntaps = draws ? draws->ntaps : 0;
+        ARS_CHECK(!draws || draws->noise_len == g.late_len || draws->noise == nullptr,
+                  "render: noise length does not match the IR geometry");
+        ARS_CHECK(g.late_len == 0 || (draws && draws->noise), "render: tail noise missing");
+        const IrSpec sp = ir_spec(p->rate, p->ir_duration, p->absorption, p->directionality, p->diffusion, g, ntaps);
+        std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
+        // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, so `strength` may die)
+        const i64* d_delay = upload("ir.delay", draws ? (const i64*)draws->tap_delay : nullptr, (size_t)ntaps);
+        const double* d_strength = upload("ir.strength", strength.data(), (size_t)ntaps);
+        float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();
+        float* d_late = c.buf("ir.late", sizeof(float) * (size_t)g.length).as<float>();
+        ir_synth(sp, d_delay, d_strength, draws ? draws->noise : nullptr, d_early, d_late);
+        fs.mode = FILT_SPLIT;
+        fs.level0 = (g.length > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;     // rs.py:360
+        fs.level1 = (g.length > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;       // rs.py:369
+        if (p->air_absorption > 0.01 && N >= 2) fill_air(fs, N, p->rate, p->air_absorption);   // rs.py:378, 312-317
+        spectral_filter(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st);
+    }
+    if (d_out_stereo) {
+        ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
+        guard_apply(d_out_stereo, N * 2, &st->max_stereo);
+    }
+    if (!d_out_f32 && !d_out_pcm && !metrics) return;
+    const TailSpec ts = make_tail(N, p->layout, p->rate, p->x, p->y, p->z);
+    tail_maxes(y, ts, st);
+    float* d_mono = nullptr;
+    if (metrics && p->want_lufs) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
+    tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
+    if (metrics) {
+        memset(metrics, 0, sizeof(*metrics));
+        metrics->lufs_status = ARS_LUFS_SKIPPED;
+        if (d_mono) lufs_of(d_mono, N, p->rate, st, metrics);
+        RenderState h;
+        download(&h, st, 1);
+        sync();
+        finish_metrics(h, N * ts.C, metrics);
+    }
+}
+
+}  // namespace ars
+
+using namespace ars;
+
+extern "C" {
+
+int ars_init(int device) {
+    try {
+        ctx_init(device);
+        return ARS_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return ARS_ERR_INTERNAL;
+    }
+}
+
+void ars_shutdown(void) { ctx_shutdown(); }
+
+int ars_sync(void) {
+    ARS_API_BEGIN
+    sync();
+    ARS_API_END
+}
+
+const char* ars_last_error(void) { return last_error_cstr(); }
+const char* ars_version(void) { return "ars_b200 0.1 (sm_100a)"; }
+uint64_t ars_launch_count(void) { return ctx_ready() ? ctx().launches : 0; }
+void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
+
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+int ars_timer_begin(void) {
+    ARS_API_BEGIN
+    if (!g_ev0) { ARS_CUDA(cudaEventCreate(&g_ev0)); ARS_CUDA(cudaEventCreate(&g_ev1)); }
+    ARS_CUDA(cudaEventRecord(g_ev0, ctx().stream));
+    ARS_API_END
+}
+
+int ars_timer_end(float* ms) {
+    ARS_API_BEGIN
+    ARS_CHECK(g_ev0 && ms, "ars_timer_end without ars_timer_begin");
+    ARS_CUDA(cudaEventRecord(g_ev1, ctx().stream));
+    ARS_CUDA(cudaEventSynchronize(g_ev1));
+    ARS_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    ARS_API_END
+}
+
+int ars_profile_begin(void) {
+    ARS_API_BEGIN
+    fft_profile_begin();
+    ARS_API_END
+}
+
+int ars_profile_end(int64_t* launches, double* ms, double* bytes) {
+    ARS_API_BEGIN
+    long long l = 0;
+    double m = 0.0, b = 0.0;
+    fft_profile_end(&l, &m, &b);
+    if (launches) *launches = l;
+    if (ms) *ms = m;
+    if (bytes) *bytes = b;
+    ARS_API_END
+}
+
+int ars_ir_geometry(double rate, double ir_duration, double ir_max_delay, double ir_split_time, int64_t* length,
+                    int64_t* split, int64_t* tap_hi, int64_t* late_len) {
+    if (!(rate >= 1.0) || !(ir_duration > 0)) { set_last_error("ars_ir_geometry: rate and duration must be positive"); return ARS_ERR_ARG; }
+    const IrGeom g = ir_geometry(rate, ir_duration, ir_max_delay, ir_split_time);
+    if (length) *length = g.length;
+    if (split) *split = g.split;
+    if (tap_hi) *tap_hi = g.tap_hi;
+    if (late_len) *late_len = g.late_len;
+    return ARS_OK;
+}
+
+int ars_ir_synth(double rate, double ir_duration, double ir_max_delay, double absorption, double directionality,
+                 double ir_split_time, double diffusion, const ArsIrDraws* draws, float* early, float* late,
+                 int64_t length) {
+    ARS_API_BEGIN
+    ARS_CHECK(rate >= 1.0 && ir_duration > 0 && early && late, "ars_ir_synth: bad arguments");
+    const IrGeom g = ir_geometry(rate, ir_duration, ir_max_delay, ir_split_time);
+    ARS_CHECK(g.length == length, "ars_ir_synth: output length does not match max(1, int(duration * rate))");
+    const int ntaps = draws ? draws->ntaps : 0;
+    ARS_CHECK(g.late_len == 0 || (draws && draws->noise && draws->noise_len == g.late_len),
+              "ars_ir_synth: tail noise missing or of the wrong length");
+    const IrSpec sp = ir_spec(rate, ir_duration, absorption, directionality, diffusion, g, ntaps);
+    std::vector<double> strength = tap_strengths(draws, absorption, directionality, g.tap_hi);
+    const i64* d_delay = upload("ir.delay", draws ? (const i64*)draws->tap_delay : nullptr, (size_t)ntaps);
+    const double* d_strength = upload("ir.strength", strength.data(), (size_t)ntaps);
+    const double* d_noise = upload("ir.noise", draws ? draws->noise : nullptr, (size_t)g.late_len);
+    Ctx& c = ctx();
+    float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();
+    float* d_late = c.buf("ir.late", sizeof(float) * (size_t)g.length).as<float>();
+    ir_synth(sp, d_delay, d_strength, d_noise, d_early, d_late);
+    download(early, d_early, (size_t)g.length);
+    download(late, d_late, (size_t)g.length);
+    sync();
+    ARS_API_END
+}
+
+int ars_air_filter(const float* sig, int64_t n, double rate, double air, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(sig && out && n >= 2 && rate > 0, "ars_air_filter: needs an (n >= 2, 2) signal");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", sig, (size_t)n * 2);
+    RenderState* st = fresh_state();
+    FilterSpec fs;
+    fs.mode = FILT_MASK;
+    fs.N = n;
+    fill_air(fs, n, rate, air);
+    float2* y = c.buf("render.y", sizeof(float2) * (size_t)n).as<float2>();
+    spectral_filter(d_x, n, 2, nullptr, 0, nullptr, 0, fs, y, st);
+    download(out, reinterpret_cast<const float*>(y), (size_t)n * 2);
+    sync();
+    ARS_API_END
+}
+
+int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n_wet, int32_t ch, double dry_wet,
+                    double kill_start, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(ch >= 1 && n_dry >= 0 && n_wet >= 0 && out, "ars_dry_wet_mix: bad arguments");
+    const i64 total = std::max(n_dry, n_wet);
+    if (total == 0) return ARS_OK;
+    Ctx& c = ctx();
+    const float* d_dry = upload("in.dry", dry, (size_t)(n_dry * ch));
+    const float* d_wet = upload("in.wet", wet, (size_t)(n_wet * ch));
+    float* d_out = c.buf("out.f32", sizeof(float) * (size_t)(total * ch)).as<float>();
+    double dw, dmf;
+    dry_gain_factor(dry_wet, kill_start, &dw, &dmf);
+    mix_dry_wet(d_dry, n_dry, d_wet, n_wet, ch, dmf, dw, d_out);
+    download(out, d_out, (size_t)(total * ch));
+    sync();
+    ARS_API_END
+}
+
+int64_t ars_convolve_out_len(int64_t n, int64_t len_early, int64_t len_late) {
+    // rs.py:351-355 (a missing IR stands for zeros(1))
+    if (len_early <= 0) len_early = 1;
+    if (len_late <= 0) len_late = 1;
+    return std::max<i64>(n, std::max(n + len_early - 1, n + len_late - 1));
+}
+
+int ars_convolve_split(const float* data, int64_t n, int32_t cin, const float* early, int64_t len_early,
+                       const float* late, int64_t len_late, double early_level, double late_level, double dry_wet,
+                       double bass_gain, double treble_gain, double rate, double kill_start, double air_absorption,
+                       float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && out && n > 0 && cin >= 1 && rate > 0, "ars_convolve_split: bad arguments");
+    Ctx& c = ctx();
+    if (!early) len_early = 0;
+    if (!late) len_late = 0;
+    const i64 N = ars_convolve_out_len(n, len_early, len_late);
+    const float* d_x = upload("in.x", data, (size_t)n * cin);
+    const float* d_e = len_early > 0 ? upload("in.early", early, (size_t)len_early) : nullptr;
+    const float* d_l = len_late > 0 ? upload("in.late", late, (size_t)len_late) : nullptr;
+    RenderState* st = fresh_state();
+    FilterSpec fs;
+    common_filter_spec(fs, N, rate, dry_wet, kill_start, bass_gain, treble_gain);
+    fs.mode = FILT_SPLIT;
+    fs.level0 = (len_early > 1 && early_level > 1e-6) ? early_level : 0.0;          // rs.py:360
+    fs.level1 = (len_late > 1 && late_level > 1e-6) ? late_level : 0.0;            // rs.py:369
+    if (air_absorption > 0.01 && N >= 2) fill_air(fs, N, rate, air_absorption);     // rs.py:378
+    float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
+    spectral_filter(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st);
+    guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:402-404
+    download(out, reinterpret_cast<const float*>(y), (size_t)N * 2);
+    sync();
+    ARS_API_END
+}
+
+int ars_convolve_external(const float* data, int64_t n, int32_t cin, const float* ir, int64_t L, double dry_wet,
+                          double bass_gain, double treble_gain, double rate, double kill_start, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && out && ir && n > 0 && cin >= 1 && L >= 1 && rate > 0, "ars_convolve_external: bad arguments");
+    Ctx& c = ctx();
+    const i64 N = n + L - 1;
+    const float* d_x = upload("in.x", data, (size_t)n * cin);
+    const float* d_ir = upload("in.ir", ir, (size_t)L * 2);
+    RenderState* st = fresh_state();
+    FilterSpec fs;
+    common_filter_spec(fs, N, rate, dry_wet, kill_start, bass_gain, treble_gain);
+    fs.mode = FILT_EXT;
+    float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
+    spectral_filter(d_x, n, cin, d_ir, L, nullptr, 0, fs, y, st);
+    guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:456-458
+    download(out, reinterpret_cast<const float*>(y), (size_t)N * 2);
+    sync();
+    ARS_API_END
+}
+
+int ars_pan(const float* stereo, int64_t n, double x, double y, double z, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(stereo && out && n > 0, "ars_pan: bad arguments");
+    Ctx& c = ctx();
+    const float* d_s = upload("in.x", stereo, (size_t)n * 2);
+    float* d_six = c.buf("out.f32", sizeof(float) * (size_t)n * 6).as<float>();
+    RenderState* st = fresh_state();
+    const TailSpec ts = make_tail(n, LAYOUT_5_1, 48000.0, x, y, z);
+    pan_stage(d_s, n, ts, d_six);
+    absmax_f32(d_six, n * 6, &st->max_pan);
+    guard_apply(d_six, n * 6, &st->max_pan);                                          // rs.py:497-499
+    download(out, d_six, (size_t)n * 6);
+    sync();
+    ARS_API_END
+}
+
+int ars_delay(const float* sig, int64_t n, int32_t ch, int64_t delay_samples, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(sig && out && n > 0 && ch >= 1, "ars_delay: bad arguments");
+    Ctx& c = ctx();
+    const float* d_in = upload("in.x", sig, (size_t)n * ch);
+    float* d_out = c.buf("out.f32", sizeof(float) * (size_t)n * ch).as<float>();
+    delay_stage(d_in, n, ch, delay_samples, d_out);
+    download(out, d_out, (size_t)n * ch);
+    sync();
+    ARS_API_END
+}
+
+int ars_layout_channels(int32_t layout) { return layout_ok(layout) ? layout_channels(layout) : -1; }
+
+int ars_map_channels(const float* six, int64_t n, int32_t layout, double rate, double z, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(six && out && n > 0 && layout_ok(layout) && rate > 0, "ars_map_channels: bad arguments");
+    Ctx& c = ctx();
+    const float* d_six = upload("in.x", six, (size_t)n * 6);
+    const TailSpec ts = make_tail(n, layout, rate, 0.5, 0.5, z);
+    float* d_out = c.buf("out.f32", sizeof(float) * (size_t)n * ts.C).as<float>();
+    RenderState* st = fresh_state();
+    map_stage(d_six, n, ts, d_out);
+    absmax_f32(d_out, n * ts.C, &st->max_map);
+    guard_apply(d_out, n * ts.C, &st->max_map);                                       // rs.py:558-560
+    download(out, d_out, (size_t)n * ts.C);
+    sync();
+    ARS_API_END
+}
+
+int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t want_lufs, ArsMetrics* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && out && n > 0 && ch >= 1 && rate > 0, "ars_metrics: bad arguments");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", data, (size_t)n * ch);
+    RenderState* st = fresh_state();
+    float* d_mono = want_lufs ? c.buf("render.mono", sizeof(float) * (size_t)n).as<float>() : nullptr;
+    sums_stage(d_x, n, ch, st, d_mono);
+    memset(out, 0, sizeof(*out));
+    out->lufs_status = ARS_LUFS_SKIPPED;
+    if (want_lufs) lufs_of(d_mono, n, rate, st, out);
+    RenderState h;
+    download(&h, st, 1);
+    sync();
+    finish_metrics(h, n * ch, out);
+    ARS_API_END
+}
+
+int ars_pcm16(const float* data, int64_t count, int16_t* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && out && count > 0, "ars_pcm16: bad arguments");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", data, (size_t)count);
+    short* d_p = c.buf("out.pcm", sizeof(short) * (size_t)count).as<short>();
+    pcm16_stage(d_x, count, d_p);
+    download(reinterpret_cast<short*>(out), d_p, (size_t)count);
+    sync();
+    ARS_API_END
+}
+
+int64_t ars_render_out_len(const ArsRenderParams* p, int64_t n, int64_t ext_ir_len) {
+    if (!p || n <= 0) return 0;
+    return render_out_len(p, n, ext_ir_len);
+}
+
+int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int32_t cin, const float* ext_ir,
+               int64_t ext_ir_len, const ArsIrDraws* draws, float* out_stereo, float* out_f32, int16_t* out_pcm,
+               ArsMetrics* metrics) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && in && n > 0 && cin >= 1 && layout_ok(p->layout), "ars_render: bad arguments");
+    Ctx& c = ctx();
+    const i64 N = render_out_len(p, n, ext_ir_len);
+    const int C = layout_channels(p->layout);
+    const float* d_in = upload("in.x", in, (size_t)n * cin);
+    const float* d_ir = nullptr;
+    ArsIrDraws dd;
+    memset(&dd, 0, sizeof dd);
+    if (p->external_ir) {
+        ARS_CHECK(ext_ir && ext_ir_len >= 1, "ars_render: external IR missing");
+        d_ir = upload("in.ir", ext_ir, (size_t)ext_ir_len * 2);
+    } else if (draws) {
+        dd = *draws;
+        dd.noise = upload("ir.noise", draws->noise, (size_t)std::max<i64>(0, draws->noise_len));
+    }
+    float* d_st = out_stereo ? c.buf("out.stereo", sizeof(float) * (size_t)N * 2).as<float>() : nullptr;
+    float* d_f = out_f32 ? c.buf("out.f32", sizeof(float) * (size_t)N * C).as<float>() : nullptr;
+    short* d_p = out_pcm ? c.buf("out.pcm", sizeof(short) * (size_t)N * C).as<short>() : nullptr;
+    render_core(p, d_in, n, cin, d_ir, ext_ir_len, p->external_ir ? nullptr : &dd, d_st, d_f, d_p, metrics);
+    if (out_stereo) download(out_stereo, d_st, (size_t)N * 2);
+    if (out_f32) download(out_f32, d_f, (size_t)N * C);
+    if (out_pcm) download(reinterpret_cast<short*>(out_pcm), d_p, (size_t)N * C);
+    sync();
+    ARS_API_END
+}
+
+int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                   int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                   int16_t* d_out_pcm, ArsMetrics* metrics) {
+    ARS_API_BEGIN
+    render_core(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32,
+                reinterpret_cast<short*>(d_out_pcm), metrics);
+    ARS_API_END
+}
+
+}  // extern "C"

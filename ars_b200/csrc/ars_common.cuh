@@ -1,0 +1,118 @@
+// Shared plumbing for libars_b200: error handling, the per-process context
+// (device, stream, workspace cache, plan caches) and small device helpers.
+// sm_100a only; no CPU fallback anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ars {
+
+typedef long long i64;
+
+// ---------------------------------------------------------------- errors ----
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define ARS_CUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            char _b[512];                                                               \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,       \
+                     cudaGetErrorString(_e));                                           \
+            throw ::ars::Error(2, _b);                                                  \
+        }                                                                               \
+    } while (0)
+
+#define ARS_CHECK(cond, msg)                                                            \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            char _b[512];                                                               \
+            snprintf(_b, sizeof _b, "%s:%d: %s", __FILE__, __LINE__, (msg));            \
+            throw ::ars::Error(1, _b);                                                  \
+        }                                                                               \
+    } while (0)
+
+#define ARS_LAUNCH_CHECK() ARS_CUDA(cudaGetLastError())
+
+void set_last_error(const char* msg);
+
+// ------------------------------------------------------------- device mem ---
+// Grow-only device buffer. Workspaces are cached in the context by name so a
+// render of the same shape does not call cudaMalloc in steady state.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes);
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct FftPlan;        // fft_plan.cu
+struct BluesteinPlan;  // bluestein.cu
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    std::recursive_mutex mu;
+    std::map<std::string, DevBuf> ws;                 // named workspaces
+    std::map<int, FftPlan*> fft_plans;                // by log2(M)
+    std::map<i64, BluesteinPlan*> blue_plans;         // by N
+    std::vector<i64> blue_lru;
+    size_t blue_bytes = 0;
+    unsigned long long launches = 0;                  // kernels launched by this library
+    void* pinned = nullptr;                           // small pinned scratch for D2H scalars
+    size_t pinned_cap = 0;
+
+    DevBuf& buf(const char* name, size_t bytes) {
+        DevBuf& b = ws[name];
+        b.reserve(bytes);
+        return b;
+    }
+    void* pinned_scratch(size_t bytes);
+};
+
+Ctx& ctx();                 // throws if ars_init was not called
+bool ctx_ready();
+void ctx_init(int device);
+void ctx_shutdown();
+
+inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
+
+// ------------------------------------------------------------ device math ---
+struct c32 { float x, y; };
+
+__host__ __device__ inline float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ inline float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__host__ __device__ inline float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// monotone map of |x| to an unsigned so atomicMax works on floats (NaN sorts above inf;
+// callers that must ignore NaN clear it first).
+__host__ __device__ inline unsigned abs_bits(float v) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(v) & 0x7fffffffu;
+#else
+    unsigned u; memcpy(&u, &v, 4); return u & 0x7fffffffu;
+#endif
+}
+
+inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ars

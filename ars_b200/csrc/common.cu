@@ -1,0 +1,89 @@
+// Context, workspace cache and error plumbing of libars_b200.
+#include "ars_common.cuh"
+
+namespace ars {
+
+static Ctx* g_ctx = nullptr;
+static std::mutex g_ctx_mu;
+static thread_local std::string t_last_error;
+
+void set_last_error(const char* msg) { t_last_error = msg ? msg : ""; }
+const char* last_error_cstr() { return t_last_error.c_str(); }
+
+void DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) { ARS_CUDA(cudaFree(p)); p = nullptr; cap = 0; }
+    // round up so slightly different clip lengths reuse the same allocation
+    size_t want = (bytes + (size_t)(1 << 20) - 1) & ~((size_t)(1 << 20) - 1);
+    if (bytes < (1 << 20)) want = (bytes + 255) & ~(size_t)255;
+    ARS_CUDA(cudaMalloc(&p, want));
+    cap = want;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+void* Ctx::pinned_scratch(size_t bytes) {
+    if (bytes > pinned_cap) {
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        ARS_CUDA(cudaMallocHost(&pinned, want));
+        pinned_cap = want;
+    }
+    return pinned;
+}
+
+bool ctx_ready() { return g_ctx != nullptr; }
+
+Ctx& ctx() {
+    if (!g_ctx) throw Error(3, "ars_init() has not been called (no CUDA context; this library has no CPU path)");
+    return *g_ctx;
+}
+
+void ctx_init(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx) {
+        if (g_ctx->device == device || device < 0) return;
+        throw Error(1, "ars_init: already initialised on another device (call ars_shutdown first)");
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(3, std::string("ars_init: no CUDA device available (") + cudaGetErrorString(e) +
+                           "); libars_b200 has no CPU fallback");
+    if (device < 0) device = 0;
+    if (device >= count) throw Error(1, "ars_init: device index out of range");
+    ARS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ARS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        throw Error(3, "ars_init: this build carries sm_100a code only (needs a Blackwell B200-class GPU)");
+    Ctx* c = new Ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ARS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_ctx = c;
+}
+
+void fft_release_plans();       // fft_plan.cu
+void bluestein_release_plans(); // bluestein.cu
+
+void ctx_shutdown() {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!g_ctx) return;
+    cudaSetDevice(g_ctx->device);
+    cudaStreamSynchronize(g_ctx->stream);
+    bluestein_release_plans();
+    fft_release_plans();
+    for (auto& kv : g_ctx->ws) kv.second.release();
+    if (g_ctx->pinned) cudaFreeHost(g_ctx->pinned);
+    cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+}  // namespace ars

@@ -1,0 +1,390 @@
+// Epilogue kernels (see epilogue.cuh).  All of them are one-touch HBM streams: grid-stride,
+// grid = a multiple of the SM count, vector loads/stores, block reduce + one atomic per block.
+#include "epilogue.cuh"
+
+namespace ars {
+
+static inline int stream_grid(i64 items, int per_block = 256) {
+    const i64 need = (items + per_block - 1) / per_block;
+    const i64 cap = (i64)ctx().sm_count * 8;
+    return (int)std::max<i64>(1, std::min(need, cap));
+}
+
+// ----------------------------------------------------------- frame math ------
+struct Guard { int mode; float m; };      // 0: leave, 1: divide by m, 2: flush to zero
+
+__device__ __forceinline__ Guard make_guard(unsigned bits) {
+    // rs.py:402-404 / 497-499 / 558-560: max > 1 -> x / max ; any(x) and max < 1e-9 -> zeros
+    const float m = __uint_as_float(bits);
+    Guard g;
+    g.m = m;
+    g.mode = (m > 1.0f) ? 1 : ((m > 0.f && m < 1e-9f) ? 2 : 0);
+    return g;
+}
+__device__ __forceinline__ float guard1(float v, const Guard& g) {
+    return g.mode == 0 ? v : (g.mode == 1 ? __fdiv_rn(v, g.m) : 0.f);
+}
+
+__device__ __forceinline__ void pan6(float L, float R, const TailSpec& ts, float (&o)[6]) {
+    // rs.py:485-494 (float32 array times Python float => float32 multiply)
+    const float mono = __fmul_rn(__fadd_rn(L, R), 0.707f);
+    o[0] = __fmul_rn(L, ts.g_fl);
+    o[1] = __fmul_rn(R, ts.g_fr);
+    o[2] = __fmul_rn(mono, ts.g_c);
+    o[3] = __fmul_rn(mono, ts.g_lfe);
+    o[4] = __fmul_rn(L, ts.g_rl);
+    o[5] = __fmul_rn(R, ts.g_rr);
+}
+
+// out channels of one frame from its (guarded) six channels and the (guarded) rear pair d frames earlier
+__device__ __forceinline__ void map_frame(const float (&s)[6], float rl_d, float rr_d, const TailSpec& ts,
+                                          float (&o)[8]) {
+    if (ts.layout == LAYOUT_STEREO) {           // rs.py:533-535
+        o[0] = __fadd_rn(__fadd_rn(s[0], __fmul_rn(s[2], 0.707f)), __fmul_rn(s[4], 0.5f));
+        o[1] = __fadd_rn(__fadd_rn(s[1], __fmul_rn(s[2], 0.707f)), __fmul_rn(s[5], 0.5f));
+        return;
+    }
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) o[c] = s[c];
+    if (ts.layout == LAYOUT_7_1) {              // rs.py:541-545
+        o[6] = __fmul_rn(rl_d, 0.7f);
+        o[7] = __fmul_rn(rr_d, 0.7f);
+    } else if (ts.layout == LAYOUT_5_1_2) {     // rs.py:548-554: float64 product, rounded on store
+        o[6] = __double2float_rn(__dmul_rn((double)rl_d, ts.height_gain));
+        o[7] = __double2float_rn(__dmul_rn((double)rr_d, ts.height_gain));
+    }
+}
+
+__device__ __forceinline__ unsigned warp_max(unsigned m) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+__device__ __forceinline__ void block_atomic_max(unsigned m, unsigned* dst) {
+    __shared__ unsigned s_m[32];
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x + 31) / 32) ? s_m[threadIdx.x] : 0u;
+        m = warp_max(m);
+        if (threadIdx.x == 0 && m) atomicMax(dst, m);
+    }
+}
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+    __shared__ double s_v[32];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x + 31) / 32) ? s_v[threadIdx.x] : 0.0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(dst, v);
+    }
+}
+
+// ------------------------------------------------------- fused tail kernels --
+__global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st) {
+    const Guard g1 = make_guard(st->max_stereo);
+    unsigned m = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+        const float2 v = __ldg(y + i);
+        float s[6];
+        pan6(guard1(v.x, g1), guard1(v.y, g1), ts, s);
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) m = max(m, abs_bits(s[c]));
+    }
+    block_atomic_max(m, &st->max_pan);
+}
+
+__device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
+                                          const Guard& g2, float (&o)[8]) {
+    const float2 v = __ldg(y + i);
+    float s[6];
+    pan6(guard1(v.x, g1), guard1(v.y, g1), ts, s);
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = guard1(s[c], g2);
+    float rl_d = 0.f, rr_d = 0.f;
+    if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
+        // a delay <= 0 leaves the signal where it is (rs.py:510-511)
+        const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0)));
+        rl_d = guard1(__fmul_rn(guard1(w.x, g1), ts.g_rl), g2);
+        rr_d = guard1(__fmul_rn(guard1(w.y, g1), ts.g_rr), g2);
+    }
+    map_frame(s, rl_d, rr_d, ts, o);
+}
+
+__global__ void __launch_bounds__(256) map_max_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st) {
+    const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
+    unsigned m = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+        float o[8];
+        frame_out(y, i, ts, g1, g2, o);
+        #pragma unroll
+        for (int c = 0; c < 8; ++c) if (c < ts.C) m = max(m, abs_bits(o[c]));
+    }
+    block_atomic_max(m, &st->max_map);
+}
+
+__device__ __forceinline__ short pcm_of(float v) {
+    // np.clip(+-0.9999) in float32, NaN -> 0, then lrintf(x * 32767.0f)   (rs.py:1082-1084)
+    if (v != v) v = 0.f;
+    v = fminf(fmaxf(v, -0.9999f), 0.9999f);
+    return (short)__float2int_rn(__fmul_rn(v, 32767.0f));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st,
+                                                    float* __restrict__ out, short* __restrict__ pcm,
+                                                    float* __restrict__ mono) {
+    const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
+    const Guard g3 = make_guard(ts.layout == LAYOUT_5_1 ? 0u : st->max_map);
+    unsigned pk = 0;
+    double ss = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+        float o[8];
+        frame_out(y, i, ts, g1, g2, o);
+        #pragma unroll
+        for (int c = 0; c < C; ++c) {
+            o[c] = guard1(o[c], g3);
+            pk = max(pk, abs_bits(o[c]));
+            ss += (double)__fmul_rn(o[c], o[c]);
+        }
+        if (out) {
+            float* p = out + i * C;
+            if (C == 8) {
+                reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+                #pragma unroll
+                for (int c = 0; c < C; c += 2) reinterpret_cast<float2*>(p)[c >> 1] = make_float2(o[c], o[c + 1]);
+            }
+        }
+        if (pcm) {
+            short q[8];
+            #pragma unroll
+            for (int c = 0; c < C; ++c) q[c] = pcm_of(o[c]);
+            short* p = pcm + i * C;
+            if (C == 8) {
+                uint4 u;
+                u.x = (unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16);
+                u.y = (unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16);
+                u.z = (unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16);
+                u.w = (unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16);
+                *reinterpret_cast<uint4*>(p) = u;
+            } else {
+                #pragma unroll
+                for (int c = 0; c < C; c += 2)
+                    reinterpret_cast<unsigned*>(p)[c >> 1] =
+                        (unsigned short)q[c] | ((unsigned)(unsigned short)q[c + 1] << 16);
+            }
+        }
+        if (mono) mono[i] = __fdiv_rn(__fadd_rn(o[0], o[1]), 2.0f);     // np.mean(data[:, :2], axis=1), rs.py:688
+    }
+    block_atomic_max(pk, &st->peak_final);
+    block_atomic_add(ss, &st->sumsq);
+}
+
+void tail_maxes(const float2* d_y, const TailSpec& ts, RenderState* d_state) {
+    if (ts.N <= 0) return;
+    Ctx& c = ctx();
+    pan_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    if (ts.layout != LAYOUT_5_1) {
+        map_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+}
+
+void tail_final(const float2* d_y, const TailSpec& ts, RenderState* d_state, float* d_out, short* d_pcm,
+                float* d_mono) {
+    if (ts.N <= 0) return;
+    Ctx& c = ctx();
+    const int grid = stream_grid(ts.N);
+    if (ts.C == 2) final_kernel<2><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
+    else if (ts.C == 6) final_kernel<6><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
+    else final_kernel<8><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+// --------------------------------------------------------- stage kernels -----
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, i64 count, unsigned* dst) {
+    unsigned m = 0;
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, step = (i64)gridDim.x * blockDim.x;
+    const i64 n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? count / 4 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (i64 i = tid; i < n4; i += step) {
+        const float4 v = __ldg(x4 + i);
+        m = max(max(m, abs_bits(v.x)), max(abs_bits(v.y), max(abs_bits(v.z), abs_bits(v.w))));
+    }
+    for (i64 i = n4 * 4 + tid; i < count; i += step) m = max(m, abs_bits(__ldg(x + i)));
+    block_atomic_max(m, dst);
+}
+void absmax_f32(const float* d_x, i64 count, unsigned* d_maxbits) {
+    if (count <= 0) return;
+    absmax_kernel<<<stream_grid(count / 4 + 1), 256, 0, ctx().stream>>>(d_x, count, d_maxbits);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) guard_kernel(float* __restrict__ x, i64 count, const unsigned* maxbits) {
+    const Guard g = make_guard(*maxbits);
+    if (g.mode == 0) return;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x)
+        x[i] = guard1(x[i], g);
+}
+void guard_apply(float* d_x, i64 count, const unsigned* d_maxbits) {
+    if (count <= 0) return;
+    guard_kernel<<<stream_grid(count), 256, 0, ctx().stream>>>(d_x, count, d_maxbits);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+// rs.py:113-121: (dmf*(1-dw)) * dry + dw * wet over the common length, the longer tail appended scaled;
+// np.float64 scalars => float64 products and sum, rounded to float32 once.
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ dry, const float* __restrict__ wet, i64 count,
+                                                  double dry_scale, double dw, float* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x)
+        out[i] = __double2float_rn(__dadd_rn(__dmul_rn(dry_scale, (double)dry[i]), __dmul_rn(dw, (double)wet[i])));
+}
+__global__ void __launch_bounds__(256) mix_tail_kernel(const float* __restrict__ src, i64 lo, i64 hi, double s0, double s1,
+                                                       int two, float* __restrict__ out) {
+    for (i64 i = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (i64)gridDim.x * blockDim.x) {
+        double v = __dmul_rn((double)src[i], s0);
+        if (two) v = __dmul_rn(v, s1);
+        out[i] = __double2float_rn(v);
+    }
+}
+void mix_dry_wet(const float* d_dry, i64 n_dry, const float* d_wet, i64 n_wet, int ch, double dmf, double dw,
+                 float* d_out) {
+    // dmf = dry_mix_factor; the common part uses (dmf * (1 - dw)) as one float64 scalar (rs.py:113)
+    const i64 c_dry = n_dry * ch, c_wet = n_wet * ch;
+    const i64 common = std::min(c_dry, c_wet), total = std::max(c_dry, c_wet);
+    if (total <= 0) return;
+    Ctx& c = ctx();
+    const double dry_scale = dmf * (1.0 - dw);
+    if (common > 0) {
+        mix_kernel<<<stream_grid(common), 256, 0, c.stream>>>(d_dry, d_wet, common, dry_scale, dw, d_out);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+    if (c_dry > common) {          // rs.py:117: dry[min_len:] * dmf * (1.0 - dw)  (two successive float64 multiplies)
+        mix_tail_kernel<<<stream_grid(c_dry - common), 256, 0, c.stream>>>(d_dry, common, c_dry, dmf, 1.0 - dw, 1, d_out);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    } else if (c_wet > common) {   // rs.py:119: wet[min_len:] * dw
+        mix_tail_kernel<<<stream_grid(c_wet - common), 256, 0, c.stream>>>(d_wet, common, c_wet, dw, 1.0, 0, d_out);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+}
+
+__global__ void __launch_bounds__(256) pan_kernel(const float2* __restrict__ s, TailSpec ts, float* __restrict__ six) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+        const float2 v = __ldg(s + i);
+        float o[6];
+        pan6(v.x, v.y, ts, o);
+        float2* p = reinterpret_cast<float2*>(six + i * 6);
+        p[0] = make_float2(o[0], o[1]);
+        p[1] = make_float2(o[2], o[3]);
+        p[2] = make_float2(o[4], o[5]);
+    }
+}
+void pan_stage(const float* d_stereo, i64 N, const TailSpec& ts_in, float* d_six) {
+    if (N <= 0) return;
+    TailSpec ts = ts_in;
+    ts.N = N;
+    pan_kernel<<<stream_grid(N), 256, 0, ctx().stream>>>(reinterpret_cast<const float2*>(d_stereo), ts, d_six);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) map_kernel(const float* __restrict__ six, TailSpec ts, float* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+        float s[6], o[8];
+        const float2* p = reinterpret_cast<const float2*>(six + i * 6);
+        const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y; s[4] = c.x; s[5] = c.y;
+        float rl_d = 0.f, rr_d = 0.f;
+        if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
+            const float2 d = __ldg(reinterpret_cast<const float2*>(six + (i - (ts.delay > 0 ? ts.delay : 0)) * 6) + 2);
+            rl_d = d.x; rr_d = d.y;
+        }
+        map_frame(s, rl_d, rr_d, ts, o);
+        #pragma unroll
+        for (int ch = 0; ch < 8; ++ch) if (ch < ts.C) out[i * ts.C + ch] = o[ch];
+    }
+}
+void map_stage(const float* d_six, i64 N, const TailSpec& ts_in, float* d_out) {
+    if (N <= 0) return;
+    TailSpec ts = ts_in;
+    ts.N = N;
+    map_kernel<<<stream_grid(N), 256, 0, ctx().stream>>>(d_six, ts, d_out);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) delay_kernel(const float* __restrict__ in, i64 count, i64 shift, float* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x)
+        out[i] = i >= shift ? in[i - shift] : 0.f;
+}
+void delay_stage(const float* d_in, i64 N, int ch, i64 delay, float* d_out) {
+    if (N <= 0 || ch <= 0) return;
+    delay_kernel<<<stream_grid(N * ch), 256, 0, ctx().stream>>>(d_in, N * ch, std::max<i64>(0, delay) * ch, d_out);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) pcm16_kernel(const float* __restrict__ x, i64 count, short* __restrict__ pcm) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x)
+        pcm[i] = pcm_of(__ldg(x + i));
+}
+void pcm16_stage(const float* d_x, i64 count, short* d_pcm) {
+    if (count <= 0) return;
+    pcm16_kernel<<<stream_grid(count), 256, 0, ctx().stream>>>(d_x, count, d_pcm);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) sums_kernel(const float* __restrict__ x, i64 N, int C, RenderState* st,
+                                                   float* __restrict__ mono) {
+    unsigned pk = 0;
+    double ss = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (i64)gridDim.x * blockDim.x) {
+        const float* p = x + i * C;
+        for (int c = 0; c < C; ++c) {
+            const float v = __ldg(p + c);
+            pk = max(pk, abs_bits(v));
+            ss += (double)__fmul_rn(v, v);
+        }
+        if (mono) mono[i] = C >= 2 ? __fdiv_rn(__fadd_rn(__ldg(p), __ldg(p + 1)), 2.0f) : __ldg(p);
+    }
+    block_atomic_max(pk, &st->peak_final);
+    block_atomic_add(ss, &st->sumsq);
+}
+void sums_stage(const float* d_x, i64 N, int C, RenderState* d_state, float* d_mono) {
+    if (N <= 0 || C <= 0) return;
+    sums_kernel<<<stream_grid(N), 256, 0, ctx().stream>>>(d_x, N, C, d_state, d_mono);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+__global__ void __launch_bounds__(256) stereo_from_kernel(const float* __restrict__ x, i64 n, int cin, float2* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const float l = x[i * cin];
+        out[i] = make_float2(l, cin > 1 ? x[i * cin + 1] : l);
+    }
+}
+void stereo_from(const float* d_x, i64 n, int cin, float* d_out) {
+    if (n <= 0) return;
+    stereo_from_kernel<<<stream_grid(n), 256, 0, ctx().stream>>>(d_x, n, cin, reinterpret_cast<float2*>(d_out));
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+}  // namespace ars

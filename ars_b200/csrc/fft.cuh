@@ -1,0 +1,504 @@
+// Power-of-two complex64 FFT engine for sm_100a (hand-written; cuFFT is not used).
+//
+// A length-M transform (M = 2^m, m <= 30) is a short sequence of in-place "passes"
+// over an M-element complex buffer in HBM.  Each pass moves a tile through shared
+// memory exactly once (read 8 B + write 8 B per element), does a complete
+// R-point sub-transform of every tile column with register-resident radix-8/16
+// butterflies, and applies the inter-pass twiddle on the way out.
+//
+//   forward  = decimation in frequency: strided passes first (segment length
+//              Lg = M, M/R1, ...), the contiguous pass last; output is left in a
+//              digit-permuted order;
+//   inverse  = the exact algebraic inverse (decimation in time, conjugate
+//              twiddles, passes and stages in reverse order); it consumes the
+//              permuted order and produces natural order.
+//
+// Because every use in this library is  IFFT(FFT(a) .* S)  with S produced by the same
+// forward transform, no reordering pass is ever needed.  Loads of the first pass and
+// stores of the last pass go through small functors (Ld / St) so chirp multiplies,
+// zero padding, spectrum products, scaling and the abs-max reduction are fused into
+// the passes instead of costing extra trips through HBM.
+#pragma once
+#include "ars_common.cuh"
+
+#ifdef __CUDA_ARCH__
+#define ARS_LDG(p) __ldg(p)
+#else
+#define ARS_LDG(p) (*(p))
+#endif
+#define ARS_HD __host__ __device__ __forceinline__
+
+namespace ars {
+namespace fft {
+
+// ------------------------------------------------------------------ radices ---
+template <int LOGR> struct Rad;
+#define ARS_RAD(L, N, A, B, C, D)                                   \
+    template <> struct Rad<L> {                                     \
+        static constexpr int n = N;                                 \
+        static constexpr int r0 = A, r1 = B, r2 = C, r3 = D;        \
+        static __host__ __device__ constexpr int r(int s) { return s == 0 ? A : s == 1 ? B : s == 2 ? C : D; } \
+    };
+ARS_RAD(1, 1, 2, 1, 1, 1)
+ARS_RAD(2, 1, 4, 1, 1, 1)
+ARS_RAD(3, 1, 8, 1, 1, 1)
+ARS_RAD(4, 1, 16, 1, 1, 1)
+ARS_RAD(5, 2, 8, 4, 1, 1)
+ARS_RAD(6, 2, 8, 8, 1, 1)
+ARS_RAD(7, 2, 16, 8, 1, 1)
+ARS_RAD(8, 2, 16, 16, 1, 1)
+ARS_RAD(9, 3, 8, 8, 8, 1)
+ARS_RAD(10, 3, 16, 8, 8, 1)
+ARS_RAD(11, 3, 16, 16, 8, 1)
+ARS_RAD(12, 3, 16, 16, 16, 1)
+ARS_RAD(13, 4, 16, 8, 8, 8)
+#undef ARS_RAD
+
+constexpr int TWN_LOG = 13;            // local twiddle table: w_8192^e
+constexpr int TWN = 1 << TWN_LOG;
+constexpr int BIG_LO_LOG = 15;         // two-level table for w_M^e
+
+// ---------------------------------------------------------------- butterflies -
+template <bool INV> ARS_HD float2 mul_mi(float2 a) {
+    // forward: multiply by -i ; inverse: multiply by +i
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+constexpr float COS16[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                             0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                             -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
+                             0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+constexpr float SIN16[16] = {0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                             1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                             0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                             -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+
+// a * w_16^E  (forward: w = exp(-2 pi i/16); inverse: conjugate)
+template <int E, bool INV> ARS_HD float2 mulw16(float2 a) {
+    constexpr int e = E & 15;
+    if constexpr (e == 0) return a;
+    else if constexpr (e == 4) return mul_mi<INV>(a);
+    else if constexpr (e == 8) return make_float2(-a.x, -a.y);
+    else if constexpr (e == 12) return mul_mi<!INV>(a);
+    else {
+        constexpr float c = COS16[e];
+        constexpr float s = INV ? SIN16[e] : -SIN16[e];
+        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+template <bool INV> ARS_HD void bf4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+// natural-order in, natural-order out R-point DFT held in registers
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<2, INV> {
+    static ARS_HD void run(float2 (&v)[2]) {
+        float2 t = v[0]; v[0] = cadd(t, v[1]); v[1] = csub(t, v[1]);
+    }
+};
+template <bool INV> struct Dft<4, INV> {
+    static ARS_HD void run(float2 (&v)[4]) { bf4<INV>(v[0], v[1], v[2], v[3]); }
+};
+template <bool INV> struct Dft<8, INV> {
+    static ARS_HD void run(float2 (&v)[8]) {
+        bf4<INV>(v[0], v[2], v[4], v[6]);
+        bf4<INV>(v[1], v[3], v[5], v[7]);
+        float2 b1 = mulw16<2, INV>(v[3]), b2 = mulw16<4, INV>(v[5]), b3 = mulw16<6, INV>(v[7]);
+        float2 o0 = cadd(v[0], v[1]), o4 = csub(v[0], v[1]);
+        float2 o1 = cadd(v[2], b1), o5 = csub(v[2], b1);
+        float2 o2 = cadd(v[4], b2), o6 = csub(v[4], b2);
+        float2 o3 = cadd(v[6], b3), o7 = csub(v[6], b3);
+        v[0] = o0; v[1] = o1; v[2] = o2; v[3] = o3; v[4] = o4; v[5] = o5; v[6] = o6; v[7] = o7;
+    }
+};
+template <bool INV> struct Dft<16, INV> {
+    static ARS_HD void run(float2 (&v)[16]) {
+        bf4<INV>(v[0], v[4], v[8], v[12]);
+        bf4<INV>(v[1], v[5], v[9], v[13]);
+        bf4<INV>(v[2], v[6], v[10], v[14]);
+        bf4<INV>(v[3], v[7], v[11], v[15]);
+        // v[n2 + 4*k1] *= w16^(n2*k1)
+        v[5] = mulw16<1, INV>(v[5]);  v[6] = mulw16<2, INV>(v[6]);   v[7] = mulw16<3, INV>(v[7]);
+        v[9] = mulw16<2, INV>(v[9]);  v[10] = mulw16<4, INV>(v[10]); v[11] = mulw16<6, INV>(v[11]);
+        v[13] = mulw16<3, INV>(v[13]); v[14] = mulw16<6, INV>(v[14]); v[15] = mulw16<9, INV>(v[15]);
+        bf4<INV>(v[0], v[1], v[2], v[3]);
+        bf4<INV>(v[4], v[5], v[6], v[7]);
+        bf4<INV>(v[8], v[9], v[10], v[11]);
+        bf4<INV>(v[12], v[13], v[14], v[15]);
+        // X[k1 + 4*k2] sits in v[4*k1 + k2]: transpose
+        float2 t;
+        t = v[1]; v[1] = v[4]; v[4] = t;   t = v[2]; v[2] = v[8]; v[8] = t;
+        t = v[3]; v[3] = v[12]; v[12] = t; t = v[6]; v[6] = v[9]; v[9] = t;
+        t = v[7]; v[7] = v[13]; v[13] = t; t = v[11]; v[11] = v[14]; v[14] = t;
+    }
+};
+
+// ------------------------------------------------------------- Ld / St functors
+enum LdMode { LD_PLAIN = 0, LD_MULSPEC, LD_CHIRP_X2, LD_CHIRP_XC, LD_CHIRP_PAIR, LD_CHIRP_B, LD_CHIRP_C,
+              LD_REAL_PAIR };
+enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL };
+
+struct Ld {
+    int mode = LD_PLAIN;
+    const float2* a = nullptr;      // complex source / work buffer
+    const float2* b = nullptr;      // second complex operand (spectrum or chirp)
+    const float* f0 = nullptr;      // real sources
+    const float* f1 = nullptr;
+    i64 nvalid = 0;                 // elements of the source that exist (rest is zero padding)
+    i64 nvalid1 = 0;
+    i64 N = 0, M = 0;
+    int cin = 2;
+    ARS_HD float2 operator()(i64 idx) const {
+        switch (mode) {
+            case LD_PLAIN: return a[idx];
+            case LD_MULSPEC: return cmul(a[idx], b[idx]);
+            case LD_CHIRP_X2:      // interleaved stereo frames = complex samples L + iR
+                return idx < nvalid ? cmul(ARS_LDG(reinterpret_cast<const float2*>(f0) + idx), ARS_LDG(b + idx))
+                                    : make_float2(0.f, 0.f);
+            case LD_CHIRP_XC: {    // (frames, cin) floats: cin == 1 duplicates, cin > 2 keeps the first two
+                if (idx >= nvalid) return make_float2(0.f, 0.f);
+                float l = ARS_LDG(f0 + idx * cin);
+                float r = cin > 1 ? ARS_LDG(f0 + idx * cin + 1) : l;
+                return cmul(make_float2(l, r), ARS_LDG(b + idx));
+            }
+            case LD_CHIRP_PAIR: {  // two real arrays packed as re + i*im (each may be absent / shorter)
+                float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
+                float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
+                if (idx >= N) return make_float2(0.f, 0.f);
+                return cmul(make_float2(l, r), ARS_LDG(b + idx));
+            }
+            case LD_CHIRP_B: {     // Bluestein kernel: conj(chirp) on (-N, N), wrapped modulo M
+                if (idx < N) return cconj(ARS_LDG(b + idx));
+                if (idx > M - N) return cconj(ARS_LDG(b + (M - idx)));
+                return make_float2(0.f, 0.f);
+            }
+            case LD_CHIRP_C:       // complex N-vector times chirp
+                return idx < nvalid ? cmul(ARS_LDG(a + idx), ARS_LDG(b + idx)) : make_float2(0.f, 0.f);
+            case LD_REAL_PAIR: {   // no chirp: plain zero-padded packing (power-of-two convolution path)
+                float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
+                float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
+                return make_float2(l, r);
+            }
+        }
+        return make_float2(0.f, 0.f);
+    }
+};
+
+struct St {
+    int mode = ST_PLAIN;
+    float2* a = nullptr;
+    const float2* chirp = nullptr;
+    i64 N = 0;
+    float scale = 1.f;
+    unsigned* maxbits = nullptr;     // ST_FINAL: abs-max over everything stored (uint bits of |x|)
+    unsigned local_max = 0;
+    ARS_HD void operator()(i64 idx, float2 v) {
+        switch (mode) {
+            case ST_PLAIN: a[idx] = v; break;
+            case ST_SCALE: a[idx] = cscale(v, scale); break;
+            case ST_CHIRP:
+                if (idx < N) a[idx] = cmul(v, ARS_LDG(chirp + idx));
+                break;
+            case ST_FINAL:
+                if (idx < N) {
+                    float2 y = cmul(v, ARS_LDG(chirp + idx));
+                    y = make_float2(y.x * scale, -y.y * scale);
+                    a[idx] = y;
+                    unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y);
+                    unsigned mm = m0 > m1 ? m0 : m1;
+                    if (mm > local_max) local_max = mm;
+                }
+                break;
+        }
+    }
+    ARS_HD void finish() {
+        if (mode == ST_FINAL && maxbits) {
+#ifdef __CUDA_ARCH__
+            unsigned m = local_max;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0 && m) atomicMax(maxbits, m);
+#else
+            if (local_max > *maxbits) *maxbits = local_max;
+#endif
+        }
+    }
+};
+
+// ------------------------------------------------------------------ twiddles --
+struct Tw {
+    const float2* local;    // w_TWN^e, e < TWN
+    const float2* lo;       // w_M^e, e < min(M, 2^15)
+    const float2* hi;       // w_M^(e << 15), e < M >> 15 (null when M <= 2^15)
+};
+
+template <bool INV> ARS_HD float2 tw_local(const Tw& tw, int e) {
+    float2 w = ARS_LDG(tw.local + e);
+    return INV ? cconj(w) : w;
+}
+template <bool INV> ARS_HD float2 tw_big(const Tw& tw, unsigned e) {
+    float2 w = ARS_LDG(tw.lo + (e & ((1u << BIG_LO_LOG) - 1)));
+    if (tw.hi) w = cmul(w, ARS_LDG(tw.hi + (e >> BIG_LO_LOG)));
+    return INV ? cconj(w) : w;
+}
+
+// -------------------------------------------------------------- tile layouts --
+// Strided pass: tile = R rows (stride `stride` elements apart in HBM) x T adjacent columns.
+template <int LOGR, int LOGT> struct StridedLayout {
+    static constexpr int R = 1 << LOGR, T = 1 << LOGT, C = T;
+    static constexpr int SMEM_ELEMS = R * T + ((R * T) >> 4);
+    static ARS_HD int bfly(int q) { return q >> LOGT; }
+    static ARS_HD int col(int q) { return q & (T - 1); }
+    static ARS_HD int sidx(int row, int c) { int i = (row << LOGT) + c; return i + (i >> 4); }
+};
+// Contiguous pass: tile = C whole R-point segments.
+template <int LOGR, int LOGC> struct ContigLayout {
+    static constexpr int R = 1 << LOGR, C = 1 << LOGC;
+    static constexpr int SMEM_ELEMS = R * C + ((R * C) >> 4);
+    static ARS_HD int sidx(int row, int c) { int i = (c << LOGR) + row; return i + (i >> 4); }
+};
+
+struct PassArgs {
+    i64 M;          // transform length
+    int logM;
+    int logLg;      // strided: segment length of this pass (Lg); contiguous: == LOGR
+    Tw tw;
+};
+
+template <int LOGR> struct Prod {   // product of the radices before stage s
+    static __host__ __device__ constexpr int before(int s) {
+        int p = 1;
+        for (int i = 0; i < s; ++i) p *= Rad<LOGR>::r(i);
+        return p;
+    }
+};
+
+// digit-reversed output index of slot (b, k) in the last stage (see file header)
+template <int LOGR> ARS_HD int kfull_of(int b, int k) {
+    constexpr int n = Rad<LOGR>::n;
+    constexpr int R = 1 << LOGR;
+    constexpr int rl = Rad<LOGR>::r(n - 1);
+    int kf = 0;
+    int mul = 1;
+    #pragma unroll
+    for (int s = 0; s < n - 1; ++s) {
+        const int rs = Rad<LOGR>::r(s);
+        const int W = R / (Prod<LOGR>::before(s + 1) * rl);     // weight of digit k_s inside b
+        int ks = (b / W) % rs;
+        kf += ks * mul;
+        mul *= rs;
+    }
+    return kf + k * mul;
+}
+
+// One DIF (forward) or DIT (inverse) stage S of the R-point column transforms of a tile.
+//   GIDX_FIRST(row, c): HBM index of tile element (row, c) on the natural-order side
+//   GIDX_LAST(b, k, c): HBM index of output k of last-stage butterfly b on the permuted side
+template <int LOGR, int S, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast,
+                                          unsigned col0, int tid) {
+    constexpr int R = 1 << LOGR;
+    constexpr int n = Rad<LOGR>::n;
+    constexpr int r = Rad<LOGR>::r(S);
+    constexpr int Ls = R / Prod<LOGR>::before(S);
+    constexpr int sub = Ls / r;
+    constexpr bool first = (S == 0), last = (S == n - 1);
+    constexpr int NB = R / r;                  // butterflies per column
+    constexpr int TOTAL = NB * LAYOUT::C;
+    constexpr int TWSTEP = TWN / Ls;
+
+    for (int q = tid; q < TOTAL; q += NT) {
+        int b, c;
+        if constexpr (STRIDED) { b = LAYOUT::bfly(q); c = LAYOUT::col(q); }
+        else { b = q % NB; c = q / NB; }
+        const int seg = b / sub, i = b % sub;
+        const int row0 = seg * Ls + i;
+        float2 v[r];
+        if constexpr (!INV) {
+            #pragma unroll
+            for (int t = 0; t < r; ++t) {
+                const int row = row0 + t * sub;
+                v[t] = first ? ld(gfirst(row, c)) : sm[LAYOUT::sidx(row, c)];
+            }
+            Dft<r, false>::run(v);
+            if constexpr (!last) {
+                #pragma unroll
+                for (int k = 1; k < r; ++k) v[k] = cmul(v[k], tw_local<false>(pa.tw, i * k * TWSTEP));
+                #pragma unroll
+                for (int k = 0; k < r; ++k) sm[LAYOUT::sidx(row0 + k * sub, c)] = v[k];
+            } else {
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    if constexpr (STRIDED) {
+                        const unsigned kf = (unsigned)kfull_of<LOGR>(b, k);
+                        const unsigned e = ((col0 + (unsigned)c) * kf) << (pa.logM - pa.logLg);
+                        v[k] = cmul(v[k], tw_big<false>(pa.tw, e));
+                    }
+                    st(glast(b, k, c), v[k]);
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < r; ++k) {
+                if constexpr (last) {
+                    v[k] = ld(glast(b, k, c));
+                    if constexpr (STRIDED) {
+                        const unsigned kf = (unsigned)kfull_of<LOGR>(b, k);
+                        const unsigned e = ((col0 + (unsigned)c) * kf) << (pa.logM - pa.logLg);
+                        v[k] = cmul(v[k], tw_big<true>(pa.tw, e));
+                    }
+                } else {
+                    v[k] = sm[LAYOUT::sidx(row0 + k * sub, c)];
+                    if (k) v[k] = cmul(v[k], tw_local<true>(pa.tw, i * k * TWSTEP));
+                }
+            }
+            Dft<r, true>::run(v);
+            #pragma unroll
+            for (int t = 0; t < r; ++t) {
+                const int row = row0 + t * sub;
+                if constexpr (first) st(gfirst(row, c), v[t]);
+                else sm[LAYOUT::sidx(row, c)] = v[t];
+            }
+        }
+    }
+}
+
+#define ARS_STAGE(S_) run_stage<LOGR, S_, INV, STRIDED, NT, LAYOUT>(sm, ld, st, pa, gfirst, glast, col0, tid)
+template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+__device__ __forceinline__ void run_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast,
+                                         unsigned col0) {
+    constexpr int n = Rad<LOGR>::n;
+    const int tid = (int)threadIdx.x;
+    if constexpr (!INV) {
+        ARS_STAGE(0);
+        if constexpr (n > 1) { __syncthreads(); ARS_STAGE(1); }
+        if constexpr (n > 2) { __syncthreads(); ARS_STAGE(2); }
+        if constexpr (n > 3) { __syncthreads(); ARS_STAGE(3); }
+    } else {
+        if constexpr (n > 3) { ARS_STAGE(3); __syncthreads(); }
+        if constexpr (n > 2) { ARS_STAGE(2); __syncthreads(); }
+        if constexpr (n > 1) { ARS_STAGE(1); __syncthreads(); }
+        ARS_STAGE(0);
+    }
+    st.finish();
+}
+
+// Host emulation of one tile (tests/host_emul): the same stage code, "threads" run one after
+// another, a barrier is simply the end of the loop over threads.
+template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+inline void emulate_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast, unsigned col0) {
+    constexpr int n = Rad<LOGR>::n;
+#define ARS_ALL(S_) for (int tid = 0; tid < NT; ++tid) ARS_STAGE(S_)
+    if constexpr (!INV) {
+        ARS_ALL(0);
+        if constexpr (n > 1) { ARS_ALL(1); }
+        if constexpr (n > 2) { ARS_ALL(2); }
+        if constexpr (n > 3) { ARS_ALL(3); }
+    } else {
+        if constexpr (n > 3) { ARS_ALL(3); }
+        if constexpr (n > 2) { ARS_ALL(2); }
+        if constexpr (n > 1) { ARS_ALL(1); }
+        ARS_ALL(0);
+    }
+#undef ARS_ALL
+    st.finish();
+}
+
+// ------------------------------------------------------------------- kernels --
+// HBM index maps of a tile.  "first" = natural-order side, "last" = permuted side.
+template <int LOGR> struct StridedFirst {
+    i64 base; int logStride;
+    ARS_HD i64 operator()(int row, int c) const { return base + ((i64)row << logStride) + c; }
+};
+template <int LOGR> struct StridedLast {
+    i64 base; int logStride;
+    ARS_HD i64 operator()(int b, int k, int c) const {
+        constexpr int rl = Rad<LOGR>::r(Rad<LOGR>::n - 1);
+        return base + ((i64)(b * rl + k) << logStride) + c;
+    }
+};
+template <int LOGR> struct ContigFirst {
+    i64 base;
+    ARS_HD i64 operator()(int row, int c) const { return base + ((i64)c << LOGR) + row; }
+};
+// permuted side of the contiguous pass: output k of last-stage butterfly b is parked at
+// k*(R/rl) + b (not b*rl + k) so that adjacent lanes touch adjacent addresses
+template <int LOGR> struct ContigLast {
+    i64 base;
+    ARS_HD i64 operator()(int b, int k, int c) const {
+        constexpr int rl = Rad<LOGR>::r(Rad<LOGR>::n - 1);
+        return base + ((i64)c << LOGR) + k * ((1 << LOGR) / rl) + b;
+    }
+};
+
+// tile (g, cb) of a strided pass over segments of length Lg = 2^logLg covers rows
+// t = 0..R-1 at  g*Lg + t*(Lg/R) + cb*T + c
+template <int LOGR, int LOGT> struct StridedTile {
+    i64 base; unsigned col0; int logStride;
+    ARS_HD StridedTile(i64 tile, const PassArgs& pa) {
+        logStride = pa.logLg - LOGR;
+        const int sh = logStride - LOGT;
+        const i64 g = tile >> sh;
+        const unsigned cb = (unsigned)(tile & (((i64)1 << sh) - 1));
+        col0 = cb << LOGT;
+        base = (g << pa.logLg) + col0;
+    }
+};
+
+template <int LOGR, int LOGT, bool INV, int NT>
+__global__ void __launch_bounds__(NT) pass_strided_kernel(Ld ld, St st, PassArgs pa) {
+    extern __shared__ float2 sm[];
+    const StridedTile<LOGR, LOGT> t((i64)blockIdx.x, pa);
+    run_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>>(
+        sm, ld, st, pa, StridedFirst<LOGR>{t.base, t.logStride}, StridedLast<LOGR>{t.base, t.logStride}, t.col0);
+}
+
+// Contiguous pass: tile = C whole segments of R adjacent elements.
+template <int LOGR, int LOGC, bool INV, int NT>
+__global__ void __launch_bounds__(NT) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
+    extern __shared__ float2 sm[];
+    const i64 base = (i64)blockIdx.x << (LOGR + LOGC);
+    run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>>(sm, ld, st, pa, ContigFirst<LOGR>{base},
+                                                             ContigLast<LOGR>{base}, 0u);
+}
+
+}  // namespace fft
+
+// instantiated (logR, logT|logC) pass variants; the launcher and the host emulator share the list
+#define ARS_STRIDED_CASES(X) X(4, 9) X(5, 8) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 2)
+#define ARS_CONTIG_CASES(X)                                                                         \
+    X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(5, 0) X(6, 0) X(7, 0) X(8, 0) X(9, 0) X(10, 0) X(11, 0) X(12, 0) \
+    X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1)
+
+// ------------------------------------------------------------------ host API --
+struct FftPass {
+    bool strided;
+    int logR;
+    int logT;       // strided: log2 columns per tile; contiguous: log2 segments per tile
+    int logLg;
+};
+
+struct FftPlan {
+    int logM = 0;
+    i64 M = 0;
+    std::vector<FftPass> passes;   // forward order
+    DevBuf tw_lo, tw_hi;
+    fft::Tw tw{};
+};
+
+std::vector<FftPass> fft_decompose(int logM);
+FftPlan* get_fft_plan(int logM);
+
+// Forward transform: first pass reads through `ld`, everything else works in `work`
+// (M complex), last pass writes through `st` (permuted order).
+void fft_forward(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st);
+// Inverse transform: first pass reads through `ld` (permuted order), last pass writes natural
+// order through `st`.  Unnormalised.
+void fft_inverse(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st);
+
+int next_pow2_log(i64 n);
+
+}  // namespace ars

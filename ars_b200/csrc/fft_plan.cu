@@ -1,0 +1,220 @@
+// FFT plans (pass decomposition + twiddle tables) and the launchers for fft.cuh.
+#include "fft.cuh"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace ars {
+
+using namespace fft;
+
+
+// ----------------------------------------------------------------- tables ----
+__global__ void twiddle_table_kernel(float2* out, int count, double step_turns) {
+    // out[e] = exp(-2 pi i * e * step_turns), evaluated in double
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    double s, c;
+    sincospi(-2.0 * (double)e * step_turns, &s, &c);
+    out[e] = make_float2((float)c, (float)s);
+}
+
+static DevBuf g_tw_local;
+
+static const float2* local_table() {
+    if (!g_tw_local.p) {
+        g_tw_local.reserve(sizeof(float2) * TWN);
+        twiddle_table_kernel<<<ceil_div(TWN, 256), 256, 0, ctx().stream>>>(g_tw_local.as<float2>(), TWN, 1.0 / TWN);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+    return g_tw_local.as<float2>();
+}
+
+void fft_release_plans() {
+    if (ctx_ready()) {
+        for (auto& kv : ctx().fft_plans) { kv.second->tw_lo.release(); kv.second->tw_hi.release(); delete kv.second; }
+        ctx().fft_plans.clear();
+    }
+    g_tw_local.release();
+}
+
+}  // namespace ars
+#include "fft_decompose.inc"
+namespace ars {
+
+FftPlan* get_fft_plan(int logM) {
+    Ctx& c = ctx();
+    auto it = c.fft_plans.find(logM);
+    if (it != c.fft_plans.end()) return it->second;
+    ARS_CHECK(logM >= 1 && logM <= 30, "FFT length out of range (2^1 .. 2^30)");
+    FftPlan* p = new FftPlan();
+    p->logM = logM;
+    p->M = (i64)1 << logM;
+    p->passes = fft_decompose(logM);
+    const int nlo = (int)std::min<i64>(p->M, (i64)1 << BIG_LO_LOG);
+    p->tw_lo.reserve(sizeof(float2) * nlo);
+    twiddle_table_kernel<<<ceil_div(nlo, 256), 256, 0, c.stream>>>(p->tw_lo.as<float2>(), nlo, 1.0 / (double)p->M);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    p->tw.lo = p->tw_lo.as<float2>();
+    p->tw.hi = nullptr;
+    if (logM > BIG_LO_LOG) {
+        const int nhi = 1 << (logM - BIG_LO_LOG);
+        p->tw_hi.reserve(sizeof(float2) * nhi);
+        twiddle_table_kernel<<<ceil_div(nhi, 256), 256, 0, c.stream>>>(p->tw_hi.as<float2>(), nhi,
+                                                                      (double)(1 << BIG_LO_LOG) / (double)p->M);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        p->tw.hi = p->tw_hi.as<float2>();
+    }
+    p->tw.local = local_table();
+    c.fft_plans[logM] = p;
+    return p;
+}
+
+// ---------------------------------------------------------------- profiling ---
+// Optional per-launch CUDA-event timing of the FFT pass kernels (the dominant kernels of a render);
+// bench.py turns it on for a separate, untimed run to get the roofline numerator and denominator.
+struct PassProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;     // pairs (start, stop)
+    size_t used = 0;
+    double bytes = 0.0;              // algorithmic bytes of the recorded launches
+} g_prof;
+
+static double ld_bytes(const Ld& ld, i64 M) {
+    switch (ld.mode) {
+        case LD_PLAIN: return 8.0 * (double)M;
+        case LD_MULSPEC: return 16.0 * (double)M;
+        case LD_CHIRP_X2: return 16.0 * (double)ld.nvalid;
+        case LD_CHIRP_XC: return (8.0 + 4.0 * std::min(ld.cin, 2)) * (double)ld.nvalid;
+        case LD_CHIRP_PAIR: return 4.0 * (double)(ld.nvalid + ld.nvalid1) + 8.0 * (double)std::max(ld.nvalid, ld.nvalid1);
+        case LD_CHIRP_B: return 8.0 * (double)(2 * ld.N - 1);
+        case LD_CHIRP_C: return 16.0 * (double)ld.nvalid;
+        case LD_REAL_PAIR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
+    }
+    return 0.0;
+}
+static double st_bytes(const St& st, i64 M) {
+    switch (st.mode) {
+        case ST_PLAIN: case ST_SCALE: return 8.0 * (double)M;
+        case ST_CHIRP: case ST_FINAL: return 16.0 * (double)st.N;
+    }
+    return 0.0;
+}
+
+void fft_profile_begin() {
+    g_prof.on = true;
+    g_prof.used = 0;
+    g_prof.bytes = 0.0;
+}
+// -> launches, total milliseconds, algorithmic bytes
+void fft_profile_end(long long* launches, double* ms, double* bytes) {
+    ARS_CUDA(cudaStreamSynchronize(ctx().stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        float t = 0.f;
+        ARS_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+        tot += t;
+    }
+    *launches = (long long)(g_prof.used / 2);
+    *ms = tot;
+    *bytes = g_prof.bytes;
+    g_prof.on = false;
+}
+static cudaEvent_t prof_event() {
+    if (g_prof.used == g_prof.ev.size()) {
+        cudaEvent_t e;
+        ARS_CUDA(cudaEventCreate(&e));
+        g_prof.ev.push_back(e);
+    }
+    return g_prof.ev[g_prof.used++];
+}
+
+// --------------------------------------------------------------- launchers ---
+constexpr int NT = 256;
+
+template <int LOGR, int LOGT, bool INV>
+static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = StridedLayout<LOGR, LOGT>;
+    static bool attr_done = false;
+    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
+    auto k = pass_strided_kernel<LOGR, LOGT, INV, NT>;
+    if (!attr_done && smem > 48 * 1024) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const i64 tiles = pa.M >> (LOGR + LOGT);
+    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+template <int LOGR, int LOGC, bool INV>
+static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = ContigLayout<LOGR, LOGC>;
+    static bool attr_done = false;
+    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
+    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT>;
+    if (!attr_done && smem > 48 * 1024) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const i64 tiles = pa.M >> (LOGR + LOGC);
+    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+template <bool INV>
+static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const St& st) {
+    PassArgs pa;
+    pa.M = p->M;
+    pa.logM = p->logM;
+    pa.logLg = ps.logLg;
+    pa.tw = p->tw;
+    struct ProfScope {
+        bool on;
+        ProfScope(const Ld& l, const St& s, i64 M) : on(g_prof.on) {
+            if (on) { g_prof.bytes += ld_bytes(l, M) + st_bytes(s, M); ARS_CUDA(cudaEventRecord(prof_event(), ctx().stream)); }
+        }
+        ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
+    } prof_scope(ld, st, p->M);
+    if (ps.strided) {
+        ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
+#define S_CASE(R, T) if (ps.logR == R && ps.logT == T) return launch_strided<R, T, INV>(ld, st, pa);
+        ARS_STRIDED_CASES(S_CASE)
+#undef S_CASE
+        ARS_CHECK(false, "no strided FFT pass kernel for this (logR, logT)");
+    } else {
+#define C_CASE(R, C) if (ps.logR == R && ps.logT == C) return launch_contig<R, C, INV>(ld, st, pa);
+        ARS_CONTIG_CASES(C_CASE)
+#undef C_CASE
+        ARS_CHECK(false, "no contiguous FFT pass kernel for this (logR, logC)");
+    }
+}
+
+void fft_forward(FftPlan* p, const Ld& ld_first, float2* work, const St& st_last) {
+    const int np = (int)p->passes.size();
+    for (int i = 0; i < np; ++i) {
+        Ld ld;
+        St st;
+        if (i == 0) ld = ld_first; else { ld.mode = LD_PLAIN; ld.a = work; }
+        if (i == np - 1) st = st_last; else { st.mode = ST_PLAIN; st.a = work; }
+        launch_pass<false>(p, p->passes[i], ld, st);
+    }
+}
+
+void fft_inverse(FftPlan* p, const Ld& ld_first, float2* work, const St& st_last) {
+    const int np = (int)p->passes.size();
+    for (int i = np - 1; i >= 0; --i) {
+        Ld ld;
+        St st;
+        if (i == np - 1) ld = ld_first; else { ld.mode = LD_PLAIN; ld.a = work; }
+        if (i == 0) st = st_last; else { st.mode = ST_PLAIN; st.a = work; }
+        launch_pass<true>(p, p->passes[i], ld, st);
+    }
+}
+
+}  // namespace ars

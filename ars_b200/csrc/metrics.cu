@@ -1,0 +1,237 @@
+// Result metrics (calculate_audio_metrics, rs.py:674-711): sample peak and RMS come from the
+// running sums of the epilogue; this file adds the K-weighted, gated integrated loudness that
+// the reference obtains from pyloudnorm (restated in SURVEY.md App. B -- PARITY UNPINNED, the
+// package is not installable here).
+//
+// The two K-weighting biquads are IIR recurrences over the whole signal.  They are evaluated
+// as a parallel scan of affine maps in float64: every thread filters a 32-sample chunk from a
+// zero state, the chunk end-states are combined with precomputed powers of the 2x2 state
+// matrix (block scan, then a short serial scan over block aggregates), and a second sweep
+// re-filters every chunk from its true start state.  As in pyloudnorm, the stage output is
+// rounded to float32 before the next stage reads it.
+#include "metrics.cuh"
+
+#include <cmath>
+
+namespace ars {
+
+constexpr int CH = 32;                // samples per thread
+constexpr int NTB = 256;              // threads per block
+constexpr int BS = CH * NTB;          // samples per block
+
+struct Biquad {                       // normalised (a0 = 1)
+    double b0, b1, b2, a1, a2;
+};
+struct Mat2 { double m00, m01, m10, m11; };
+struct ScanCoef {
+    Biquad q;
+    Mat2 pw[9];                       // A^(CH * 2^k), k = 0..8  (pw[8] = A^BS)
+};
+
+static Mat2 mat_mul(const Mat2& a, const Mat2& b) {
+    return {a.m00 * b.m00 + a.m01 * b.m10, a.m00 * b.m01 + a.m01 * b.m11,
+            a.m10 * b.m00 + a.m11 * b.m10, a.m10 * b.m01 + a.m11 * b.m11};
+}
+
+static ScanCoef make_coef(const Biquad& q) {
+    ScanCoef c;
+    c.q = q;
+    Mat2 a = {-q.a1, 1.0, -q.a2, 0.0};      // direct form II transposed state matrix
+    Mat2 p = a;
+    for (int i = 1; i < CH; i <<= 1) p = mat_mul(p, p);     // A^CH (CH is a power of two)
+    c.pw[0] = p;
+    for (int k = 1; k < 9; ++k) c.pw[k] = mat_mul(c.pw[k - 1], c.pw[k - 1]);
+    return c;
+}
+
+__device__ __forceinline__ double2 mat_vec(const Mat2& m, double2 v) {
+    return make_double2(m.m00 * v.x + m.m01 * v.y, m.m10 * v.x + m.m11 * v.y);
+}
+
+// scipy.signal.lfilter's recurrence (direct form II transposed)
+__device__ __forceinline__ double df2t(const Biquad& q, double x, double2& z) {
+    const double y = q.b0 * x + z.x;
+    z.x = q.b1 * x - q.a1 * y + z.y;
+    z.y = q.b2 * x - q.a2 * y;
+    return y;
+}
+
+// PHASE 0: per-block aggregate end state (zero start).  PHASE 1: real output, block start states given.
+template <int PHASE>
+__global__ void __launch_bounds__(NTB) biquad_kernel(const float* __restrict__ x, i64 N, ScanCoef cf,
+                                                     double2* __restrict__ block_state, float* __restrict__ y) {
+    __shared__ float sx[NTB * (CH + 1)];
+    __shared__ double2 sv[NTB];
+    const i64 base = (i64)blockIdx.x * BS;
+    const int t = threadIdx.x;
+    for (int i = t; i < BS; i += NTB) {
+        const i64 g = base + i;
+        sx[(i / CH) * (CH + 1) + (i % CH)] = g < N ? x[g] : 0.f;
+    }
+    __syncthreads();
+    float* mine = sx + t * (CH + 1);
+    double2 z = make_double2(0.0, 0.0);
+    #pragma unroll 8
+    for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
+    // inclusive scan of w_t = P w_{t-1} + g_t with P = A^CH; the block's start state enters at t = 0
+    double2 v = z;
+    if (PHASE == 1 && t == 0) {
+        const double2 s0 = block_state[blockIdx.x];
+        const double2 ps = mat_vec(cf.pw[0], s0);
+        v.x += ps.x; v.y += ps.y;
+    }
+    sv[t] = v;
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int off = 1 << k;
+        double2 add = make_double2(0.0, 0.0);
+        if (t >= off) add = mat_vec(cf.pw[k], sv[t - off]);
+        __syncthreads();
+        v.x += add.x; v.y += add.y;
+        sv[t] = v;
+        __syncthreads();
+    }
+    if (PHASE == 0) {
+        if (t == NTB - 1) block_state[blockIdx.x] = v;       // aggregate: end state from a zero start
+        return;
+    }
+    double2 s = (t == 0) ? block_state[blockIdx.x] : sv[t - 1];
+    #pragma unroll 8
+    for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(cf.q, (double)mine[j], s);   // float32 store, as pyloudnorm
+    __syncthreads();
+    for (int i = t; i < BS; i += NTB) {
+        const i64 g = base + i;
+        if (g < N) y[g] = sx[(i / CH) * (CH + 1) + (i % CH)];
+    }
+}
+
+// exclusive serial scan over block aggregates: start[b+1] = A^BS start[b] + agg[b]
+__global__ void block_scan_kernel(double2* state, int nblocks, Mat2 pbs) {
+    if (blockIdx.x || threadIdx.x) return;
+    double2 s = make_double2(0.0, 0.0);
+    for (int b = 0; b < nblocks; ++b) {
+        const double2 agg = state[b];
+        state[b] = s;
+        const double2 ps = mat_vec(pbs, s);
+        s = make_double2(ps.x + agg.x, ps.y + agg.y);
+    }
+}
+
+// z_j = sum(y[l_j:u_j]^2) / (T_g * rate) over the 400 ms gating blocks (75 % overlap)
+__global__ void __launch_bounds__(256) gate_energy_kernel(const float* __restrict__ y, i64 N, double rate, int nblocks,
+                                                          double* __restrict__ z) {
+    const int j = blockIdx.x;
+    if (j >= nblocks) return;
+    const double Tg = 0.4, step = 0.25;
+    // int(T_g * (j * step) * rate), int(T_g * (j * step + 1) * rate)  -- same operation order as pyloudnorm
+    i64 lo = (i64)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
+    i64 hi = (i64)__dmul_rn(__dmul_rn(Tg, __dadd_rn(__dmul_rn((double)j, step), 1.0)), rate);
+    lo = max((i64)0, min(lo, N));
+    hi = max(lo, min(hi, N));
+    double acc = 0.0;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float v = __ldg(y + i);
+        acc += (double)__fmul_rn(v, v);
+    }
+    __shared__ double s[8];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += s[w];
+        z[j] = __dmul_rn(1.0 / __dmul_rn(Tg, rate), tot);
+    }
+}
+
+static void k_weighting(double rate, Biquad out[2]) {
+    // pyloudnorm IIRfilter coefficients: high shelf +4 dB @1500 Hz Q=1/sqrt2, high pass 38 Hz Q=0.5
+    const double PI = 3.14159265358979323846;
+    {
+        const double G = 4.0, Q = 1.0 / std::sqrt(2.0), fc = 1500.0;
+        const double A = std::pow(10.0, G / 40.0);
+        const double w0 = 2.0 * PI * (fc / rate);
+        const double al = std::sin(w0) / (2.0 * Q);
+        const double cw = std::cos(w0), sA = std::sqrt(A);
+        const double b0 = A * ((A + 1) + (A - 1) * cw + 2 * sA * al);
+        const double b1 = -2 * A * ((A - 1) + (A + 1) * cw);
+        const double b2 = A * ((A + 1) + (A - 1) * cw - 2 * sA * al);
+        const double a0 = (A + 1) - (A - 1) * cw + 2 * sA * al;
+        const double a1 = 2 * ((A - 1) - (A + 1) * cw);
+        const double a2 = (A + 1) - (A - 1) * cw - 2 * sA * al;
+        out[0] = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    }
+    {
+        const double Q = 0.5, fc = 38.0;
+        const double w0 = 2.0 * PI * (fc / rate);
+        const double al = std::sin(w0) / (2.0 * Q);
+        const double cw = std::cos(w0);
+        const double b0 = (1 + cw) / 2, b1 = -(1 + cw), b2 = (1 + cw) / 2;
+        const double a0 = 1 + al, a1 = -2 * cw, a2 = 1 - al;
+        out[1] = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    }
+}
+
+static void run_biquad(const float* d_in, float* d_out, i64 N, const Biquad& q) {
+    Ctx& c = ctx();
+    const int nblocks = (int)((N + BS - 1) / BS);
+    ScanCoef cf = make_coef(q);
+    double2* st = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
+    biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_in, N, cf, st, nullptr);
+    ARS_LAUNCH_CHECK();
+    block_scan_kernel<<<1, 32, 0, c.stream>>>(st, nblocks, cf.pw[8]);
+    ARS_LAUNCH_CHECK();
+    biquad_kernel<1><<<nblocks, NTB, 0, c.stream>>>(d_in, N, cf, st, d_out);
+    ARS_LAUNCH_CHECK();
+    count_launch(3);
+}
+
+int loudness_blocks(i64 N, double rate) {
+    // pyloudnorm: numBlocks = int(np.round(((T - T_g) / (T_g * step))) + 1); np.round = half to even
+    const double T = (double)N / rate;
+    const double v = (T - 0.4) / (0.4 * 0.25);
+    return (int)(std::nearbyint(v) + 1);
+}
+
+// returns status: 0 = value, 1 = too short (pyloudnorm raises -> reference reports None)
+int integrated_loudness(const float* d_mono, i64 N, double rate, double* lufs) {
+    Ctx& c = ctx();
+    *lufs = 0.0;
+    if (!((double)N >= 0.4 * rate)) return 1;            // "Audio must have length greater than the block size"
+    Biquad q[2];
+    k_weighting(rate, q);
+    float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
+    float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
+    run_biquad(d_mono, y1, N, q[0]);
+    run_biquad(y1, y2, N, q[1]);
+    const int nb = loudness_blocks(N, rate);
+    if (nb <= 0) return 1;
+    double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
+    gate_energy_kernel<<<nb, 256, 0, c.stream>>>(y2, N, rate, nb, dz);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    std::vector<double> z(nb);
+    ARS_CUDA(cudaMemcpyAsync(z.data(), dz, sizeof(double) * nb, cudaMemcpyDeviceToHost, c.stream));
+    ARS_CUDA(cudaStreamSynchronize(c.stream));
+    // gating (BS.1770-4 as pyloudnorm implements it, mono => channel gain 1)
+    double sum_abs = 0.0;
+    int n_abs = 0;
+    std::vector<double> l(nb);
+    for (int j = 0; j < nb; ++j) {
+        l[j] = -0.691 + 10.0 * std::log10(z[j]);
+        if (l[j] >= -70.0) { sum_abs += z[j]; ++n_abs; }
+    }
+    double rel = NAN;
+    if (n_abs > 0) rel = -0.691 + 10.0 * std::log10(sum_abs / n_abs) - 10.0;
+    double sum_rel = 0.0;
+    int n_rel = 0;
+    for (int j = 0; j < nb; ++j)
+        if (l[j] > rel && l[j] > -70.0) { sum_rel += z[j]; ++n_rel; }
+    const double zavg = n_rel > 0 ? sum_rel / n_rel : 0.0;
+    *lufs = -0.691 + 10.0 * std::log10(zavg);            // log10(0) = -inf, as numpy (with a warning)
+    return 0;
+}
+
+}  // namespace ars

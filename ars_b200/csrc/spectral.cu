@@ -1,0 +1,283 @@
+// Bluestein N-point DFTs and the fused per-bin transfer function (see spectral.cuh).
+#include "spectral.cuh"
+
+#include <cmath>
+
+namespace ars {
+
+using namespace fft;
+
+// ------------------------------------------------------------------ plans ----
+// chirp[n] = exp(-i pi n^2 / N).  n^2 mod 2N is formed exactly in 64-bit integers
+// (n < 2^31), the angle is evaluated in double.
+__global__ void chirp_kernel(float2* out, i64 N) {
+    i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    unsigned long long q = ((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * N);
+    double s, c;
+    sincospi(-(double)q / (double)N, &s, &c);
+    out[n] = make_float2((float)c, (float)s);
+}
+
+static const size_t BLUE_CACHE_BYTES = (size_t)48 << 30;   // plan cache cap (HBM is 180 GB)
+static const size_t BLUE_CACHE_PLANS = 16;
+
+static void drop_plan(Ctx& c, i64 N) {
+    auto it = c.blue_plans.find(N);
+    if (it == c.blue_plans.end()) return;
+    BluesteinPlan* p = it->second;
+    c.blue_bytes -= p->bytes;
+    p->chirp.release();
+    p->bspec.release();
+    delete p;
+    c.blue_plans.erase(it);
+}
+
+void bluestein_release_plans() {
+    if (!ctx_ready()) return;
+    Ctx& c = ctx();
+    while (!c.blue_plans.empty()) drop_plan(c, c.blue_plans.begin()->first);
+    c.blue_lru.clear();
+}
+
+BluesteinPlan* get_bluestein_plan(i64 N) {
+    Ctx& c = ctx();
+    ARS_CHECK(N >= 1 && N <= ((i64)1 << 29), "signal length out of range for the exact-N spectral stage");
+    auto it = c.blue_plans.find(N);
+    if (it != c.blue_plans.end()) {
+        for (size_t i = 0; i < c.blue_lru.size(); ++i)
+            if (c.blue_lru[i] == N) { c.blue_lru.erase(c.blue_lru.begin() + i); break; }
+        c.blue_lru.push_back(N);
+        return it->second;
+    }
+    BluesteinPlan* p = new BluesteinPlan();
+    p->N = N;
+    p->logM = std::max(1, next_pow2_log(2 * N - 1));
+    p->M = (i64)1 << p->logM;
+    p->bytes = sizeof(float2) * (size_t)(N + p->M);
+    // make room first (the stream is in-order, so freeing after queued work is safe only after a sync)
+    while (!c.blue_lru.empty() &&
+           (c.blue_bytes + p->bytes > BLUE_CACHE_BYTES || c.blue_plans.size() >= BLUE_CACHE_PLANS)) {
+        ARS_CUDA(cudaStreamSynchronize(c.stream));
+        drop_plan(c, c.blue_lru.front());
+        c.blue_lru.erase(c.blue_lru.begin());
+    }
+    p->fft = get_fft_plan(p->logM);
+    p->chirp.reserve(sizeof(float2) * (size_t)N);
+    p->bspec.reserve(sizeof(float2) * (size_t)p->M);
+    chirp_kernel<<<ceil_div(N, 256), 256, 0, c.stream>>>(p->chirp.as<float2>(), N);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    Ld ld;
+    ld.mode = LD_CHIRP_B;
+    ld.b = p->chirp.as<float2>();
+    ld.N = N;
+    ld.M = p->M;
+    St st;
+    st.mode = ST_SCALE;
+    st.a = p->bspec.as<float2>();
+    st.scale = 1.0f / (float)p->M;
+    fft_forward(p->fft, ld, p->bspec.as<float2>(), st);
+    c.blue_plans[N] = p;
+    c.blue_lru.push_back(N);
+    c.blue_bytes += p->bytes;
+    return p;
+}
+
+void bluestein_dft(BluesteinPlan* bp, Ld ld, float2* work, St st) {
+    ld.b = bp->chirp.as<float2>();
+    ld.N = bp->N;
+    ld.M = bp->M;
+    St mid;
+    mid.mode = ST_PLAIN;
+    mid.a = work;
+    fft_forward(bp->fft, ld, work, mid);
+    Ld l2;
+    l2.mode = LD_MULSPEC;
+    l2.a = work;
+    l2.b = bp->bspec.as<float2>();
+    st.chirp = bp->chirp.as<float2>();
+    st.N = bp->N;
+    fft_inverse(bp->fft, l2, work, st);
+}
+
+// -------------------------------------------------------- bin boundaries -----
+// numpy: freqs = arange(N//2 + 1) * (1.0 / (N * d)), d = 1.0 / rate   (all float64)
+static inline double bin_spacing(i64 N, double rate) {
+    const double d = 1.0 / rate;
+    return 1.0 / ((double)N * d);
+}
+// first k in [0, K] with k*val >= thr (K + 1 if none)
+static i64 first_ge(double thr, double val, i64 K) {
+    if (!(val > 0)) return K + 1;
+    double g = std::ceil(thr / val);
+    i64 k = g < 0 ? 0 : (g > (double)K + 2 ? K + 2 : (i64)g);
+    while (k > 0 && (double)(k - 1) * val >= thr) --k;
+    while (k <= K && (double)k * val < thr) ++k;
+    return k > K ? K + 1 : k;
+}
+// first k with k*val > thr
+static i64 first_gt(double thr, double val, i64 K) {
+    if (!(val > 0)) return K + 1;
+    double g = std::floor(thr / val);
+    i64 k = g < 0 ? 0 : (g > (double)K + 2 ? K + 2 : (i64)g);
+    while (k > 0 && (double)(k - 1) * val > thr) --k;
+    while (k <= K && !((double)k * val > thr)) ++k;
+    return k > K ? K + 1 : k;
+}
+
+void fill_eq(FilterSpec& fs, i64 N, double rate, double bass, double treble) {
+    // rs.py:389-396 -- caller decides whether the EQ runs at all (np.isclose gate)
+    const i64 K = N / 2;
+    const double val = bin_spacing(N, rate);
+    fs.eq_on = 1;
+    fs.kb_lo = first_gt(1e-6, val, K);              // freqs > 1e-6
+    fs.kb_hi = first_gt(250.0, val, K) - 1;         // freqs <= 250
+    i64 kt = first_ge(4000.0, val, K);
+    fs.kt_lo = kt > K ? -1 : kt;
+    fs.bass = (float)std::min(5.0, std::max(0.1, bass));
+    fs.treble = (float)std::min(5.0, std::max(0.1, treble));
+}
+
+void fill_air(FilterSpec& fs, i64 N, double rate, double air) {
+    // rs.py:316-331
+    const i64 K = N / 2;
+    const double val = bin_spacing(N, rate);
+    fs.val = val;
+    fs.ftop = (double)K * val;
+    const i64 ka = first_ge(2000.0, val, K);
+    fs.air_on = (ka <= K && fs.ftop > 2000.0) ? 1 : 0;
+    fs.ka = ka;
+    fs.depth = std::min(1.0, std::max(0.0, air)) * 0.8;
+}
+
+// ------------------------------------------------------------ mid kernel -----
+__device__ __forceinline__ float gain_eq(const FilterSpec& fs, i64 kk) {
+    float g = 1.f;
+    if (fs.eq_on) {
+        if (kk >= fs.kb_lo && kk <= fs.kb_hi) g *= fs.bass;
+        if (fs.kt_lo >= 0 && kk >= fs.kt_lo) g *= fs.treble;
+    }
+    return g;
+}
+__device__ __forceinline__ float gain_air(const FilterSpec& fs, i64 kk) {
+    if (!fs.air_on || kk < fs.ka) return 1.f;
+    double ramp = ((double)kk * fs.val - 2000.0) / (fs.ftop - 2000.0);
+    ramp = fmin(fmax(ramp, 0.0), 1.0);
+    return (float)(1.0 - ramp * fs.depth);
+}
+
+// In place on Z (N complex): Z[k] <- conj( X_L[k] T_L[k] + i X_R[k] T_R[k] ) for the bin pair
+// (k, N-k).  P holds DFT_N(h0 + i h1) (unused for FILT_MASK).
+__global__ void __launch_bounds__(256) transfer_kernel(float2* __restrict__ Z, const float2* __restrict__ P,
+                                                       FilterSpec fs, const RenderState* __restrict__ state) {
+    const i64 N = fs.N;
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > N / 2) return;
+    const i64 km = (k == 0) ? 0 : N - k;
+    const float2 zk = Z[k], zm = Z[km];
+    // per-channel spectra of the two real signals packed in Z
+    const float2 xl = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 xr = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+    const float geq = gain_eq(fs, k);
+    float2 tl, tr;
+    if (fs.mode == FILT_MASK) {
+        const float g = geq * gain_air(fs, k);
+        tl = tr = make_float2(g, 0.f);
+    } else {
+        const float2 pk = P[k], pm = P[km];
+        const float2 h0 = make_float2(0.5f * (pk.x + pm.x), 0.5f * (pk.y - pm.y));
+        const float2 h1 = make_float2(0.5f * (pk.y + pm.y), -0.5f * (pk.x - pm.x));
+        const float dg = (float)fs.dry_gain, dw = (float)fs.dw;
+        if (fs.mode == FILT_SPLIT) {
+            const float c0 = state->ir_any0 ? (float)fs.level0 : 0.f;
+            const float c1 = state->ir_any1 ? (float)fs.level1 * gain_air(fs, k) : 0.f;
+            float2 t = make_float2(c0 * h0.x + c1 * h1.x, c0 * h0.y + c1 * h1.y);
+            t = make_float2((dg + dw * t.x) * geq, (dw * t.y) * geq);
+            tl = tr = t;
+        } else {
+            tl = make_float2((dg + dw * h0.x) * geq, (dw * h0.y) * geq);
+            tr = make_float2((dg + dw * h1.x) * geq, (dw * h1.y) * geq);
+        }
+    }
+    const float2 yl = cmul(xl, tl), yr = cmul(xr, tr);
+    // Y[k] = yl + i yr ; Y[N-k] = conj(yl) + i conj(yr) ; store conj(Y)
+    Z[k] = make_float2(yl.x - yr.y, -(yl.y + yr.x));
+    if (km != k) Z[km] = make_float2(yl.x + yr.y, -(yr.x - yl.y));
+}
+
+__global__ void ir_flags_kernel(const float* a, i64 na, i64 stride_a, const float* b, i64 nb, i64 stride_b,
+                                RenderState* state) {
+    // np.any(ir) for both IR parts
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 step = (i64)gridDim.x * blockDim.x;
+    bool fa = false, fb = false;
+    for (i64 j = i; j < na; j += step) fa |= (a[j * stride_a] != 0.f);
+    for (i64 j = i; j < nb; j += step) fb |= (b[j * stride_b] != 0.f);
+    if (__any_sync(0xffffffffu, fa) && (threadIdx.x & 31) == 0) state->ir_any0 = 1u;
+    if (__any_sync(0xffffffffu, fb) && (threadIdx.x & 31) == 0) state->ir_any1 = 1u;
+}
+
+void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                     const FilterSpec& fs_in, float2* d_y, RenderState* d_state) {
+    Ctx& c = ctx();
+    FilterSpec fs = fs_in;
+    const i64 N = fs.N;
+    ARS_CHECK(N >= 1 && n >= 0 && n <= N, "spectral_filter: bad lengths");
+    BluesteinPlan* bp = get_bluestein_plan(N);
+    float2* work = c.buf("spec.work", sizeof(float2) * (size_t)bp->M).as<float2>();
+    float2* Z = c.buf("spec.Z", sizeof(float2) * (size_t)N).as<float2>();
+    float2* P = nullptr;
+
+    if (fs.mode != FILT_MASK) {
+        if (!d_ir0) L0 = 0;
+        if (!d_ir1) L1 = 0;
+        ARS_CHECK(L0 >= 0 && L0 <= N && L1 >= 0 && L1 <= N, "spectral_filter: IR longer than the output");
+        P = c.buf("spec.P", sizeof(float2) * (size_t)N).as<float2>();
+        Ld ld;
+        if (fs.mode == FILT_SPLIT) {
+            ld.mode = LD_CHIRP_PAIR;
+            ld.f0 = d_ir0; ld.nvalid = L0;
+            ld.f1 = d_ir1; ld.nvalid1 = L1;
+            ir_flags_kernel<<<64, 256, 0, c.stream>>>(d_ir0, L0, 1, d_ir1, L1, 1, d_state);
+            ARS_LAUNCH_CHECK();
+            count_launch();
+        } else {
+            ARS_CHECK(d_ir0 != nullptr && L0 >= 1, "spectral_filter: external IR missing");
+            ld.mode = LD_CHIRP_X2;
+            ld.f0 = d_ir0; ld.nvalid = L0;
+        }
+        St st;
+        st.mode = ST_CHIRP;
+        st.a = P;
+        bluestein_dft(bp, ld, work, st);
+    }
+    {
+        Ld ld;
+        if (cin == 2) { ld.mode = LD_CHIRP_X2; }
+        else { ld.mode = LD_CHIRP_XC; ld.cin = cin; }
+        ld.f0 = d_x;
+        ld.nvalid = n;
+        St st;
+        st.mode = ST_CHIRP;
+        st.a = Z;
+        bluestein_dft(bp, ld, work, st);
+    }
+    transfer_kernel<<<ceil_div(N / 2 + 1, 256), 256, 0, c.stream>>>(Z, P, fs, d_state);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    {
+        Ld ld;
+        ld.mode = LD_CHIRP_C;
+        ld.a = Z;
+        ld.nvalid = N;
+        St st;
+        st.mode = ST_FINAL;
+        st.a = d_y;
+        st.scale = 1.0f / (float)N;
+        st.maxbits = &d_state->max_stereo;
+        bluestein_dft(bp, ld, work, st);
+    }
+}
+
+}  // namespace ars

@@ -1,0 +1,167 @@
+/* libars_b200 -- C ABI of the B200 (sm_100a) render path of Audio Raytracing Studio.
+ *
+ * The reference (CipherCorePro/Audio-Raytracing-Studio, raytracer_studio.py = "rs.py") has no
+ * FFI of its own: its boundary is the Python module namespace.  Each entry point below replaces
+ * the array work of one reference function (cited per function); the Python drop-in
+ * `ars_b200/raytracer_studio.py` binds them with ctypes and keeps the reference's signatures.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; arrays are C-contiguous, frames-major ("(frames, channels)"),
+ *     float32 unless stated; the caller owns every buffer;
+ *   - every function returns 0 on success, non-zero on failure; ars_last_error() gives the
+ *     message of the calling thread's last failure; nothing throws across the ABI;
+ *   - there is NO CPU path: without a CUDA device (sm_100) ars_init() fails and every other
+ *     call returns ARS_ERR_NO_DEVICE;
+ *   - calls are serialised on one internal CUDA stream and are safe to issue from any thread;
+ *   - "_dev" variants take device pointers, enqueue on the library stream and return without
+ *     waiting (ars_sync() waits); all other variants take host pointers and copy both ways.
+ */
+#ifndef ARS_B200_H
+#define ARS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ARS_API __attribute__((visibility("default")))
+#else
+#define ARS_API
+#endif
+
+#define ARS_OK 0
+#define ARS_ERR_ARG 1
+#define ARS_ERR_CUDA 2
+#define ARS_ERR_NO_DEVICE 3
+#define ARS_ERR_INTERNAL 4
+
+/* rs.py:37-42 CHANNEL_LAYOUTS, in the order the reference lists them */
+#define ARS_LAYOUT_STEREO 0   /* "Stereo"               2 ch: FL FR */
+#define ARS_LAYOUT_5_1 1      /* "5.1 (Standard)"       6 ch: FL FR C LFE RL RR */
+#define ARS_LAYOUT_7_1 2      /* "7.1 (Surround)"       8 ch: ... SL SR  (12 ms, x0.7) */
+#define ARS_LAYOUT_5_1_2 3    /* "5.1.2 (Atmos Light)"  8 ch: ... TFL TFR (18 ms, x0.6*z) */
+
+#define ARS_LUFS_OK 0         /* metrics.lufs holds a value (may be -inf)                     */
+#define ARS_LUFS_NONE 1       /* shorter than one 400 ms block: the reference reports None    */
+#define ARS_LUFS_SKIPPED 2    /* loudness was not requested                                   */
+
+typedef struct ArsMetrics {   /* calculate_audio_metrics, rs.py:674-698 */
+    double lufs;              /* integrated loudness of mean(ch0, ch1)  (rs.py:687-691)       */
+    int32_t lufs_status;      /* ARS_LUFS_*                                                   */
+    int32_t reserved;
+    double peak_linear;       /* max |x| over all channels (rs.py:695)                        */
+    double rms_linear;        /* sqrt(mean(x^2)) over all channels (rs.py:696)                */
+    double true_peak_dbfs;    /* 20 log10(peak) or -inf (rs.py:697)                           */
+    double rms_dbfs;          /* 20 log10(rms)  or -inf (rs.py:698)                           */
+} ArsMetrics;
+
+/* Random draws of generate_impulse_response_split_3d replayed by the caller
+ * (np.random.randint / uniform in the reference's call order, rs.py:262,264,285). */
+typedef struct ArsIrDraws {
+    const int64_t* tap_delay;   /* ntaps accepted delays (0 < d < split), draw order          */
+    const double* tap_base;     /* ntaps base strengths, uniform(0.3, 0.8)                    */
+    int32_t ntaps;
+    int32_t reserved;
+    const double* noise;        /* late_len raw tail noise, uniform(-1, 1)                    */
+    int64_t noise_len;          /* = length - split                                            */
+} ArsIrDraws;
+
+/* Scalars of one render, already shaped by the host prologue (rs.py:157-236). */
+typedef struct ArsRenderParams {
+    double rate;                /* sample rate                                                 */
+    int32_t external_ir;        /* 0: procedural hall (rs.py:1047-1056)  1: stereo IR (1027-1045) */
+    int32_t layout;             /* ARS_LAYOUT_*                                                */
+    /* procedural IR (ignored when external_ir) -- arguments of rs.py:238 */
+    double ir_duration, ir_max_delay, absorption, directionality, ir_split_time, diffusion;
+    /* mix / EQ -- arguments of rs.py:338 / 410 (levels already adapted, rs.py:168-182) */
+    double early_level, late_level, dry_wet, kill_start, bass_gain, treble_gain, air_absorption;
+    /* position -- rs.py:464, 517 */
+    double x, y, z;
+    int32_t want_lufs;          /* 1: also run the loudness meter                               */
+    int32_t reserved;
+} ArsRenderParams;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+ARS_API int ars_init(int device);                 /* device < 0: device 0.  Idempotent.                 */
+ARS_API void ars_shutdown(void);
+ARS_API int ars_sync(void);                       /* wait for everything enqueued by _dev calls         */
+ARS_API const char* ars_last_error(void);
+ARS_API const char* ars_version(void);
+ARS_API uint64_t ars_launch_count(void);          /* kernels this library has launched so far           */
+ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
+/* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
+ARS_API int ars_timer_begin(void);
+ARS_API int ars_timer_end(float* ms);
+/* Per-launch event timing of the FFT pass kernels (the dominant kernels): between begin and end every
+ * pass launch is bracketed by events; end reports their count, summed duration and algorithmic bytes. */
+ARS_API int ars_profile_begin(void);
+ARS_API int ars_profile_end(int64_t* launches, double* ms, double* bytes);
+
+/* ---- stage entry points (host pointers), one per reference function ------------------------- */
+
+/* generate_impulse_response_split_3d, rs.py:238-305.  early/late: float32[length],
+ * length = max(1, (int64)(ir_duration * rate)).  Returns ARS_ERR_ARG if `length` disagrees. */
+ARS_API int ars_ir_synth(double rate, double ir_duration, double ir_max_delay, double absorption,
+                 double directionality, double ir_split_time, double diffusion, const ArsIrDraws* draws,
+                 float* early, float* late, int64_t length);
+/* integer geometry used by the caller to size the draws: rs.py:249,254-255,259,271-272 */
+ARS_API int ars_ir_geometry(double rate, double ir_duration, double ir_max_delay, double ir_split_time,
+                    int64_t* length, int64_t* split, int64_t* tap_hi, int64_t* late_len);
+
+/* apply_simple_lp_filter, rs.py:310-333, on an (n, 2) signal; caller applies the `< 0.01` gate. */
+ARS_API int ars_air_filter(const float* sig, int64_t n, double rate, double air, float* out);
+
+/* dynamic_dry_wet_mix, rs.py:84-121; out has max(n_dry, n_wet) frames of `ch` channels. */
+ARS_API int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n_wet, int32_t ch,
+                    double dry_wet, double kill_start, float* out);
+
+/* convolve_audio_split_3d, rs.py:338-408.  data: (n, cin) with cin == 1 (duplicated), 2, or > 2
+ * (first two used); early/late: float32[L_early], float32[L_late] (either may be NULL/0 =
+ * "zeros(1)").  out: (n_out, 2), n_out = ars_convolve_out_len(n, L_early, L_late). */
+ARS_API int64_t ars_convolve_out_len(int64_t n, int64_t len_early, int64_t len_late);
+ARS_API int ars_convolve_split(const float* data, int64_t n, int32_t cin, const float* early, int64_t len_early,
+                       const float* late, int64_t len_late, double early_level, double late_level,
+                       double dry_wet, double bass_gain, double treble_gain, double rate, double kill_start,
+                       double air_absorption, float* out);
+
+/* convolve_audio_external_ir, rs.py:410-462.  ir: (L, 2).  out: (n + L - 1, 2). */
+ARS_API int ars_convolve_external(const float* data, int64_t n, int32_t cin, const float* ir, int64_t L,
+                          double dry_wet, double bass_gain, double treble_gain, double rate,
+                          double kill_start, float* out);
+
+/* apply_surround_panning_3d, rs.py:464-501.  stereo: (n, 2); out: (n, 6). */
+ARS_API int ars_pan(const float* stereo, int64_t n, double x, double y, double z, float* out);
+
+/* apply_delay, rs.py:507-515.  (n, ch) -> (n, ch). */
+ARS_API int ars_delay(const float* sig, int64_t n, int32_t ch, int64_t delay_samples, float* out);
+
+/* map_channels, rs.py:517-563.  six: (n, 6); out: (n, C), C = ars_layout_channels(layout). */
+ARS_API int ars_layout_channels(int32_t layout);
+ARS_API int ars_map_channels(const float* six, int64_t n, int32_t layout, double rate, double z, float* out);
+
+/* calculate_audio_metrics, rs.py:674-698.  data: (n, ch). */
+ARS_API int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t want_lufs, ArsMetrics* out);
+
+/* clip + scrub + float->PCM16, rs.py:1082-1084 (libsndfile rule lrintf(x * 32767)). */
+ARS_API int ars_pcm16(const float* data, int64_t count, int16_t* out);
+
+/* ---- the whole render on arrays: compute part of apply_raytrace_convolution_3d, rs.py:1020-1084
+ * in: (n, cin) float32.  ext_ir: (L, 2) when params->external_ir, else NULL and `draws` feeds the
+ * procedural IR.  Outputs (any may be NULL): out_stereo (N, 2) = the convolution stage result,
+ * out_f32 (N, C) pre-clip final, out_pcm (N, C) int16, metrics.  N = ars_render_out_len(...). */
+ARS_API int64_t ars_render_out_len(const ArsRenderParams* p, int64_t n, int64_t ext_ir_len);
+ARS_API int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int32_t cin, const float* ext_ir,
+               int64_t ext_ir_len, const ArsIrDraws* draws, float* out_stereo, float* out_f32,
+               int16_t* out_pcm, ArsMetrics* metrics);
+/* Same with every array pointer (including those inside `draws`) on the device.  Asynchronous
+ * unless `metrics` is non-NULL (the loudness gate needs the block energies on the host). */
+ARS_API int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                   int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                   int16_t* d_out_pcm, ArsMetrics* metrics);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARS_B200_H */

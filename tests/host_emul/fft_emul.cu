@@ -1,0 +1,241 @@
+// Host emulation of the FFT pass kernels (no GPU needed).
+//
+// The stage code in ars_b200/csrc/fft.cuh is __host__ __device__; here its "threads"
+// run one after another on the CPU so the index maps, twiddles, pass decomposition and
+// the Bluestein wiring can be checked in the authoring container.  Checks:
+//   1. IFFT(FFT(a) .* FFT(b)) / M == circular convolution (double-precision reference)
+//   2. Bluestein DFT_N built from those transforms == direct DFT (double) for arbitrary N
+// Usage: fft_emul <logM>...   |   fft_emul blue <N>...
+// Exit code 0 when every max error is below 2e-5 (relative to the result's peak).
+#include "../../ars_b200/csrc/fft.cuh"
+
+#include <cmath>
+#include <complex>
+#include <cstdlib>
+#include <random>
+
+using namespace ars;
+using namespace ars::fft;
+typedef std::complex<double> cd;
+
+static std::vector<float2> g_local, g_lo, g_hi;
+
+static void make_tables(int logM, Tw& tw) {
+    const double PI = 3.14159265358979323846;
+    g_local.resize(TWN);
+    for (int e = 0; e < TWN; ++e) {
+        double a = -2.0 * PI * e / TWN;
+        g_local[e] = make_float2((float)cos(a), (float)sin(a));
+    }
+    const i64 M = (i64)1 << logM;
+    const int nlo = (int)std::min<i64>(M, (i64)1 << BIG_LO_LOG);
+    g_lo.resize(nlo);
+    for (int e = 0; e < nlo; ++e) {
+        double a = -2.0 * PI * (double)e / (double)M;
+        g_lo[e] = make_float2((float)cos(a), (float)sin(a));
+    }
+    tw.local = g_local.data();
+    tw.lo = g_lo.data();
+    tw.hi = nullptr;
+    if (logM > BIG_LO_LOG) {
+        const int nhi = 1 << (logM - BIG_LO_LOG);
+        g_hi.resize(nhi);
+        for (int e = 0; e < nhi; ++e) {
+            double a = -2.0 * PI * (double)e * (double)(1 << BIG_LO_LOG) / (double)M;
+            g_hi[e] = make_float2((float)cos(a), (float)sin(a));
+        }
+        tw.hi = g_hi.data();
+    }
+}
+
+constexpr int NT = 256;
+
+template <int LOGR, int LOGT, bool INV> static void emu_strided(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = StridedLayout<LOGR, LOGT>;
+    std::vector<float2> sm(L::SMEM_ELEMS);
+    const i64 tiles = pa.M >> (LOGR + LOGT);
+    for (i64 tile = 0; tile < tiles; ++tile) {
+        Ld l = ld;
+        St s = st;
+        StridedTile<LOGR, LOGT> t(tile, pa);
+        emulate_tile<LOGR, INV, true, NT, L>(sm.data(), l, s, pa, StridedFirst<LOGR>{t.base, t.logStride},
+                                            StridedLast<LOGR>{t.base, t.logStride}, t.col0);
+    }
+}
+template <int LOGR, int LOGC, bool INV> static void emu_contig(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = ContigLayout<LOGR, LOGC>;
+    std::vector<float2> sm(L::SMEM_ELEMS);
+    const i64 tiles = pa.M >> (LOGR + LOGC);
+    for (i64 tile = 0; tile < tiles; ++tile) {
+        Ld l = ld;
+        St s = st;
+        const i64 base = tile << (LOGR + LOGC);
+        emulate_tile<LOGR, INV, false, NT, L>(sm.data(), l, s, pa, ContigFirst<LOGR>{base}, ContigLast<LOGR>{base}, 0u);
+    }
+}
+
+template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& ps, const Ld& ld, const St& st) {
+    PassArgs pa;
+    pa.M = (i64)1 << logM;
+    pa.logM = logM;
+    pa.logLg = ps.logLg;
+    pa.tw = tw;
+    if (ps.strided) {
+        if (ps.logLg - ps.logR < ps.logT) { printf("bad plan: strided pass narrower than tile\n"); exit(2); }
+#define S_CASE(R, T) if (ps.logR == R && ps.logT == T) return emu_strided<R, T, INV>(ld, st, pa);
+        ARS_STRIDED_CASES(S_CASE)
+#undef S_CASE
+    } else {
+#define C_CASE(R, C) if (ps.logR == R && ps.logT == C) return emu_contig<R, C, INV>(ld, st, pa);
+        ARS_CONTIG_CASES(C_CASE)
+#undef C_CASE
+    }
+    printf("no kernel variant for pass (strided=%d logR=%d logT=%d)\n", (int)ps.strided, ps.logR, ps.logT);
+    exit(2);
+}
+
+struct EmuPlan { int logM; std::vector<FftPass> passes; Tw tw; };
+
+static void emu_forward(const EmuPlan& p, const Ld& ld_first, float2* work, const St& st_last) {
+    const int np = (int)p.passes.size();
+    for (int i = 0; i < np; ++i) {
+        Ld ld; St st;
+        if (i == 0) ld = ld_first; else { ld.mode = LD_PLAIN; ld.a = work; }
+        if (i == np - 1) st = st_last; else { st.mode = ST_PLAIN; st.a = work; }
+        emu_pass<false>(p.logM, p.tw, p.passes[i], ld, st);
+    }
+}
+static void emu_inverse(const EmuPlan& p, const Ld& ld_first, float2* work, const St& st_last) {
+    const int np = (int)p.passes.size();
+    for (int i = np - 1; i >= 0; --i) {
+        Ld ld; St st;
+        if (i == np - 1) ld = ld_first; else { ld.mode = LD_PLAIN; ld.a = work; }
+        if (i == 0) st = st_last; else { st.mode = ST_PLAIN; st.a = work; }
+        emu_pass<true>(p.logM, p.tw, p.passes[i], ld, st);
+    }
+}
+
+// double-precision radix-2 reference FFT
+static void ref_fft(std::vector<cd>& a, bool inv) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const double PI = 3.14159265358979323846;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        double ang = 2 * PI / (double)len * (inv ? 1 : -1);
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                cd w(cos(ang * (double)k), sin(ang * (double)k));
+                cd u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+// the real planner (shared with fft_plan.cu)
+#include "../../ars_b200/csrc/fft_decompose.inc"
+
+static int check_conv(int logM) {
+    EmuPlan p;
+    p.logM = logM;
+    p.passes = fft_decompose(logM);
+    make_tables(logM, p.tw);
+    const i64 M = (i64)1 << logM;
+    printf("logM=%d passes:", logM);
+    for (auto& ps : p.passes) printf(" %s(R=2^%d,T=2^%d,Lg=2^%d)", ps.strided ? "S" : "C", ps.logR, ps.logT, ps.logLg);
+    printf("\n");
+    std::mt19937 rng(logM);
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<float2> a(M), b(M), A(M), B(M), out(M);
+    for (i64 i = 0; i < M; ++i) { a[i] = make_float2(U(rng), U(rng)); b[i] = make_float2(0.f, 0.f); }
+    // b: a short random kernel so the reference result has O(1) dynamic range
+    const int K = (int)std::min<i64>(M, 40);
+    for (int i = 0; i < K; ++i) b[(i * 977 + 3) % M] = make_float2(U(rng), U(rng));
+    Ld ld; St st;
+    ld.mode = LD_PLAIN; ld.a = a.data(); st.mode = ST_PLAIN; st.a = A.data();
+    emu_forward(p, ld, A.data(), st);
+    ld.a = b.data(); st.a = B.data(); st.mode = ST_SCALE; st.scale = 1.0f / (float)M;
+    emu_forward(p, ld, B.data(), st);
+    ld.mode = LD_MULSPEC; ld.a = A.data(); ld.b = B.data();
+    st.mode = ST_PLAIN; st.a = out.data();
+    emu_inverse(p, ld, A.data(), st);
+    std::vector<cd> ra(M), rb(M);
+    for (i64 i = 0; i < M; ++i) { ra[i] = cd(a[i].x, a[i].y); rb[i] = cd(b[i].x, b[i].y); }
+    ref_fft(ra, false); ref_fft(rb, false);
+    for (i64 i = 0; i < M; ++i) ra[i] *= rb[i];
+    ref_fft(ra, true);
+    double maxerr = 0, peak = 0;
+    for (i64 i = 0; i < M; ++i) {
+        cd r = ra[i] / (double)M;
+        peak = std::max(peak, std::abs(r));
+        maxerr = std::max(maxerr, std::abs(r - cd(out[i].x, out[i].y)));
+    }
+    // forward spectrum must be a permutation of the true DFT: compare sorted magnitudes cheaply via sums
+    printf("  conv: max err %.3e (peak %.3f) rel %.3e\n", maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5) ? 0 : 1;
+}
+
+static int check_bluestein(i64 N) {
+    const int logM = std::max(1, next_pow2_log(2 * N - 1));
+    const i64 M = (i64)1 << logM;
+    EmuPlan p;
+    p.logM = logM;
+    p.passes = fft_decompose(logM);
+    make_tables(logM, p.tw);
+    const double PI = 3.14159265358979323846;
+    std::vector<float2> chirp(N);
+    for (i64 n = 0; n < N; ++n) {
+        i64 q = (n * n) % (2 * N);
+        double a = -PI * (double)q / (double)N;
+        chirp[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<float2> Bs(M), W(M), Z(N);
+    Ld ld; St st;
+    ld.mode = LD_CHIRP_B; ld.b = chirp.data(); ld.N = N; ld.M = M;
+    st.mode = ST_SCALE; st.a = Bs.data(); st.scale = 1.0f / (float)M;
+    emu_forward(p, ld, Bs.data(), st);
+    // input: interleaved stereo frames, n < N valid
+    std::mt19937 rng((unsigned)N);
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    const i64 nv = N - N / 5;
+    std::vector<float> x(2 * nv);
+    for (auto& v : x) v = U(rng);
+    ld = Ld(); ld.mode = LD_CHIRP_X2; ld.f0 = x.data(); ld.b = chirp.data(); ld.nvalid = nv; ld.N = N; ld.M = M;
+    st = St(); st.mode = ST_PLAIN; st.a = W.data();
+    emu_forward(p, ld, W.data(), st);
+    ld = Ld(); ld.mode = LD_MULSPEC; ld.a = W.data(); ld.b = Bs.data();
+    st = St(); st.mode = ST_CHIRP; st.a = Z.data(); st.chirp = chirp.data(); st.N = N;
+    emu_inverse(p, ld, W.data(), st);
+    // direct DFT on a sample of bins (all bins when N is small)
+    double maxerr = 0, peak = 0;
+    const i64 step = std::max<i64>(1, N / 97);
+    for (i64 k = 0; k < N; k += step) {
+        cd acc = 0;
+        for (i64 n = 0; n < nv; ++n) {
+            i64 e = (n * k) % N;
+            double a = -2 * PI * (double)e / (double)N;
+            acc += cd(x[2 * n], x[2 * n + 1]) * cd(cos(a), sin(a));
+        }
+        peak = std::max(peak, std::abs(acc));
+        maxerr = std::max(maxerr, std::abs(acc - cd(Z[k].x, Z[k].y)));
+    }
+    printf("bluestein N=%lld M=2^%d: max err %.3e (peak %.2f) rel %.3e\n", (long long)N, logM, maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5) ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+    int bad = 0;
+    bool blue = false;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "blue")) { blue = true; continue; }
+        if (blue) bad += check_bluestein(atoll(argv[i]));
+        else bad += check_conv(atoi(argv[i]));
+    }
+    printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
+    return bad ? 1 : 0;
+}

@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in module) against
+  (1) golden vectors produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py), and
+  (2) the CPU oracle (oracle/ars_oracle.py) on fresh seeded inputs.
+
+Bars (BASELINE.json north_star): float stages within max |err| <= 1e-5 of full scale
+(full scale = max(1, peak of the reference result)); integer / element-wise float32 stages
+(dry/wet mix, pan, map, PCM16) bit-exact.
+"""
+import numpy as np
+import pytest
+
+import ars_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+HALLS = ["Plate", "Room", "Cathedral", "Garage"]
+MATERIALS = ["Stein", "Holz", "Teppich", "Glas", "Beton", "Vorhang (schwer)", "Gummi"]
+LAYOUTS = ["Stereo", "5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)", "9.1.6"]
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    return float(np.max(np.abs(got - ref)) / max(1.0, float(np.max(np.abs(ref)))))
+
+
+def snr_db(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    noise = np.sum((got - ref) ** 2)
+    sig = np.sum(ref ** 2)
+    if noise == 0:
+        return np.inf
+    return 10 * np.log10(sig / noise) if sig > 0 else -np.inf
+
+
+# ------------------------------------------------------------------ scalars (host) ----------
+def test_scalar_prologue_matches_golden(rs, golden):
+    g = golden("scalars")
+    halls = [str(h) for h in g["halls"]]
+    for row in g["table"]:
+        hall = halls[int(row[0])]
+        room, x, y, z, dif, dw, e, l = row[1:9]
+        assert tuple(float(v) for v in rs.adjust_parameters_for_3d(hall, room, z)) == tuple(row[9:13])
+        assert float(rs.compute_final_directionality_3d(x, y, z, hall, dif, dw)) == row[13]
+        ae, al = rs.adapt_early_late_levels(dw, e, l)
+        assert (float(ae), float(al)) == (row[14], row[15])
+
+
+# ------------------------------------------------------------------ IR synthesis -------------
+def test_ir_synth_matches_golden(rs, golden):
+    g = golden("ir")
+    for i, m in enumerate(g["meta"]):
+        rate, mat, dif, seed = int(m[0]), MATERIALS[int(m[2])], m[7], int(m[9])
+        dur, refl, mdel, split, direc = m[10], int(m[11]), m[12], m[13], m[14]
+        np.random.seed(seed)
+        e, l = rs.generate_impulse_response_split_3d(rate, dur, refl, mdel, mat, direc, split, dif)
+        assert e.dtype == np.float32 and l.dtype == np.float32
+        assert e.shape == g[f"early{i}"].shape
+        # taps: scatter + normalise replay float64->float32 roundings exactly
+        assert np.array_equal(e, g[f"early{i}"]), f"early taps differ in case {i}"
+        # tail: float64 boxcar / std / pow with a different summation order -> at most float32 ulps
+        assert rel_err(l, g[f"late{i}"]) <= 2e-7, f"late tail case {i}"
+    e, l = rs.generate_impulse_response_split_3d(0, 1.0, 10, 0.05, "Holz", 0.5, 0.05, 0.5)
+    assert np.array_equal(e, g["early_bad"]) and np.array_equal(l, g["late_bad"])
+
+
+def test_ir_synth_rng_consumption_matches_oracle(rs):
+    # after the call the global generator must be where the reference leaves it
+    for seed in (1, 2):
+        np.random.seed(seed)
+        rs.generate_impulse_response_split_3d(48000, 1.2, 30, 0.05, "Stein", 0.4, 0.07, 0.5)
+        a = np.random.uniform()
+        np.random.seed(seed)
+        orc.generate_ir(48000, 1.2, 30, 0.05, "Stein", 0.4, 0.07, 0.5)
+        assert a == np.random.uniform()
+
+
+# ------------------------------------------------------------------ spectral stages ---------
+@pytest.mark.parametrize("tag", ["odd", "even", "short"])
+def test_air_filter_matches_golden(rs, golden, tag):
+    g = golden("air_filter")
+    sig = g[f"in_{tag}"]
+    for air in (0.005, 0.1, 0.65, 1.7):
+        got = rs.apply_simple_lp_filter(sig, 48000, air)
+        assert rel_err(got, g[f"air_{tag}_{air}"]) <= TOL
+    got = rs.apply_simple_lp_filter(sig, 3000, 0.5)
+    assert rel_err(got, g[f"air_{tag}_lowrate"]) <= TOL
+
+
+def test_dry_wet_mix_bit_exact(rs, golden):
+    g = golden("dry_wet")
+    for i in range(8):
+        dw, ks = g[f"par{i}"]
+        got = rs.dynamic_dry_wet_mix(g[f"dry{i}"], g[f"wet{i}"], dw, ks)
+        assert got.dtype == np.float32
+        assert np.array_equal(got, g[f"mix{i}"]), f"case {i}"
+
+
+def test_convolve_split_matches_golden(rs, golden):
+    g = golden("convolve")
+    keys = [str(k) for k in g["x_keys"]]
+    for i, p in enumerate(g["split_par"]):
+        x = g["x_" + keys[int(p[0])]]
+        el, ll, dw, b, t, ks, air = p[1:8]
+        got = rs.convolve_audio_split_3d(x, g["early"], g["late"], el, ll, dw, b, t, 48000, ks, air)
+        ref = g[f"split{i}"]
+        assert got.dtype == np.float32
+        assert rel_err(got, ref) <= TOL, f"split case {i}: {rel_err(got, ref):.3e}"
+        if np.any(ref):
+            assert snr_db(got, ref) >= 100.0, f"split case {i}: SNR {snr_db(got, ref):.1f} dB"
+
+
+def test_convolve_external_matches_golden(rs, golden):
+    g = golden("convolve")
+    keys = [str(k) for k in g["x_keys"]]
+    for i, p in enumerate(g["ext_par"]):
+        x = g["x_" + keys[int(p[0])]]
+        dw, b, t, ks = p[1:5]
+        got = rs.convolve_audio_external_ir(x, g["ext_ir"], dw, b, t, 48000, ks)
+        ref = g[f"ext{i}"]
+        assert rel_err(got, ref) <= TOL, f"ext case {i}: {rel_err(got, ref):.3e}"
+        assert snr_db(got, ref) >= 100.0
+    bad = rs.convolve_audio_external_ir(g["x_stereo"], g["ext_ir"][:, 0], .5, 1.0, 1.0, 48000, .5)
+    assert np.array_equal(bad, g["ext_badir"])
+    assert rs.convolve_audio_external_ir(np.zeros((0, 2), np.float32), g["ext_ir"], .5).shape == (0, 2)
+    assert rs.convolve_audio_split_3d(None, g["early"], g["late"], .5, .5, .5).shape == (0, 2)
+
+
+# ------------------------------------------------------------------ pan / map --------------
+def test_pan_and_map_bit_exact(rs, golden):
+    g = golden("pan_map")
+    keys = [str(k) for k in g["sig_keys"]]
+    for idx, p in enumerate(g["par"]):
+        s = g["s_" + keys[int(p[0])]]
+        x, y, z = p[1:4]
+        six = rs.apply_surround_panning_3d(s, x, y, z)
+        assert np.array_equal(six, g[f"pan{idx}"]), f"pan case {idx}"
+        for li, lay in enumerate(LAYOUTS):
+            src = g[f"pan{idx}"].copy()
+            m, names = rs.map_channels(src, lay, 48000, z)
+            assert np.array_equal(m, g[f"map{idx}_{li}"]), f"map case {idx} layout {lay}"
+            if lay in ("5.1 (Standard)", "9.1.6"):
+                assert m is src           # the reference hands back the input object
+    m, _ = rs.map_channels(g["pan_441"].copy(), "7.1 (Surround)", 44100, .8)
+    assert np.array_equal(m, g["map_441_71"])
+    m, _ = rs.map_channels(g["pan_441"].copy(), "5.1.2 (Atmos Light)", 44100, .8)
+    assert np.array_equal(m, g["map_441_512"])
+    assert rs.apply_surround_panning_3d(None, .5, .5, .5).shape == (0, 6)
+    assert rs.map_channels(np.zeros((5, 4), np.float32), "Stereo", 48000)[0].shape == (0, 2)
+
+
+def test_apply_delay(rs):
+    a = np.random.default_rng(0).standard_normal((100, 3)).astype(np.float32)
+    assert np.array_equal(rs.apply_delay(a, 7), orc.delay_rows(a, 7))
+    assert np.array_equal(rs.apply_delay(a, 1000), np.zeros_like(a))
+    assert rs.apply_delay(a, 0) is a
+
+
+# ------------------------------------------------------------------ metrics / PCM ----------
+def test_metrics_peak_rms_match_golden(rs, golden):
+    g = golden("metrics_pipeline")
+    for i in range(4):
+        m = rs.calculate_audio_metrics(g[f"m_in{i}"], 48000)
+        ref = g[f"m_out{i}"]
+        for got, want in ((m["true_peak_dbfs"], ref[0]), (m["rms_dbfs"], ref[1])):
+            if np.isinf(want):
+                assert got == want
+            else:
+                assert abs(got - want) <= 1e-4
+
+
+def test_lufs_matches_oracle_restatement(rs):
+    g = np.random.default_rng(7)
+    for n, c, amp, rate in ((48000 * 3, 2, 0.2, 48000), (44100 * 2 + 123, 6, 0.05, 44100), (30000, 1, 0.5, 16000)):
+        d = (amp * g.standard_normal((n, c))).astype(np.float32)
+        d[: n // 3] *= 0.01          # quiet stretch so the relative gate matters
+        want = orc.metrics(d, rate)["lufs"]
+        got = rs.calculate_audio_metrics(d, rate)["lufs"]
+        assert abs(got - want) <= 2e-3, (got, want)
+    short = (0.1 * g.standard_normal((1000, 2))).astype(np.float32)
+    assert rs.calculate_audio_metrics(short, 48000)["lufs"] is None        # < 400 ms
+    assert rs.calculate_audio_metrics(np.zeros((48000, 2), np.float32), 48000)["lufs"] == -np.inf
+
+
+def test_pcm16_bit_exact(rs):
+    g = np.random.default_rng(8)
+    x = (0.6 * g.standard_normal((20001, 6))).astype(np.float32)
+    x[5, 2] = np.nan
+    x[6, 1] = np.inf
+    x[7, 0] = -np.inf
+    x[8, :] = [0.5 / 32767, 1.5 / 32767, 2.5 / 32767, -0.5 / 32767, -1.5 / 32767, 0.99995]
+    assert np.array_equal(rs.float_to_pcm16(x), orc.pcm16(x))
+
+
+# ------------------------------------------------------------------ whole pipeline ---------
+def test_pipeline_matches_golden(rs, golden):
+    g = golden("metrics_pipeline")
+    for i, p in enumerate(g["pipe_par"]):
+        n, ch, rate, ext = int(p[0]), int(p[1]), int(p[2]), bool(p[3])
+        hall, room, dif, air, e, l, dw, ks, b, t, x, y, z = (HALLS[int(p[4])],) + tuple(p[5:17])
+        mat, lay, seed = MATERIALS[int(p[17])], LAYOUTS[int(p[18])], int(p[19])
+        np.random.seed(seed)
+        res = rs.render_array(g[f"pipe_in{i}"], rate, external_ir_data=g["pipe_ir"] if ext else None,
+                              hall_type=hall, room_size=room, diffusion=dif, air_absorption=air, base_early_level=e,
+                              base_late_level=l, dry_wet=dw, dry_wet_kill_start=ks, bass_gain=b, treble_gain=t,
+                              x_pos=x, y_pos=y, z_pos=z, material=mat, target_channel_layout=lay)
+        ref = g[f"pipe_out{i}"]                       # what the reference handed to sf.write (clipped float32)
+        got = np.clip(res["final"], -0.9999, 0.9999)
+        assert rel_err(got, ref) <= TOL, f"pipeline case {i}: {rel_err(got, ref):.3e}"
+        # int16 frames: identical rounding rule on nearly identical floats -> at most 1 LSB apart, almost never
+        ref_pcm = orc.pcm16(ref)
+        diff = np.abs(res["pcm"].astype(np.int32) - ref_pcm.astype(np.int32))
+        assert diff.max() <= 1 and np.mean(diff != 0) < 2e-3, (diff.max(), np.mean(diff != 0))
+        # and bit-exact against the shared rule applied to our own float output
+        assert np.array_equal(res["pcm"], orc.pcm16(res["final"]))
+        assert rs._metrics_text(res["metrics"]) == str(g[f"pipe_text{i}"]), (rs._metrics_text(res["metrics"]),
+                                                                         str(g[f"pipe_text{i}"]))
+
+
+def test_file_level_entry_point(rs, tmp_path):
+    from ars_b200 import wavio
+    g = np.random.default_rng(9)
+    x = (0.25 * g.standard_normal((24000, 2))).astype(np.float32)
+    src = tmp_path / "in.wav"
+    wavio.write_float32(str(src), x, 48000)
+    np.random.seed(5)
+    p1, p2, text = rs.apply_raytrace_convolution_3d(str(src), None, False, "Room", 120, .5, .1, .8, .6, .5, .5, 1.2, .9,
+                                                    .4, .5, .6, "Holz", "7.1 (Surround)")
+    assert p1 is not None and p1 == p2 and text.startswith("LUFS: ")
+    pcm, rate = wavio.read(p1)
+    np.random.seed(5)
+    ref = orc.render(x, 48000, hall="Room", room_size=120, diffusion=.5, air=.1, early=.8, late=.6, dry_wet_amount=.5,
+                     kill_start=.5, bass=1.2, treble=.9, x=.4, y=.5, z=.6, material="Holz", layout="7.1 (Surround)")
+    assert rate == 48000 and pcm.shape == ref["pcm"].shape
+    d = np.abs(np.round(pcm * 32768).astype(np.int32) - ref["pcm"].astype(np.int32))
+    assert d.max() <= 1
+    bad = rs.apply_raytrace_convolution_3d(str(tmp_path / "missing.wav"), None, False, "Room", 120, .5, .1, .8, .6, .5,
+                                           .5, 1., 1., .5, .5, .5, "Holz", "Stereo")
+    assert bad[0] is None and bad[1] is None and bad[2].startswith("Fehler beim Laden")
+
+
+# ------------------------------------------------------------------ larger sizes ------------
+def test_cfg1_external_ir_vs_oracle(rs):
+    """BASELINE configs[0]: 10 s 48 kHz stereo sweep (x) 2 s synthetic stereo IR, stereo out."""
+    rate = 48000
+    t = np.arange(10 * rate) / rate
+    l = (0.5 * np.sin(2 * np.pi * (20 * t + (19980 / 20) * t * t))).astype(np.float32)
+    x = np.stack((l, l[::-1]), axis=1)
+    g = np.random.default_rng(1)
+    ir = (g.standard_normal((2 * rate, 2)) * np.exp(-np.arange(2 * rate) / (0.3 * rate))[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir))
+    for bass, treble in ((1.0, 1.0), (1.2, 0.9)):
+        want = orc.render(x, rate, external_ir=ir, dry_wet_amount=.5, kill_start=.5, bass=bass, treble=treble,
+                          layout="Stereo", with_lufs=False)
+        got = rs.render_array(x, rate, external_ir_data=ir, want_stereo=True, dry_wet=.5, dry_wet_kill_start=.5,
+                              bass_gain=bass, treble_gain=treble, target_channel_layout="Stereo")
+        assert rel_err(got["stereo"], want["stereo"]) <= TOL
+        assert rel_err(got["final"], want["final"]) <= TOL
+        assert snr_db(got["final"], want["final"]) >= 100.0
+
+
+def test_cfg2_like_room_render_vs_oracle(rs):
+    """BASELINE configs[1] at 1/6 length: mono -> 5.1, Room / Holz / 200 m^3, air 0.1, EQ 1.5 / 0.8."""
+    rate = 48000
+    x = (0.3 * np.random.default_rng(0).standard_normal(10 * rate)).astype(np.float32)
+    kw = dict(hall="Room", room_size=200., diffusion=.5, air=.1, early=.8, late=.6, dry_wet_amount=.6, kill_start=.5,
+              bass=1.5, treble=.8, x=.3, y=.4, z=.6, material="Holz", layout="5.1 (Standard)")
+    np.random.seed(11)
+    want = orc.render(x, rate, **kw)
+    np.random.seed(11)
+    got = rs.render_array(x, rate, want_stereo=True, hall_type="Room", room_size=200., diffusion=.5, air_absorption=.1,
+                          base_early_level=.8, base_late_level=.6, dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.5,
+                          treble_gain=.8, x_pos=.3, y_pos=.4, z_pos=.6, material="Holz",
+                          target_channel_layout="5.1 (Standard)")
+    assert got["final"].shape == want["final"].shape == (10 * rate + 90504 - 1, 6)
+    assert rel_err(got["stereo"], want["stereo"]) <= TOL
+    assert rel_err(got["final"], want["final"]) <= TOL
+    assert snr_db(got["final"], want["final"]) >= 100.0
+    d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) < 2e-3
+    for k in ("true_peak_dbfs", "rms_dbfs"):
+        assert abs(got["metrics"][k] - want["metrics"][k]) <= 1e-3
+    assert abs(got["metrics"]["lufs"] - want["metrics"]["lufs"]) <= 5e-3
+
+
+def test_linearity_and_shift_at_full_size(rs):
+    """Size-independent properties at a BASELINE-scale length (60 s): with EQ/air on but every
+    normaliser idle the render is linear, so render(a*x) == a*render(x)."""
+    rate = 48000
+    g = np.random.default_rng(3)
+    x = (0.05 * g.standard_normal((60 * rate, 2))).astype(np.float32)
+    kw = dict(hall_type="Cathedral", room_size=817., diffusion=.3, air_absorption=.2, dry_wet=.4, bass_gain=1.3,
+              treble_gain=.7, target_channel_layout="5.1.2 (Atmos Light)", want_metrics=False, want_pcm=False)
+    np.random.seed(21)
+    a = rs.render_array(x, rate, **kw)["final"]
+    np.random.seed(21)
+    b = rs.render_array((2.0 * x).astype(np.float32), rate, **kw)["final"]
+    assert np.max(np.abs(a)) < 0.5
+    assert rel_err(b, 2.0 * a) <= 2e-6

@@ -122,11 +122,11 @@ static TailSpec make_tail(i64 N, int layout, double rate, double x_, double y_, 
     const double pull = (0.5 - z) * (std::fabs(y - 0.5) * 0.3);
     const double gf = std::max(0.0, std::sqrt(1.0 - y) + pull), gb = std::max(0.0, std::sqrt(y) - pull);
     const double PI = 3.141592653589793;       // math.pi
-    ts.g_fl = (float)(gl * gf);
-    ts.g_fr = (float)(gr * gf);
-    ts.g_rl = (float)(gl * gb);
-    ts.g_rr = (float)(gr * gb);
-    ts.g_c = (float)(std::cos((x - 0.5) * PI) * gf);
+    ts.g_fl = gl * gf;
+    ts.g_fr = gr * gf;
+    ts.g_rl = gl * gb;
+    ts.g_rr = gr * gb;
+    ts.g_c = std::cos((x - 0.5) * PI) * gf;
     ts.g_lfe = 0.15f;
     const i64 r = (i64)rate;
     if (layout == LAYOUT_7_1) ts.delay = (i64)((double)(r * 12) / 1000.0);       // int(rate * 12 / 1000)

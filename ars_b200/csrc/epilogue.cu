@@ -26,14 +26,15 @@ __device__ __forceinline__ float guard1(float v, const Guard& g) {
 }
 
 __device__ __forceinline__ void pan6(float L, float R, const TailSpec& ts, float (&o)[6]) {
-    // rs.py:485-494 (float32 array times Python float => float32 multiply)
+    // rs.py:484-494: the mono mix and the LFE use Python-float (weak) gains => float32 multiplies; the
+    // position gains are np.float64 => float64 product, rounded on the store into the float32 array
     const float mono = __fmul_rn(__fadd_rn(L, R), 0.707f);
-    o[0] = __fmul_rn(L, ts.g_fl);
-    o[1] = __fmul_rn(R, ts.g_fr);
-    o[2] = __fmul_rn(mono, ts.g_c);
+    o[0] = __double2float_rn(__dmul_rn((double)L, ts.g_fl));
+    o[1] = __double2float_rn(__dmul_rn((double)R, ts.g_fr));
+    o[2] = __double2float_rn(__dmul_rn((double)mono, ts.g_c));
     o[3] = __fmul_rn(mono, ts.g_lfe);
-    o[4] = __fmul_rn(L, ts.g_rl);
-    o[5] = __fmul_rn(R, ts.g_rr);
+    o[4] = __double2float_rn(__dmul_rn((double)L, ts.g_rl));
+    o[5] = __double2float_rn(__dmul_rn((double)R, ts.g_rr));
 }
 
 // out channels of one frame from its (guarded) six channels and the (guarded) rear pair d frames earlier
@@ -110,8 +111,8 @@ __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, c
     if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
         // a delay <= 0 leaves the signal where it is (rs.py:510-511)
         const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0)));
-        rl_d = guard1(__fmul_rn(guard1(w.x, g1), ts.g_rl), g2);
-        rr_d = guard1(__fmul_rn(guard1(w.y, g1), ts.g_rr), g2);
+        rl_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.x, g1), ts.g_rl)), g2);
+        rr_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.y, g1), ts.g_rr)), g2);
     }
     map_frame(s, rl_d, rr_d, ts, o);
 }

@@ -16,7 +16,10 @@ struct TailSpec {
     int layout = LAYOUT_5_1;
     int C = 6;
     i64 delay = 0;               // frames: int(rate*12/1000) for 7.1, int(rate*18/1000) for 5.1.2
-    float g_fl = 0, g_fr = 0, g_c = 0, g_lfe = 0, g_rl = 0, g_rr = 0;   // rs.py:482-485 (float32 of the Python floats)
+    // rs.py:475-485: x, y, z are np.float64 (np.clip), so gain_f / gain_re and every product with them are
+    // np.float64 => `audio * fl` is formed in float64 and rounded when stored into the float32 array.
+    double g_fl = 0, g_fr = 0, g_c = 0, g_rl = 0, g_rr = 0;
+    float g_lfe = 0.15f;         // Python float (weak) => float32 multiply (rs.py:485)
     double height_gain = 0.0;    // clip(z,0,1)*0.6, np.float64 => product formed in double (rs.py:550-553)
 };
 

@@ -54,8 +54,6 @@ ARS_RAD(12, 3, 16, 16, 16, 1)
 ARS_RAD(13, 4, 16, 8, 8, 8)
 #undef ARS_RAD
 
-constexpr int TWN_LOG = 13;            // local twiddle table: w_8192^e
-constexpr int TWN = 1 << TWN_LOG;
 constexpr int BIG_LO_LOG = 15;         // two-level table for w_M^e
 
 // ---------------------------------------------------------------- butterflies -
@@ -151,37 +149,46 @@ struct Ld {
     i64 nvalid1 = 0;
     i64 N = 0, M = 0;
     int cin = 2;
+    // MODE >= 0: compile-time access mode (fast kernels); MODE < 0: runtime switch on `mode` (generic kernels)
+    template <int MODE> ARS_HD float2 get(i64 idx) const {
+        if constexpr (MODE < 0) return (*this)(idx);
+        else if constexpr (MODE == LD_PLAIN) return a[idx];
+        else if constexpr (MODE == LD_MULSPEC) return cmul(a[idx], ARS_LDG(b + idx));
+        else if constexpr (MODE == LD_CHIRP_X2) {      // interleaved stereo frames = complex samples L + iR
+            return idx < nvalid ? cmul(ARS_LDG(reinterpret_cast<const float2*>(f0) + idx), ARS_LDG(b + idx))
+                                : make_float2(0.f, 0.f);
+        } else if constexpr (MODE == LD_CHIRP_XC) {    // (frames, cin) floats: cin == 1 duplicates, cin > 2 keeps the first two
+            if (idx >= nvalid) return make_float2(0.f, 0.f);
+            const float l = ARS_LDG(f0 + idx * cin);
+            const float r = cin > 1 ? ARS_LDG(f0 + idx * cin + 1) : l;
+            return cmul(make_float2(l, r), ARS_LDG(b + idx));
+        } else if constexpr (MODE == LD_CHIRP_PAIR) {  // two real arrays packed as re + i*im (each may be absent / shorter)
+            const float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
+            const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
+            if (idx >= N) return make_float2(0.f, 0.f);
+            return cmul(make_float2(l, r), ARS_LDG(b + idx));
+        } else if constexpr (MODE == LD_CHIRP_B) {     // Bluestein kernel: conj(chirp) on (-N, N), wrapped modulo M
+            if (idx < N) return cconj(ARS_LDG(b + idx));
+            if (idx > M - N) return cconj(ARS_LDG(b + (M - idx)));
+            return make_float2(0.f, 0.f);
+        } else if constexpr (MODE == LD_CHIRP_C) {     // complex N-vector times chirp
+            return idx < nvalid ? cmul(ARS_LDG(a + idx), ARS_LDG(b + idx)) : make_float2(0.f, 0.f);
+        } else {                                       // LD_REAL_PAIR: plain zero-padded packing
+            const float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
+            const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
+            return make_float2(l, r);
+        }
+    }
     ARS_HD float2 operator()(i64 idx) const {
         switch (mode) {
-            case LD_PLAIN: return a[idx];
-            case LD_MULSPEC: return cmul(a[idx], b[idx]);
-            case LD_CHIRP_X2:      // interleaved stereo frames = complex samples L + iR
-                return idx < nvalid ? cmul(ARS_LDG(reinterpret_cast<const float2*>(f0) + idx), ARS_LDG(b + idx))
-                                    : make_float2(0.f, 0.f);
-            case LD_CHIRP_XC: {    // (frames, cin) floats: cin == 1 duplicates, cin > 2 keeps the first two
-                if (idx >= nvalid) return make_float2(0.f, 0.f);
-                float l = ARS_LDG(f0 + idx * cin);
-                float r = cin > 1 ? ARS_LDG(f0 + idx * cin + 1) : l;
-                return cmul(make_float2(l, r), ARS_LDG(b + idx));
-            }
-            case LD_CHIRP_PAIR: {  // two real arrays packed as re + i*im (each may be absent / shorter)
-                float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
-                float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
-                if (idx >= N) return make_float2(0.f, 0.f);
-                return cmul(make_float2(l, r), ARS_LDG(b + idx));
-            }
-            case LD_CHIRP_B: {     // Bluestein kernel: conj(chirp) on (-N, N), wrapped modulo M
-                if (idx < N) return cconj(ARS_LDG(b + idx));
-                if (idx > M - N) return cconj(ARS_LDG(b + (M - idx)));
-                return make_float2(0.f, 0.f);
-            }
-            case LD_CHIRP_C:       // complex N-vector times chirp
-                return idx < nvalid ? cmul(ARS_LDG(a + idx), ARS_LDG(b + idx)) : make_float2(0.f, 0.f);
-            case LD_REAL_PAIR: {   // no chirp: plain zero-padded packing (power-of-two convolution path)
-                float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
-                float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
-                return make_float2(l, r);
-            }
+            case LD_PLAIN: return get<LD_PLAIN>(idx);
+            case LD_MULSPEC: return get<LD_MULSPEC>(idx);
+            case LD_CHIRP_X2: return get<LD_CHIRP_X2>(idx);
+            case LD_CHIRP_XC: return get<LD_CHIRP_XC>(idx);
+            case LD_CHIRP_PAIR: return get<LD_CHIRP_PAIR>(idx);
+            case LD_CHIRP_B: return get<LD_CHIRP_B>(idx);
+            case LD_CHIRP_C: return get<LD_CHIRP_C>(idx);
+            case LD_REAL_PAIR: return get<LD_REAL_PAIR>(idx);
         }
         return make_float2(0.f, 0.f);
     }
@@ -195,25 +202,43 @@ struct St {
     float scale = 1.f;
     unsigned* maxbits = nullptr;     // ST_FINAL: abs-max over everything stored (uint bits of |x|)
     unsigned local_max = 0;
-    ARS_HD void operator()(i64 idx, float2 v) {
-        switch (mode) {
-            case ST_PLAIN: a[idx] = v; break;
-            case ST_SCALE: a[idx] = cscale(v, scale); break;
-            case ST_CHIRP:
-                if (idx < N) a[idx] = cmul(v, ARS_LDG(chirp + idx));
-                break;
-            case ST_FINAL:
-                if (idx < N) {
-                    float2 y = cmul(v, ARS_LDG(chirp + idx));
-                    y = make_float2(y.x * scale, -y.y * scale);
-                    a[idx] = y;
-                    unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y);
-                    unsigned mm = m0 > m1 ? m0 : m1;
-                    if (mm > local_max) local_max = mm;
-                }
-                break;
+    // chirp operand of the store, fetched early so its latency overlaps the butterfly
+    template <int MODE> ARS_HD float2 pre(i64 idx) const {
+        if constexpr (MODE < 0) {
+            if ((mode == ST_CHIRP || mode == ST_FINAL) && idx < N) return ARS_LDG(chirp + idx);
+            return make_float2(1.f, 0.f);
+        } else if constexpr (MODE == ST_CHIRP || MODE == ST_FINAL) {
+            return idx < N ? ARS_LDG(chirp + idx) : make_float2(1.f, 0.f);
+        } else {
+            return make_float2(1.f, 0.f);
         }
     }
+    template <int MODE> ARS_HD void put(i64 idx, float2 v, float2 aux) {
+        if constexpr (MODE < 0) {
+            switch (mode) {
+                case ST_PLAIN: put<ST_PLAIN>(idx, v, aux); break;
+                case ST_SCALE: put<ST_SCALE>(idx, v, aux); break;
+                case ST_CHIRP: put<ST_CHIRP>(idx, v, aux); break;
+                case ST_FINAL: put<ST_FINAL>(idx, v, aux); break;
+            }
+        } else if constexpr (MODE == ST_PLAIN) {
+            a[idx] = v;
+        } else if constexpr (MODE == ST_SCALE) {
+            a[idx] = cscale(v, scale);
+        } else if constexpr (MODE == ST_CHIRP) {
+            if (idx < N) a[idx] = cmul(v, aux);
+        } else {
+            if (idx < N) {
+                float2 y = cmul(v, aux);
+                y = make_float2(y.x * scale, -y.y * scale);
+                a[idx] = y;
+                const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y);
+                const unsigned mm = m0 > m1 ? m0 : m1;
+                if (mm > local_max) local_max = mm;
+            }
+        }
+    }
+    template <int MODE> ARS_HD void put(i64 idx, float2 v) { put<MODE>(idx, v, pre<MODE>(idx)); }
     ARS_HD void finish() {
         if (mode == ST_FINAL && maxbits) {
 #ifdef __CUDA_ARCH__
@@ -230,19 +255,41 @@ struct St {
 
 // ------------------------------------------------------------------ twiddles --
 struct Tw {
-    const float2* local;    // w_TWN^e, e < TWN
+    const float2* stage;    // per-stage tables: for Ls = 2^l, entry [stage_off(l) + j*(Ls/2) + i] = w_Ls^(i * 2^j), j < 4
     const float2* lo;       // w_M^e, e < min(M, 2^15)
     const float2* hi;       // w_M^(e << 15), e < M >> 15 (null when M <= 2^15)
 };
+constexpr int STAGE_LOG_MAX = 13;
+ARS_HD constexpr int stage_off(int l) { return 2 * ((1 << l) - 2); }
+constexpr int STAGE_TABLE_ELEMS = 2 * ((1 << (STAGE_LOG_MAX + 1)) - 2);
 
-template <bool INV> ARS_HD float2 tw_local(const Tw& tw, int e) {
-    float2 w = ARS_LDG(tw.local + e);
-    return INV ? cconj(w) : w;
-}
 template <bool INV> ARS_HD float2 tw_big(const Tw& tw, unsigned e) {
     float2 w = ARS_LDG(tw.lo + (e & ((1u << BIG_LO_LOG) - 1)));
     if (tw.hi) w = cmul(w, ARS_LDG(tw.hi + (e >> BIG_LO_LOG)));
     return INV ? cconj(w) : w;
+}
+
+// w[k] = w[1]^k for k < r from the exactly tabulated w[1], w[2], w[4], w[8] (at most three products deep)
+template <int r> ARS_HD void expand_pow(float2 (&w)[r]) {
+    if constexpr (r >= 4) w[3] = cmul(w[2], w[1]);
+    if constexpr (r >= 8) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); }
+    if constexpr (r >= 16) {
+        w[9] = cmul(w[8], w[1]);  w[10] = cmul(w[8], w[2]); w[11] = cmul(w[8], w[3]); w[12] = cmul(w[8], w[4]);
+        w[13] = cmul(w[8], w[5]); w[14] = cmul(w[8], w[6]); w[15] = cmul(w[8], w[7]);
+    }
+}
+constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// local stage twiddles w_Ls^(i*k), k < r: four coalesced table reads (lanes hold consecutive i) + products
+template <int Ls, int r, bool INV> ARS_HD void stage_twiddles(const Tw& tw, int i, float2 (&w)[r]) {
+    constexpr int l = ilog2(Ls);
+    const float2* t = tw.stage + stage_off(l) + i;
+    #pragma unroll
+    for (int j = 0; (1 << j) < r; ++j) {
+        float2 x = ARS_LDG(t + j * (Ls / 2));
+        w[1 << j] = INV ? cconj(x) : x;
+    }
+    expand_pow<r>(w);
 }
 
 // -------------------------------------------------------------- tile layouts --
@@ -297,7 +344,8 @@ template <int LOGR> ARS_HD int kfull_of(int b, int k) {
 // One DIF (forward) or DIT (inverse) stage S of the R-point column transforms of a tile.
 //   GIDX_FIRST(row, c): HBM index of tile element (row, c) on the natural-order side
 //   GIDX_LAST(b, k, c): HBM index of output k of last-stage butterfly b on the permuted side
-template <int LOGR, int S, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+template <int LOGR, int S, bool INV, bool STRIDED, int NT, class LAYOUT, int LDM, int STM, class LD, class ST, class GF,
+          class GL>
 ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast,
                                           unsigned col0, int tid) {
     constexpr int R = 1 << LOGR;
@@ -308,7 +356,22 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
     constexpr bool first = (S == 0), last = (S == n - 1);
     constexpr int NB = R / r;                  // butterflies per column
     constexpr int TOTAL = NB * LAYOUT::C;
-    constexpr int TWSTEP = TWN / Ls;
+    static_assert(!STRIDED || NT % LAYOUT::C == 0, "a thread must stay in one tile column");
+
+    // inter-pass twiddle w_Lg^(i * kf), kf = kb(b) + k * mul: per-thread powers P[k] = w^(i*mul*k) (the column
+    // i is fixed per thread) and one per-butterfly factor Q = w^(i*kb); both from exact two-level table reads
+    constexpr int mul = R / r;                 // = product of the radices before the last stage (when `last`)
+    float2 P[r];
+    unsigned icol = 0;
+    const unsigned shift = (unsigned)(pa.logM - pa.logLg);
+    const unsigned emask = (unsigned)(pa.M - 1);
+    if constexpr (STRIDED && last) {
+        icol = col0 + (unsigned)(tid & (LAYOUT::C - 1));
+        const unsigned eP = (icol * (unsigned)mul) << shift;
+        #pragma unroll
+        for (int j = 0; (1 << j) < r; ++j) P[1 << j] = tw_big<INV>(pa.tw, (eP << j) & emask);
+        expand_pow<r>(P);
+    }
 
     for (int q = tid; q < TOTAL; q += NT) {
         int b, c;
@@ -321,53 +384,63 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
             #pragma unroll
             for (int t = 0; t < r; ++t) {
                 const int row = row0 + t * sub;
-                v[t] = first ? ld(gfirst(row, c)) : sm[LAYOUT::sidx(row, c)];
+                if constexpr (first) v[t] = ld.template get<LDM>(gfirst(row, c));
+                else v[t] = sm[LAYOUT::sidx(row, c)];
             }
-            Dft<r, false>::run(v);
             if constexpr (!last) {
+                float2 w[r];
+                stage_twiddles<Ls, r, false>(pa.tw, i, w);
+                Dft<r, false>::run(v);
                 #pragma unroll
-                for (int k = 1; k < r; ++k) v[k] = cmul(v[k], tw_local<false>(pa.tw, i * k * TWSTEP));
+                for (int k = 1; k < r; ++k) v[k] = cmul(v[k], w[k]);
                 #pragma unroll
                 for (int k = 0; k < r; ++k) sm[LAYOUT::sidx(row0 + k * sub, c)] = v[k];
             } else {
+                float2 Q = make_float2(1.f, 0.f);
+                if constexpr (STRIDED) Q = tw_big<false>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
+                Dft<r, false>::run(v);
                 #pragma unroll
                 for (int k = 0; k < r; ++k) {
-                    if constexpr (STRIDED) {
-                        const unsigned kf = (unsigned)kfull_of<LOGR>(b, k);
-                        const unsigned e = ((col0 + (unsigned)c) * kf) << (pa.logM - pa.logLg);
-                        v[k] = cmul(v[k], tw_big<false>(pa.tw, e));
-                    }
-                    st(glast(b, k, c), v[k]);
+                    if constexpr (STRIDED) v[k] = cmul(v[k], k ? cmul(Q, P[k]) : Q);
+                    st.template put<STM>(glast(b, k, c), v[k]);
                 }
             }
         } else {
-            #pragma unroll
-            for (int k = 0; k < r; ++k) {
-                if constexpr (last) {
-                    v[k] = ld(glast(b, k, c));
-                    if constexpr (STRIDED) {
-                        const unsigned kf = (unsigned)kfull_of<LOGR>(b, k);
-                        const unsigned e = ((col0 + (unsigned)c) * kf) << (pa.logM - pa.logLg);
-                        v[k] = cmul(v[k], tw_big<true>(pa.tw, e));
-                    }
-                } else {
-                    v[k] = sm[LAYOUT::sidx(row0 + k * sub, c)];
-                    if (k) v[k] = cmul(v[k], tw_local<true>(pa.tw, i * k * TWSTEP));
+            if constexpr (last) {
+                float2 Q = make_float2(1.f, 0.f);
+                if constexpr (STRIDED) Q = tw_big<true>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
+                #pragma unroll
+                for (int k = 0; k < r; ++k) v[k] = ld.template get<LDM>(glast(b, k, c));
+                if constexpr (STRIDED) {
+                    #pragma unroll
+                    for (int k = 0; k < r; ++k) v[k] = cmul(v[k], k ? cmul(Q, P[k]) : Q);
                 }
+            } else {
+                float2 w[r];
+                stage_twiddles<Ls, r, true>(pa.tw, i, w);
+                #pragma unroll
+                for (int k = 0; k < r; ++k) v[k] = sm[LAYOUT::sidx(row0 + k * sub, c)];
+                #pragma unroll
+                for (int k = 1; k < r; ++k) v[k] = cmul(v[k], w[k]);
             }
-            Dft<r, true>::run(v);
-            #pragma unroll
-            for (int t = 0; t < r; ++t) {
-                const int row = row0 + t * sub;
-                if constexpr (first) st(gfirst(row, c), v[t]);
-                else sm[LAYOUT::sidx(row, c)] = v[t];
+            if constexpr (first) {
+                float2 aux[r];
+                #pragma unroll
+                for (int t = 0; t < r; ++t) aux[t] = st.template pre<STM>(gfirst(row0 + t * sub, c));
+                Dft<r, true>::run(v);
+                #pragma unroll
+                for (int t = 0; t < r; ++t) st.template put<STM>(gfirst(row0 + t * sub, c), v[t], aux[t]);
+            } else {
+                Dft<r, true>::run(v);
+                #pragma unroll
+                for (int t = 0; t < r; ++t) sm[LAYOUT::sidx(row0 + t * sub, c)] = v[t];
             }
         }
     }
 }
 
-#define ARS_STAGE(S_) run_stage<LOGR, S_, INV, STRIDED, NT, LAYOUT>(sm, ld, st, pa, gfirst, glast, col0, tid)
-template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+#define ARS_STAGE(S_) run_stage<LOGR, S_, INV, STRIDED, NT, LAYOUT, LDM, STM>(sm, ld, st, pa, gfirst, glast, col0, tid)
+template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, int LDM, int STM, class LD, class ST, class GF, class GL>
 __device__ __forceinline__ void run_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast,
                                          unsigned col0) {
     constexpr int n = Rad<LOGR>::n;
@@ -388,7 +461,7 @@ __device__ __forceinline__ void run_tile(float2* sm, LD& ld, ST& st, const PassA
 
 // Host emulation of one tile (tests/host_emul): the same stage code, "threads" run one after
 // another, a barrier is simply the end of the loop over threads.
-template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, class LD, class ST, class GF, class GL>
+template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, int LDM, int STM, class LD, class ST, class GF, class GL>
 inline void emulate_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst, GL glast, unsigned col0) {
     constexpr int n = Rad<LOGR>::n;
 #define ARS_ALL(S_) for (int tid = 0; tid < NT; ++tid) ARS_STAGE(S_)
@@ -448,30 +521,34 @@ template <int LOGR, int LOGT> struct StridedTile {
     }
 };
 
-template <int LOGR, int LOGT, bool INV, int NT>
+template <int LOGR, int LOGT, bool INV, int NT, int LDM, int STM>
 __global__ void __launch_bounds__(NT) pass_strided_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
     const StridedTile<LOGR, LOGT> t((i64)blockIdx.x, pa);
-    run_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>>(
+    run_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>, LDM, STM>(
         sm, ld, st, pa, StridedFirst<LOGR>{t.base, t.logStride}, StridedLast<LOGR>{t.base, t.logStride}, t.col0);
 }
 
 // Contiguous pass: tile = C whole segments of R adjacent elements.
-template <int LOGR, int LOGC, bool INV, int NT>
+template <int LOGR, int LOGC, bool INV, int NT, int LDM, int STM>
 __global__ void __launch_bounds__(NT) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
     const i64 base = (i64)blockIdx.x << (LOGR + LOGC);
-    run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>>(sm, ld, st, pa, ContigFirst<LOGR>{base},
+    run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>, LDM, STM>(sm, ld, st, pa, ContigFirst<LOGR>{base},
                                                              ContigLast<LOGR>{base}, 0u);
 }
 
 }  // namespace fft
 
 // instantiated (logR, logT|logC) pass variants; the launcher and the host emulator share the list
-#define ARS_STRIDED_CASES(X) X(4, 9) X(5, 8) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 2)
+#define ARS_STRIDED_CASES(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 2)
 #define ARS_CONTIG_CASES(X)                                                                         \
     X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(5, 0) X(6, 0) X(7, 0) X(8, 0) X(9, 0) X(10, 0) X(11, 0) X(12, 0) \
     X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1)
+
+// variants that also get compile-time-mode ("fast") instantiations: the ones big transforms are planned with
+#define ARS_FAST_STRIDED(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4)
+#define ARS_FAST_CONTIG(X) X(12, 1)
 
 // ------------------------------------------------------------------ host API --
 struct FftPass {

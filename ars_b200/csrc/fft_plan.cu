@@ -19,12 +19,26 @@ __global__ void twiddle_table_kernel(float2* out, int count, double step_turns) 
     out[e] = make_float2((float)c, (float)s);
 }
 
+// per-stage local twiddles, shared by every plan: for Ls = 2^l, [stage_off(l) + j*(Ls/2) + i] = w_Ls^(i * 2^j)
+__global__ void stage_table_kernel(float2* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= STAGE_TABLE_ELEMS) return;
+    int l = 1;
+    while (l < STAGE_LOG_MAX && idx >= stage_off(l + 1)) ++l;
+    const int Ls = 1 << l, rel = idx - stage_off(l);
+    const int j = rel / (Ls / 2), i = rel % (Ls / 2);
+    const long long e = ((long long)i << j) % Ls;
+    double s, c;
+    sincospi(-2.0 * (double)e / (double)Ls, &s, &c);
+    out[idx] = make_float2((float)c, (float)s);
+}
+
 static DevBuf g_tw_local;
 
 static const float2* local_table() {
     if (!g_tw_local.p) {
-        g_tw_local.reserve(sizeof(float2) * TWN);
-        twiddle_table_kernel<<<ceil_div(TWN, 256), 256, 0, ctx().stream>>>(g_tw_local.as<float2>(), TWN, 1.0 / TWN);
+        g_tw_local.reserve(sizeof(float2) * STAGE_TABLE_ELEMS);
+        stage_table_kernel<<<ceil_div(STAGE_TABLE_ELEMS, 256), 256, 0, ctx().stream>>>(g_tw_local.as<float2>());
         ARS_LAUNCH_CHECK();
         count_launch();
     }
@@ -43,8 +57,11 @@ void fft_release_plans() {
 #include "fft_decompose.inc"
 namespace ars {
 
+static bool g_fast = true;     // ARS_FFT_GENERIC=1 forces the runtime-switch kernels (debug / A-B runs)
+
 FftPlan* get_fft_plan(int logM) {
     Ctx& c = ctx();
+    g_fast = env_int("ARS_FFT_GENERIC", 0) == 0;
     auto it = c.fft_plans.find(logM);
     if (it != c.fft_plans.end()) return it->second;
     ARS_CHECK(logM >= 1 && logM <= 30, "FFT length out of range (2^1 .. 2^30)");
@@ -68,7 +85,7 @@ FftPlan* get_fft_plan(int logM) {
         count_launch();
         p->tw.hi = p->tw_hi.as<float2>();
     }
-    p->tw.local = local_table();
+    p->tw.stage = local_table();
     c.fft_plans[logM] = p;
     return p;
 }
@@ -135,12 +152,12 @@ static cudaEvent_t prof_event() {
 // --------------------------------------------------------------- launchers ---
 constexpr int NT = 256;
 
-template <int LOGR, int LOGT, bool INV>
+template <int LOGR, int LOGT, bool INV, int LDM, int STM>
 static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = StridedLayout<LOGR, LOGT>;
     static bool attr_done = false;
     const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
-    auto k = pass_strided_kernel<LOGR, LOGT, INV, NT>;
+    auto k = pass_strided_kernel<LOGR, LOGT, INV, NT, LDM, STM>;
     if (!attr_done && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -151,12 +168,12 @@ static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     count_launch();
 }
 
-template <int LOGR, int LOGC, bool INV>
+template <int LOGR, int LOGC, bool INV, int LDM, int STM>
 static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = ContigLayout<LOGR, LOGC>;
     static bool attr_done = false;
     const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
-    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT>;
+    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT, LDM, STM>;
     if (!attr_done && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -165,6 +182,44 @@ static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
     ARS_LAUNCH_CHECK();
     count_launch();
+}
+
+
+// Compile-time (load mode, store mode) pairs that occur in big transforms:
+//   forward first pass : LD_CHIRP_* -> ST_PLAIN (strided)      forward other passes: PLAIN -> PLAIN
+//   inverse first pass : LD_MULSPEC -> ST_PLAIN (contiguous)   inverse last pass   : PLAIN -> ST_CHIRP | ST_FINAL (strided)
+template <bool INV>
+static bool launch_fast(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa) {
+    if (!g_fast) return false;
+    const int lm = ld.mode, sm = st.mode;
+    if (ps.strided) {
+#define F_CASE(R, T)                                                                                              \
+        if (ps.logR == R && ps.logT == T) {                                                                       \
+            if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_strided<R, T, INV, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; } \
+            if constexpr (!INV) {                                                                                 \
+                if (sm == ST_PLAIN && lm == LD_CHIRP_X2) { launch_strided<R, T, false, LD_CHIRP_X2, ST_PLAIN>(ld, st, pa); return true; } \
+                if (sm == ST_PLAIN && lm == LD_CHIRP_XC) { launch_strided<R, T, false, LD_CHIRP_XC, ST_PLAIN>(ld, st, pa); return true; } \
+                if (sm == ST_PLAIN && lm == LD_CHIRP_PAIR) { launch_strided<R, T, false, LD_CHIRP_PAIR, ST_PLAIN>(ld, st, pa); return true; } \
+                if (sm == ST_PLAIN && lm == LD_CHIRP_C) { launch_strided<R, T, false, LD_CHIRP_C, ST_PLAIN>(ld, st, pa); return true; } \
+            } else {                                                                                              \
+                if (lm == LD_PLAIN && sm == ST_CHIRP) { launch_strided<R, T, true, LD_PLAIN, ST_CHIRP>(ld, st, pa); return true; } \
+                if (lm == LD_PLAIN && sm == ST_FINAL) { launch_strided<R, T, true, LD_PLAIN, ST_FINAL>(ld, st, pa); return true; } \
+            }                                                                                                     \
+        }
+        ARS_FAST_STRIDED(F_CASE)
+#undef F_CASE
+    } else {
+#define F_CASE(R, C)                                                                                              \
+        if (ps.logR == R && ps.logT == C) {                                                                       \
+            if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_contig<R, C, INV, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; } \
+            if constexpr (INV) {                                                                                  \
+                if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
+            }                                                                                                     \
+        }
+        ARS_FAST_CONTIG(F_CASE)
+#undef F_CASE
+    }
+    return false;
 }
 
 template <bool INV>
@@ -181,14 +236,15 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
         }
         ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
     } prof_scope(ld, st, p->M);
+    if (ps.strided) ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
+    if (launch_fast<INV>(ps, ld, st, pa)) return;
     if (ps.strided) {
-        ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
-#define S_CASE(R, T) if (ps.logR == R && ps.logT == T) return launch_strided<R, T, INV>(ld, st, pa);
+#define S_CASE(R, T) if (ps.logR == R && ps.logT == T) return launch_strided<R, T, INV, -1, -1>(ld, st, pa);
         ARS_STRIDED_CASES(S_CASE)
 #undef S_CASE
         ARS_CHECK(false, "no strided FFT pass kernel for this (logR, logT)");
     } else {
-#define C_CASE(R, C) if (ps.logR == R && ps.logT == C) return launch_contig<R, C, INV>(ld, st, pa);
+#define C_CASE(R, C) if (ps.logR == R && ps.logT == C) return launch_contig<R, C, INV, -1, -1>(ld, st, pa);
         ARS_CONTIG_CASES(C_CASE)
 #undef C_CASE
         ARS_CHECK(false, "no contiguous FFT pass kernel for this (logR, logC)");

@@ -106,15 +106,39 @@ __global__ void __launch_bounds__(NTB) biquad_kernel(const float* __restrict__ x
     }
 }
 
-// exclusive serial scan over block aggregates: start[b+1] = A^BS start[b] + agg[b]
-__global__ void block_scan_kernel(double2* state, int nblocks, Mat2 pbs) {
-    if (blockIdx.x || threadIdx.x) return;
-    double2 s = make_double2(0.0, 0.0);
-    for (int b = 0; b < nblocks; ++b) {
-        const double2 agg = state[b];
-        state[b] = s;
-        const double2 ps = mat_vec(pbs, s);
-        s = make_double2(ps.x + agg.x, ps.y + agg.y);
+// exclusive scan over block aggregates: start[b+1] = A^BS start[b] + agg[b].  One CTA of 1024 threads,
+// Hillis-Steele over tiles of 1024 aggregates with the powers (A^BS)^(2^k) and a running carry.
+struct BlockPow { Mat2 p[10]; };
+__global__ void __launch_bounds__(1024) block_scan_kernel(double2* state, int nblocks, BlockPow bp) {
+    __shared__ double2 sv[1024];
+    __shared__ double2 carry;
+    const int t = threadIdx.x;
+    if (t == 0) carry = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int b = base + t;
+        double2 v = b < nblocks ? state[b] : make_double2(0.0, 0.0);
+        if (t == 0) {
+            const double2 pc = mat_vec(bp.p[0], carry);
+            v.x += pc.x; v.y += pc.y;
+        }
+        sv[t] = v;
+        __syncthreads();
+        #pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const int off = 1 << k;
+            double2 add = make_double2(0.0, 0.0);
+            if (t >= off) add = mat_vec(bp.p[k], sv[t - off]);
+            __syncthreads();
+            v.x += add.x; v.y += add.y;
+            sv[t] = v;
+            __syncthreads();
+        }
+        const double2 start = (t == 0) ? carry : sv[t - 1];
+        if (b < nblocks) state[b] = start;
+        __syncthreads();
+        if (t == 1023) carry = v;
+        __syncthreads();
     }
 }
 
@@ -181,7 +205,10 @@ static void run_biquad(const float* d_in, float* d_out, i64 N, const Biquad& q) 
     double2* st = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
     biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_in, N, cf, st, nullptr);
     ARS_LAUNCH_CHECK();
-    block_scan_kernel<<<1, 32, 0, c.stream>>>(st, nblocks, cf.pw[8]);
+    BlockPow bp;
+    bp.p[0] = cf.pw[8];
+    for (int k = 1; k < 10; ++k) bp.p[k] = mat_mul(bp.p[k - 1], bp.p[k - 1]);
+    block_scan_kernel<<<1, 1024, 0, c.stream>>>(st, nblocks, bp);
     ARS_LAUNCH_CHECK();
     biquad_kernel<1><<<nblocks, NTB, 0, c.stream>>>(d_in, N, cf, st, d_out);
     ARS_LAUNCH_CHECK();

@@ -338,7 +338,8 @@ def convolve_external(data, ir, dry_wet_amount, bass=1.0, treble=1.0, rate=44100
 # panner and channel mapper (a10-a12)
 # --------------------------------------------------------------------------
 def pan_gains(x, y, z):
-    """rs.py:468,475-485 -> dict of Python-float gains (weak scalars => float32 math)."""
+    """rs.py:468,475-485 -> dict of gains.  x, y, z come out of np.clip as np.float64, so every position gain is an
+    np.float64 (strong) scalar: `audio * gain` is formed in float64 and rounded on the store into float32."""
     x, y, z = (np.clip(float(v), 0.0, 1.0) for v in (x, y, z))
     gl, gr = math.sqrt(1.0 - x), math.sqrt(x)
     pull = (0.5 - z) * (abs(y - 0.5) * 0.3)

@@ -22,10 +22,15 @@ static std::vector<float2> g_local, g_lo, g_hi;
 
 static void make_tables(int logM, Tw& tw) {
     const double PI = 3.14159265358979323846;
-    g_local.resize(TWN);
-    for (int e = 0; e < TWN; ++e) {
-        double a = -2.0 * PI * e / TWN;
-        g_local[e] = make_float2((float)cos(a), (float)sin(a));
+    g_local.resize(STAGE_TABLE_ELEMS);
+    for (int l = 1; l <= STAGE_LOG_MAX; ++l) {
+        const int Ls = 1 << l;
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < Ls / 2; ++i) {
+                const long long e = ((long long)i << j) % Ls;
+                double a = -2.0 * PI * (double)e / (double)Ls;
+                g_local[stage_off(l) + j * (Ls / 2) + i] = make_float2((float)cos(a), (float)sin(a));
+            }
     }
     const i64 M = (i64)1 << logM;
     const int nlo = (int)std::min<i64>(M, (i64)1 << BIG_LO_LOG);
@@ -34,7 +39,7 @@ static void make_tables(int logM, Tw& tw) {
         double a = -2.0 * PI * (double)e / (double)M;
         g_lo[e] = make_float2((float)cos(a), (float)sin(a));
     }
-    tw.local = g_local.data();
+    tw.stage = g_local.data();
     tw.lo = g_lo.data();
     tw.hi = nullptr;
     if (logM > BIG_LO_LOG) {
@@ -50,7 +55,7 @@ static void make_tables(int logM, Tw& tw) {
 
 constexpr int NT = 256;
 
-template <int LOGR, int LOGT, bool INV> static void emu_strided(const Ld& ld, const St& st, const PassArgs& pa) {
+template <int LOGR, int LOGT, bool INV, int LDM = -1, int STM = -1> static void emu_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = StridedLayout<LOGR, LOGT>;
     std::vector<float2> sm(L::SMEM_ELEMS);
     const i64 tiles = pa.M >> (LOGR + LOGT);
@@ -58,11 +63,11 @@ template <int LOGR, int LOGT, bool INV> static void emu_strided(const Ld& ld, co
         Ld l = ld;
         St s = st;
         StridedTile<LOGR, LOGT> t(tile, pa);
-        emulate_tile<LOGR, INV, true, NT, L>(sm.data(), l, s, pa, StridedFirst<LOGR>{t.base, t.logStride},
+        emulate_tile<LOGR, INV, true, NT, L, LDM, STM>(sm.data(), l, s, pa, StridedFirst<LOGR>{t.base, t.logStride},
                                             StridedLast<LOGR>{t.base, t.logStride}, t.col0);
     }
 }
-template <int LOGR, int LOGC, bool INV> static void emu_contig(const Ld& ld, const St& st, const PassArgs& pa) {
+template <int LOGR, int LOGC, bool INV, int LDM = -1, int STM = -1> static void emu_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = ContigLayout<LOGR, LOGC>;
     std::vector<float2> sm(L::SMEM_ELEMS);
     const i64 tiles = pa.M >> (LOGR + LOGC);
@@ -70,7 +75,7 @@ template <int LOGR, int LOGC, bool INV> static void emu_contig(const Ld& ld, con
         Ld l = ld;
         St s = st;
         const i64 base = tile << (LOGR + LOGC);
-        emulate_tile<LOGR, INV, false, NT, L>(sm.data(), l, s, pa, ContigFirst<LOGR>{base}, ContigLast<LOGR>{base}, 0u);
+        emulate_tile<LOGR, INV, false, NT, L, LDM, STM>(sm.data(), l, s, pa, ContigFirst<LOGR>{base}, ContigLast<LOGR>{base}, 0u);
     }
 }
 

@@ -43,6 +43,13 @@ class ArsRenderParams(C.Structure):
                 ("want_lufs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ArsClip(C.Structure):
+    _fields_ = [("params", C.POINTER(ArsRenderParams)), ("in_", C.c_void_p), ("n", C.c_int64), ("cin", C.c_int32),
+                ("reserved", C.c_int32), ("ext_ir", C.c_void_p), ("ext_ir_len", C.c_int64),
+                ("draws", C.POINTER(ArsIrDraws)), ("out_f32", C.c_void_p), ("out_pcm", C.c_void_p),
+                ("metrics", C.POINTER(ArsMetrics))]
+
+
 _d, _i32, _i64, _p = C.c_double, C.c_int32, C.c_int64, C.c_void_p
 
 # name -> (restype, argtypes); must list every symbol include/ars_b200.h declares
@@ -73,6 +80,7 @@ PROTOTYPES = {
                              _p, _p, _p, C.POINTER(ArsMetrics)]),
     "ars_render_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),
                                  _p, _p, _p, C.POINTER(ArsMetrics)]),
+    "ars_render_batch": (C.c_int, [C.POINTER(ArsClip), _i32]),
     "ars_timer_begin": (C.c_int, []),
     "ars_timer_end": (C.c_int, [C.POINTER(C.c_float)]),
     "ars_profile_begin": (C.c_int, []),

@@ -40,9 +40,9 @@ template <class T> static void download(T* host, const T* dev, size_t count) {
 }
 static void sync() { ARS_CUDA(cudaStreamSynchronize(ctx().stream)); }
 
-static RenderState* fresh_state() {
+static RenderState* fresh_state(int slot = 0) {
     Ctx& c = ctx();
-    RenderState* st = c.buf("state", sizeof(RenderState)).as<RenderState>();
+    RenderState* st = c.buf(slot ? "state.1" : "state.0", sizeof(RenderState)).as<RenderState>();
     ARS_CUDA(cudaMemsetAsync(st, 0, sizeof(RenderState), c.stream));
     return st;
 }
@@ -135,7 +135,8 @@ static TailSpec make_tail(i64 N, int layout, double rate, double x_, double y_, 
     return ts;
 }
 
-static void finish_metrics(const RenderState& st, i64 count, ArsMetrics* m) {
+static void finish_metrics(const RenderState& st, i64 count, int lufs_status, ArsMetrics* m) {
+    memset(m, 0, sizeof(*m));
     const float peak = [&] { float f; unsigned u = st.peak_final; memcpy(&f, &u, 4); return f; }();
     const double inf = std::numeric_limits<double>::infinity();
     m->peak_linear = (double)peak;
@@ -143,29 +144,14 @@ static void finish_metrics(const RenderState& st, i64 count, ArsMetrics* m) {
     m->rms_linear = (double)rms;
     m->true_peak_dbfs = (double)peak > 1e-15 ? 20.0 * std::log10((double)peak) : -inf;
     m->rms_dbfs = (double)rms > 1e-15 ? 20.0 * std::log10((double)rms) : -inf;
+    m->lufs_status = lufs_status;
+    m->lufs = lufs_status == ARS_LUFS_OK ? st.lufs : 0.0;
 }
 
-// loudness of the mono feed already on the device (rs.py:685-691)
-static void lufs_of(const float* d_mono, i64 N, double rate, RenderState* d_state, ArsMetrics* m) {
-    Ctx& c = ctx();
-    unsigned* mb = c.buf("lufs.max", sizeof(unsigned)).as<unsigned>();
-    ARS_CUDA(cudaMemsetAsync(mb, 0, sizeof(unsigned), c.stream));
-    absmax_f32(d_mono, N, mb);
-    unsigned bits = 0;
-    download(&bits, mb, 1);
-    sync();
-    float pk;
-    memcpy(&pk, &bits, 4);
-    if (pk < 1e-6f) {                      // rs.py:689
-        m->lufs = -std::numeric_limits<double>::infinity();
-        m->lufs_status = ARS_LUFS_OK;
-        return;
-    }
-    double l = 0.0;
-    const int s = integrated_loudness(d_mono, N, rate, &l);
-    m->lufs = s == 0 ? l : 0.0;
-    m->lufs_status = s == 0 ? ARS_LUFS_OK : ARS_LUFS_NONE;
-    (void)d_state;
+// enqueue the loudness meter on the mono feed (rs.py:685-691); the value lands in d_state->lufs
+static int lufs_enqueue(const float* d_mono, i64 N, double rate, RenderState* d_state) {
+    const int s = integrated_loudness_async(d_mono, N, rate, &d_state->mono_max, &d_state->lufs);
+    return s == 0 ? ARS_LUFS_OK : ARS_LUFS_NONE;
 }
 
 static int layout_ok(int layout) { return layout >= LAYOUT_STEREO && layout <= LAYOUT_5_1_2; }
@@ -187,15 +173,16 @@ static void common_filter_spec(FilterSpec& fs, i64 N, double rate, double dry_we
     if (N >= 2 && !(is_close_to_one(bass) && is_close_to_one(treble))) fill_eq(fs, N, rate, bass, treble);   // rs.py:389-391
 }
 
-// all pointers on the device except draws->tap_* (host); draws->noise on the device
+// All pointers on the device except draws->tap_* (host); draws->noise on the device.  Nothing here waits for
+// the GPU: the metrics end up in *st (device) and *lufs_status says how to read st->lufs.
 static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int cin, const float* d_ext_ir, i64 ext_len,
                         const ArsIrDraws* draws, float* d_out_stereo, float* d_out_f32, short* d_out_pcm,
-                        ArsMetrics* metrics) {
+                        RenderState* st, bool want_metrics, int* lufs_status) {
     Ctx& c = ctx();
     ARS_CHECK(p && d_in && n > 0 && cin >= 1, "render: empty input");
     ARS_CHECK(p->rate >= 1.0, "render: bad sample rate");
     ARS_CHECK(layout_ok(p->layout), "render: unknown layout id");
-    RenderState* st = fresh_state();
+    if (lufs_status) *lufs_status = ARS_LUFS_SKIPPED;
     const i64 N = render_out_len(p, n, ext_len);
     float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
     FilterSpec fs;
@@ -229,21 +216,52 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
         guard_apply(d_out_stereo, N * 2, &st->max_stereo);
     }
-    if (!d_out_f32 && !d_out_pcm && !metrics) return;
+    if (!d_out_f32 && !d_out_pcm && !want_metrics) return;
     const TailSpec ts = make_tail(N, p->layout, p->rate, p->x, p->y, p->z);
     tail_maxes(y, ts, st);
     float* d_mono = nullptr;
-    if (metrics && p->want_lufs) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
+    if (want_metrics && p->want_lufs) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
     tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
-    if (metrics) {
-        memset(metrics, 0, sizeof(*metrics));
-        metrics->lufs_status = ARS_LUFS_SKIPPED;
-        if (d_mono) lufs_of(d_mono, N, p->rate, st, metrics);
-        RenderState h;
-        download(&h, st, 1);
-        sync();
-        finish_metrics(h, N * ts.C, metrics);
+    if (d_mono && lufs_status) *lufs_status = lufs_enqueue(d_mono, N, p->rate, st);
+}
+
+// ------------------------------------------------------------ copy pipeline ----
+// Batched renders overlap the host->device copy of clip i+1 and the device->host copy of clip i-1 with the
+// compute of clip i: two buffer slots, one copy stream per direction, events between them.
+struct Pipe {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr};     // H2D of the slot finished
+    cudaEvent_t done[2] = {nullptr, nullptr};         // compute of the slot finished (inputs free, outputs ready)
+    cudaEvent_t out_free[2] = {nullptr, nullptr};     // D2H of the slot finished (outputs free)
+    RenderState* h_state = nullptr;                   // pinned, one per clip of the current batch
+    size_t h_state_cap = 0;
+    void init() {
+        if (h2d) return;
+        ARS_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        ARS_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            ARS_CUDA(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+            ARS_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            ARS_CUDA(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
+        }
     }
+    RenderState* states(size_t count) {
+        if (count > h_state_cap) {
+            if (h_state) cudaFreeHost(h_state);
+            ARS_CUDA(cudaMallocHost(&h_state, sizeof(RenderState) * count));
+            h_state_cap = count;
+        }
+        return h_state;
+    }
+};
+static Pipe g_pipe;
+
+static const char* slot_name(const char* base, int slot) {
+    static thread_local char buf[2][64];
+    static thread_local int k = 0;
+    k ^= 1;
+    snprintf(buf[k], sizeof buf[k], "%s.%d", base, slot);
+    return buf[k];
 }
 
 }  // namespace ars
@@ -493,13 +511,12 @@ int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t w
     RenderState* st = fresh_state();
     float* d_mono = want_lufs ? c.buf("render.mono", sizeof(float) * (size_t)n).as<float>() : nullptr;
     sums_stage(d_x, n, ch, st, d_mono);
-    memset(out, 0, sizeof(*out));
-    out->lufs_status = ARS_LUFS_SKIPPED;
-    if (want_lufs) lufs_of(d_mono, n, rate, st, out);
+    int lufs_status = ARS_LUFS_SKIPPED;
+    if (want_lufs) lufs_status = lufs_enqueue(d_mono, n, rate, st);
     RenderState h;
     download(&h, st, 1);
     sync();
-    finish_metrics(h, n * ch, out);
+    finish_metrics(h, n * ch, lufs_status, out);
     ARS_API_END
 }
 
@@ -542,11 +559,17 @@ int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int32_t cin
     float* d_st = out_stereo ? c.buf("out.stereo", sizeof(float) * (size_t)N * 2).as<float>() : nullptr;
     float* d_f = out_f32 ? c.buf("out.f32", sizeof(float) * (size_t)N * C).as<float>() : nullptr;
     short* d_p = out_pcm ? c.buf("out.pcm", sizeof(short) * (size_t)N * C).as<short>() : nullptr;
-    render_core(p, d_in, n, cin, d_ir, ext_ir_len, p->external_ir ? nullptr : &dd, d_st, d_f, d_p, metrics);
+    RenderState* st = fresh_state();
+    int lufs_status = ARS_LUFS_SKIPPED;
+    render_core(p, d_in, n, cin, d_ir, ext_ir_len, p->external_ir ? nullptr : &dd, d_st, d_f, d_p, st, metrics != nullptr,
+                &lufs_status);
     if (out_stereo) download(out_stereo, d_st, (size_t)N * 2);
     if (out_f32) download(out_f32, d_f, (size_t)N * C);
     if (out_pcm) download(reinterpret_cast<short*>(out_pcm), d_p, (size_t)N * C);
+    RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
+    if (metrics) download(h, st, 1);
     sync();
+    if (metrics) finish_metrics(*h, N * C, lufs_status, metrics);
     ARS_API_END
 }
 
@@ -554,8 +577,82 @@ int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32
                    int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                    int16_t* d_out_pcm, ArsMetrics* metrics) {
     ARS_API_BEGIN
+    ARS_CHECK(p && layout_ok(p->layout), "ars_render_dev: bad arguments");
+    Ctx& c = ctx();
+    RenderState* st = fresh_state();
+    int lufs_status = ARS_LUFS_SKIPPED;
     render_core(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32,
-                reinterpret_cast<short*>(d_out_pcm), metrics);
+                reinterpret_cast<short*>(d_out_pcm), st, metrics != nullptr, &lufs_status);
+    if (metrics) {
+        const i64 N = render_out_len(p, n, ext_ir_len);
+        RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
+        download(h, st, 1);
+        sync();
+        finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics);
+    }
+    ARS_API_END
+}
+
+int ars_render_batch(const ArsClip* clips, int32_t count) {
+    ARS_API_BEGIN
+    ARS_CHECK(clips && count >= 0, "ars_render_batch: bad arguments");
+    if (count == 0) return ARS_OK;
+    Ctx& c = ctx();
+    Pipe& pp = g_pipe;
+    pp.init();
+    RenderState* h_states = pp.states((size_t)count);
+    std::vector<int> lufs_status((size_t)count, ARS_LUFS_SKIPPED);
+    std::vector<i64> out_count((size_t)count, 0);
+    // everything queued earlier on the compute stream must be finished before the copy streams touch buffers
+    sync();
+    for (int i = 0; i < count; ++i) {
+        const ArsClip& k = clips[i];
+        const ArsRenderParams* p = k.params;
+        ARS_CHECK(p && k.in && k.n > 0 && k.cin >= 1 && layout_ok(p->layout), "ars_render_batch: bad clip");
+        const int slot = i & 1;
+        const i64 N = render_out_len(p, k.n, k.ext_ir_len);
+        const int C = layout_channels(p->layout);
+        out_count[(size_t)i] = N * C;
+        // ---- host -> device on the copy stream (the slot's inputs are free once clip i-2 has been computed)
+        if (i >= 2) ARS_CUDA(cudaStreamWaitEvent(pp.h2d, pp.done[slot], 0));
+        float* d_in = c.buf(slot_name("in.x", slot), sizeof(float) * (size_t)k.n * k.cin).as<float>();
+        ARS_CUDA(cudaMemcpyAsync(d_in, k.in, sizeof(float) * (size_t)k.n * k.cin, cudaMemcpyHostToDevice, pp.h2d));
+        const float* d_ir = nullptr;
+        ArsIrDraws dd;
+        memset(&dd, 0, sizeof dd);
+        if (p->external_ir) {
+            ARS_CHECK(k.ext_ir && k.ext_ir_len >= 1, "ars_render_batch: external IR missing");
+            float* d = c.buf(slot_name("in.ir", slot), sizeof(float) * (size_t)k.ext_ir_len * 2).as<float>();
+            ARS_CUDA(cudaMemcpyAsync(d, k.ext_ir, sizeof(float) * (size_t)k.ext_ir_len * 2, cudaMemcpyHostToDevice, pp.h2d));
+            d_ir = d;
+        } else if (k.draws) {
+            dd = *k.draws;
+            const size_t nl = (size_t)std::max<i64>(0, k.draws->noise_len);
+            double* d = c.buf(slot_name("ir.noise", slot), sizeof(double) * std::max<size_t>(nl, 1)).as<double>();
+            if (nl) ARS_CUDA(cudaMemcpyAsync(d, k.draws->noise, sizeof(double) * nl, cudaMemcpyHostToDevice, pp.h2d));
+            dd.noise = d;
+        }
+        ARS_CUDA(cudaEventRecord(pp.in_ready[slot], pp.h2d));
+        // ---- compute (waits for its inputs, and for the slot's previous outputs to have left the device)
+        float* d_f = k.out_f32 ? c.buf(slot_name("out.f32", slot), sizeof(float) * (size_t)N * C).as<float>() : nullptr;
+        short* d_p = k.out_pcm ? c.buf(slot_name("out.pcm", slot), sizeof(short) * (size_t)N * C).as<short>() : nullptr;
+        ARS_CUDA(cudaStreamWaitEvent(c.stream, pp.in_ready[slot], 0));
+        if (i >= 2) ARS_CUDA(cudaStreamWaitEvent(c.stream, pp.out_free[slot], 0));
+        RenderState* st = fresh_state(slot);
+        render_core(p, d_in, k.n, k.cin, d_ir, k.ext_ir_len, p->external_ir ? nullptr : &dd, nullptr, d_f, d_p, st,
+                    k.metrics != nullptr, &lufs_status[(size_t)i]);
+        ARS_CUDA(cudaEventRecord(pp.done[slot], c.stream));
+        // ---- device -> host on the other copy stream
+        ARS_CUDA(cudaStreamWaitEvent(pp.d2h, pp.done[slot], 0));
+        if (k.out_f32) ARS_CUDA(cudaMemcpyAsync(k.out_f32, d_f, sizeof(float) * (size_t)N * C, cudaMemcpyDeviceToHost, pp.d2h));
+        if (k.out_pcm) ARS_CUDA(cudaMemcpyAsync(k.out_pcm, d_p, sizeof(short) * (size_t)N * C, cudaMemcpyDeviceToHost, pp.d2h));
+        if (k.metrics) ARS_CUDA(cudaMemcpyAsync(&h_states[i], st, sizeof(RenderState), cudaMemcpyDeviceToHost, pp.d2h));
+        ARS_CUDA(cudaEventRecord(pp.out_free[slot], pp.d2h));
+    }
+    ARS_CUDA(cudaStreamSynchronize(pp.d2h));
+    ARS_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < count; ++i)
+        if (clips[i].metrics) finish_metrics(h_states[i], out_count[(size_t)i], lufs_status[(size_t)i], clips[i].metrics);
     ARS_API_END
 }
 

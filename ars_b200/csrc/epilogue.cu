@@ -71,6 +71,7 @@ __device__ __forceinline__ void block_atomic_max(unsigned m, unsigned* dst) {
         m = warp_max(m);
         if (threadIdx.x == 0 && m) atomicMax(dst, m);
     }
+    __syncthreads();      // the staging array is reused by the next reduction of the same block
 }
 __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
     __shared__ double s_v[32];
@@ -84,6 +85,7 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (threadIdx.x == 0) atomicAdd(dst, v);
     }
+    __syncthreads();
 }
 
 // ------------------------------------------------------- fused tail kernels --
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
                                                     float* __restrict__ mono) {
     const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
     const Guard g3 = make_guard(ts.layout == LAYOUT_5_1 ? 0u : st->max_map);
-    unsigned pk = 0;
+    unsigned pk = 0, mm = 0;
     double ss = 0.0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
         float o[8];
@@ -182,9 +184,14 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
                         (unsigned short)q[c] | ((unsigned)(unsigned short)q[c + 1] << 16);
             }
         }
-        if (mono) mono[i] = __fdiv_rn(__fadd_rn(o[0], o[1]), 2.0f);     // np.mean(data[:, :2], axis=1), rs.py:688
+        if (mono) {
+            const float mv = __fdiv_rn(__fadd_rn(o[0], o[1]), 2.0f);    // np.mean(data[:, :2], axis=1), rs.py:688
+            mono[i] = mv;
+            mm = max(mm, abs_bits(mv));
+        }
     }
     block_atomic_max(pk, &st->peak_final);
+    block_atomic_max(mm, &st->mono_max);
     block_atomic_add(ss, &st->sumsq);
 }
 
@@ -354,7 +361,7 @@ void pcm16_stage(const float* d_x, i64 count, short* d_pcm) {
 
 __global__ void __launch_bounds__(256) sums_kernel(const float* __restrict__ x, i64 N, int C, RenderState* st,
                                                    float* __restrict__ mono) {
-    unsigned pk = 0;
+    unsigned pk = 0, mm = 0;
     double ss = 0.0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (i64)gridDim.x * blockDim.x) {
         const float* p = x + i * C;
@@ -363,9 +370,14 @@ __global__ void __launch_bounds__(256) sums_kernel(const float* __restrict__ x, 
             pk = max(pk, abs_bits(v));
             ss += (double)__fmul_rn(v, v);
         }
-        if (mono) mono[i] = C >= 2 ? __fdiv_rn(__fadd_rn(__ldg(p), __ldg(p + 1)), 2.0f) : __ldg(p);
+        if (mono) {
+            const float mv = C >= 2 ? __fdiv_rn(__fadd_rn(__ldg(p), __ldg(p + 1)), 2.0f) : __ldg(p);
+            mono[i] = mv;
+            mm = max(mm, abs_bits(mv));
+        }
     }
     block_atomic_max(pk, &st->peak_final);
+    block_atomic_max(mm, &st->mono_max);
     block_atomic_add(ss, &st->sumsq);
 }
 void sums_stage(const float* d_x, i64 N, int C, RenderState* d_state, float* d_mono) {

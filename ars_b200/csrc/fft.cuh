@@ -57,6 +57,38 @@ ARS_RAD(13, 4, 16, 8, 8, 8)
 constexpr int BIG_LO_LOG = 15;         // two-level table for w_M^e
 
 // ---------------------------------------------------------------- butterflies -
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FFMA2: one instruction per complex add) -- the butterflies are
+// mostly complex additions, so this nearly halves their instruction count.  Results are bit-identical to the
+// scalar forms (each component is one IEEE add; a - b is fma(b, -1, a)).  The host build uses the scalar forms.
+ARS_HD float2 padd(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return cadd(a, b);
+#endif
+}
+ARS_HD float2 psub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(b, make_float2(-1.f, -1.f), a);
+#else
+    return csub(a, b);
+#endif
+}
+// t + (-/+ i) d  and  t - (-/+ i) d   (forward: -i, inverse: +i)
+template <bool INV> ARS_HD void rot_addsub(float2 t, float2 d, float2& plus, float2& minus) {
+#ifdef __CUDA_ARCH__
+    const float2 sw = make_float2(d.y, d.x);
+    const float2 cp = INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f);
+    const float2 cm = INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f);
+    plus = __ffma2_rn(sw, cp, t);
+    minus = __ffma2_rn(sw, cm, t);
+#else
+    const float2 r = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    plus = cadd(t, r);
+    minus = csub(t, r);
+#endif
+}
+
 template <bool INV> ARS_HD float2 mul_mi(float2 a) {
     // forward: multiply by -i ; inverse: multiply by +i
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -86,15 +118,16 @@ template <int E, bool INV> ARS_HD float2 mulw16(float2 a) {
 }
 
 template <bool INV> ARS_HD void bf4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
-    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+    const float2 t0 = padd(a0, a2), t1 = psub(a0, a2), t2 = padd(a1, a3), d = psub(a1, a3);
+    a0 = padd(t0, t2); a2 = psub(t0, t2);
+    rot_addsub<INV>(t1, d, a1, a3);
 }
 
 // natural-order in, natural-order out R-point DFT held in registers
 template <int R, bool INV> struct Dft;
 template <bool INV> struct Dft<2, INV> {
     static ARS_HD void run(float2 (&v)[2]) {
-        float2 t = v[0]; v[0] = cadd(t, v[1]); v[1] = csub(t, v[1]);
+        float2 t = v[0]; v[0] = padd(t, v[1]); v[1] = psub(t, v[1]);
     }
 };
 template <bool INV> struct Dft<4, INV> {
@@ -104,11 +137,12 @@ template <bool INV> struct Dft<8, INV> {
     static ARS_HD void run(float2 (&v)[8]) {
         bf4<INV>(v[0], v[2], v[4], v[6]);
         bf4<INV>(v[1], v[3], v[5], v[7]);
-        float2 b1 = mulw16<2, INV>(v[3]), b2 = mulw16<4, INV>(v[5]), b3 = mulw16<6, INV>(v[7]);
-        float2 o0 = cadd(v[0], v[1]), o4 = csub(v[0], v[1]);
-        float2 o1 = cadd(v[2], b1), o5 = csub(v[2], b1);
-        float2 o2 = cadd(v[4], b2), o6 = csub(v[4], b2);
-        float2 o3 = cadd(v[6], b3), o7 = csub(v[6], b3);
+        float2 b1 = mulw16<2, INV>(v[3]), b3 = mulw16<6, INV>(v[7]);
+        float2 o0 = padd(v[0], v[1]), o4 = psub(v[0], v[1]);
+        float2 o1 = padd(v[2], b1), o5 = psub(v[2], b1);
+        float2 o2, o6;
+        rot_addsub<INV>(v[4], v[5], o2, o6);
+        float2 o3 = padd(v[6], b3), o7 = psub(v[6], b3);
         v[0] = o0; v[1] = o1; v[2] = o2; v[3] = o3; v[4] = o4; v[5] = o5; v[6] = o6; v[7] = o7;
     }
 };
@@ -296,6 +330,7 @@ template <int Ls, int r, bool INV> ARS_HD void stage_twiddles(const Tw& tw, int 
 // Strided pass: tile = R rows (stride `stride` elements apart in HBM) x T adjacent columns.
 template <int LOGR, int LOGT> struct StridedLayout {
     static constexpr int R = 1 << LOGR, T = 1 << LOGT, C = T;
+    static constexpr int ROW_PITCH = T;                 // slots between consecutive rows of a column
     static constexpr int SMEM_ELEMS = R * T + ((R * T) >> 4);
     static ARS_HD int bfly(int q) { return q >> LOGT; }
     static ARS_HD int col(int q) { return q & (T - 1); }
@@ -304,6 +339,7 @@ template <int LOGR, int LOGT> struct StridedLayout {
 // Contiguous pass: tile = C whole R-point segments.
 template <int LOGR, int LOGC> struct ContigLayout {
     static constexpr int R = 1 << LOGR, C = 1 << LOGC;
+    static constexpr int ROW_PITCH = 1;
     static constexpr int SMEM_ELEMS = R * C + ((R * C) >> 4);
     static ARS_HD int sidx(int row, int c) { int i = (c << LOGR) + row; return i + (i >> 4); }
 };
@@ -373,19 +409,31 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
         expand_pow<r>(P);
     }
 
+    // Index arithmetic is strength-reduced by hand: HBM indices advance by a per-stage 64-bit step, shared-memory
+    // slots by a compile-time step whenever the padding term is linear in the row (row step * row pitch % 16 == 0).
+    const i64 fstep = gfirst.step() * (i64)sub;            // natural side: rows are `sub` apart
+    const i64 lstep = glast.step();                         // permuted side: consecutive outputs k
+    constexpr int PITCH = LAYOUT::ROW_PITCH;
+    constexpr bool LIN = ((sub * PITCH) % 16) == 0;
+    constexpr int SSTEP = sub * PITCH + (sub * PITCH) / 16;
+#define ARS_SM(t_) sm[LIN ? (s0 + (t_) * SSTEP) : LAYOUT::sidx(row0 + (t_) * sub, c)]
+
     for (int q = tid; q < TOTAL; q += NT) {
         int b, c;
         if constexpr (STRIDED) { b = LAYOUT::bfly(q); c = LAYOUT::col(q); }
         else { b = q % NB; c = q / NB; }
         const int seg = b / sub, i = b % sub;
         const int row0 = seg * Ls + i;
+        const int s0 = LAYOUT::sidx(row0, c);
         float2 v[r];
         if constexpr (!INV) {
-            #pragma unroll
-            for (int t = 0; t < r; ++t) {
-                const int row = row0 + t * sub;
-                if constexpr (first) v[t] = ld.template get<LDM>(gfirst(row, c));
-                else v[t] = sm[LAYOUT::sidx(row, c)];
+            if constexpr (first) {
+                i64 idx = gfirst(row0, c);
+                #pragma unroll
+                for (int t = 0; t < r; ++t) { v[t] = ld.template get<LDM>(idx); idx += fstep; }
+            } else {
+                #pragma unroll
+                for (int t = 0; t < r; ++t) v[t] = ARS_SM(t);
             }
             if constexpr (!last) {
                 float2 w[r];
@@ -394,23 +442,26 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 #pragma unroll
                 for (int k = 1; k < r; ++k) v[k] = cmul(v[k], w[k]);
                 #pragma unroll
-                for (int k = 0; k < r; ++k) sm[LAYOUT::sidx(row0 + k * sub, c)] = v[k];
+                for (int k = 0; k < r; ++k) ARS_SM(k) = v[k];
             } else {
                 float2 Q = make_float2(1.f, 0.f);
                 if constexpr (STRIDED) Q = tw_big<false>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
                 Dft<r, false>::run(v);
+                i64 idx = glast(b, c);
                 #pragma unroll
                 for (int k = 0; k < r; ++k) {
                     if constexpr (STRIDED) v[k] = cmul(v[k], k ? cmul(Q, P[k]) : Q);
-                    st.template put<STM>(glast(b, k, c), v[k]);
+                    st.template put<STM>(idx, v[k]);
+                    idx += lstep;
                 }
             }
         } else {
             if constexpr (last) {
                 float2 Q = make_float2(1.f, 0.f);
                 if constexpr (STRIDED) Q = tw_big<true>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
+                i64 idx = glast(b, c);
                 #pragma unroll
-                for (int k = 0; k < r; ++k) v[k] = ld.template get<LDM>(glast(b, k, c));
+                for (int k = 0; k < r; ++k) { v[k] = ld.template get<LDM>(idx); idx += lstep; }
                 if constexpr (STRIDED) {
                     #pragma unroll
                     for (int k = 0; k < r; ++k) v[k] = cmul(v[k], k ? cmul(Q, P[k]) : Q);
@@ -419,24 +470,27 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 float2 w[r];
                 stage_twiddles<Ls, r, true>(pa.tw, i, w);
                 #pragma unroll
-                for (int k = 0; k < r; ++k) v[k] = sm[LAYOUT::sidx(row0 + k * sub, c)];
+                for (int k = 0; k < r; ++k) v[k] = ARS_SM(k);
                 #pragma unroll
                 for (int k = 1; k < r; ++k) v[k] = cmul(v[k], w[k]);
             }
             if constexpr (first) {
                 float2 aux[r];
+                const i64 idx0 = gfirst(row0, c);
                 #pragma unroll
-                for (int t = 0; t < r; ++t) aux[t] = st.template pre<STM>(gfirst(row0 + t * sub, c));
+                for (int t = 0; t < r; ++t) aux[t] = st.template pre<STM>(idx0 + t * fstep);
                 Dft<r, true>::run(v);
+                i64 idx = idx0;
                 #pragma unroll
-                for (int t = 0; t < r; ++t) st.template put<STM>(gfirst(row0 + t * sub, c), v[t], aux[t]);
+                for (int t = 0; t < r; ++t) { st.template put<STM>(idx, v[t], aux[t]); idx += fstep; }
             } else {
                 Dft<r, true>::run(v);
                 #pragma unroll
-                for (int t = 0; t < r; ++t) sm[LAYOUT::sidx(row0 + t * sub, c)] = v[t];
+                for (int t = 0; t < r; ++t) ARS_SM(t) = v[t];
             }
         }
     }
+#undef ARS_SM
 }
 
 #define ARS_STAGE(S_) run_stage<LOGR, S_, INV, STRIDED, NT, LAYOUT, LDM, STM>(sm, ld, st, pa, gfirst, glast, col0, tid)
@@ -485,26 +539,27 @@ inline void emulate_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfir
 template <int LOGR> struct StridedFirst {
     i64 base; int logStride;
     ARS_HD i64 operator()(int row, int c) const { return base + ((i64)row << logStride) + c; }
+    ARS_HD i64 step() const { return (i64)1 << logStride; }          // HBM index step per row
 };
 template <int LOGR> struct StridedLast {
     i64 base; int logStride;
-    ARS_HD i64 operator()(int b, int k, int c) const {
+    ARS_HD i64 operator()(int b, int c) const {                       // output k = 0 of last-stage butterfly b
         constexpr int rl = Rad<LOGR>::r(Rad<LOGR>::n - 1);
-        return base + ((i64)(b * rl + k) << logStride) + c;
+        return base + ((i64)(b * rl) << logStride) + c;
     }
+    ARS_HD i64 step() const { return (i64)1 << logStride; }          // per output k
 };
 template <int LOGR> struct ContigFirst {
     i64 base;
     ARS_HD i64 operator()(int row, int c) const { return base + ((i64)c << LOGR) + row; }
+    ARS_HD constexpr i64 step() const { return 1; }
 };
 // permuted side of the contiguous pass: output k of last-stage butterfly b is parked at
 // k*(R/rl) + b (not b*rl + k) so that adjacent lanes touch adjacent addresses
 template <int LOGR> struct ContigLast {
     i64 base;
-    ARS_HD i64 operator()(int b, int k, int c) const {
-        constexpr int rl = Rad<LOGR>::r(Rad<LOGR>::n - 1);
-        return base + ((i64)c << LOGR) + k * ((1 << LOGR) / rl) + b;
-    }
+    ARS_HD i64 operator()(int b, int c) const { return base + ((i64)c << LOGR) + b; }
+    ARS_HD constexpr i64 step() const { return (1 << LOGR) / Rad<LOGR>::r(Rad<LOGR>::n - 1); }
 };
 
 // tile (g, cb) of a strided pass over segments of length Lg = 2^logLg covers rows
@@ -541,14 +596,14 @@ __global__ void __launch_bounds__(NT) pass_contig_kernel(Ld ld, St st, PassArgs 
 }  // namespace fft
 
 // instantiated (logR, logT|logC) pass variants; the launcher and the host emulator share the list
-#define ARS_STRIDED_CASES(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 2)
+#define ARS_STRIDED_CASES(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2)
 #define ARS_CONTIG_CASES(X)                                                                         \
     X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(5, 0) X(6, 0) X(7, 0) X(8, 0) X(9, 0) X(10, 0) X(11, 0) X(12, 0) \
-    X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1)
+    X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
 
 // variants that also get compile-time-mode ("fast") instantiations: the ones big transforms are planned with
-#define ARS_FAST_STRIDED(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4)
-#define ARS_FAST_CONTIG(X) X(12, 1)
+#define ARS_FAST_STRIDED(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2)
+#define ARS_FAST_CONTIG(X) X(12, 1) X(13, 0) X(11, 2) X(10, 3) X(9, 4) X(8, 5)
 
 // ------------------------------------------------------------------ host API --
 struct FftPass {

@@ -12,6 +12,7 @@
 #include "metrics.cuh"
 
 #include <cmath>
+#include <math_constants.h>
 
 namespace ars {
 
@@ -222,42 +223,64 @@ int loudness_blocks(i64 N, double rate) {
     return (int)(std::nearbyint(v) + 1);
 }
 
-// returns status: 0 = value, 1 = too short (pyloudnorm raises -> reference reports None)
-int integrated_loudness(const float* d_mono, i64 N, double rate, double* lufs) {
+__device__ __forceinline__ void block_sum_dc(double& v, int& n) {
+    __shared__ double sv[32];
+    __shared__ int sn[32];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    v = 0.0; n = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { v += sv[w]; n += sn[w]; }     // same order in every thread
+    __syncthreads();
+}
+
+// BS.1770-4 gating exactly as pyloudnorm implements it (mono => channel gain 1), one CTA over the block
+// energies: absolute gate at -70 LUFS, relative gate 10 LU under the abs-gated mean, loudness of the survivors.
+// Also applies the reference's silence test (rs.py:689): peak of the mono feed < 1e-6 -> -inf.
+__global__ void __launch_bounds__(1024) gate_kernel(const double* __restrict__ z, int nb, const unsigned* __restrict__ mono_max,
+                                                    double* lufs_out) {
+    if (__uint_as_float(*mono_max) < 1e-6f) {
+        if (threadIdx.x == 0) *lufs_out = -CUDART_INF;
+        return;
+    }
+    double s = 0.0;
+    int n = 0;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const double l = -0.691 + 10.0 * log10(z[j]);
+        if (l >= -70.0) { s += z[j]; ++n; }
+    }
+    block_sum_dc(s, n);
+    const double rel = n > 0 ? -0.691 + 10.0 * log10(s / (double)n) - 10.0 : CUDART_NAN;
+    double s2 = 0.0;
+    int n2 = 0;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const double l = -0.691 + 10.0 * log10(z[j]);
+        if (l > rel && l > -70.0) { s2 += z[j]; ++n2; }
+    }
+    block_sum_dc(s2, n2);
+    if (threadIdx.x == 0) *lufs_out = -0.691 + 10.0 * log10(n2 > 0 ? s2 / (double)n2 : 0.0);   // log10(0) = -inf, as numpy
+}
+
+// Enqueues the whole loudness measurement; *d_lufs receives the value.  Returns 1 (and enqueues nothing)
+// when the signal is shorter than one 400 ms block (pyloudnorm raises -> the reference reports None).
+int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs) {
     Ctx& c = ctx();
-    *lufs = 0.0;
     if (!((double)N >= 0.4 * rate)) return 1;            // "Audio must have length greater than the block size"
+    const int nb = loudness_blocks(N, rate);
+    if (nb <= 0) return 1;
     Biquad q[2];
     k_weighting(rate, q);
     float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
     float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
     run_biquad(d_mono, y1, N, q[0]);
     run_biquad(y1, y2, N, q[1]);
-    const int nb = loudness_blocks(N, rate);
-    if (nb <= 0) return 1;
     double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
     gate_energy_kernel<<<nb, 256, 0, c.stream>>>(y2, N, rate, nb, dz);
     ARS_LAUNCH_CHECK();
-    count_launch();
-    std::vector<double> z(nb);
-    ARS_CUDA(cudaMemcpyAsync(z.data(), dz, sizeof(double) * nb, cudaMemcpyDeviceToHost, c.stream));
-    ARS_CUDA(cudaStreamSynchronize(c.stream));
-    // gating (BS.1770-4 as pyloudnorm implements it, mono => channel gain 1)
-    double sum_abs = 0.0;
-    int n_abs = 0;
-    std::vector<double> l(nb);
-    for (int j = 0; j < nb; ++j) {
-        l[j] = -0.691 + 10.0 * std::log10(z[j]);
-        if (l[j] >= -70.0) { sum_abs += z[j]; ++n_abs; }
-    }
-    double rel = NAN;
-    if (n_abs > 0) rel = -0.691 + 10.0 * std::log10(sum_abs / n_abs) - 10.0;
-    double sum_rel = 0.0;
-    int n_rel = 0;
-    for (int j = 0; j < nb; ++j)
-        if (l[j] > rel && l[j] > -70.0) { sum_rel += z[j]; ++n_rel; }
-    const double zavg = n_rel > 0 ? sum_rel / n_rel : 0.0;
-    *lufs = -0.691 + 10.0 * std::log10(zavg);            // log10(0) = -inf, as numpy (with a warning)
+    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs);
+    ARS_LAUNCH_CHECK();
+    count_launch(2);
     return 0;
 }
 

@@ -5,9 +5,9 @@
 namespace ars {
 
 int loudness_blocks(i64 N, double rate);
-// d_mono: float32[N] on the device (mean of the first two output channels, rs.py:687-688).
-// Returns 0 and *lufs on success, 1 when the signal is shorter than one 400 ms block.
-// Synchronises the library stream (the gating runs on the host over a few thousand block energies).
-int integrated_loudness(const float* d_mono, i64 N, double rate, double* lufs);
+// d_mono: float32[N] on the device (mean of the first two output channels, rs.py:687-688); d_mono_max: bits of
+// max |mono|.  Enqueues biquads, block energies and the gate on the library stream; *d_lufs (device) receives
+// the loudness (-inf for silence).  Returns 1 without enqueuing when the signal is shorter than one 400 ms block.
+int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs);
 
 }  // namespace ars

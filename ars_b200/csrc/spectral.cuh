@@ -62,10 +62,10 @@ struct RenderState {
     unsigned max_map;          // bits of max |out| before its guard
     unsigned ir_any0, ir_any1; // non-zero IR parts (np.any(ir), rs.py:360,369)
     unsigned peak_final;       // bits of max |final| (metrics)
-    unsigned nonfinite;        // count of non-finite samples seen by the PCM packer
-    unsigned pad;
+    unsigned mono_max;         // bits of max |mean(ch0, ch1)| (the loudness meter's silence test, rs.py:689)
+    unsigned max_l, max_r, max_lr;   // bits of max |L|, |R|, |float32(L + R)| of the spectral-stage output
     double sumsq;              // sum of final^2 over all channels (metrics)
-    double lufs_pad;
+    double lufs;               // integrated loudness, written by the gate kernel
 };
 
 // y[N] (float2 = L,R) = filter(x) ; writes max |y| bits into state->max_stereo.

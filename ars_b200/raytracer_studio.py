@@ -473,6 +473,60 @@ def render_array(samples, rate, *, external_ir_data=None, want_stereo=False, wan
             "metrics": _metrics_dict(m) if m is not None else None, "pcm": pcm}
 
 
+def render_batch(jobs, *, want_float=False, want_pcm=True, want_metrics=True):
+    """Render a list of independent clips with the copy/compute pipeline of `ars_render_batch` (the batch form
+    of apply_raytrace_convolution_3d's compute part).  Each job is a dict: samples, rate, optional
+    external_ir_data, optional seed (np.random.seed before that clip's draws, as a caller of the reference would
+    do), and the keyword settings of `render_array`.  -> list of dict(final, names, metrics, pcm)."""
+    lib = _lib()
+    keep: list = []
+    clips = (_capi.ArsClip * len(jobs))()
+    outs = []
+    for i, job in enumerate(jobs):
+        job = dict(job)
+        x = _as_frames(job.pop("samples"))
+        rate = job.pop("rate")
+        ir = job.pop("external_ir_data", None)
+        seed = job.pop("seed", None)
+        n, cin = x.shape
+        if n == 0:
+            raise ValueError("Audiodatei ist leer.")
+        p, refl = make_render_params(rate, external_ir=ir is not None, want_lufs=want_metrics, **job)
+        L = 0
+        draws = None
+        if ir is not None:
+            ir = np.ascontiguousarray(ir, dtype=_F32)
+            if ir.ndim != 2 or ir.shape[1] != 2 or ir.shape[0] == 0:
+                raise ValueError("Externe IR muss Stereo sein.")
+            L = ir.shape[0]
+        else:
+            if seed is not None:
+                np.random.seed(seed)
+            taps, bases, noise = draw_ir_randoms(int(rate), p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+            draws = _capi.make_draws(taps, bases, noise, keep)
+        N = lib.ars_render_out_len(p, n, L)
+        layout = job.get("target_channel_layout", DEFAULT_CHANNEL_LAYOUT)
+        if layout not in CHANNEL_LAYOUTS:
+            layout = DEFAULT_CHANNEL_LAYOUT
+        C = CHANNEL_LAYOUTS[layout]["channels"]
+        final = np.empty((N, C), _F32) if want_float else None
+        pcm = np.empty((N, C), np.int16) if want_pcm else None
+        m = ArsMetrics() if want_metrics else None
+        keep += [x, ir, p, draws, m]
+        k = clips[i]
+        k.params = _capi.C.pointer(p)
+        k.in_ = _capi.ptr(x)
+        k.n, k.cin = n, cin
+        k.ext_ir, k.ext_ir_len = _capi.ptr(ir), L
+        k.draws = _capi.C.pointer(draws) if draws is not None else None
+        k.out_f32, k.out_pcm = _capi.ptr(final), _capi.ptr(pcm)
+        k.metrics = _capi.C.pointer(m) if m is not None else None
+        outs.append((final, pcm, m, CHANNEL_LAYOUTS[layout]["names"]))
+    _capi.check(lib.ars_render_batch(clips, len(jobs)), "ars_render_batch")
+    return [{"final": f, "pcm": q, "names": nm, "metrics": _metrics_dict(m) if m is not None else None}
+            for (f, q, m, nm) in outs]
+
+
 def _metrics_text(mt):
     """rs.py:1071-1075."""
     lufs, peak, rms = mt.get("lufs"), mt.get("true_peak_dbfs"), mt.get("rms_dbfs")

@@ -161,6 +161,26 @@ ARS_API int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t 
                    int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                    int16_t* d_out_pcm, ArsMetrics* metrics);
 
+
+/* ---- a batch of independent renders (host buffers; pin them for full overlap) -----------------
+ * Clip i+1's host->device copy and clip i-1's device->host copy overlap clip i's compute
+ * (two buffer slots, one copy stream per direction).  Results are identical to calling
+ * ars_render on every clip in turn.  Returns when every output buffer is filled. */
+typedef struct ArsClip {
+    const ArsRenderParams* params;
+    const float* in;            /* (n, cin) float32                                            */
+    int64_t n;
+    int32_t cin;
+    int32_t reserved;
+    const float* ext_ir;        /* (ext_ir_len, 2) when params->external_ir, else NULL         */
+    int64_t ext_ir_len;
+    const ArsIrDraws* draws;    /* procedural-IR draws (host pointers), NULL for external IR   */
+    float* out_f32;             /* (N, C) or NULL                                              */
+    int16_t* out_pcm;           /* (N, C) or NULL                                              */
+    ArsMetrics* metrics;        /* or NULL                                                     */
+} ArsClip;
+ARS_API int ars_render_batch(const ArsClip* clips, int32_t count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,8 +89,29 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
 }
 
 // ------------------------------------------------------- fused tail kernels --
+// max |six| before its guard.  When the stereo peak guard is idle (the common case) the maximum follows exactly
+// from three maxima the last FFT pass already tracked -- every pan channel is a monotone function of |L|, |R| or
+// |float32(L + R)| (non-negative gains, monotone rounding) -- so no pass over the signal is needed.
 __global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st) {
     const Guard g1 = make_guard(st->max_stereo);
+    if (g1.mode == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            float s[6];
+            const float l = __uint_as_float(st->max_l), r = __uint_as_float(st->max_r);
+            const float mono = __fmul_rn(__uint_as_float(st->max_lr), 0.707f);
+            s[0] = __double2float_rn(__dmul_rn((double)l, ts.g_fl));
+            s[1] = __double2float_rn(__dmul_rn((double)r, ts.g_fr));
+            s[2] = __double2float_rn(__dmul_rn((double)mono, ts.g_c));
+            s[3] = __fmul_rn(mono, ts.g_lfe);
+            s[4] = __double2float_rn(__dmul_rn((double)l, ts.g_rl));
+            s[5] = __double2float_rn(__dmul_rn((double)r, ts.g_rr));
+            unsigned m = 0;
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) m = max(m, abs_bits(s[c]));
+            st->max_pan = m;
+        }
+        return;
+    }
     unsigned m = 0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
         const float2 v = __ldg(y + i);
@@ -143,18 +164,22 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
                                                     float* __restrict__ out, short* __restrict__ pcm,
                                                     float* __restrict__ mono) {
     const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
-    const Guard g3 = make_guard(ts.layout == LAYOUT_5_1 ? 0u : st->max_map);
+    // 5.1 / 7.1 / 5.1.2 carry the six channels through unchanged and add only attenuated (x0.7, x<=0.6) delayed
+    // copies, so their maximum is the guarded six-channel maximum (<= 1, or >= 1e-9): that guard never fires
+    const Guard g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
     unsigned pk = 0, mm = 0;
     double ss = 0.0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
         float o[8];
         frame_out(y, i, ts, g1, g2, o);
+        float fs = 0.f;        // one frame's squares in float32 (numpy squares in float32 too), then one conversion
         #pragma unroll
         for (int c = 0; c < C; ++c) {
             o[c] = guard1(o[c], g3);
             pk = max(pk, abs_bits(o[c]));
-            ss += (double)__fmul_rn(o[c], o[c]);
+            fs = __fmaf_rn(o[c], o[c], fs);
         }
+        ss += (double)fs;
         if (out) {
             float* p = out + i * C;
             if (C == 8) {
@@ -201,7 +226,7 @@ void tail_maxes(const float2* d_y, const TailSpec& ts, RenderState* d_state) {
     pan_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
     ARS_LAUNCH_CHECK();
     count_launch();
-    if (ts.layout != LAYOUT_5_1) {
+    if (ts.layout == LAYOUT_STEREO) {
         map_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
         ARS_LAUNCH_CHECK();
         count_launch();

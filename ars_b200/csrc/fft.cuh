@@ -60,6 +60,13 @@ constexpr int BIG_LO_LOG = 15;         // two-level table for w_M^e
 // Packed FP32x2 arithmetic (Blackwell FADD2 / FFMA2: one instruction per complex add) -- the butterflies are
 // mostly complex additions, so this nearly halves their instruction count.  Results are bit-identical to the
 // scalar forms (each component is one IEEE add; a - b is fma(b, -1, a)).  The host build uses the scalar forms.
+ARS_HD float fadd_rn(float a, float b) {      // a float32 add that can never be contracted into an FMA
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
 ARS_HD float2 padd(float2 a, float2 b) {
 #ifdef __CUDA_ARCH__
     return __fadd2_rn(a, b);
@@ -234,8 +241,8 @@ struct St {
     const float2* chirp = nullptr;
     i64 N = 0;
     float scale = 1.f;
-    unsigned* maxbits = nullptr;     // ST_FINAL: abs-max over everything stored (uint bits of |x|)
-    unsigned local_max = 0;
+    unsigned* maxbits = nullptr;     // ST_FINAL: 4 words: bits of max |x|, max |x.re|, max |x.im|, max |f32(re + im)|
+    unsigned local_max = 0, local_l = 0, local_r = 0, local_lr = 0;
     // chirp operand of the store, fetched early so its latency overlaps the butterfly
     template <int MODE> ARS_HD float2 pre(i64 idx) const {
         if constexpr (MODE < 0) {
@@ -266,22 +273,28 @@ struct St {
                 float2 y = cmul(v, aux);
                 y = make_float2(y.x * scale, -y.y * scale);
                 a[idx] = y;
-                const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y);
-                const unsigned mm = m0 > m1 ? m0 : m1;
-                if (mm > local_max) local_max = mm;
+                const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
+                if (m0 > local_l) local_l = m0;
+                if (m1 > local_r) local_r = m1;
+                if (m2 > local_lr) local_lr = m2;
             }
         }
     }
     template <int MODE> ARS_HD void put(i64 idx, float2 v) { put<MODE>(idx, v, pre<MODE>(idx)); }
     ARS_HD void finish() {
         if (mode == ST_FINAL && maxbits) {
+            local_max = local_l > local_r ? local_l : local_r;
 #ifdef __CUDA_ARCH__
-            unsigned m = local_max;
+            unsigned m[4] = {local_max, local_l, local_r, local_lr};
             #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if ((threadIdx.x & 31) == 0 && m) atomicMax(maxbits, m);
+            for (int q = 0; q < 4; ++q) {
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m[q] = max(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
+                if ((threadIdx.x & 31) == 0 && m[q]) atomicMax(maxbits + q, m[q]);
+            }
 #else
-            if (local_max > *maxbits) *maxbits = local_max;
+            const unsigned m[4] = {local_max, local_l, local_r, local_lr};
+            for (int q = 0; q < 4; ++q) if (m[q] > maxbits[q]) maxbits[q] = m[q];
 #endif
         }
     }

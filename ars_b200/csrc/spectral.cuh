@@ -57,13 +57,15 @@ void fill_air(FilterSpec& fs, i64 N, double rate, double air);
 
 // Device-side flags/scalars a render chain shares between kernels (no host round trips).
 struct RenderState {
-    unsigned max_stereo;       // bits of max |y| out of the spectral stage (before the peak guard)
+    // first four words are written together by the last FFT pass (St::finish): bits of max |y| over both
+    // channels, max |L|, max |R| and max |float32(L + R)| of the spectral-stage output (before the peak guard)
+    unsigned max_stereo, max_l, max_r, max_lr;
     unsigned max_pan;          // bits of max |six| before its guard
     unsigned max_map;          // bits of max |out| before its guard
     unsigned ir_any0, ir_any1; // non-zero IR parts (np.any(ir), rs.py:360,369)
     unsigned peak_final;       // bits of max |final| (metrics)
     unsigned mono_max;         // bits of max |mean(ch0, ch1)| (the loudness meter's silence test, rs.py:689)
-    unsigned max_l, max_r, max_lr;   // bits of max |L|, |R|, |float32(L + R)| of the spectral-stage output
+    unsigned pad0, pad1;
     double sumsq;              // sum of final^2 over all channels (metrics)
     double lufs;               // integrated loudness, written by the gate kernel
 };

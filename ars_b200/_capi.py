@@ -81,6 +81,14 @@ PROTOTYPES = {
     "ars_render_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),
                                  _p, _p, _p, C.POINTER(ArsMetrics)]),
     "ars_render_batch": (C.c_int, [C.POINTER(ArsClip), _i32]),
+    "ars_set_option": (C.c_int, [C.c_char_p, _i32]),
+    "ars_state_bytes": (_i64, []),
+    "ars_ols_block_frames": (_i64, []),
+    "ars_long_convolve_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _i64,
+                                        _i64, _p, _i64, _p]),
+    "ars_long_tail_dev": (C.c_int, [C.POINTER(ArsRenderParams), _i32, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "ars_loudness_dev": (C.c_int, [_p, _i64, _d, _p, C.POINTER(_i32)]),
+    "ars_state_metrics": (C.c_int, [_p, _i64, _i32, C.POINTER(ArsMetrics)]),
     "ars_timer_begin": (C.c_int, []),
     "ars_timer_end": (C.c_int, [C.POINTER(C.c_float)]),
     "ars_profile_begin": (C.c_int, []),
@@ -139,6 +147,10 @@ def init(device: int | None = None):
     check(lib.ars_init(int(device)), "ars_init")
     _inited = True
     return lib
+
+
+def set_option(key: str, value: int):
+    check(init().ars_set_option(key.encode(), int(value)), "ars_set_option")
 
 
 def shutdown():

@@ -7,6 +7,7 @@
 #include "epilogue.cuh"
 #include "ir_synth.cuh"
 #include "metrics.cuh"
+#include "upols.cuh"
 
 namespace ars {
 const char* last_error_cstr();
@@ -26,6 +27,19 @@ void fft_profile_end(long long* launches, double* ms, double* bytes);
         set_last_error(e.what());                                       \
         return ARS_ERR_INTERNAL;                                        \
     }
+
+// run-time options (ars_set_option)
+static int g_opt_upols = 1;        // 1: use overlap-save whenever no exact-N mask is active; 0: always the N-point path
+static int g_opt_upols_logf = 13;  // 2B = 2^logF points per overlap-save transform (12 or 13)
+
+// the convolution stage: overlap-save when the render has no spectral mask, else the exact N-point filter
+static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                              const FilterSpec& fs, float2* d_y, RenderState* st) {
+    if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK)
+        upols_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, g_opt_upols_logf);
+    else
+        spectral_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st);
+}
 
 static inline double clip(double v, double lo, double hi) { return std::min(hi, std::max(lo, v)); }
 
@@ -190,7 +204,7 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
     if (p->external_ir) {
         ARS_CHECK(d_ext_ir && ext_len >= 1, "render: external IR missing");
         fs.mode = FILT_EXT;
-        spectral_filter(d_in, n, cin, d_ext_ir, ext_len, nullptr, 0, fs, y, st);
+        convolution_stage(d_in, n, cin, d_ext_ir, ext_len, nullptr, 0, fs, y, st);
     } else {
         ARS_CHECK(p->ir_duration > 0, "render: IR duration must be positive");
         const IrGeom g = ir_geometry(p->rate, p->ir_duration, p->ir_max_delay, p->ir_split_time);
@@ -210,7 +224,7 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         fs.level0 = (g.length > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;     // rs.py:360
         fs.level1 = (g.length > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;       // rs.py:369
         if (p->air_absorption > 0.01 && N >= 2) fill_air(fs, N, p->rate, p->air_absorption);   // rs.py:378, 312-317
-        spectral_filter(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st);
+        convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st);
     }
     if (d_out_stereo) {
         ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
@@ -311,6 +325,15 @@ int ars_timer_end(float* ms) {
     ARS_CUDA(cudaEventRecord(g_ev1, ctx().stream));
     ARS_CUDA(cudaEventSynchronize(g_ev1));
     ARS_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    ARS_API_END
+}
+
+int ars_set_option(const char* key, int32_t value) {
+    ARS_API_BEGIN
+    ARS_CHECK(key, "ars_set_option: null key");
+    if (!strcmp(key, "upols")) g_opt_upols = value ? 1 : 0;
+    else if (!strcmp(key, "upols_logf")) { ARS_CHECK(value == 12 || value == 13, "upols_logf must be 12 or 13"); g_opt_upols_logf = value; }
+    else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END
 }
 
@@ -430,7 +453,7 @@ int ars_convolve_split(const float* data, int64_t n, int32_t cin, const float* e
     fs.level1 = (len_late > 1 && late_level > 1e-6) ? late_level : 0.0;            // rs.py:369
     if (air_absorption > 0.01 && N >= 2) fill_air(fs, N, rate, air_absorption);     // rs.py:378
     float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
-    spectral_filter(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st);
+    convolution_stage(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st);
     guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:402-404
     download(out, reinterpret_cast<const float*>(y), (size_t)N * 2);
     sync();
@@ -450,7 +473,7 @@ int ars_convolve_external(const float* data, int64_t n, int32_t cin, const float
     common_filter_spec(fs, N, rate, dry_wet, kill_start, bass_gain, treble_gain);
     fs.mode = FILT_EXT;
     float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
-    spectral_filter(d_x, n, cin, d_ir, L, nullptr, 0, fs, y, st);
+    convolution_stage(d_x, n, cin, d_ir, L, nullptr, 0, fs, y, st);
     guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:456-458
     download(out, reinterpret_cast<const float*>(y), (size_t)N * 2);
     sync();
@@ -590,6 +613,77 @@ int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32
         sync();
         finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics);
     }
+    ARS_API_END
+}
+
+// ---- block-sharded long render (mask-free): building blocks for one rank of a multi-GPU render ----
+int64_t ars_state_bytes(void) { return (int64_t)sizeof(RenderState); }
+int64_t ars_ols_block_frames(void) { return (int64_t)1 << (g_opt_upols_logf - 1); }
+
+int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, int64_t x_frame0, int64_t x_frames, int64_t n_total,
+                          int32_t cin, const float* d_ir0, int64_t L0, const float* d_ir1, int64_t L1,
+                          int64_t block_lo, int64_t block_hi, float* d_y, int64_t y_frame0, void* d_state) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && d_x && d_y && d_state && n_total > 0 && cin >= 1 && d_ir0 && L0 >= 1, "ars_long_convolve_dev: bad arguments");
+    const i64 L = p->external_ir ? L0 : std::max<i64>(L0, d_ir1 ? L1 : 0);
+    const i64 N = n_total + L - 1;
+    FilterSpec fs;
+    common_filter_spec(fs, N, p->rate, p->dry_wet, p->kill_start, p->bass_gain, p->treble_gain);
+    if (p->external_ir) {
+        fs.mode = FILT_EXT;
+    } else {
+        fs.mode = FILT_SPLIT;
+        fs.level0 = (L0 > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;
+        fs.level1 = (d_ir1 && L1 > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;
+        if (p->air_absorption > 0.01 && N >= 2) fill_air(fs, N, p->rate, p->air_absorption);
+    }
+    ARS_CHECK(upols_applicable(fs), "ars_long_convolve_dev: EQ / air absorption need the global N-point transform; "
+                                    "only mask-free renders shard by block ranges (use ars_render on one GPU)");
+    OlsRange rg;
+    rg.block_lo = block_lo;
+    rg.block_hi = block_hi;
+    rg.x_frame0 = x_frame0;
+    rg.x_frames = x_frames;
+    rg.y_frame0 = y_frame0;
+    upols_filter(d_x, n_total, cin, d_ir0, L0, p->external_ir ? nullptr : d_ir1, L1, fs, reinterpret_cast<float2*>(d_y),
+                 static_cast<RenderState*>(d_state), g_opt_upols_logf, rg);
+    ARS_API_END
+}
+
+int ars_long_tail_dev(const ArsRenderParams* p, int32_t phase, const float* d_y, int64_t y_frame0, int64_t frame_lo,
+                      int64_t frame_hi, int64_t N_total, void* d_state, float* d_out_f32, int16_t* d_out_pcm,
+                      float* d_mono) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && d_y && d_state && layout_ok(p->layout) && frame_lo >= 0 && frame_hi <= N_total && phase >= 0 && phase <= 2,
+              "ars_long_tail_dev: bad arguments");
+    TailSpec ts = make_tail(N_total, p->layout, p->rate, p->x, p->y, p->z);
+    ts.i_lo = frame_lo;
+    ts.i_hi = frame_hi;
+    ts.y0 = y_frame0;
+    ts.out0 = frame_lo;
+    ARS_CHECK(y_frame0 <= std::max<i64>(0, frame_lo - ts.delay), "ars_long_tail_dev: y slice lacks the delay halo");
+    const float2* y = reinterpret_cast<const float2*>(d_y);
+    RenderState* st = static_cast<RenderState*>(d_state);
+    if (phase == 0) tail_pan_max(y, ts, st);
+    else if (phase == 1) tail_map_max(y, ts, st);
+    else tail_final(y, ts, st, d_out_f32, reinterpret_cast<short*>(d_out_pcm), d_mono);
+    ARS_API_END
+}
+
+int ars_loudness_dev(const float* d_mono, int64_t N, double rate, void* d_state, int32_t* lufs_status) {
+    ARS_API_BEGIN
+    ARS_CHECK(d_mono && d_state && N > 0 && rate > 0 && lufs_status, "ars_loudness_dev: bad arguments");
+    *lufs_status = lufs_enqueue(d_mono, N, rate, static_cast<RenderState*>(d_state));
+    ARS_API_END
+}
+
+int ars_state_metrics(const void* d_state, int64_t sample_count, int32_t lufs_status, ArsMetrics* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(d_state && out, "ars_state_metrics: bad arguments");
+    RenderState h;
+    download(&h, static_cast<const RenderState*>(d_state), 1);
+    sync();
+    finish_metrics(h, sample_count, lufs_status, out);
     ARS_API_END
 }
 

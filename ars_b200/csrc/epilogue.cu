@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__
         return;
     }
     unsigned m = 0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
-        const float2 v = __ldg(y + i);
+    for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
+        const float2 v = __ldg(y + (i - ts.y0));
         float s[6];
         pan6(guard1(v.x, g1), guard1(v.y, g1), ts, s);
         #pragma unroll
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__
 
 __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
                                           const Guard& g2, float (&o)[8]) {
-    const float2 v = __ldg(y + i);
+    const float2 v = __ldg(y + (i - ts.y0));
     float s[6];
     pan6(guard1(v.x, g1), guard1(v.y, g1), ts, s);
     #pragma unroll
@@ -133,7 +133,7 @@ __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, c
     float rl_d = 0.f, rr_d = 0.f;
     if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
         // a delay <= 0 leaves the signal where it is (rs.py:510-511)
-        const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0)));
+        const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0) - ts.y0));
         rl_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.x, g1), ts.g_rl)), g2);
         rr_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.y, g1), ts.g_rr)), g2);
     }
@@ -143,7 +143,7 @@ __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, c
 __global__ void __launch_bounds__(256) map_max_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st) {
     const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
     unsigned m = 0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+    for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
         float o[8];
         frame_out(y, i, ts, g1, g2, o);
         #pragma unroll
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
     const Guard g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
     unsigned pk = 0, mm = 0;
     double ss = 0.0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.N; i += (i64)gridDim.x * blockDim.x) {
+    for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
         float o[8];
         frame_out(y, i, ts, g1, g2, o);
         float fs = 0.f;        // one frame's squares in float32 (numpy squares in float32 too), then one conversion
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
         }
         ss += (double)fs;
         if (out) {
-            float* p = out + i * C;
+            float* p = out + (i - ts.out0) * C;
             if (C == 8) {
                 reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
                 reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
             short q[8];
             #pragma unroll
             for (int c = 0; c < C; ++c) q[c] = pcm_of(o[c]);
-            short* p = pcm + i * C;
+            short* p = pcm + (i - ts.out0) * C;
             if (C == 8) {
                 uint4 u;
                 u.x = (unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
         }
         if (mono) {
             const float mv = __fdiv_rn(__fadd_rn(o[0], o[1]), 2.0f);    // np.mean(data[:, :2], axis=1), rs.py:688
-            mono[i] = mv;
+            mono[i - ts.out0] = mv;
             mm = max(mm, abs_bits(mv));
         }
     }
@@ -220,24 +220,48 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
     block_atomic_add(ss, &st->sumsq);
 }
 
-void tail_maxes(const float2* d_y, const TailSpec& ts, RenderState* d_state) {
+static TailSpec with_window(const TailSpec& in) {
+    TailSpec ts = in;
+    if (ts.i_hi < 0) ts.i_hi = ts.N;
+    return ts;
+}
+
+void tail_pan_max(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) {
+    const TailSpec ts = with_window(ts_in);
+    if (ts.i_hi <= ts.i_lo) return;
+    pan_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, ctx().stream>>>(d_y, ts, d_state);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+void tail_map_max(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) {
+    const TailSpec ts = with_window(ts_in);
+    if (ts.i_hi <= ts.i_lo || ts.layout != LAYOUT_STEREO) return;
+    map_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, ctx().stream>>>(d_y, ts, d_state);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+void tail_maxes(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) {
+    const TailSpec ts = with_window(ts_in);
     if (ts.N <= 0) return;
     Ctx& c = ctx();
-    pan_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
+    pan_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, c.stream>>>(d_y, ts, d_state);
     ARS_LAUNCH_CHECK();
     count_launch();
     if (ts.layout == LAYOUT_STEREO) {
-        map_max_kernel<<<stream_grid(ts.N), 256, 0, c.stream>>>(d_y, ts, d_state);
+        map_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, c.stream>>>(d_y, ts, d_state);
         ARS_LAUNCH_CHECK();
         count_launch();
     }
 }
 
-void tail_final(const float2* d_y, const TailSpec& ts, RenderState* d_state, float* d_out, short* d_pcm,
+void tail_final(const float2* d_y, const TailSpec& ts_in, RenderState* d_state, float* d_out, short* d_pcm,
                 float* d_mono) {
-    if (ts.N <= 0) return;
+    const TailSpec ts = with_window(ts_in);
+    if (ts.N <= 0 || ts.i_hi <= ts.i_lo) return;
     Ctx& c = ctx();
-    const int grid = stream_grid(ts.N);
+    const int grid = stream_grid(ts.i_hi - ts.i_lo);
     if (ts.C == 2) final_kernel<2><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
     else if (ts.C == 6) final_kernel<6><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
     else final_kernel<8><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);

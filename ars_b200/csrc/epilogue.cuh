@@ -12,7 +12,10 @@ namespace ars {
 enum Layout { LAYOUT_STEREO = 0, LAYOUT_5_1 = 1, LAYOUT_7_1 = 2, LAYOUT_5_1_2 = 3 };
 
 struct TailSpec {
-    i64 N = 0;
+    i64 N = 0;                   // frames of the whole render
+    // frame window of this call (block-sharded long renders): process absolute frames [i_lo, i_hi); y[0] is absolute
+    // frame y0 (must reach back `delay` frames before i_lo); outputs are written relative to frame out0.
+    i64 i_lo = 0, i_hi = -1, y0 = 0, out0 = 0;
     int layout = LAYOUT_5_1;
     int C = 6;
     i64 delay = 0;               // frames: int(rate*12/1000) for 7.1, int(rate*18/1000) for 5.1.2
@@ -28,6 +31,8 @@ inline int layout_channels(int layout) { return layout == LAYOUT_STEREO ? 2 : la
 // y: (N) float2 straight out of the spectral stage (unnormalised; its abs-max bits are in
 // state->max_stereo).  Computes state->max_pan and state->max_map.
 void tail_maxes(const float2* d_y, const TailSpec& ts, RenderState* d_state);
+void tail_pan_max(const float2* d_y, const TailSpec& ts, RenderState* d_state);     // the two halves of tail_maxes, so a
+void tail_map_max(const float2* d_y, const TailSpec& ts, RenderState* d_state);     // sharded render can reduce in between
 // Writes the final (pre-clip) float32 frames and/or the int16 PCM frames and/or the mono
 // loudness feed mean(ch0, ch1); accumulates peak_final and sumsq in the state.
 void tail_final(const float2* d_y, const TailSpec& ts, RenderState* d_state, float* d_out, short* d_pcm,

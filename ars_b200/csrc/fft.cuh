@@ -177,8 +177,8 @@ template <bool INV> struct Dft<16, INV> {
 
 // ------------------------------------------------------------- Ld / St functors
 enum LdMode { LD_PLAIN = 0, LD_MULSPEC, LD_CHIRP_X2, LD_CHIRP_XC, LD_CHIRP_PAIR, LD_CHIRP_B, LD_CHIRP_C,
-              LD_REAL_PAIR };
-enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL };
+              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC };
+enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS };
 
 struct Ld {
     int mode = LD_PLAIN;
@@ -190,6 +190,16 @@ struct Ld {
     i64 nvalid1 = 0;
     i64 N = 0, M = 0;
     int cin = 2;
+    // overlap-save (upols.cu): segment s of 2^logF points = hop-B window of the signal / partition of the IR
+    const float2* a2 = nullptr;     // LD_OLS_MAC: second delay line (spectra of the conjugated signal), or null
+    const float2* b2 = nullptr;     // LD_OLS_MAC: its coefficient spectra
+    const unsigned char* nz = nullptr;   // LD_OLS_MAC: per-partition "has non-zero taps" flags
+    int P = 0;                      // partitions
+    int logF = 13;                  // log2 of the segment (FFT) length; hop B = F / 2
+    float c0 = 1.f, c1 = 0.f;       // LD_OLS_IR: tap = c0 * f0[i*cin] + c1 * f1[i*cin]; LD_OLS_X: c1 = -1 conjugates
+    i64 seg0 = 0;                   // LD_OLS_X: absolute block index of the launch's segment 0
+    i64 frame0 = 0;                 // LD_OLS_X: absolute frame index of f0[0] (a rank may hold a slice of the signal)
+    i64 lookback = 0;               // LD_OLS_MAC: delay-line segments that exist before the launch's segment 0
     // MODE >= 0: compile-time access mode (fast kernels); MODE < 0: runtime switch on `mode` (generic kernels)
     template <int MODE> ARS_HD float2 get(i64 idx) const {
         if constexpr (MODE < 0) return (*this)(idx);
@@ -214,10 +224,65 @@ struct Ld {
             return make_float2(0.f, 0.f);
         } else if constexpr (MODE == LD_CHIRP_C) {     // complex N-vector times chirp
             return idx < nvalid ? cmul(ARS_LDG(a + idx), ARS_LDG(b + idx)) : make_float2(0.f, 0.f);
+        } else if constexpr (MODE == LD_OLS_X) {       // overlap-save window s: frames [(s-1)B, (s+1)B) of the zero-padded signal
+            const i64 seg = seg0 + (idx >> logF);
+            const i64 fr = ((seg - 1) << (logF - 1)) + (idx & (((i64)1 << logF) - 1)) - frame0;
+            if (fr < 0 || fr >= nvalid) return make_float2(0.f, 0.f);      // nvalid = frames held at f0
+            const float l = ARS_LDG(f0 + fr * cin);
+            const float r = cin > 1 ? ARS_LDG(f0 + fr * cin + 1) : l;
+            return make_float2(l, c1 < 0.f ? -r : r);
+        } else if constexpr (MODE == LD_OLS_IR) {      // IR partition p: taps [pB, (p+1)B), zero-padded to 2B, real
+            const i64 seg = idx >> logF;
+            const i64 t = idx & (((i64)1 << logF) - 1);
+            const i64 i = (seg << (logF - 1)) + t;
+            if (t >= ((i64)1 << (logF - 1))) return make_float2(0.f, 0.f);
+            const float u = (f0 && i < nvalid) ? ARS_LDG(f0 + i * cin) : 0.f;
+            const float v = (f1 && i < nvalid1) ? ARS_LDG(f1 + i * cin) : 0.f;
+            return make_float2(c0 * u + c1 * v, 0.f);
+        } else if constexpr (MODE == LD_OLS_MAC) {     // Y_s = sum_p X_{s-p} H_p (+ Xc_{s-p} Hc_p)
+            float2 acc[1];
+            get_mac<1>(idx, 0, acc);
+            return acc[0];
         } else {                                       // LD_REAL_PAIR: plain zero-padded packing
             const float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
             const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
             return make_float2(l, r);
+        }
+    }
+    // The complex multiply-accumulate over the partitions, fused into the loads of the inverse transform:
+    // r spectrum bins of one butterfly at a time, so 2r (4r) independent loads are in flight per partition.
+    template <int r> ARS_HD void get_mac(i64 idx0, i64 step, float2 (&v)[r]) const {
+        const i64 F = (i64)1 << logF;
+        const i64 seg = idx0 >> logF;
+        const i64 t0 = idx0 & (F - 1);
+        #pragma unroll
+        for (int k = 0; k < r; ++k) v[k] = make_float2(0.f, 0.f);
+        const i64 reach = seg + lookback;
+        const int pmax = (int)(reach < (i64)(P - 1) ? reach : (i64)(P - 1));
+        for (int p = 0; p <= pmax; ++p) {
+            if (nz && !nz[p]) continue;
+            const float2* x = a + ((seg - p) << logF) + t0;
+            const float2* h = b + ((i64)p << logF) + t0;
+            #pragma unroll
+            for (int k = 0; k < r; ++k) {
+                const float2 xv = ARS_LDG(x + k * step), hv = ARS_LDG(h + k * step);
+                v[k].x = fmaf(xv.x, hv.x, v[k].x);
+                v[k].x = fmaf(-xv.y, hv.y, v[k].x);
+                v[k].y = fmaf(xv.x, hv.y, v[k].y);
+                v[k].y = fmaf(xv.y, hv.x, v[k].y);
+            }
+            if (a2) {
+                const float2* x2 = a2 + ((seg - p) << logF) + t0;
+                const float2* h2 = b2 + ((i64)p << logF) + t0;
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const float2 xv = ARS_LDG(x2 + k * step), hv = ARS_LDG(h2 + k * step);
+                    v[k].x = fmaf(xv.x, hv.x, v[k].x);
+                    v[k].x = fmaf(-xv.y, hv.y, v[k].x);
+                    v[k].y = fmaf(xv.x, hv.y, v[k].y);
+                    v[k].y = fmaf(xv.y, hv.x, v[k].y);
+                }
+            }
         }
     }
     ARS_HD float2 operator()(i64 idx) const {
@@ -230,6 +295,9 @@ struct Ld {
             case LD_CHIRP_B: return get<LD_CHIRP_B>(idx);
             case LD_CHIRP_C: return get<LD_CHIRP_C>(idx);
             case LD_REAL_PAIR: return get<LD_REAL_PAIR>(idx);
+            case LD_OLS_X: return get<LD_OLS_X>(idx);
+            case LD_OLS_IR: return get<LD_OLS_IR>(idx);
+            case LD_OLS_MAC: return get<LD_OLS_MAC>(idx);
         }
         return make_float2(0.f, 0.f);
     }
@@ -241,6 +309,14 @@ struct St {
     const float2* chirp = nullptr;
     i64 N = 0;
     float scale = 1.f;
+    // ST_OLS: keep the second half of every overlap-save segment, mix with the dry frame, track the maxima
+    const float* dry = nullptr;      // (n, cin) input frames
+    int cin = 2;
+    i64 n = 0;                       // input frames (dry is zero beyond)
+    int logF = 13;
+    float dg = 0.f, dw = 1.f;        // y = dg * dry + dw * wet   (rs.py:113)
+    i64 seg0 = 0;                    // absolute block index of the launch's segment 0
+    i64 frame0 = 0, dry_frame0 = 0;  // absolute frame index of a[0] / dry[0]; N = absolute end frame (exclusive)
     unsigned* maxbits = nullptr;     // ST_FINAL: 4 words: bits of max |x|, max |x.re|, max |x.im|, max |f32(re + im)|
     unsigned local_max = 0, local_l = 0, local_r = 0, local_lr = 0;
     // chirp operand of the store, fetched early so its latency overlaps the butterfly
@@ -261,6 +337,7 @@ struct St {
                 case ST_SCALE: put<ST_SCALE>(idx, v, aux); break;
                 case ST_CHIRP: put<ST_CHIRP>(idx, v, aux); break;
                 case ST_FINAL: put<ST_FINAL>(idx, v, aux); break;
+                case ST_OLS: put<ST_OLS>(idx, v, aux); break;
             }
         } else if constexpr (MODE == ST_PLAIN) {
             a[idx] = v;
@@ -268,6 +345,24 @@ struct St {
             a[idx] = cscale(v, scale);
         } else if constexpr (MODE == ST_CHIRP) {
             if (idx < N) a[idx] = cmul(v, aux);
+        } else if constexpr (MODE == ST_OLS) {
+            const i64 F = (i64)1 << logF, B = F >> 1;
+            const i64 t = idx & (F - 1);
+            const i64 fr = ((seg0 + (idx >> logF)) << (logF - 1)) + (t - B);       // absolute output frame
+            if (t >= B && fr < N) {
+                float l = 0.f, r = 0.f;
+                const i64 df = fr - dry_frame0;
+                if (df >= 0 && df < n) {                                           // n = dry frames held at `dry`
+                    l = ARS_LDG(dry + df * cin);
+                    r = cin > 1 ? ARS_LDG(dry + df * cin + 1) : l;
+                }
+                const float2 y = make_float2(dg * l + dw * v.x, dg * r + dw * v.y);
+                a[fr - frame0] = y;
+                const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
+                if (m0 > local_l) local_l = m0;
+                if (m1 > local_r) local_r = m1;
+                if (m2 > local_lr) local_lr = m2;
+            }
         } else {
             if (idx < N) {
                 float2 y = cmul(v, aux);
@@ -282,7 +377,7 @@ struct St {
     }
     template <int MODE> ARS_HD void put(i64 idx, float2 v) { put<MODE>(idx, v, pre<MODE>(idx)); }
     ARS_HD void finish() {
-        if (mode == ST_FINAL && maxbits) {
+        if ((mode == ST_FINAL || mode == ST_OLS) && maxbits) {
             local_max = local_l > local_r ? local_l : local_r;
 #ifdef __CUDA_ARCH__
             unsigned m[4] = {local_max, local_l, local_r, local_lr};
@@ -473,8 +568,11 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 float2 Q = make_float2(1.f, 0.f);
                 if constexpr (STRIDED) Q = tw_big<true>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
                 i64 idx = glast(b, c);
-                #pragma unroll
-                for (int k = 0; k < r; ++k) { v[k] = ld.template get<LDM>(idx); idx += lstep; }
+                if constexpr (LDM == LD_OLS_MAC) ld.template get_mac<r>(idx, lstep, v);
+                else {
+                    #pragma unroll
+                    for (int k = 0; k < r; ++k) { v[k] = ld.template get<LDM>(idx); idx += lstep; }
+                }
                 if constexpr (STRIDED) {
                     #pragma unroll
                     for (int k = 0; k < r; ++k) v[k] = cmul(v[k], k ? cmul(Q, P[k]) : Q);
@@ -615,8 +713,8 @@ __global__ void __launch_bounds__(NT) pass_contig_kernel(Ld ld, St st, PassArgs 
     X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(13, 0)
 
 // variants that also get compile-time-mode ("fast") instantiations: the ones big transforms are planned with
-#define ARS_FAST_STRIDED(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4) X(10, 3) X(11, 2) X(12, 1) X(12, 2)
-#define ARS_FAST_CONTIG(X) X(12, 1) X(13, 0) X(11, 2) X(10, 3) X(9, 4) X(8, 5)
+#define ARS_FAST_STRIDED(X) X(6, 7) X(7, 6) X(8, 5) X(9, 4)
+#define ARS_FAST_CONTIG(X) X(12, 1) X(13, 0)
 
 // ------------------------------------------------------------------ host API --
 struct FftPass {
@@ -643,6 +741,10 @@ void fft_forward(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st)
 // Inverse transform: first pass reads through `ld` (permuted order), last pass writes natural
 // order through `st`.  Unnormalised.
 void fft_inverse(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st);
+// One contiguous pass over `nseg` independent 2^logF-point segments (logF = 12 or 13; nseg a multiple of
+// fft_segment_tile(logF)): the block transforms of the overlap-save convolution.
+int fft_segment_tile(int logF);
+void fft_segments(int logF, i64 nseg, const fft::Ld& ld, const fft::St& st, bool inverse);
 
 int next_pow2_log(i64 n);
 

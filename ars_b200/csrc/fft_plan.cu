@@ -110,6 +110,9 @@ static double ld_bytes(const Ld& ld, i64 M) {
         case LD_CHIRP_B: return 8.0 * (double)(2 * ld.N - 1);
         case LD_CHIRP_C: return 16.0 * (double)ld.nvalid;
         case LD_REAL_PAIR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
+        case LD_OLS_X: return 8.0 * (double)ld.nvalid;
+        case LD_OLS_IR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
+        case LD_OLS_MAC: return 8.0 * (double)M;       // compulsory: each delay-line spectrum once
     }
     return 0.0;
 }
@@ -117,6 +120,7 @@ static double st_bytes(const St& st, i64 M) {
     switch (st.mode) {
         case ST_PLAIN: case ST_SCALE: return 8.0 * (double)M;
         case ST_CHIRP: case ST_FINAL: return 16.0 * (double)st.N;
+        case ST_OLS: return 16.0 * (double)st.N;
     }
     return 0.0;
 }
@@ -214,6 +218,9 @@ static bool launch_fast(const FftPass& ps, const Ld& ld, const St& st, const Pas
             if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_contig<R, C, INV, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; } \
             if constexpr (INV) {                                                                                  \
                 if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
+                if (lm == LD_OLS_MAC && sm == ST_OLS) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS>(ld, st, pa); return true; } \
+            } else {                                                                                              \
+                if (lm == LD_OLS_X && sm == ST_PLAIN) { launch_contig<R, C, false, LD_OLS_X, ST_PLAIN>(ld, st, pa); return true; } \
             }                                                                                                     \
         }
         ARS_FAST_CONTIG(F_CASE)
@@ -249,6 +256,21 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
 #undef C_CASE
         ARS_CHECK(false, "no contiguous FFT pass kernel for this (logR, logC)");
     }
+}
+
+int fft_segment_tile(int logF) { return logF == 12 ? 2 : 1; }
+
+void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) {
+    ARS_CHECK(logF == 12 || logF == 13, "fft_segments: segment length must be 2^12 or 2^13");
+    ARS_CHECK(nseg > 0 && nseg % fft_segment_tile(logF) == 0, "fft_segments: segment count not a multiple of the tile");
+    FftPlan tmp;                       // a plan-less pass: only the stage tables are needed
+    tmp.logM = 0;
+    tmp.M = nseg << logF;
+    tmp.tw.stage = local_table();
+    tmp.tw.lo = tmp.tw.hi = nullptr;
+    const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
+    if (inverse) launch_pass<true>(&tmp, ps, ld, st);
+    else launch_pass<false>(&tmp, ps, ld, st);
 }
 
 void fft_forward(FftPlan* p, const Ld& ld_first, float2* work, const St& st_last) {

@@ -1,0 +1,226 @@
+// Uniformly partitioned overlap-save convolution on the FFT engine (K2-K4 of SURVEY.md section 2.3).
+//
+//   K2  IR partitions:   H_p = FFT_2B( taps [pB, (p+1)B) zero-padded ), p < P = ceil(L / B), pre-scaled by 1/2B,
+//                        computed once per render; a flag per partition marks all-zero partitions (the procedural
+//                        late tail is exactly zero a few thousand samples past the split).
+//   K3  delay line:      X_s = FFT_2B( frames [(s-1)B, (s+1)B) of the zero-padded signal ), both channels in one
+//                        complex transform (L + iR).
+//   K4  MAC + inverse:   y block s = IFFT_2B( sum_p X_{s-p} H_p )[B : 2B]; the complex multiply-accumulate over the
+//                        partitions runs inside the first load of the inverse transform (Ld::get_mac), the dry/wet
+//                        mix and the abs-max tracking inside its last store (St::put<ST_OLS>).
+//
+// Every transform is ONE contiguous pass of the FFT engine (a 2B-point segment fits a tile: 2B = 4096 or 8192), in
+// the engine's permuted spectrum order -- H and X come out of the same forward transform, so the order never matters.
+// A stereo IR needs the two channels' spectra separated; instead of un-permuting bins, the conjugated signal is
+// transformed as well:  X_L H_L + i X_R H_R = Z (H_L + H_R)/2 + Zc (H_L - H_R)/2  with Z = FFT(L + iR),
+// Zc = FFT(L - iR).
+#include "upols.cuh"
+
+namespace ars {
+
+using namespace fft;
+
+__global__ void __launch_bounds__(256) partition_flags_kernel(const float* a, i64 na, const float* b, i64 nb, int stride,
+                                                              float c0, float c1, int logB, unsigned char* nz, int P) {
+    // nz[p] = any(c0*a[i] + c1*b[i] != 0 for i in partition p)
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    const i64 lo = (i64)p << logB, hi = lo + ((i64)1 << logB);
+    bool f = false;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float u = (a && i < na) ? a[i * stride] : 0.f;
+        const float v = (b && i < nb) ? b[i * stride] : 0.f;
+        f |= (c0 * u + c1 * v) != 0.f;
+    }
+    const int any = __syncthreads_or(f ? 1 : 0);
+    if (threadIdx.x == 0) nz[p] = any ? 1 : 0;
+}
+
+// Register-tiled multiply-accumulate over the partitions for long dense IRs:  Y_j[t] = sum_p X_{j-p}[t] H_p[t].
+// A thread owns one spectrum bin t and JT consecutive output blocks; per partition it loads ONE new delay-line
+// value and ONE coefficient (both coalesced over t) and does JT complex MACs, the JT-deep window of X sliding
+// through registers (the p loop is unrolled by JT so the rotation is pure register renaming).  L2 traffic per
+// MAC drops by JT against the fused-prologue form, which re-reads X and H for every block.
+template <int JT>
+__global__ void __launch_bounds__(256) ols_mac_kernel(const float2* __restrict__ X, const float2* __restrict__ H,
+                                                      const float2* __restrict__ X2, const float2* __restrict__ H2,
+                                                      float2* __restrict__ Y, int logF, int P, i64 lookback, i64 run) {
+    const i64 F = (i64)1 << logF;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;           // bin
+    const i64 j0 = (i64)blockIdx.y * JT;                                // first output block of this thread
+    if (t >= F) return;
+    float2 acc[JT];
+    #pragma unroll
+    for (int q = 0; q < JT; ++q) acc[q] = make_float2(0.f, 0.f);
+    for (int pass = 0; pass < 2; ++pass) {
+        const float2* x = pass == 0 ? X : X2;
+        const float2* h = pass == 0 ? H : H2;
+        if (!x) break;
+        // window w[q] = X_{j0 + q - p}; element with block index < -lookback does not exist (zero)
+        float2 w[JT];
+        #pragma unroll
+        for (int q = 0; q < JT; ++q) {
+            const i64 jb = j0 + q;                                      // p = 0
+            w[q] = (jb < run + 0 && jb + lookback >= 0) ? __ldg(x + jb * F + t) : make_float2(0.f, 0.f);
+        }
+        for (int p0 = 0; p0 < P; p0 += JT) {
+            #pragma unroll
+            for (int u = 0; u < JT; ++u) {
+                const int p = p0 + u;
+                if (p < P) {
+                    const float2 hv = __ldg(h + (i64)p * F + t);
+                    // at partition p the window slot for output q is w[(q - u) mod JT] (rotated u times)
+                    #pragma unroll
+                    for (int q = 0; q < JT; ++q) {
+                        const float2 xv = w[(q - u + JT) % JT];
+                        acc[q].x = fmaf(xv.x, hv.x, acc[q].x);       // four FMAs per complex MAC
+                        acc[q].x = fmaf(-xv.y, hv.y, acc[q].x);
+                        acc[q].y = fmaf(xv.x, hv.y, acc[q].y);
+                        acc[q].y = fmaf(xv.y, hv.x, acc[q].y);
+                    }
+                    // slide: the slot that held X_{j0 + JT-1 - p} (output JT-1) now takes X_{j0 - p - 1} (output 0 at p+1)
+                    const i64 jn = j0 - p - 1;
+                    w[(JT - 1 - u + JT) % JT] = (jn + lookback >= 0) ? __ldg(x + jn * F + t) : make_float2(0.f, 0.f);
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int q = 0; q < JT; ++q)
+        if (j0 + q < run) Y[(j0 + q) * F + t] = acc[q];
+}
+
+__global__ void or_flags_kernel(unsigned char* a, const unsigned char* b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] |= b[i];
+}
+
+void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                  const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg) {
+    Ctx& c = ctx();
+    ARS_CHECK(upols_applicable(fs), "upols_filter: an exact-N spectral mask is active");
+    ARS_CHECK(fs.mode == FILT_SPLIT || fs.mode == FILT_EXT, "upols_filter: needs an IR");
+    const i64 N = fs.N;
+    const int logB = logF - 1;
+    const i64 B = (i64)1 << logB, F = (i64)1 << logF;
+    if (!d_ir0) L0 = 0;
+    if (!d_ir1) L1 = 0;
+    const bool ext = fs.mode == FILT_EXT;
+    const i64 L = ext ? L0 : std::max(L0, L1);
+    const int tile = fft_segment_tile(logF);
+    const int P = (int)std::max<i64>(1, (L + B - 1) / B);
+    const int Ppad = ((P + tile - 1) / tile) * tile;
+    const i64 nblk_all = (N + B - 1) / B;                     // output blocks of the whole render
+    const i64 block_lo = rg.block_lo;
+    const i64 block_hi = (rg.block_hi < 0 || rg.block_hi > nblk_all) ? nblk_all : rg.block_hi;
+    ARS_CHECK(block_lo >= 0 && block_lo < block_hi, "upols_filter: empty block range");
+    const i64 x_frames = rg.x_frames < 0 ? n - rg.x_frame0 : rg.x_frames;
+    // stored delay-line segments: absolute blocks [seg0, seg0 + nseg); blocks before 0 do not exist
+    const i64 seg0 = std::max<i64>(0, block_lo - (P - 1));
+    const i64 skip = block_lo - seg0;                         // halo segments in front of the computed range
+    const i64 run = ((block_hi - block_lo + tile - 1) / tile) * tile;
+    const i64 nseg = ((skip + run + tile - 1) / tile) * tile;
+    {   // the slice handed in must cover every existing frame the stored windows read
+        const i64 need_lo = std::max<i64>(0, (seg0 - 1) * B), need_hi = std::min<i64>(n, (seg0 + nseg) * B);
+        ARS_CHECK(rg.x_frame0 <= need_lo && rg.x_frame0 + x_frames >= std::min(need_hi, std::min<i64>(n, block_hi * B)),
+                  "upols_filter: the input slice does not cover the block range plus its halo");
+    }
+
+    // ---- K2: IR partition spectra (+ flags) ----
+    const int nspec = ext ? 2 : 1;
+    float2* H = c.buf("ols.H", sizeof(float2) * (size_t)(Ppad * F) * nspec).as<float2>();
+    unsigned char* nz = c.buf("ols.nz", (size_t)Ppad).as<unsigned char>();
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld;
+        ld.mode = LD_OLS_IR;
+        ld.logF = logF;
+        if (ext) {          // A = (hL + hR) / 2 ; Bc = (hL - hR) / 2 from the interleaved stereo IR
+            ld.f0 = d_ir0; ld.f1 = d_ir0 + 1; ld.cin = 2; ld.nvalid = ld.nvalid1 = L0;
+            ld.c0 = 0.5f; ld.c1 = k == 0 ? 0.5f : -0.5f;
+        } else {            // h = level0 * early + level1 * late (a zero part contributes nothing: rs.py:360,369)
+            ld.f0 = d_ir0; ld.f1 = d_ir1; ld.cin = 1; ld.nvalid = L0; ld.nvalid1 = L1;
+            ld.c0 = (float)fs.level0; ld.c1 = (float)fs.level1;
+        }
+        St st;
+        st.mode = ST_SCALE;
+        st.a = H + (size_t)k * Ppad * F;
+        st.scale = 1.0f / (float)F;
+        fft_segments(logF, Ppad, ld, st, false);
+    }
+    ARS_CUDA(cudaMemsetAsync(nz, 0, (size_t)Ppad, c.stream));
+    if (ext) {              // a partition is skipped only when both channels' taps vanish there
+        unsigned char* nz2 = c.buf("ols.nz2", (size_t)Ppad).as<unsigned char>();
+        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz, P);
+        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0 + 1, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz2, P);
+        or_flags_kernel<<<ceil_div(P, 256), 256, 0, c.stream>>>(nz, nz2, P);
+        ARS_LAUNCH_CHECK();
+        count_launch(3);
+    } else {
+        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, d_ir1, L1, 1, (float)fs.level0, (float)fs.level1, logB,
+                                                        nz, P);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+
+    // ---- K3: frequency-domain delay line ----
+    float2* X = c.buf("ols.X", sizeof(float2) * (size_t)(nseg * F) * nspec).as<float2>();
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld;
+        ld.mode = LD_OLS_X;
+        ld.logF = logF;
+        ld.f0 = d_x;
+        ld.frame0 = rg.x_frame0;
+        ld.nvalid = std::min<i64>(x_frames, n - rg.x_frame0);      // frames beyond n are zero padding
+        ld.cin = cin;
+        ld.seg0 = seg0;
+        ld.c1 = k == 0 ? 0.f : -1.f;                                 // second spectrum: the conjugated signal
+        St st;
+        st.mode = ST_PLAIN;
+        st.a = X + (size_t)k * nseg * F;
+        fft_segments(logF, nseg, ld, st, false);
+    }
+
+    // ---- K4: MAC over the partitions + inverse transform; dry/wet + maxima fused into the last store ----
+    // Short IRs (and procedural ones, whose tail partitions are all zero and skipped): the MAC runs inside the first
+    // load of the inverse transform.  Long dense IRs: the register-tiled MAC kernel writes Y, the inverse reads it.
+    const bool tiled = ext && P > 8;
+    Ld ld;
+    ld.logF = logF;
+    if (tiled) {
+        constexpr int JT = 16;
+        float2* Y = c.buf("ols.Y", sizeof(float2) * (size_t)(run * F)).as<float2>();
+        const dim3 grid((unsigned)((F + 255) / 256), (unsigned)((run + JT - 1) / JT));
+        ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, X + (size_t)nseg * F + skip * F,
+                                                       H + (size_t)Ppad * F, Y, logF, P, skip, run);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        ld.mode = LD_PLAIN;
+        ld.a = Y;
+    } else {
+        ld.mode = LD_OLS_MAC;
+        ld.a = X + skip * F;                    // the launch's segment 0 = stored segment `skip`
+        ld.b = H;
+        ld.a2 = ext ? X + (size_t)nseg * F + skip * F : nullptr;
+        ld.b2 = ext ? H + (size_t)Ppad * F : nullptr;
+        ld.nz = nz;
+        ld.P = P;
+        ld.lookback = skip;
+    }
+    St st;
+    st.mode = ST_OLS;
+    st.logF = logF;
+    st.seg0 = block_lo;
+    st.a = d_y;
+    st.frame0 = rg.y_frame0;
+    st.N = std::min<i64>(N, block_hi * B);
+    st.dry = d_x;
+    st.dry_frame0 = rg.x_frame0;
+    st.n = std::min<i64>(x_frames, n - rg.x_frame0);
+    st.cin = cin;
+    st.dg = (float)fs.dry_gain;
+    st.dw = (float)fs.dw;
+    st.maxbits = &d_state->max_stereo;
+    fft_segments(logF, run, ld, st, true);
+}
+
+}  // namespace ars

@@ -50,11 +50,26 @@ WORKLOADS = {
                                base_late_level=.6, dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.5, treble_gain=.8,
                                x_pos=.3, y_pos=.4, z_pos=.6, material="Holz",
                                target_channel_layout="5.1 (Standard)")),
+    # BASELINE.json configs[4] (single-GPU slice): long stereo render (x) dense stereo IR, EQ flat -> the
+    # partitioned overlap-save path; default 600 s (x) 8 s, override with --seconds / --ir-seconds
+    "cfg5": dict(desc="configs[4]: long 48 kHz stereo clip (x) dense external stereo IR, EQ flat, dw 0.5, 5.1 out "
+                      "(overlap-save convolution path)",
+                 seconds=600, cin=2, amp=0.1, data_seed=5, np_seed=0, ext_ir_seconds=8.0,
+                 settings=dict(dry_wet=.5, dry_wet_kill_start=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.5, y_pos=.5,
+                               z_pos=.5, target_channel_layout="5.1 (Standard)")),
 }
 ORACLE_KW = {"hall_type": "hall", "room_size": "room_size", "diffusion": "diffusion", "air_absorption": "air",
              "base_early_level": "early", "base_late_level": "late", "dry_wet": "dry_wet_amount",
              "dry_wet_kill_start": "kill_start", "bass_gain": "bass", "treble_gain": "treble", "x_pos": "x",
              "y_pos": "y", "z_pos": "z", "material": "material", "target_channel_layout": "layout"}
+
+
+def make_ir(seconds):
+    """Dense synthetic stereo IR: Gaussian noise under an exponential decay (RT60 ~ 0.6 L), peak-normalised."""
+    L = int(seconds * RATE)
+    g = np.random.default_rng(6)
+    ir = g.standard_normal((L, 2), dtype=np.float32) * np.exp(-6.9 * np.arange(L, dtype=np.float32) / (0.6 * L))[:, None]
+    return (ir / np.max(np.abs(ir)) / np.float32(20.0)).astype(np.float32)
 
 
 def make_clip(w, seconds, seed_offset=0):
@@ -205,10 +220,20 @@ def run_ours(args):
     x = make_clip(w, seconds, rank)
     x2 = x if x.ndim == 2 else x[:, None]
     n, cin = x2.shape
-    p, refl = rs.make_render_params(RATE, want_lufs=True, **w["settings"])
-    np.random.seed(w["np_seed"] + rank)
-    taps, bases, noise = rs.draw_ir_randoms(RATE, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
-    N = int(lib.ars_render_out_len(p, n, 0))
+    ext = "ext_ir_seconds" in w
+    p, refl = rs.make_render_params(RATE, want_lufs=True, external_ir=ext, **w["settings"])
+    L = 0
+    h_ir = d_ir = None
+    if ext:
+        ir = make_ir(args.ir_seconds or w["ext_ir_seconds"])
+        L = ir.shape[0]
+        h_ir = torch.from_numpy(ir).pin_memory()
+        d_ir = h_ir.cuda()
+        taps, bases, noise = np.zeros(0, np.int64), np.zeros(0), np.zeros(0)
+    else:
+        np.random.seed(w["np_seed"] + rank)
+        taps, bases, noise = rs.draw_ir_randoms(RATE, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+    N = int(lib.ars_render_out_len(p, n, L))
     C = rs.CHANNEL_LAYOUTS[w["settings"]["target_channel_layout"]]["channels"]
 
     # pinned host buffers (e2e) and device-resident copies (value)
@@ -225,13 +250,16 @@ def run_ours(args):
     draws_d.noise_len = int(noise.size)
     m = ArsMetrics()
 
+    d_ir_ptr = d_ir.data_ptr() if ext else None
+    h_ir_ptr = h_ir.data_ptr() if ext else None
+
     def step_dev():
-        _capi.check(lib.ars_render_dev(p, d_in.data_ptr(), n, cin, None, 0, draws_d, None, None, d_pcm.data_ptr(), m),
-                    "ars_render_dev")
+        _capi.check(lib.ars_render_dev(p, d_in.data_ptr(), n, cin, d_ir_ptr, L, None if ext else draws_d, None, None,
+                                       d_pcm.data_ptr(), m), "ars_render_dev")
 
     def step_host():
-        _capi.check(lib.ars_render(p, h_in.data_ptr(), n, cin, None, 0, draws_h, None, None, h_pcm.data_ptr(), m),
-                    "ars_render")
+        _capi.check(lib.ars_render(p, h_in.data_ptr(), n, cin, h_ir_ptr, L, None if ext else draws_h, None, None,
+                                   h_pcm.data_ptr(), m), "ars_render")
 
     def barrier():
         if world > 1:
@@ -278,7 +306,10 @@ def run_ours(args):
             k.params = _capi.C.pointer(p)
             k.in_ = h_in.data_ptr()
             k.n, k.cin = n, cin
-            k.draws = _capi.C.pointer(draws_h)
+            if ext:
+                k.ext_ir, k.ext_ir_len = h_ir_ptr, L
+            else:
+                k.draws = _capi.C.pointer(draws_h)
             k.out_pcm = (h_pcm if i % 2 == 0 else h_pcm2).data_ptr()
             k.metrics = _capi.C.pointer(ms_list[i])
         _capi.check(lib.ars_render_batch(clips, count), "ars_render_batch")
@@ -329,12 +360,13 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "clip_seconds": seconds, "frames_in": n, "frames_out": N,
                    "channels_out": C, "clips_per_step": world, "parallelism": f"clip-sharded x{world}",
+                   "ir_frames": L if ext else int(p.ir_duration * RATE),
                    "l2": "working set (input 8*n B, 8*M B FFT buffers, M = 2^%d) exceeds the 126 MB L2; no flush needed"
                          % int(np.ceil(np.log2(2 * N - 1)))},
         "e2e": {"value": total_seconds / (e2e_ms * 1e-3), "unit": "audio-seconds/s", "ms_per_step": e2e_ms / args.steps,
                 "call": "ars_render_batch (host buffers, copy/compute pipelined across the steps' clips)",
                 "single_call_ms": single_ms,
-                "h2d_bytes_per_step": int(h_in.numel() * 4 + noise.size * 8 + taps.size * 16),
+                "h2d_bytes_per_step": int(h_in.numel() * 4 + noise.size * 8 + taps.size * 16 + L * 8),
                 "d2h_bytes_per_step": int(h_pcm.numel() * 2 + 56)},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -350,7 +382,7 @@ def run_ours(args):
                                           "N-point DFT the reference's EQ/air masks require needs 6 multi-pass FFTs"},
         "metrics_of_last_render": metrics_dev,
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not ext:
         line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample_seconds)
     print(json.dumps(line))
     if world > 1:
@@ -365,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--seconds", type=float, default=0.0, help="override the clip length (default: the config's)")
+    ap.add_argument("--ir-seconds", type=float, default=0.0, help="external-IR length for cfg5")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -91,6 +91,10 @@ ARS_API const char* ars_last_error(void);
 ARS_API const char* ars_version(void);
 ARS_API uint64_t ars_launch_count(void);          /* kernels this library has launched so far           */
 ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
+/* Options: "upols" (1 = use the partitioned overlap-save convolution whenever a render has no exact-N
+ * spectral mask, i.e. air <= 0.01 and both EQ gains ~ 1 [default]; 0 = always the N-point spectral filter),
+ * "upols_logf" (12 | 13: points per overlap-save transform = 2^logf, hop = half of it). */
+ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);
 ARS_API int ars_timer_end(float* ms);
@@ -180,6 +184,38 @@ typedef struct ArsClip {
     ArsMetrics* metrics;        /* or NULL                                                     */
 } ArsClip;
 ARS_API int ars_render_batch(const ArsClip* clips, int32_t count);
+
+
+/* ---- one long mask-free render split by overlap-save block ranges (one rank of a multi-GPU render) ------
+ * Only renders without an exact-N spectral mask (air <= 0.01, both EQ gains ~ 1) shard this way; the others need
+ * the global N-point transform and run on one GPU (ars_render).  All pointers are device pointers.
+ *
+ * The per-render device state is an opaque block of ars_state_bytes() bytes, zeroed by the caller.  Its words
+ * are what the ranks reduce between the phases (all values are bit patterns of non-negative floats, so an
+ * integer MAX is a float MAX):
+ *   uint32 [0..3] max |y|, max |L|, max |R|, max |float32(L+R)| of the convolution output  -> MAX after convolve
+ *   uint32 [4] max |six| (pan)                                                       -> MAX after tail phase 0
+ *   uint32 [5] max |out| (Stereo map only)                                           -> MAX after tail phase 1
+ *   uint32 [8] peak, [9] loudness-feed peak -> MAX ; double at byte 48: sum of squares -> SUM  (after phase 2)
+ *   double at byte 56: integrated loudness (written by ars_loudness_dev)
+ * Blocks are ars_ols_block_frames() frames long.  Rank r computes output blocks [block_lo, block_hi) from an
+ * input slice that starts at absolute frame x_frame0 and holds x_frames frames; it must reach back
+ * (P - 1 + 1) blocks before block_lo (P = ceil(L / block)) or to frame 0.  y / outputs are slices too. */
+ARS_API int64_t ars_state_bytes(void);
+ARS_API int64_t ars_ols_block_frames(void);
+ARS_API int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, int64_t x_frame0, int64_t x_frames,
+                                  int64_t n_total, int32_t cin, const float* d_ir0, int64_t L0, const float* d_ir1,
+                                  int64_t L1, int64_t block_lo, int64_t block_hi, float* d_y, int64_t y_frame0,
+                                  void* d_state);
+/* phase 0: pan maximum; 1: map maximum (Stereo layout only, no-op otherwise); 2: final pass writing the PCM /
+ * float / loudness-feed slices for frames [frame_lo, frame_hi) (outputs are indexed from frame_lo). */
+ARS_API int ars_long_tail_dev(const ArsRenderParams* p, int32_t phase, const float* d_y, int64_t y_frame0,
+                              int64_t frame_lo, int64_t frame_hi, int64_t N_total, void* d_state, float* d_out_f32,
+                              int16_t* d_out_pcm, float* d_mono);
+/* loudness meter on a (gathered) mono feed; enqueued, result lands in the state block */
+ARS_API int ars_loudness_dev(const float* d_mono, int64_t N, double rate, void* d_state, int32_t* lufs_status);
+/* read the state block back and turn it into metrics (synchronises) */
+ARS_API int ars_state_metrics(const void* d_state, int64_t sample_count, int32_t lufs_status, ArsMetrics* out);
 
 #ifdef __cplusplus
 }

@@ -233,7 +233,96 @@ static int check_bluestein(i64 N) {
     return (maxerr / peak < 2e-5) ? 0 : 1;
 }
 
+// Overlap-save wiring (upols.cu) on the host: IR partitions, delay line, fused MAC + inverse, block ranges.
+static void emu_segments(int logF, i64 nseg, const Tw& tw, const Ld& ld, const St& st, bool inverse) {
+    const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
+    EmuPlan p;
+    p.logM = 0;
+    PassArgs pa;
+    pa.M = nseg << logF; pa.logM = 0; pa.logLg = logF; pa.tw = tw;
+    if (logF == 12) { if (inverse) emu_contig<12, 1, true>(ld, st, pa); else emu_contig<12, 1, false>(ld, st, pa); }
+    else { if (inverse) emu_contig<13, 0, true>(ld, st, pa); else emu_contig<13, 0, false>(ld, st, pa); }
+    (void)ps;
+}
+
+static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_hi) {
+    Tw tw;
+    make_tables(logF, tw);
+    const i64 B = (i64)1 << (logF - 1), F = (i64)1 << logF;
+    const int tile = logF == 12 ? 2 : 1;
+    const i64 N = n + L - 1;
+    std::mt19937 rng((unsigned)(n * 31 + L));
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<float> x(2 * n), ir(2 * L);
+    for (auto& v : x) v = U(rng);
+    for (i64 i = 0; i < L; ++i) { float d = expf(-(float)i / (0.3f * L)); ir[2 * i] = U(rng) * d; ir[2 * i + 1] = ext ? U(rng) * d : ir[2 * i]; }
+    // make one partition all-zero to exercise the skip flags
+    if (L > 3 * B) for (i64 i = B; i < 2 * B; ++i) ir[2 * i] = ir[2 * i + 1] = 0.f;
+    const int P = (int)((L + B - 1) / B), Ppad = ((P + tile - 1) / tile) * tile;
+    const i64 nblk_all = (N + B - 1) / B;
+    if (block_hi < 0 || block_hi > nblk_all) block_hi = nblk_all;
+    const i64 seg0 = std::max<i64>(0, block_lo - (P - 1)), skip = block_lo - seg0;
+    const i64 run = ((block_hi - block_lo + tile - 1) / tile) * tile;
+    const i64 nseg = ((skip + run + tile - 1) / tile) * tile;
+    const int nspec = ext ? 2 : 1;
+    std::vector<float2> H((size_t)Ppad * F * nspec), X((size_t)nseg * F * nspec), y(N, make_float2(0, 0));
+    std::vector<unsigned char> nz(Ppad, 0);
+    for (int p = 0; p < P; ++p)
+        for (i64 i = p * B; i < std::min(L, (p + 1) * B); ++i) if (ir[2 * i] != 0.f || ir[2 * i + 1] != 0.f) nz[p] = 1;
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld; ld.mode = LD_OLS_IR; ld.logF = logF; ld.f0 = ir.data(); ld.f1 = ir.data() + 1; ld.cin = 2;
+        ld.nvalid = ld.nvalid1 = L;
+        if (ext) { ld.c0 = 0.5f; ld.c1 = k == 0 ? 0.5f : -0.5f; } else { ld.c0 = 1.f; ld.c1 = 0.f; }
+        St st; st.mode = ST_SCALE; st.a = H.data() + (size_t)k * Ppad * F; st.scale = 1.0f / (float)F;
+        emu_segments(logF, Ppad, tw, ld, st, false);
+    }
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld; ld.mode = LD_OLS_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = 2;
+        ld.seg0 = seg0; ld.c1 = k == 0 ? 0.f : -1.f;
+        St st; st.mode = ST_PLAIN; st.a = X.data() + (size_t)k * nseg * F;
+        emu_segments(logF, nseg, tw, ld, st, false);
+    }
+    unsigned maxbits[4] = {0, 0, 0, 0};
+    {
+        Ld ld; ld.mode = LD_OLS_MAC; ld.logF = logF; ld.a = X.data() + skip * F; ld.b = H.data();
+        ld.a2 = ext ? X.data() + (size_t)nseg * F + skip * F : nullptr; ld.b2 = ext ? H.data() + (size_t)Ppad * F : nullptr;
+        ld.nz = nz.data(); ld.P = P; ld.lookback = skip;
+        St st; st.mode = ST_OLS; st.logF = logF; st.seg0 = block_lo; st.a = y.data(); st.frame0 = 0;
+        st.N = std::min<i64>(N, block_hi * B); st.dry = x.data(); st.dry_frame0 = 0; st.n = n; st.cin = 2;
+        st.dg = 0.25f; st.dw = 0.5f; st.maxbits = maxbits;
+        emu_segments(logF, run, tw, ld, st, true);
+    }
+    double maxerr = 0, peak = 0;
+    const i64 f_lo = block_lo * B, f_hi = std::min<i64>(N, block_hi * B);
+    const i64 stepf = std::max<i64>(1, (f_hi - f_lo) / 400);
+    for (i64 f = f_lo; f < f_hi; f += stepf) {
+        double wl = 0, wr = 0;
+        for (i64 m = std::max<i64>(0, f - n + 1); m < std::min<i64>(L, f + 1); ++m) {
+            wl += (double)ir[2 * m] * x[2 * (f - m)];
+            wr += (double)ir[2 * m + 1] * x[2 * (f - m) + 1];
+        }
+        const double rl = 0.25 * (f < n ? x[2 * f] : 0) + 0.5 * wl, rr = 0.25 * (f < n ? x[2 * f + 1] : 0) + 0.5 * wr;
+        peak = std::max(peak, std::max(fabs(rl), fabs(rr)));
+        maxerr = std::max(maxerr, std::max(fabs(rl - y[f].x), fabs(rr - y[f].y)));
+    }
+    printf("ols logF=%d n=%lld L=%lld ext=%d blocks[%lld,%lld): max err %.3e (peak %.2f) rel %.3e\n", logF, (long long)n,
+           (long long)L, (int)ext, (long long)block_lo, (long long)block_hi, maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5 && maxbits[0] != 0) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "ols")) {
+        int bad = 0;
+        bad += check_ols(12, 20000, 5000, false, 0, -1);
+        bad += check_ols(13, 50001, 20000, false, 0, -1);
+        bad += check_ols(12, 30000, 9000, true, 0, -1);
+        bad += check_ols(13, 70000, 9000, true, 3, 9);
+        bad += check_ols(12, 60000, 7000, false, 5, 12);
+        bad += check_ols(12, 60000, 7000, false, 12, -1);
+        bad += check_ols(13, 3000, 100, false, 0, -1);
+        printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
+        return bad ? 1 : 0;
+    }
     int bad = 0;
     bool blue = false;
     for (int i = 1; i < argc; ++i) {

@@ -328,3 +328,104 @@ def test_batch_pipeline_equals_single_renders(rs):
         assert np.array_equal(a["final"], b["final"])
         assert np.array_equal(a["pcm"], b["pcm"])
         assert a["metrics"] == b["metrics"]
+
+
+@pytest.mark.parametrize("logf", [12, 13])
+def test_overlap_save_path_matches_oracle_and_n_point_path(rs, golden, logf):
+    """Mask-free renders run through the partitioned overlap-save convolution (K2-K4).  Same bars as the N-point
+    path, checked against the golden vectors, the oracle, and against the N-point path itself."""
+    from ars_b200 import _capi
+    g = golden("convolve")
+    keys = [str(k) for k in g["x_keys"]]
+    try:
+        _capi.set_option("upols_logf", logf)
+        for use in (1, 0):
+            _capi.set_option("upols", use)
+            for i, p in enumerate(g["split_par"]):
+                el, ll, dw, b, t, ks, air = p[1:8]
+                if air > 0.01 or b != 1.0 or t != 1.0:
+                    continue                                    # masked cases never take the overlap-save path
+                got = rs.convolve_audio_split_3d(g["x_" + keys[int(p[0])]], g["early"], g["late"], el, ll, dw, b, t, 48000,
+                                                 ks, air)
+                assert rel_err(got, g[f"split{i}"]) <= TOL, (use, i, rel_err(got, g[f"split{i}"]))
+            for i, p in enumerate(g["ext_par"]):
+                dw, b, t, ks = p[1:5]
+                if b != 1.0 or t != 1.0:
+                    continue
+                got = rs.convolve_audio_external_ir(g["x_" + keys[int(p[0])]], g["ext_ir"], dw, b, t, 48000, ks)
+                assert rel_err(got, g[f"ext{i}"]) <= TOL, (use, i)
+                assert snr_db(got, g[f"ext{i}"]) >= 100.0
+        # a longer dense stereo IR (many partitions, one of them silent) against scipy through the oracle
+        rg = np.random.default_rng(31)
+        x = (0.2 * rg.standard_normal((150001, 2))).astype(np.float32)
+        ir = (rg.standard_normal((40000, 2)) * np.exp(-np.arange(40000) / 9000.0)[:, None]).astype(np.float32)
+        ir[8192:12288] = 0
+        ir /= np.max(np.abs(ir)) * 40
+        want = orc.convolve_external(x, ir, .7, 1.0, 1.0, 48000, .5)
+        _capi.set_option("upols", 1)
+        a = rs.convolve_audio_external_ir(x, ir, .7, 1.0, 1.0, 48000, .5)
+        _capi.set_option("upols", 0)
+        b = rs.convolve_audio_external_ir(x, ir, .7, 1.0, 1.0, 48000, .5)
+        assert rel_err(a, want) <= TOL and rel_err(b, want) <= TOL and rel_err(a, b) <= TOL
+        assert snr_db(a, want) >= 100.0
+        # whole render, procedural IR, mono input, 7.1
+        kw = dict(hall_type="Plate", room_size=300., air_absorption=0.0, dry_wet=.45, bass_gain=1.0, treble_gain=1.0,
+                  x_pos=.6, y_pos=.3, z_pos=.8, material="Glas", target_channel_layout="7.1 (Surround)")
+        xm = (0.3 * rg.standard_normal(96000)).astype(np.float32)
+        res = []
+        for use in (1, 0):
+            _capi.set_option("upols", use)
+            np.random.seed(77)
+            res.append(rs.render_array(xm, 48000, want_stereo=True, **kw))
+        np.random.seed(77)
+        want = orc.render(xm, 48000, hall="Plate", room_size=300., air=0.0, dry_wet_amount=.45, x=.6, y=.3, z=.8,
+                          material="Glas", layout="7.1 (Surround)")
+        for r in res:
+            assert rel_err(r["final"], want["final"]) <= TOL
+            assert abs(r["metrics"]["lufs"] - want["metrics"]["lufs"]) <= 5e-3
+    finally:
+        _capi.set_option("upols", 1)
+        _capi.set_option("upols_logf", 13)
+
+
+@pytest.mark.parametrize("layout", ["5.1 (Standard)", "5.1.2 (Atmos Light)", "Stereo"])
+def test_block_sharded_long_render_is_bit_identical(rs, layout):
+    """splitting a mask-free render by overlap-save block ranges must not change a bit.
+    Several ranks are emulated on the one GPU; the collectives between the phases are done with numpy."""
+    import torch
+    from ars_b200 import sharding as sh
+    g = np.random.default_rng(41)
+    rate = 48000
+    x = (0.9 * g.standard_normal((230011, 2))).astype(np.float32)          # loud: the stereo guard and the pan guard fire
+    ir = (g.standard_normal((21000, 2)) * np.exp(-np.arange(21000) / 5000.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir)) * 8
+    settings = dict(dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.3, y_pos=.6, z_pos=.7,
+                    target_channel_layout=layout)
+    whole = rs.render_array(x, rate, external_ir_data=ir, **settings)
+    for world in (1, 3):
+        ranks = [sh.LongRenderRank(x, rate, ir, settings, r, world) for r in range(world)]
+
+        def reduce(view_of, op):
+            vals = torch.stack([view_of(r).clone() for r in ranks])
+            red = vals.max(dim=0).values if op == "max" else vals.sum(dim=0)
+            for r in ranks:
+                view_of(r).copy_(red)
+            torch.cuda.synchronize()
+
+        for r in ranks: r.convolve()
+        reduce(lambda r: r.words()[0:4], "max")
+        for r in ranks: r.pan_max()
+        reduce(lambda r: r.words()[4:5], "max")
+        for r in ranks: r.map_max()
+        reduce(lambda r: r.words()[5:6], "max")
+        for r in ranks: r.final()
+        reduce(lambda r: r.words()[8:10], "max")
+        reduce(lambda r: r.sumsq(), "sum")
+        pcm = torch.cat([r.d_pcm[:r.frames()] for r in ranks], dim=0).cpu().numpy()
+        mono = torch.cat([r.d_mono[:r.frames()] for r in ranks], dim=0).contiguous()
+        m = sh.finish_long_render(ranks[0], mono, ranks[0].N * ranks[0].C)
+        assert pcm.shape == whole["pcm"].shape
+        assert np.array_equal(pcm, whole["pcm"]), f"world {world}: PCM differs from the single-GPU render"
+        assert m["true_peak_dbfs"] == whole["metrics"]["true_peak_dbfs"]
+        assert abs(m["rms_dbfs"] - whole["metrics"]["rms_dbfs"]) < 1e-6
+        assert abs(m["lufs"] - whole["metrics"]["lufs"]) < 1e-9

@@ -52,6 +52,8 @@ def test_fft_engine_host_emulation():
     assert r.returncode == 0, r.stdout[-2000:]
     r = subprocess.run([exe, "blue", "1", "2", "3", "37", "4099", "6000", "70001"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+    r = subprocess.run([exe, "ols"], capture_output=True, text=True)      # overlap-save wiring incl. block ranges
+    assert r.returncode == 0, r.stdout[-2000:]
     env = dict(os.environ, ARS_FFT_PLAN="6,6,7")
     r = subprocess.run([exe, "19"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-2000:]

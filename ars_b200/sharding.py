@@ -231,13 +231,14 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, **settin
     mono_pad = torch.zeros(pad, dtype=torch.float32, device=dev)
     pcm_pad[:r.frames()] = r.d_pcm[:r.frames()]
     mono_pad[:r.frames()] = r.d_mono[:r.frames()]
-    pcm_list = [torch.empty_like(pcm_pad) for _ in range(world)] if rank == 0 else None
+    pcm_bytes = pcm_pad.view(torch.uint8)                   # NCCL has no int16: ship the PCM frames as bytes
+    byte_list = [torch.empty_like(pcm_bytes) for _ in range(world)] if rank == 0 else None
     mono_list = [torch.empty_like(mono_pad) for _ in range(world)] if rank == 0 else None
-    dist.gather(pcm_pad, pcm_list, dst=0, group=group)       # output segments gathered over NVLink
+    dist.gather(pcm_bytes, byte_list, dst=0, group=group)    # output segments gathered over NVLink
     dist.gather(mono_pad, mono_list, dst=0, group=group)
     if rank != 0:
         return None
-    pcm = torch.cat([t[:c] for t, c in zip(pcm_list, counts)], dim=0)
+    pcm = torch.cat([t.view(torch.int16)[:c] for t, c in zip(byte_list, counts)], dim=0)
     mono = torch.cat([t[:c] for t, c in zip(mono_list, counts)], dim=0).contiguous()
     metrics = finish_long_render(r, mono, r.N * r.C)
     return {"pcm": pcm.cpu().numpy(), "metrics": metrics, "names": names}

@@ -14,7 +14,8 @@ void DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return;
     if (p) { ARS_CUDA(cudaFree(p)); p = nullptr; cap = 0; }
     // round up so slightly different clip lengths reuse the same allocation
-    size_t want = (bytes + (size_t)(1 << 20) - 1) & ~((size_t)(1 << 20) - 1);
+    // (and with 25 % head-room, so a batch of clips of varying length settles after a few reallocations)
+    size_t want = (bytes + bytes / 4 + (size_t)(1 << 20) - 1) & ~((size_t)(1 << 20) - 1);
     if (bytes < (1 << 20)) want = (bytes + 255) & ~(size_t)255;
     ARS_CUDA(cudaMalloc(&p, want));
     cap = want;

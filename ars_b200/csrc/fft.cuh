@@ -688,7 +688,7 @@ template <int LOGR, int LOGT> struct StridedTile {
 };
 
 template <int LOGR, int LOGT, bool INV, int NT, int LDM, int STM>
-__global__ void __launch_bounds__(NT) pass_strided_kernel(Ld ld, St st, PassArgs pa) {
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_strided_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
     const StridedTile<LOGR, LOGT> t((i64)blockIdx.x, pa);
     run_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>, LDM, STM>(
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(NT) pass_strided_kernel(Ld ld, St st, PassArgs
 
 // Contiguous pass: tile = C whole segments of R adjacent elements.
 template <int LOGR, int LOGC, bool INV, int NT, int LDM, int STM>
-__global__ void __launch_bounds__(NT) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
     const i64 base = (i64)blockIdx.x << (LOGR + LOGC);
     run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>, LDM, STM>(sm, ld, st, pa, ContigFirst<LOGR>{base},

@@ -154,7 +154,7 @@ static cudaEvent_t prof_event() {
 }
 
 // --------------------------------------------------------------- launchers ---
-constexpr int NT = 256;
+constexpr int NT = 512;
 
 template <int LOGR, int LOGT, bool INV, int LDM, int STM>
 static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {

@@ -22,13 +22,37 @@ __global__ void chirp_kernel(float2* out, i64 N) {
 static const size_t BLUE_CACHE_BYTES = (size_t)48 << 30;   // plan cache cap (HBM is 180 GB)
 static const size_t BLUE_CACHE_PLANS = 16;
 
-static void drop_plan(Ctx& c, i64 N) {
+// Buffers of evicted plans are recycled, not freed: everything runs in order on the library's compute stream, so a
+// buffer can be handed to the next plan without waiting (cudaFree / cudaMalloc would serialise the whole pipeline
+// for every clip of a batch whose clips all have different lengths).
+static std::vector<DevBuf> g_plan_pool;
+
+static DevBuf take_buffer(size_t bytes) {
+    int best = -1;
+    for (size_t i = 0; i < g_plan_pool.size(); ++i)
+        if (g_plan_pool[i].cap >= bytes && (best < 0 || g_plan_pool[i].cap < g_plan_pool[(size_t)best].cap)) best = (int)i;
+    DevBuf b;
+    if (best >= 0 && g_plan_pool[(size_t)best].cap <= 2 * bytes + ((size_t)1 << 20)) {
+        b = g_plan_pool[(size_t)best];
+        g_plan_pool.erase(g_plan_pool.begin() + best);
+        return b;
+    }
+    b.reserve(bytes);
+    return b;
+}
+
+static void drop_plan(Ctx& c, i64 N, bool to_pool) {
     auto it = c.blue_plans.find(N);
     if (it == c.blue_plans.end()) return;
     BluesteinPlan* p = it->second;
     c.blue_bytes -= p->bytes;
-    p->chirp.release();
-    p->bspec.release();
+    if (to_pool && g_plan_pool.size() < 32) {
+        g_plan_pool.push_back(p->chirp);
+        g_plan_pool.push_back(p->bspec);
+    } else {
+        p->chirp.release();
+        p->bspec.release();
+    }
     delete p;
     c.blue_plans.erase(it);
 }
@@ -36,8 +60,10 @@ static void drop_plan(Ctx& c, i64 N) {
 void bluestein_release_plans() {
     if (!ctx_ready()) return;
     Ctx& c = ctx();
-    while (!c.blue_plans.empty()) drop_plan(c, c.blue_plans.begin()->first);
+    while (!c.blue_plans.empty()) drop_plan(c, c.blue_plans.begin()->first, false);
     c.blue_lru.clear();
+    for (auto& b : g_plan_pool) b.release();
+    g_plan_pool.clear();
 }
 
 BluesteinPlan* get_bluestein_plan(i64 N) {
@@ -55,16 +81,14 @@ BluesteinPlan* get_bluestein_plan(i64 N) {
     p->logM = std::max(1, next_pow2_log(2 * N - 1));
     p->M = (i64)1 << p->logM;
     p->bytes = sizeof(float2) * (size_t)(N + p->M);
-    // make room first (the stream is in-order, so freeing after queued work is safe only after a sync)
     while (!c.blue_lru.empty() &&
            (c.blue_bytes + p->bytes > BLUE_CACHE_BYTES || c.blue_plans.size() >= BLUE_CACHE_PLANS)) {
-        ARS_CUDA(cudaStreamSynchronize(c.stream));
-        drop_plan(c, c.blue_lru.front());
+        drop_plan(c, c.blue_lru.front(), true);
         c.blue_lru.erase(c.blue_lru.begin());
     }
     p->fft = get_fft_plan(p->logM);
-    p->chirp.reserve(sizeof(float2) * (size_t)N);
-    p->bspec.reserve(sizeof(float2) * (size_t)p->M);
+    p->chirp = take_buffer(sizeof(float2) * (size_t)N);
+    p->bspec = take_buffer(sizeof(float2) * (size_t)p->M);
     chirp_kernel<<<ceil_div(N, 256), 256, 0, c.stream>>>(p->chirp.as<float2>(), N);
     ARS_LAUNCH_CHECK();
     count_launch();

@@ -389,20 +389,122 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def cfg4_presets(count, first=0):
+    """BASELINE configs[3] / SURVEY 8(d): random presets drawn from the UI ranges, one np.random seed per clip."""
+    halls = ["Plate", "Room", "Cathedral"]
+    mats = ["Stein", "Holz", "Teppich", "Glas", "Beton", "Vorhang (schwer)"]
+    out = []
+    for i in range(first, first + count):
+        g = np.random.default_rng([4, i])
+        u = g.uniform(0, 1, 7)
+        out.append(dict(seed=1000 + i, hall_type=halls[int(g.integers(3))], material=mats[int(g.integers(6))],
+                        room_size=float(10 * g.integers(1, 101)), diffusion=u[0], air_absorption=u[1], dry_wet=u[2],
+                        dry_wet_kill_start=u[3], x_pos=u[4], y_pos=u[5], z_pos=u[6],
+                        base_early_level=float(g.uniform(0, 2)), base_late_level=float(g.uniform(0, 2)),
+                        bass_gain=1.0 if g.uniform() < .5 else float(g.uniform(.1, 5)),
+                        treble_gain=1.0 if g.uniform() < .5 else float(g.uniform(.1, 5)),
+                        target_channel_layout="7.1 (Surround)"))
+    return out
+
+
+def run_cfg4(args):
+    """Batch of 30 s stereo clips with random presets (configs[3]); clips are split over the ranks, no collective on
+    the data path.  Not the headline line: an extra measurement of the small-clip regime (FFT buffers fit the L2)."""
+    import torch
+    import torch.distributed as dist
+    from ars_b200 import _capi, raytracer_studio as rs, sharding as sh
+    from ars_b200._capi import ArsMetrics
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _capi.init(local)
+    total = args.clips
+    mine = sh.partition_clips([1] * total, world)[rank]
+    presets = cfg4_presets(total)
+    n = int(30 * RATE)
+    distinct = 8                                       # distinct input buffers, reused round-robin
+    h_in = [torch.from_numpy((0.25 * np.random.default_rng(4000 + j).standard_normal((n, 2), dtype=np.float32))
+                             .astype(np.float32)).pin_memory() for j in range(distinct)]
+    keep, clips_meta = [], []
+    for i in mine:
+        st = dict(presets[i])
+        seed = st.pop("seed")
+        p, refl = rs.make_render_params(RATE, want_lufs=True, **st)
+        np.random.seed(seed)
+        taps, bases, noise = rs.draw_ir_randoms(RATE, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+        h_noise = torch.from_numpy(noise).pin_memory()
+        draws = _capi.make_draws(taps, bases, h_noise.numpy(), keep)
+        N = int(lib.ars_render_out_len(p, n, 0))
+        clips_meta.append((p, draws, h_noise, N, i))
+    Nmax = max(m[3] for m in clips_meta)
+    h_pcm = [torch.empty((Nmax, 8), dtype=torch.int16).pin_memory() for _ in range(2)]
+    mets = [ArsMetrics() for _ in clips_meta]
+
+    def batch():
+        arr = (_capi.ArsClip * len(clips_meta))()
+        for j, (p, draws, h_noise, N, i) in enumerate(clips_meta):
+            k = arr[j]
+            k.params = _capi.C.pointer(p)
+            k.in_ = h_in[i % distinct].data_ptr()
+            k.n, k.cin = n, 2
+            k.draws = _capi.C.pointer(draws)
+            k.out_pcm = h_pcm[j % 2].data_ptr()
+            k.metrics = _capi.C.pointer(mets[j])
+        _capi.check(lib.ars_render_batch(arr, len(clips_meta)), "ars_render_batch")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch()                                             # warm-up: plans, workspaces
+    barrier()
+    l0 = int(lib.ars_launch_count())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch()
+    dt = time.perf_counter() - t0
+    launches = int(lib.ars_launch_count()) - l0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        secs = 30.0 * total * args.steps
+        print(json.dumps({"metric": "audio-seconds rendered per second (x realtime) @48kHz, batch of 30 s clips",
+                          "value": secs / dt, "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": 1, "ms_per_step": 1000 * dt / args.steps, "ms_per_clip": 1000 * dt / args.steps / total * world,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "gpu_launches": launches,
+                          "config": {"workload": f"configs[3]: {total} x 30 s stereo clips, random presets (SURVEY 8d), "
+                                                 "5.1 pan -> 7.1 map, metrics, int16 PCM out; host buffers in/out through "
+                                                 "ars_render_batch", "clips": total, "parallelism": f"clip-sharded x{world}"},
+                          "e2e": {"value": secs / dt, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(len(mine) * n * 8),
+                                  "d2h_bytes_per_step": int(sum(m[3] for m in clips_meta) * 16)},
+                          "example_metrics": rs._metrics_dict(mets[0])}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--clips", type=int, default=128, help="cfg4: clips in the batch (BASELINE: 1024)")
     ap.add_argument("--seconds", type=float, default=0.0, help="override the clip length (default: the config's)")
     ap.add_argument("--ir-seconds", type=float, default=0.0, help="external-IR length for cfg5")
     ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "cfg4" and args.impl != "reference":
+        run_cfg4(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -429,3 +429,68 @@ def test_block_sharded_long_render_is_bit_identical(rs, layout):
         assert m["true_peak_dbfs"] == whole["metrics"]["true_peak_dbfs"]
         assert abs(m["rms_dbfs"] - whole["metrics"]["rms_dbfs"]) < 1e-6
         assert abs(m["lufs"] - whole["metrics"]["lufs"]) < 1e-9
+
+
+def test_random_presets_vs_oracle(rs):
+    """Presets drawn from the UI ranges, plus the edge values the reference special-cases:
+    dw 0 / 1, kill 1, air just below / above its gate, gains inside np.isclose(1), odd / even N, unknown names."""
+    g = np.random.default_rng(2024)
+    halls = ["Plate", "Room", "Cathedral", "Aula"]
+    mats = ["Stein", "Holz", "Teppich", "Glas", "Beton", "Vorhang (schwer)", "Filz"]
+    lays = ["Stereo", "5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)", "22.2"]
+    edge = [dict(dry_wet=0.0), dict(dry_wet=1.0), dict(dry_wet_kill_start=1.0, dry_wet=.9), dict(air_absorption=0.0099),
+            dict(air_absorption=0.0101), dict(bass_gain=1.000009, treble_gain=0.999995), dict(bass_gain=1.00002),
+            dict(base_early_level=0.0), dict(base_late_level=1e-7), dict(x_pos=0.0, y_pos=1.0, z_pos=0.0),
+            dict(x_pos=1.7, y_pos=-0.3, z_pos=2.0), dict(dry_wet_kill_start=0.0, dry_wet=.5)]
+    worst = 0.0
+    for i in range(28):
+        n = int(g.integers(9000, 30000))
+        cin = int(g.choice([1, 2, 2, 3]))
+        x = (g.uniform(0.05, 0.9) * g.standard_normal((n, cin))).astype(np.float32)
+        if cin == 1 and i % 2:
+            x = x[:, 0]
+        kw = dict(hall_type=str(g.choice(halls)), material=str(g.choice(mats)), room_size=float(10 * g.integers(1, 101)),
+                  diffusion=float(g.uniform()), air_absorption=float(g.uniform()), dry_wet=float(g.uniform()),
+                  dry_wet_kill_start=float(g.uniform()), x_pos=float(g.uniform()), y_pos=float(g.uniform()),
+                  z_pos=float(g.uniform()), base_early_level=float(g.uniform(0, 2)), base_late_level=float(g.uniform(0, 2)),
+                  bass_gain=1.0 if g.uniform() < .5 else float(g.uniform(.1, 5)),
+                  treble_gain=1.0 if g.uniform() < .5 else float(g.uniform(.1, 5)),
+                  target_channel_layout=str(g.choice(lays)))
+        if i < len(edge):
+            kw.update(edge[i])
+        rate = int(g.choice([16000, 44100, 48000]))
+        np.random.seed(500 + i)
+        got = rs.render_array(x, rate, want_stereo=True, **kw)
+        np.random.seed(500 + i)
+        want = orc.render(x, rate, hall=kw["hall_type"], room_size=kw["room_size"], diffusion=kw["diffusion"],
+                          air=kw["air_absorption"], early=kw["base_early_level"], late=kw["base_late_level"],
+                          dry_wet_amount=kw["dry_wet"], kill_start=kw["dry_wet_kill_start"], bass=kw["bass_gain"],
+                          treble=kw["treble_gain"], x=kw["x_pos"], y=kw["y_pos"], z=kw["z_pos"], material=kw["material"],
+                          layout=kw["target_channel_layout"])
+        assert got["final"].shape == want["final"].shape, (i, kw)
+        e = max(rel_err(got["stereo"], want["stereo"]), rel_err(got["final"], want["final"]))
+        worst = max(worst, e)
+        assert e <= TOL, (i, e, kw)
+        d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+        assert d.max() <= 1, (i, kw)
+        for k in ("true_peak_dbfs", "rms_dbfs"):
+            a, b = got["metrics"][k], want["metrics"][k]
+            assert (a == b) if np.isinf(b) else abs(a - b) <= 2e-3, (i, k, a, b)
+        a, b = got["metrics"]["lufs"], want["metrics"]["lufs"]
+        assert (a is None and b is None) or (np.isinf(b) and a == b) or abs(a - b) <= 1e-2, (i, a, b)
+    print("worst relative error over the preset sweep:", worst)
+
+
+def test_silent_and_tiny_inputs(rs):
+    z = np.zeros((20000, 2), np.float32)
+    np.random.seed(1)
+    r = rs.render_array(z, 48000, hall_type="Room", bass_gain=2.0, target_channel_layout="7.1 (Surround)")
+    assert not r["final"].any() and not r["pcm"].any()
+    assert r["metrics"]["lufs"] == -np.inf and r["metrics"]["true_peak_dbfs"] == -np.inf
+    t = (1e-12 * np.random.default_rng(0).standard_normal((15000, 2))).astype(np.float32)
+    np.random.seed(1)
+    got = rs.render_array(t, 48000, hall_type="Plate", air_absorption=0.0, want_stereo=True)
+    np.random.seed(1)
+    want = orc.render(t, 48000, hall="Plate", air=0.0)
+    assert np.array_equal(got["stereo"] != 0, want["stereo"] != 0) or rel_err(got["stereo"], want["stereo"]) <= TOL
+    assert rel_err(got["final"], want["final"]) <= TOL

@@ -212,11 +212,14 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         ARS_CHECK(!draws || draws->noise_len == g.late_len || draws->noise == nullptr,
                   "render: noise length does not match the IR geometry");
         ARS_CHECK(g.late_len == 0 || (draws && draws->noise), "render: tail noise missing");
-        const IrSpec sp = ir_spec(p->rate, p->ir_duration, p->absorption, p->directionality, p->diffusion, g, ntaps);
+        IrSpec sp = ir_spec(p->rate, p->ir_duration, p->absorption, p->directionality, p->diffusion, g, ntaps);
         std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
-        // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, so `strength` may die)
-        const i64* d_delay = upload("ir.delay", draws ? (const i64*)draws->tap_delay : nullptr, (size_t)ntaps);
-        const double* d_strength = upload("ir.strength", strength.data(), (size_t)ntaps);
+        std::vector<i64> tap_pos;
+        std::vector<double> tap_val;
+        sp.ntaps = ir_early_taps(draws ? (const i64*)draws->tap_delay : nullptr, strength.data(), ntaps, g.length, tap_pos, tap_val);
+        // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, so the vectors may die)
+        const i64* d_delay = upload("ir.delay", tap_pos.data(), tap_pos.size());
+        const double* d_strength = upload("ir.strength", tap_val.data(), tap_val.size());
         float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();
         float* d_late = c.buf("ir.late", sizeof(float) * (size_t)g.length).as<float>();
         ir_synth(sp, d_delay, d_strength, draws ? draws->noise : nullptr, d_early, d_late);
@@ -375,10 +378,13 @@ int ars_ir_synth(double rate, double ir_duration, double ir_max_delay, double ab
     const int ntaps = draws ? draws->ntaps : 0;
     ARS_CHECK(g.late_len == 0 || (draws && draws->noise && draws->noise_len == g.late_len),
               "ars_ir_synth: tail noise missing or of the wrong length");
-    const IrSpec sp = ir_spec(rate, ir_duration, absorption, directionality, diffusion, g, ntaps);
+    IrSpec sp = ir_spec(rate, ir_duration, absorption, directionality, diffusion, g, ntaps);
     std::vector<double> strength = tap_strengths(draws, absorption, directionality, g.tap_hi);
-    const i64* d_delay = upload("ir.delay", draws ? (const i64*)draws->tap_delay : nullptr, (size_t)ntaps);
-    const double* d_strength = upload("ir.strength", strength.data(), (size_t)ntaps);
+    std::vector<i64> tap_pos;
+    std::vector<double> tap_val;
+    sp.ntaps = ir_early_taps(draws ? (const i64*)draws->tap_delay : nullptr, strength.data(), ntaps, g.length, tap_pos, tap_val);
+    const i64* d_delay = upload("ir.delay", tap_pos.data(), tap_pos.size());
+    const double* d_strength = upload("ir.strength", tap_val.data(), tap_val.size());
     const double* d_noise = upload("ir.noise", draws ? draws->noise : nullptr, (size_t)g.late_len);
     Ctx& c = ctx();
     float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();

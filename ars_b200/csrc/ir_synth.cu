@@ -9,6 +9,9 @@
 //          envelope, peak 0.7
 #include "ir_synth.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 namespace ars {
 
 struct IrStats {
@@ -101,29 +104,39 @@ __global__ void __launch_bounds__(256) ir_late_norm_kernel(float* __restrict__ l
         late_tail[i] = __fmul_rn(__fdiv_rn(late_tail[i], pk), 0.7f);
 }
 
-// one thread: taps collide, and the accumulation order is the reference's draw order
-__global__ void ir_early_kernel(float* __restrict__ early, i64 length, const i64* __restrict__ delay,
-                                const double* __restrict__ strength, int ntaps) {
-    if (blockIdx.x || threadIdx.x) return;
+// The early part has at most a few dozen taps: the host merges colliding taps in the reference's draw order and
+// normalises them (ir_early_taps below, same float64 -> float32 roundings as numpy); the device only scatters.
+__global__ void ir_scatter_kernel(float* __restrict__ early, i64 length, const i64* __restrict__ pos,
+                                  const double* __restrict__ val, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && pos[j] >= 0 && pos[j] < length) early[pos[j]] = (float)val[j];
+}
+
+int ir_early_taps(const i64* delay, const double* strength, int ntaps, i64 length, std::vector<i64>& pos,
+                  std::vector<double>& val) {
+    // rs.py:268: early[d] += strength  (float32 element + float64 scalar, rounded back to float32), in draw order
+    pos.clear();
+    val.clear();
+    std::vector<float> acc;
     for (int j = 0; j < ntaps; ++j) {
         const i64 d = delay[j];
         if (d < 0 || d >= length) continue;
-        early[d] = __double2float_rn(__dadd_rn((double)early[d], strength[j]));     // rs.py:268
+        size_t k = 0;
+        while (k < pos.size() && pos[k] != d) ++k;
+        if (k == pos.size()) { pos.push_back(d); acc.push_back(0.f); }
+        acc[k] = (float)((double)acc[k] + strength[j]);
     }
-    if (length <= 1) return;
-    float pk = 0.f;
-    for (int j = 0; j < ntaps; ++j) {
-        const i64 d = delay[j];
-        if (d >= 1 && d < length) pk = fmaxf(pk, fabsf(early[d]));
+    // rs.py:299-300: early[1:] = (early[1:] / max) * 0.9 when max > 1e-6 (float32 arithmetic)
+    if (length > 1) {
+        float pk = 0.f;
+        for (size_t k = 0; k < pos.size(); ++k)
+            if (pos[k] >= 1) pk = std::max(pk, std::fabs(acc[k]));
+        if (pk > 1e-6f)
+            for (size_t k = 0; k < pos.size(); ++k)
+                if (pos[k] >= 1) { const float q = acc[k] / pk; acc[k] = q * 0.9f; }
     }
-    if (!(pk > 1e-6f)) return;                        // rs.py:299-300
-    for (int j = 0; j < ntaps; ++j) {
-        const i64 d = delay[j];
-        if (d < 1 || d >= length) continue;
-        bool seen = false;
-        for (int q = 0; q < j; ++q) seen |= (delay[q] == d);
-        if (!seen) early[d] = __fmul_rn(__fdiv_rn(early[d], pk), 0.9f);
-    }
+    val.assign(acc.begin(), acc.end());
+    return (int)pos.size();
 }
 
 void ir_synth(const IrSpec& sp, const i64* d_delay, const double* d_strength, const double* d_noise, float* d_early,
@@ -132,8 +145,8 @@ void ir_synth(const IrSpec& sp, const i64* d_delay, const double* d_strength, co
     ARS_CHECK(sp.length >= 1 && sp.split >= 0 && sp.split <= sp.length, "ir_synth: bad geometry");
     ARS_CUDA(cudaMemsetAsync(d_early, 0, sizeof(float) * (size_t)sp.length, c.stream));
     ARS_CUDA(cudaMemsetAsync(d_late, 0, sizeof(float) * (size_t)sp.length, c.stream));
-    if (sp.ntaps > 0) {
-        ir_early_kernel<<<1, 32, 0, c.stream>>>(d_early, sp.length, d_delay, d_strength, sp.ntaps);
+    if (sp.ntaps > 0) {       // d_delay / d_strength hold the merged, normalised taps (ir_early_taps)
+        ir_scatter_kernel<<<ceil_div(sp.ntaps, 128), 128, 0, c.stream>>>(d_early, sp.length, d_delay, d_strength, sp.ntaps);
         ARS_LAUNCH_CHECK();
         count_launch();
     }

@@ -13,7 +13,12 @@ struct IrSpec {
     int ntaps = 0;      // taps that passed the 0 < delay < split test      rs.py:263
 };
 
-// d_delay/d_strength: ntaps entries in draw order (strength already shaped, rs.py:265-267);
+// Host side of the early part: merge the taps (draw order, collisions accumulate) and normalise them exactly as numpy
+// does (rs.py:268, 299-300).  -> number of distinct positions; pos / val are what ir_synth scatters.
+int ir_early_taps(const i64* delay, const double* strength, int ntaps, i64 length, std::vector<i64>& pos,
+                  std::vector<double>& val);
+
+// d_delay/d_strength: sp.ntaps merged positions / final float32 values from ir_early_taps (as doubles);
 // d_noise: (length - split) float64 raw uniform noise.  Outputs: float32[length] each.
 void ir_synth(const IrSpec& sp, const i64* d_delay, const double* d_strength, const double* d_noise, float* d_early,
               float* d_late);

@@ -96,7 +96,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile(delete=False, suffix=".csv", prefix="clocks_")
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -491,7 +491,7 @@ def run_cfg4(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])

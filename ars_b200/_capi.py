@@ -65,6 +65,7 @@ PROTOTYPES = {
     "ars_ir_geometry": (C.c_int, [_d, _d, _d, _d, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                                   C.POINTER(_i64)]),
     "ars_air_filter": (C.c_int, [_p, _i64, _d, _d, _p]),
+    "ars_resample": (C.c_int, [_p, _i64, _i64, _p]),
     "ars_dry_wet_mix": (C.c_int, [_p, _i64, _p, _i64, _i32, _d, _d, _p]),
     "ars_convolve_out_len": (_i64, [_i64, _i64, _i64]),
     "ars_convolve_split": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _p]),

@@ -413,6 +413,19 @@ int ars_air_filter(const float* sig, int64_t n, double rate, double air, float* 
     ARS_API_END
 }
 
+int ars_resample(const float* sig, int64_t n, int64_t num, float* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(sig && out && n >= 1 && num >= 1, "ars_resample: needs an (n >= 1, 2) signal and num >= 1");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", sig, (size_t)n * 2);
+    RenderState* st = fresh_state();
+    float2* y = c.buf("render.y", sizeof(float2) * (size_t)num).as<float2>();
+    resample_stereo(d_x, n, num, y, st);
+    download(out, reinterpret_cast<const float*>(y), (size_t)num * 2);
+    sync();
+    ARS_API_END
+}
+
 int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n_wet, int32_t ch, double dry_wet,
                     double kill_start, float* out) {
     ARS_API_BEGIN

@@ -456,6 +456,7 @@ struct PassArgs {
     i64 M;          // transform length
     int logM;
     int logLg;      // strided: segment length of this pass (Lg); contiguous: == LOGR
+    int prefetch;   // > 0: each CTA prefetches into the L2 the tile `prefetch` tiles ahead (0: off)
     Tw tw;
 };
 
@@ -624,6 +625,34 @@ __device__ __forceinline__ void run_tile(float2* sm, LD& ld, ST& st, const PassA
     st.finish();
 }
 
+// L2 prefetch of a tile a full wave ahead: the CTA that will process tile `blockIdx.x + dist` finds its loads in
+// the L2 instead of waiting on HBM, so the memory pipeline is as deep as the L2 allows rather than as deep as the
+// resident CTAs' registers.  Same element-to-thread map as the first executed stage of run_tile.
+template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, class GF, class GL>
+__device__ __forceinline__ void prefetch_tile(const float2* a, const float2* b, GF gfirst, GL glast) {
+    constexpr int n = Rad<LOGR>::n;
+    constexpr int S = INV ? n - 1 : 0;                    // the stage that reads HBM
+    constexpr int R = 1 << LOGR;
+    constexpr int r = Rad<LOGR>::r(S);
+    constexpr int Ls = R / Prod<LOGR>::before(S);
+    constexpr int sub = Ls / r;
+    constexpr int NB = R / r;
+    constexpr int TOTAL = NB * LAYOUT::C;
+    const i64 step = INV ? glast.step() : gfirst.step() * (i64)sub;
+    for (int q = (int)threadIdx.x; q < TOTAL; q += NT) {
+        int bf, c;
+        if constexpr (STRIDED) { bf = LAYOUT::bfly(q); c = LAYOUT::col(q); }
+        else { bf = q % NB; c = q / NB; }
+        i64 idx = INV ? glast(bf, c) : gfirst((bf / sub) * Ls + (bf % sub), c);
+        #pragma unroll
+        for (int t = 0; t < r; ++t) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + idx));
+            if (b) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + idx));
+            idx += step;
+        }
+    }
+}
+
 // Host emulation of one tile (tests/host_emul): the same stage code, "threads" run one after
 // another, a barrier is simply the end of the loop over threads.
 template <int LOGR, bool INV, bool STRIDED, int NT, class LAYOUT, int LDM, int STM, class LD, class ST, class GF, class GL>
@@ -690,6 +719,13 @@ template <int LOGR, int LOGT> struct StridedTile {
 template <int LOGR, int LOGT, bool INV, int NT, int LDM, int STM>
 __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_strided_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
+    if constexpr (LDM == LD_PLAIN) {
+        if (pa.prefetch > 0 && (i64)blockIdx.x + pa.prefetch < (i64)gridDim.x) {
+            const StridedTile<LOGR, LOGT> t2((i64)blockIdx.x + pa.prefetch, pa);
+            prefetch_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>>(
+                ld.a, nullptr, StridedFirst<LOGR>{t2.base, t2.logStride}, StridedLast<LOGR>{t2.base, t2.logStride});
+        }
+    }
     const StridedTile<LOGR, LOGT> t((i64)blockIdx.x, pa);
     run_tile<LOGR, INV, true, NT, StridedLayout<LOGR, LOGT>, LDM, STM>(
         sm, ld, st, pa, StridedFirst<LOGR>{t.base, t.logStride}, StridedLast<LOGR>{t.base, t.logStride}, t.col0);
@@ -699,6 +735,13 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_strided_kernel(Ld 
 template <int LOGR, int LOGC, bool INV, int NT, int LDM, int STM>
 __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
+    if constexpr (LDM == LD_PLAIN || LDM == LD_MULSPEC) {
+        if (pa.prefetch > 0 && (i64)blockIdx.x + pa.prefetch < (i64)gridDim.x) {
+            const i64 base2 = ((i64)blockIdx.x + pa.prefetch) << (LOGR + LOGC);
+            prefetch_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>>(
+                ld.a, LDM == LD_MULSPEC ? ld.b : nullptr, ContigFirst<LOGR>{base2}, ContigLast<LOGR>{base2});
+        }
+    }
     const i64 base = (i64)blockIdx.x << (LOGR + LOGC);
     run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>, LDM, STM>(sm, ld, st, pa, ContigFirst<LOGR>{base},
                                                              ContigLast<LOGR>{base}, 0u);

@@ -236,6 +236,8 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     pa.logM = p->logM;
     pa.logLg = ps.logLg;
     pa.tw = p->tw;
+    static const int pf = env_int("ARS_FFT_PREFETCH", 0);
+    pa.prefetch = pf;
     struct ProfScope {
         bool on;
         ProfScope(const Ld& l, const St& s, i64 M) : on(g_prof.on) {

@@ -242,6 +242,63 @@ __global__ void ir_flags_kernel(const float* a, i64 na, i64 stride_a, const floa
     if (__any_sync(0xffffffffu, fb) && (threadIdx.x & 31) == 0) state->ir_any1 = 1u;
 }
 
+// ---- FFT-domain resampling (scipy.signal.resample, used for an external IR whose rate differs, rs.py:1037-1040) ----
+// W (num bins) from Z (n bins) by scipy's two-sided rule: keep the m = min(n, num) lowest-frequency bins, unite /
+// split the unpaired bin at m/2 when m is even; stored conjugated for the conj(DFT(conj .)) inverse.
+__global__ void __launch_bounds__(256) resample_map_kernel(const float2* __restrict__ Z, i64 n, float2* __restrict__ W,
+                                                           i64 num) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num) return;
+    const i64 m = n < num ? n : num, m2 = m / 2 + 1;
+    float2 v = make_float2(0.f, 0.f);
+    if (k < m2) v = Z[k];
+    else if (k >= num - (m - m2)) v = Z[n - (num - k)];
+    if (m % 2 == 0) {
+        if (num < n) {                       // down-sampling: bin -m/2 of the output (= m/2, num == m) gets both
+            if (k == num - m / 2) { const float2 u = Z[n - m / 2]; v.x += u.x; v.y += u.y; }
+        } else if (n < num) {                // up-sampling: the unpaired bin is split into a pair
+            if (k == m / 2 || k == num - m / 2) { const float2 u = Z[m / 2]; v = make_float2(0.5f * u.x, 0.5f * u.y); }
+        }
+    }
+    W[k] = make_float2(v.x, -v.y);
+}
+
+void resample_stereo(const float* d_x, i64 n, i64 num, float2* d_y, RenderState* d_state) {
+    Ctx& c = ctx();
+    ARS_CHECK(n >= 1 && num >= 1, "resample: empty signal");
+    float2* Z = c.buf("spec.Z", sizeof(float2) * (size_t)n).as<float2>();
+    float2* W = c.buf("spec.P", sizeof(float2) * (size_t)num).as<float2>();
+    {
+        BluesteinPlan* bp = get_bluestein_plan(n);
+        float2* work = c.buf("spec.work", sizeof(float2) * (size_t)bp->M).as<float2>();
+        Ld ld;
+        ld.mode = LD_CHIRP_X2;
+        ld.f0 = d_x;
+        ld.nvalid = n;
+        St st;
+        st.mode = ST_CHIRP;
+        st.a = Z;
+        bluestein_dft(bp, ld, work, st);
+    }
+    resample_map_kernel<<<ceil_div(num, 256), 256, 0, c.stream>>>(Z, n, W, num);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    {
+        BluesteinPlan* bp = get_bluestein_plan(num);
+        float2* work = c.buf("spec.work", sizeof(float2) * (size_t)bp->M).as<float2>();
+        Ld ld;
+        ld.mode = LD_CHIRP_C;
+        ld.a = W;
+        ld.nvalid = num;
+        St st;
+        st.mode = ST_FINAL;
+        st.a = d_y;
+        st.scale = 1.0f / (float)n;          // ifft's 1/num times scipy's num/n
+        st.maxbits = &d_state->max_stereo;
+        bluestein_dft(bp, ld, work, st);
+    }
+}
+
 void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                      const FilterSpec& fs_in, float2* d_y, RenderState* d_state) {
     Ctx& c = ctx();

@@ -76,4 +76,7 @@ struct RenderState {
 void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                      const FilterSpec& fs, float2* d_y, RenderState* d_state);
 
+// scipy.signal.resample(x, num, axis=0) for an (n, 2) float32 signal -> (num, 2)   (rs.py:1039)
+void resample_stereo(const float* d_x, i64 n, i64 num, float2* d_y, RenderState* d_state);
+
 }  // namespace ars

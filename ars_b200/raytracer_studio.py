@@ -202,6 +202,16 @@ def apply_simple_lp_filter(signal, rate, air_absorption_factor):
         return signal
 
 
+def resample_ir(ir, num):
+    """scipy.signal.resample(ir, num, axis=0) for a stereo IR (rs.py:1039), on the GPU."""
+    a = np.ascontiguousarray(ir, dtype=_F32)
+    if a.ndim != 2 or a.shape[1] != 2 or a.shape[0] == 0 or num <= 0:
+        raise ValueError("resample_ir: needs an (n, 2) array and num > 0")
+    out = np.empty((int(num), 2), _F32)
+    _capi.check(_lib().ars_resample(_capi.ptr(a), a.shape[0], int(num), _capi.ptr(out)), "ars_resample")
+    return out
+
+
 def dynamic_dry_wet_mix(dry_signal, wet_signal, dry_wet, kill_start=0.5):
     """rs.py:84-144."""
     try:
@@ -579,13 +589,15 @@ def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_externa
                 ir, ir_rate = wavio.read(ir_path)
                 if ir.size == 0:
                     raise ValueError("Externe IR-Datei ist leer.")
-                if ir_rate != rate:
-                    raise ValueError(f"IR Rate ({ir_rate}Hz) != Audio Rate ({rate}Hz); Resampling ist in diesem "
-                                     "Build nicht enthalten (SURVEY.md section 8f item 2)")
                 if ir.ndim != 2 or ir.shape[1] != 2:
                     msg = "Externe IR muss Stereo sein."
                     print(f"ERROR: {msg}")
                     return None, None, msg
+                if ir_rate != rate:            # rs.py:1037-1040
+                    num = int(ir.shape[0] * rate / ir_rate)
+                    if num <= 0:
+                        raise ValueError("Resampling würde IR-Länge Null ergeben.")
+                    ir = resample_ir(ir, num)
             except Exception as e:
                 msg = f"Fehler Laden/Resample IR: {e}"
                 print(f"ERROR: {msg}")

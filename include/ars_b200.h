@@ -117,6 +117,10 @@ ARS_API int ars_ir_geometry(double rate, double ir_duration, double ir_max_delay
 /* apply_simple_lp_filter, rs.py:310-333, on an (n, 2) signal; caller applies the `< 0.01` gate. */
 ARS_API int ars_air_filter(const float* sig, int64_t n, double rate, double air, float* out);
 
+/* scipy.signal.resample(x, num, axis=0) of an (n, 2) signal -> (num, 2): the IR rate conversion of
+ * apply_raytrace_convolution_3d, rs.py:1037-1040 (exact n- and num-point DFTs on the GPU). */
+ARS_API int ars_resample(const float* sig, int64_t n, int64_t num, float* out);
+
 /* dynamic_dry_wet_mix, rs.py:84-121; out has max(n_dry, n_wet) frames of `ch` channels. */
 ARS_API int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n_wet, int32_t ch,
                     double dry_wet, double kill_start, float* out);

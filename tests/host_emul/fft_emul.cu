@@ -84,6 +84,7 @@ template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& 
     pa.M = (i64)1 << logM;
     pa.logM = logM;
     pa.logLg = ps.logLg;
+    pa.prefetch = 0;
     pa.tw = tw;
     if (ps.strided) {
         if (ps.logLg - ps.logR < ps.logT) { printf("bad plan: strided pass narrower than tile\n"); exit(2); }
@@ -239,7 +240,7 @@ static void emu_segments(int logF, i64 nseg, const Tw& tw, const Ld& ld, const S
     EmuPlan p;
     p.logM = 0;
     PassArgs pa;
-    pa.M = nseg << logF; pa.logM = 0; pa.logLg = logF; pa.tw = tw;
+    pa.M = nseg << logF; pa.logM = 0; pa.logLg = logF; pa.prefetch = 0; pa.tw = tw;
     if (logF == 12) { if (inverse) emu_contig<12, 1, true>(ld, st, pa); else emu_contig<12, 1, false>(ld, st, pa); }
     else { if (inverse) emu_contig<13, 0, true>(ld, st, pa); else emu_contig<13, 0, false>(ld, st, pa); }
     (void)ps;

@@ -494,3 +494,31 @@ def test_silent_and_tiny_inputs(rs):
     want = orc.render(t, 48000, hall="Plate", air=0.0)
     assert np.array_equal(got["stereo"] != 0, want["stereo"] != 0) or rel_err(got["stereo"], want["stereo"]) <= TOL
     assert rel_err(got["final"], want["final"]) <= TOL
+
+
+def test_ir_resampling_matches_scipy(rs, tmp_path):
+    """scipy.signal.resample (rs.py:1039) on the GPU: up / down, odd / even lengths, then the file-level path with
+    an external IR at another sample rate."""
+    from scipy.signal import resample
+    from ars_b200 import wavio
+    g = np.random.default_rng(55)
+    for n, num in ((4800, 5292), (4801, 4410), (6000, 3000), (3000, 6000), (4410, 4800), (5001, 7777), (64, 65), (9, 4)):
+        ir = (g.standard_normal((n, 2)) * np.exp(-np.arange(n) / (0.3 * n))[:, None]).astype(np.float32)
+        want = resample(ir, num, axis=0)
+        got = rs.resample_ir(ir, num)
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert rel_err(got, want) <= TOL, (n, num, rel_err(got, want))
+    x = (0.25 * g.standard_normal((30000, 2))).astype(np.float32)
+    ir = (g.standard_normal((8000, 2)) * np.exp(-np.arange(8000) / 1500.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir)) * 4
+    wavio.write_float32(str(tmp_path / "x.wav"), x, 48000)
+    wavio.write_float32(str(tmp_path / "ir.wav"), ir, 44100)
+    p1, _, text = rs.apply_raytrace_convolution_3d(str(tmp_path / "x.wav"), str(tmp_path / "ir.wav"), True, "Room", 100, .5,
+                                                   .1, .8, .6, .5, .5, 1.2, .9, .5, .5, .5, "Holz", "5.1 (Standard)")
+    assert p1 is not None, text
+    pcm, rate = wavio.read(p1)
+    ir_rs = resample(ir, int(8000 * 48000 / 44100), axis=0).astype(np.float32)
+    want = orc.render(x, 48000, external_ir=ir_rs, dry_wet_amount=.5, kill_start=.5, bass=1.2, treble=.9,
+                      layout="5.1 (Standard)")
+    d = np.abs(np.round(pcm * 32768).astype(np.int32) - want["pcm"].astype(np.int32))
+    assert pcm.shape == want["pcm"].shape and d.max() <= 1

@@ -457,6 +457,9 @@ struct PassArgs {
     int logM;
     int logLg;      // strided: segment length of this pass (Lg); contiguous: == LOGR
     int prefetch;   // > 0: each CTA prefetches into the L2 the tile `prefetch` tiles ahead (0: off)
+    // strided passes: lane-dependent factors of the inter-pass twiddle, laid out so that lanes read adjacent
+    // entries: [j*T + c] = w_Lg^(c * mul * 2^j) for j < 4, then [4*T + kb*T + c] = w_Lg^(c * kb) for kb < mul
+    const float2* ptab;
     Tw tw;
 };
 
@@ -510,11 +513,20 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
     unsigned icol = 0;
     const unsigned shift = (unsigned)(pa.logM - pa.logLg);
     const unsigned emask = (unsigned)(pa.M - 1);
+    // w^(i * x) with i = col0 + c splits into a CTA-uniform factor w^(col0 * x) (broadcast table reads) and a
+    // lane-dependent one w^(c * x) that comes from the pass table with adjacent lanes reading adjacent entries --
+    // per-lane gathers into the big twiddle tables cost more L1 wavefronts than the tile's data did.
+    const int cl = tid & (LAYOUT::C - 1);
     if constexpr (STRIDED && last) {
-        icol = col0 + (unsigned)(tid & (LAYOUT::C - 1));
-        const unsigned eP = (icol * (unsigned)mul) << shift;
+        icol = col0;
+        const unsigned eP = (col0 * (unsigned)mul) << shift;
         #pragma unroll
-        for (int j = 0; (1 << j) < r; ++j) P[1 << j] = tw_big<INV>(pa.tw, (eP << j) & emask);
+        for (int j = 0; (1 << j) < r; ++j) {
+            const float2 u = tw_big<INV>(pa.tw, (eP << j) & emask);
+            float2 l = ARS_LDG(pa.ptab + j * LAYOUT::C + cl);
+            if (INV) l = cconj(l);
+            P[1 << j] = cmul(u, l);
+        }
         expand_pow<r>(P);
     }
 
@@ -554,7 +566,10 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 for (int k = 0; k < r; ++k) ARS_SM(k) = v[k];
             } else {
                 float2 Q = make_float2(1.f, 0.f);
-                if constexpr (STRIDED) Q = tw_big<false>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
+                if constexpr (STRIDED) {
+                    const unsigned kb = (unsigned)kfull_of<LOGR>(b, 0);
+                    Q = cmul(tw_big<false>(pa.tw, (icol * kb) << shift), ARS_LDG(pa.ptab + (4 + kb) * LAYOUT::C + cl));
+                }
                 Dft<r, false>::run(v);
                 i64 idx = glast(b, c);
                 #pragma unroll
@@ -567,7 +582,11 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
         } else {
             if constexpr (last) {
                 float2 Q = make_float2(1.f, 0.f);
-                if constexpr (STRIDED) Q = tw_big<true>(pa.tw, (icol * (unsigned)kfull_of<LOGR>(b, 0)) << shift);
+                if constexpr (STRIDED) {
+                    const unsigned kb = (unsigned)kfull_of<LOGR>(b, 0);
+                    Q = cmul(tw_big<true>(pa.tw, (icol * kb) << shift),
+                             cconj(ARS_LDG(pa.ptab + (4 + kb) * LAYOUT::C + cl)));
+                }
                 i64 idx = glast(b, c);
                 if constexpr (LDM == LD_OLS_MAC) ld.template get_mac<r>(idx, lstep, v);
                 else {
@@ -765,13 +784,28 @@ struct FftPass {
     int logR;
     int logT;       // strided: log2 columns per tile; contiguous: log2 segments per tile
     int logLg;
+    const float2* ptab = nullptr;   // strided: PassArgs::ptab (device), built with the plan
 };
+// last radix of the stage split of an R = 2^logR point column transform
+inline int last_radix(int logR) {
+    switch (logR) {
+#define ARS_LR(L) case L: return fft::Rad<L>::r(fft::Rad<L>::n - 1);
+        ARS_LR(1) ARS_LR(2) ARS_LR(3) ARS_LR(4) ARS_LR(5) ARS_LR(6) ARS_LR(7) ARS_LR(8) ARS_LR(9) ARS_LR(10)
+        ARS_LR(11) ARS_LR(12) ARS_LR(13)
+#undef ARS_LR
+    }
+    return 2;
+}
+// entries of a strided pass table (PassArgs::ptab): (4 + mul) * T with mul = R / last radix
+inline int pass_table_mul(int logR) { return (1 << logR) / last_radix(logR); }
+inline int pass_table_elems(int logR, int logT) { return (4 + pass_table_mul(logR)) << logT; }
 
 struct FftPlan {
     int logM = 0;
     i64 M = 0;
     std::vector<FftPass> passes;   // forward order
     DevBuf tw_lo, tw_hi;
+    std::vector<DevBuf> pass_tabs;  // per strided pass: PassArgs::ptab
     fft::Tw tw{};
 };
 

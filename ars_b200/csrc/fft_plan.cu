@@ -33,6 +33,18 @@ __global__ void stage_table_kernel(float2* out) {
     out[idx] = make_float2((float)c, (float)s);
 }
 
+// lane-dependent factors of a strided pass's inter-pass twiddle (see PassArgs::ptab)
+__global__ void pass_table_kernel(float2* out, int logLg, int mul, int logT, int count) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int row = idx >> logT, c = idx & ((1 << logT) - 1);
+    const long long x = row < 4 ? ((long long)mul << row) : (long long)(row - 4);
+    const long long e = ((long long)c * x) & (((long long)1 << logLg) - 1);
+    double s, cs;
+    sincospi(-2.0 * (double)e / (double)((long long)1 << logLg), &s, &cs);
+    out[idx] = make_float2((float)cs, (float)s);
+}
+
 static DevBuf g_tw_local;
 
 static const float2* local_table() {
@@ -47,7 +59,12 @@ static const float2* local_table() {
 
 void fft_release_plans() {
     if (ctx_ready()) {
-        for (auto& kv : ctx().fft_plans) { kv.second->tw_lo.release(); kv.second->tw_hi.release(); delete kv.second; }
+        for (auto& kv : ctx().fft_plans) {
+            kv.second->tw_lo.release();
+            kv.second->tw_hi.release();
+            for (auto& t : kv.second->pass_tabs) t.release();
+            delete kv.second;
+        }
         ctx().fft_plans.clear();
     }
     g_tw_local.release();
@@ -86,6 +103,18 @@ FftPlan* get_fft_plan(int logM) {
         p->tw.hi = p->tw_hi.as<float2>();
     }
     p->tw.stage = local_table();
+    p->pass_tabs.resize(p->passes.size());
+    for (size_t i = 0; i < p->passes.size(); ++i) {
+        FftPass& ps = p->passes[i];
+        if (!ps.strided) continue;
+        const int count = pass_table_elems(ps.logR, ps.logT);
+        p->pass_tabs[i].reserve(sizeof(float2) * (size_t)count);
+        pass_table_kernel<<<ceil_div(count, 256), 256, 0, c.stream>>>(p->pass_tabs[i].as<float2>(), ps.logLg,
+                                                                     pass_table_mul(ps.logR), ps.logT, count);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        ps.ptab = p->pass_tabs[i].as<float2>();
+    }
     c.fft_plans[logM] = p;
     return p;
 }
@@ -238,6 +267,7 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     pa.tw = p->tw;
     static const int pf = env_int("ARS_FFT_PREFETCH", 0);
     pa.prefetch = pf;
+    pa.ptab = ps.ptab;
     struct ProfScope {
         bool on;
         ProfScope(const Ld& l, const St& s, i64 M) : on(g_prof.on) {

@@ -85,6 +85,7 @@ template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& 
     pa.logM = logM;
     pa.logLg = ps.logLg;
     pa.prefetch = 0;
+    pa.ptab = ps.ptab;
     pa.tw = tw;
     if (ps.strided) {
         if (ps.logLg - ps.logR < ps.logT) { printf("bad plan: strided pass narrower than tile\n"); exit(2); }
@@ -101,6 +102,28 @@ template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& 
 }
 
 struct EmuPlan { int logM; std::vector<FftPass> passes; Tw tw; };
+
+// host copy of pass_table_kernel (fft_plan.cu)
+static std::vector<std::vector<float2>> g_pass_tabs;
+static void attach_pass_tables(EmuPlan& p) {
+    const double PI = 3.14159265358979323846;
+    g_pass_tabs.clear();
+    g_pass_tabs.resize(p.passes.size());
+    for (size_t i = 0; i < p.passes.size(); ++i) {
+        FftPass& ps = p.passes[i];
+        if (!ps.strided) continue;
+        const int count = pass_table_elems(ps.logR, ps.logT), mul = pass_table_mul(ps.logR);
+        g_pass_tabs[i].resize(count);
+        for (int idx = 0; idx < count; ++idx) {
+            const int row = idx >> ps.logT, c = idx & ((1 << ps.logT) - 1);
+            const long long x = row < 4 ? ((long long)mul << row) : (long long)(row - 4);
+            const long long e = ((long long)c * x) & (((long long)1 << ps.logLg) - 1);
+            const double a = -2.0 * PI * (double)e / (double)((long long)1 << ps.logLg);
+            g_pass_tabs[i][idx] = make_float2((float)cos(a), (float)sin(a));
+        }
+        ps.ptab = g_pass_tabs[i].data();
+    }
+}
 
 static void emu_forward(const EmuPlan& p, const Ld& ld_first, float2* work, const St& st_last) {
     const int np = (int)p.passes.size();
@@ -150,6 +173,7 @@ static int check_conv(int logM) {
     EmuPlan p;
     p.logM = logM;
     p.passes = fft_decompose(logM);
+    attach_pass_tables(p);
     make_tables(logM, p.tw);
     const i64 M = (i64)1 << logM;
     printf("logM=%d passes:", logM);
@@ -192,6 +216,7 @@ static int check_bluestein(i64 N) {
     EmuPlan p;
     p.logM = logM;
     p.passes = fft_decompose(logM);
+    attach_pass_tables(p);
     make_tables(logM, p.tw);
     const double PI = 3.14159265358979323846;
     std::vector<float2> chirp(N);
@@ -240,7 +265,7 @@ static void emu_segments(int logF, i64 nseg, const Tw& tw, const Ld& ld, const S
     EmuPlan p;
     p.logM = 0;
     PassArgs pa;
-    pa.M = nseg << logF; pa.logM = 0; pa.logLg = logF; pa.prefetch = 0; pa.tw = tw;
+    pa.M = nseg << logF; pa.logM = 0; pa.logLg = logF; pa.prefetch = 0; pa.ptab = nullptr; pa.tw = tw;
     if (logF == 12) { if (inverse) emu_contig<12, 1, true>(ld, st, pa); else emu_contig<12, 1, false>(ld, st, pa); }
     else { if (inverse) emu_contig<13, 0, true>(ld, st, pa); else emu_contig<13, 0, false>(ld, st, pa); }
     (void)ps;

@@ -539,6 +539,9 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
     constexpr int SSTEP = sub * PITCH + (sub * PITCH) / 16;
 #define ARS_SM(t_) sm[LIN ? (s0 + (t_) * SSTEP) : LAYOUT::sidx(row0 + (t_) * sub, c)]
 
+    // the stage that reads HBM is unrolled over its butterflies so all of a thread's loads are in flight at once
+    constexpr int UNR = (((!INV && first) || (INV && last)) && TOTAL >= NT) ? (TOTAL / NT) : 1;
+    #pragma unroll UNR
     for (int q = tid; q < TOTAL; q += NT) {
         int b, c;
         if constexpr (STRIDED) { b = LAYOUT::bfly(q); c = LAYOUT::col(q); }

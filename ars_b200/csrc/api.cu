@@ -31,6 +31,20 @@ void fft_profile_end(long long* launches, double* ms, double* bytes);
 // run-time options (ars_set_option)
 static int g_opt_upols = 1;        // 1: use overlap-save whenever no exact-N mask is active; 0: always the N-point path
 static int g_opt_upols_logf = 13;  // 2B = 2^logF points per overlap-save transform (12 or 13)
+static int g_opt_sparse_ir = 1;    // 1: IR spectrum of sparse (procedural) IRs through the overlap-save route
+
+// number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
+static int nonzero_partitions(const float* a, i64 na, const float* b, i64 nb) {
+    const i64 L = std::max(a ? na : 0, b ? nb : 0);
+    int count = 0;
+    for (i64 lo = 0; lo < L; lo += 4096) {
+        bool f = false;
+        for (i64 i = lo; i < std::min(L, lo + 4096) && !f; ++i)
+            f = (a && i < na && a[i] != 0.f) || (b && i < nb && b[i] != 0.f);
+        count += f ? 1 : 0;
+    }
+    return count;
+}
 
 // the convolution stage: overlap-save when the render has no spectral mask, else the exact N-point filter
 static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
@@ -227,6 +241,9 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         fs.level0 = (g.length > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;     // rs.py:360
         fs.level1 = (g.length > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;       // rs.py:369
         if (p->air_absorption > 0.01 && N >= 2) fill_air(fs, N, p->rate, p->air_absorption);   // rs.py:378, 312-317
+        // a procedural IR is a few dozen taps before the split plus a tail that decays by >= 1 % per sample and is
+        // exactly zero in float32 some 10^4 samples later: a handful of non-zero partitions
+        fs.sparse_ir = g_opt_sparse_ir;
         convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st);
     }
     if (d_out_stereo) {
@@ -335,6 +352,7 @@ int ars_set_option(const char* key, int32_t value) {
     ARS_API_BEGIN
     ARS_CHECK(key, "ars_set_option: null key");
     if (!strcmp(key, "upols")) g_opt_upols = value ? 1 : 0;
+    else if (!strcmp(key, "sparse_ir")) g_opt_sparse_ir = value ? 1 : 0;
     else if (!strcmp(key, "upols_logf")) { ARS_CHECK(value == 12 || value == 13, "upols_logf must be 12 or 13"); g_opt_upols_logf = value; }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END
@@ -471,6 +489,7 @@ int ars_convolve_split(const float* data, int64_t n, int32_t cin, const float* e
     fs.level0 = (len_early > 1 && early_level > 1e-6) ? early_level : 0.0;          // rs.py:360
     fs.level1 = (len_late > 1 && late_level > 1e-6) ? late_level : 0.0;            // rs.py:369
     if (air_absorption > 0.01 && N >= 2) fill_air(fs, N, rate, air_absorption);     // rs.py:378
+    fs.sparse_ir = (g_opt_sparse_ir && nonzero_partitions(early, len_early, late, len_late) <= 12) ? 1 : 0;
     float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
     convolution_stage(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st);
     guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:402-404

@@ -177,8 +177,8 @@ template <bool INV> struct Dft<16, INV> {
 
 // ------------------------------------------------------------- Ld / St functors
 enum LdMode { LD_PLAIN = 0, LD_MULSPEC, LD_CHIRP_X2, LD_CHIRP_XC, LD_CHIRP_PAIR, LD_CHIRP_B, LD_CHIRP_C,
-              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC };
-enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS };
+              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC, LD_OLS_CHIRPSIG, LD_OLS_IRC };
+enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP };
 
 struct Ld {
     int mode = LD_PLAIN;
@@ -194,6 +194,7 @@ struct Ld {
     const float2* a2 = nullptr;     // LD_OLS_MAC: second delay line (spectra of the conjugated signal), or null
     const float2* b2 = nullptr;     // LD_OLS_MAC: its coefficient spectra
     const unsigned char* nz = nullptr;   // LD_OLS_MAC: per-partition "has non-zero taps" flags
+    const int* plist = nullptr;          // LD_OLS_MAC: compacted non-zero partition indices + count at [P] (preferred)
     int P = 0;                      // partitions
     int logF = 13;                  // log2 of the segment (FFT) length; hop B = F / 2
     float c0 = 1.f, c1 = 0.f;       // LD_OLS_IR: tap = c0 * f0[i*cin] + c1 * f1[i*cin]; LD_OLS_X: c1 = -1 conjugates
@@ -239,6 +240,23 @@ struct Ld {
             const float u = (f0 && i < nvalid) ? ARS_LDG(f0 + i * cin) : 0.f;
             const float v = (f1 && i < nvalid1) ? ARS_LDG(f1 + i * cin) : 0.f;
             return make_float2(c0 * u + c1 * v, 0.f);
+        } else if constexpr (MODE == LD_OLS_CHIRPSIG) {    // overlap-save window over the shifted Bluestein kernel:
+            // sig[f] = conj(chirp[|f - D|]) for 0 <= f < N + D, D = frame0 (short-IR spectrum path, spectral.cu)
+            const i64 seg = seg0 + (idx >> logF);
+            const i64 fr = ((seg - 1) << (logF - 1)) + (idx & (((i64)1 << logF) - 1));
+            if (fr < 0 || fr >= N + frame0) return make_float2(0.f, 0.f);
+            i64 m = fr - frame0;
+            if (m < 0) m = -m;
+            if (m >= N) return make_float2(0.f, 0.f);       // only ever multiplied by zero-padded taps
+            return cconj(ARS_LDG(b + m));
+        } else if constexpr (MODE == LD_OLS_IRC) {         // complex taps (f0 + i f1) * chirp, partition p, zero-padded
+            const i64 seg = idx >> logF;
+            const i64 t = idx & (((i64)1 << logF) - 1);
+            const i64 i = (seg << (logF - 1)) + t;
+            if (t >= ((i64)1 << (logF - 1)) || i >= N) return make_float2(0.f, 0.f);
+            const float u = (f0 && i < nvalid) ? ARS_LDG(f0 + i * cin) : 0.f;
+            const float v = (f1 && i < nvalid1) ? ARS_LDG(f1 + i * cin) : 0.f;
+            return cmul(make_float2(u, v), ARS_LDG(b + i));
         } else if constexpr (MODE == LD_OLS_MAC) {     // Y_s = sum_p X_{s-p} H_p (+ Xc_{s-p} Hc_p)
             float2 acc[1];
             get_mac<1>(idx, 0, acc);
@@ -259,8 +277,12 @@ struct Ld {
         for (int k = 0; k < r; ++k) v[k] = make_float2(0.f, 0.f);
         const i64 reach = seg + lookback;
         const int pmax = (int)(reach < (i64)(P - 1) ? reach : (i64)(P - 1));
-        for (int p = 0; p <= pmax; ++p) {
-            if (nz && !nz[p]) continue;
+        // plist (optional): ascending indices of the non-zero partitions, plist[P] = their count
+        const int np = plist ? plist[P] : P;
+        for (int q = 0; q < np; ++q) {
+            const int p = plist ? plist[q] : q;
+            if (p > pmax) break;
+            if (!plist && nz && !nz[p]) continue;
             const float2* x = a + ((seg - p) << logF) + t0;
             const float2* h = b + ((i64)p << logF) + t0;
             #pragma unroll
@@ -298,6 +320,8 @@ struct Ld {
             case LD_OLS_X: return get<LD_OLS_X>(idx);
             case LD_OLS_IR: return get<LD_OLS_IR>(idx);
             case LD_OLS_MAC: return get<LD_OLS_MAC>(idx);
+            case LD_OLS_CHIRPSIG: return get<LD_OLS_CHIRPSIG>(idx);
+            case LD_OLS_IRC: return get<LD_OLS_IRC>(idx);
         }
         return make_float2(0.f, 0.f);
     }
@@ -338,6 +362,7 @@ struct St {
                 case ST_CHIRP: put<ST_CHIRP>(idx, v, aux); break;
                 case ST_FINAL: put<ST_FINAL>(idx, v, aux); break;
                 case ST_OLS: put<ST_OLS>(idx, v, aux); break;
+                case ST_OLS_CHIRP: put<ST_OLS_CHIRP>(idx, v, aux); break;
             }
         } else if constexpr (MODE == ST_PLAIN) {
             a[idx] = v;
@@ -345,6 +370,11 @@ struct St {
             a[idx] = cscale(v, scale);
         } else if constexpr (MODE == ST_CHIRP) {
             if (idx < N) a[idx] = cmul(v, aux);
+        } else if constexpr (MODE == ST_OLS_CHIRP) {    // keep the valid half of each segment, bin k = frame - frame0
+            const i64 F = (i64)1 << logF, B = F >> 1;
+            const i64 t = idx & (F - 1);
+            const i64 k = ((seg0 + (idx >> logF)) << (logF - 1)) + (t - B) - frame0;
+            if (t >= B && k >= 0 && k < N) a[k] = cmul(v, ARS_LDG(chirp + k));
         } else if constexpr (MODE == ST_OLS) {
             const i64 F = (i64)1 << logF, B = F >> 1;
             const i64 t = idx & (F - 1);

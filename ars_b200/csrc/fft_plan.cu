@@ -142,6 +142,8 @@ static double ld_bytes(const Ld& ld, i64 M) {
         case LD_OLS_X: return 8.0 * (double)ld.nvalid;
         case LD_OLS_IR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
         case LD_OLS_MAC: return 8.0 * (double)M;       // compulsory: each delay-line spectrum once
+        case LD_OLS_CHIRPSIG: return 8.0 * (double)ld.N;
+        case LD_OLS_IRC: return 4.0 * (double)(ld.nvalid + ld.nvalid1) + 8.0 * (double)std::max(ld.nvalid, ld.nvalid1);
     }
     return 0.0;
 }
@@ -150,6 +152,7 @@ static double st_bytes(const St& st, i64 M) {
         case ST_PLAIN: case ST_SCALE: return 8.0 * (double)M;
         case ST_CHIRP: case ST_FINAL: return 16.0 * (double)st.N;
         case ST_OLS: return 16.0 * (double)st.N;
+        case ST_OLS_CHIRP: return 16.0 * (double)st.N;
     }
     return 0.0;
 }
@@ -248,6 +251,7 @@ static bool launch_fast(const FftPass& ps, const Ld& ld, const St& st, const Pas
             if constexpr (INV) {                                                                                  \
                 if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
                 if (lm == LD_OLS_MAC && sm == ST_OLS) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS>(ld, st, pa); return true; } \
+                if (lm == LD_OLS_MAC && sm == ST_OLS_CHIRP) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS_CHIRP>(ld, st, pa); return true; } \
             } else {                                                                                              \
                 if (lm == LD_OLS_X && sm == ST_PLAIN) { launch_contig<R, C, false, LD_OLS_X, ST_PLAIN>(ld, st, pa); return true; } \
             }                                                                                                     \
@@ -301,8 +305,13 @@ void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) 
     tmp.tw.stage = local_table();
     tmp.tw.lo = tmp.tw.hi = nullptr;
     const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
+    // the per-launch profile (ars_profile_*) is about the M-point passes, the dominant kernels; block transforms
+    // with a fused multiply-accumulate have a different byte / flop balance and are left out of it
+    const bool prof = g_prof.on;
+    g_prof.on = false;
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);
     else launch_pass<false>(&tmp, ps, ld, st);
+    g_prof.on = prof;
 }
 
 void fft_forward(FftPlan* p, const Ld& ld_first, float2* work, const St& st_last) {

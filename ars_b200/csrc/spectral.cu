@@ -49,9 +49,11 @@ static void drop_plan(Ctx& c, i64 N, bool to_pool) {
     if (to_pool && g_plan_pool.size() < 32) {
         g_plan_pool.push_back(p->chirp);
         g_plan_pool.push_back(p->bspec);
+        if (p->ols_x.p) g_plan_pool.push_back(p->ols_x);
     } else {
         p->chirp.release();
         p->bspec.release();
+        p->ols_x.release();
     }
     delete p;
     c.blue_plans.erase(it);
@@ -242,6 +244,108 @@ __global__ void ir_flags_kernel(const float* a, i64 na, i64 stride_a, const floa
     if (__any_sync(0xffffffffu, fb) && (threadIdx.x & 31) == 0) state->ir_any1 = 1u;
 }
 
+// ---- short-IR spectrum (see spectral.cuh) ----
+__global__ void __launch_bounds__(256) partition_any_kernel(const float* a, i64 na, const float* b, i64 nb, int logB,
+                                                            unsigned char* nz, int P) {
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    const i64 lo = (i64)p << logB, hi = lo + ((i64)1 << logB);
+    bool f = false;
+    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (a && i < na) f |= a[i] != 0.f;
+        if (b && i < nb) f |= b[i] != 0.f;
+    }
+    const int any = __syncthreads_or(f ? 1 : 0);
+    if (threadIdx.x == 0) nz[p] = any ? 1 : 0;
+}
+
+// plist[0..count) = ascending indices of flagged partitions, plist[P] = count (one thread: P is a few hundred at most)
+__global__ void compact_flags_kernel(const unsigned char* nz, int P, int* plist) {
+    if (blockIdx.x || threadIdx.x) return;
+    int n = 0;
+    for (int p = 0; p < P; ++p) if (nz[p]) plist[n++] = p;
+    plist[P] = n;
+}
+
+void ir_spectrum_short(BluesteinPlan* bp, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1, float2* d_P) {
+    Ctx& c = ctx();
+    constexpr int logF = 13, logB = 12;
+    const i64 B = (i64)1 << logB, F = (i64)1 << logF;
+    const i64 N = bp->N;
+    if (!d_ir0) L0 = 0;
+    if (!d_ir1) L1 = 0;
+    const i64 L = std::max<i64>(1, std::max(L0, L1));
+    const int P = (int)((L + B - 1) / B);
+    const i64 D = (i64)P * B;                                    // shift that makes every needed kernel index a frame >= 0
+    const i64 s_lo = P, s_hi = P + (N + B - 1) / B;             // output blocks covering frames [D, D + N)
+    // delay line of the chirp kernel: cached per (N, D)
+    if (bp->ols_D != D) {
+        const size_t need = sizeof(float2) * (size_t)(s_hi * F);
+        if (bp->ols_x.cap < need) {
+            const size_t old = bp->ols_x.cap;
+            bp->ols_x.reserve(need);
+            bp->bytes += bp->ols_x.cap - old;
+            c.blue_bytes += bp->ols_x.cap - old;
+        }
+        Ld ld;
+        ld.mode = LD_OLS_CHIRPSIG;
+        ld.logF = logF;
+        ld.b = bp->chirp.as<float2>();
+        ld.N = N;
+        ld.frame0 = D;
+        ld.seg0 = 0;
+        St st;
+        st.mode = ST_PLAIN;
+        st.a = bp->ols_x.as<float2>();
+        fft_segments(logF, s_hi, ld, st, false);
+        bp->ols_D = D;
+    }
+    // IR partition spectra of (h0 + i h1) * chirp, pre-scaled by 1/F, and their non-zero flags
+    float2* H = c.buf("irs.H", sizeof(float2) * (size_t)(P * F)).as<float2>();
+    unsigned char* nz = c.buf("irs.nz", (size_t)P).as<unsigned char>();
+    {
+        Ld ld;
+        ld.mode = LD_OLS_IRC;
+        ld.logF = logF;
+        ld.f0 = d_ir0; ld.nvalid = L0;
+        ld.f1 = d_ir1; ld.nvalid1 = L1;
+        ld.cin = 1;
+        ld.b = bp->chirp.as<float2>();
+        ld.N = N;
+        St st;
+        st.mode = ST_SCALE;
+        st.a = H;
+        st.scale = 1.0f / (float)F;
+        fft_segments(logF, P, ld, st, false);
+        partition_any_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, d_ir1, L1, logB, nz, P);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
+    int* plist = c.buf("irs.plist", sizeof(int) * (size_t)(P + 1)).as<int>();
+    compact_flags_kernel<<<1, 32, 0, c.stream>>>(nz, P, plist);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    // fused MAC + inverse; the store multiplies by chirp[k] and keeps bins 0 <= k < N
+    Ld ld;
+    ld.mode = LD_OLS_MAC;
+    ld.logF = logF;
+    ld.a = bp->ols_x.as<float2>() + s_lo * F;
+    ld.b = H;
+    ld.nz = nz;
+    ld.plist = plist;
+    ld.P = P;
+    ld.lookback = s_lo;
+    St st;
+    st.mode = ST_OLS_CHIRP;
+    st.logF = logF;
+    st.a = d_P;
+    st.chirp = bp->chirp.as<float2>();
+    st.N = N;
+    st.seg0 = s_lo;
+    st.frame0 = D;
+    fft_segments(logF, s_hi - s_lo, ld, st, true);
+}
+
 // ---- FFT-domain resampling (scipy.signal.resample, used for an external IR whose rate differs, rs.py:1037-1040) ----
 // W (num bins) from Z (n bins) by scipy's two-sided rule: keep the m = min(n, num) lowest-frequency bins, unite /
 // split the unpaired bin at m/2 when m is even; stored conjugated for the conj(DFT(conj .)) inverse.
@@ -331,7 +435,8 @@ void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L
         St st;
         st.mode = ST_CHIRP;
         st.a = P;
-        bluestein_dft(bp, ld, work, st);
+        if (fs.mode == FILT_SPLIT && fs.sparse_ir) ir_spectrum_short(bp, d_ir0, L0, d_ir1, L1, P);
+        else bluestein_dft(bp, ld, work, st);
     }
     {
         Ld ld;

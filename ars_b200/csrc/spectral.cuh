@@ -20,6 +20,9 @@ struct BluesteinPlan {
     FftPlan* fft = nullptr;
     DevBuf chirp;     // exp(-i pi n^2 / N), n < N
     DevBuf bspec;     // FFT_M of the wrapped conj chirp, permuted order, pre-scaled by 1/M
+    // short-IR spectrum path: block spectra of the shifted Bluestein kernel (overlap-save delay line), by shift D
+    DevBuf ols_x;
+    i64 ols_D = -1;
     size_t bytes = 0;
 };
 
@@ -50,6 +53,8 @@ struct FilterSpec {
     double val = 0.0;          // bin spacing as numpy computes it: 1.0 / (N * (1.0 / rate))
     double ftop = 0.0;         // freqs[-1]                            rs.py:323
     double depth = 0.0;        // clip(air, 0, 1) * 0.8                rs.py:326
+    int sparse_ir = 0;         // SPLIT: the IR's non-zero taps fill only a few 4096-tap partitions (procedural IRs):
+                               // take the overlap-save route to the IR spectrum (ir_spectrum_short)
 };
 
 void fill_eq(FilterSpec& fs, i64 N, double rate, double bass, double treble);
@@ -75,6 +80,12 @@ struct RenderState {
 //   either may be null; EXT -> ir0 = interleaved stereo IR (L0 frames), ir1 = null; MASK -> both null.
 void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                      const FilterSpec& fs, float2* d_y, RenderState* d_state);
+
+// P[k] = DFT_N(h0 + i h1)[k] for an IR whose non-zero taps sit in a few partitions of 4096 (the procedural IR): the
+// Bluestein convolution of the short chirped IR with the long chirp kernel runs as a partitioned overlap-save
+// convolution whose delay line (block spectra of the chirp) depends only on (N, L) and is cached in the plan.
+// Per render: P small IR-partition FFTs + ONE fused MAC / inverse pass, instead of two M-point transforms.
+void ir_spectrum_short(BluesteinPlan* bp, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1, float2* d_P);
 
 // scipy.signal.resample(x, num, axis=0) for an (n, 2) float32 signal -> (num, 2)   (rs.py:1039)
 void resample_stereo(const float* d_x, i64 n, i64 num, float2* d_y, RenderState* d_state);

@@ -95,6 +95,13 @@ __global__ void or_flags_kernel(unsigned char* a, const unsigned char* b, int n)
     if (i < n) a[i] |= b[i];
 }
 
+__global__ void compact_partition_flags_kernel(const unsigned char* nz, int P, int* plist) {
+    if (blockIdx.x || threadIdx.x) return;
+    int n = 0;
+    for (int p = 0; p < P; ++p) if (nz[p]) plist[n++] = p;
+    plist[P] = n;
+}
+
 void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                   const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg) {
     Ctx& c = ctx();
@@ -162,6 +169,11 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
         count_launch();
     }
 
+    int* plist = c.buf("ols.plist", sizeof(int) * (size_t)(P + 1)).as<int>();
+    compact_partition_flags_kernel<<<1, 32, 0, c.stream>>>(nz, P, plist);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+
     // ---- K3: frequency-domain delay line ----
     float2* X = c.buf("ols.X", sizeof(float2) * (size_t)(nseg * F) * nspec).as<float2>();
     for (int k = 0; k < nspec; ++k) {
@@ -203,6 +215,7 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
         ld.a2 = ext ? X + (size_t)nseg * F + skip * F : nullptr;
         ld.b2 = ext ? H + (size_t)Ppad * F : nullptr;
         ld.nz = nz;
+        ld.plist = plist;
         ld.P = P;
         ld.lookback = skip;
     }

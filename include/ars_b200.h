@@ -93,7 +93,9 @@ ARS_API uint64_t ars_launch_count(void);          /* kernels this library has la
 ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
 /* Options: "upols" (1 = use the partitioned overlap-save convolution whenever a render has no exact-N
  * spectral mask, i.e. air <= 0.01 and both EQ gains ~ 1 [default]; 0 = always the N-point spectral filter),
- * "upols_logf" (12 | 13: points per overlap-save transform = 2^logf, hop = half of it). */
+ * "upols_logf" (12 | 13: points per overlap-save transform = 2^logf, hop = half of it),
+ * "sparse_ir" (1 = IR spectra of procedural / sparse IRs through the cached overlap-save route [default]; 0 = always
+ * two M-point transforms). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);

@@ -336,7 +336,63 @@ static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_h
     return (maxerr / peak < 2e-5 && maxbits[0] != 0) ? 0 : 1;
 }
 
+// Short-IR spectrum route (spectral.cu: ir_spectrum_short): P[k] = DFT_N(h0 + i h1) through overlap-save over the
+// shifted Bluestein kernel.
+static int check_irs(i64 N, i64 L) {
+    constexpr int logF = 13, logB = 12;
+    const i64 B = (i64)1 << logB, F = (i64)1 << logF;
+    const double PI = 3.14159265358979323846;
+    Tw tw;
+    make_tables(logF, tw);
+    std::vector<float2> chirp(N);
+    for (i64 n = 0; n < N; ++n) {
+        const i64 q = (n * n) % (2 * N);
+        const double a = -PI * (double)q / (double)N;
+        chirp[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::mt19937 rng((unsigned)(N + L));
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<float> h0(L, 0.f), h1(L, 0.f);
+    for (int j = 0; j < 30; ++j) h0[1 + (j * 131) % std::min<i64>(L - 1, 4000)] += U(rng);
+    for (i64 i = std::min<i64>(L, 4500); i < std::min<i64>(L, 11000); ++i) h1[i] = U(rng) * expf(-(float)(i - 4500) / 900.f);
+    const int P = (int)((L + B - 1) / B);
+    const i64 D = (i64)P * B, s_lo = P, s_hi = P + (N + B - 1) / B;
+    std::vector<float2> X((size_t)s_hi * F), H((size_t)P * F), Pout(N, make_float2(0, 0));
+    std::vector<unsigned char> nz(P, 0);
+    for (int p = 0; p < P; ++p)
+        for (i64 i = p * B; i < std::min(L, (p + 1) * B); ++i) if (h0[i] != 0.f || h1[i] != 0.f) nz[p] = 1;
+    { Ld ld; ld.mode = LD_OLS_CHIRPSIG; ld.logF = logF; ld.b = chirp.data(); ld.N = N; ld.frame0 = D; ld.seg0 = 0;
+      St st; st.mode = ST_PLAIN; st.a = X.data(); emu_segments(logF, s_hi, tw, ld, st, false); }
+    { Ld ld; ld.mode = LD_OLS_IRC; ld.logF = logF; ld.f0 = h0.data(); ld.nvalid = L; ld.f1 = h1.data(); ld.nvalid1 = L;
+      ld.cin = 1; ld.b = chirp.data(); ld.N = N;
+      St st; st.mode = ST_SCALE; st.a = H.data(); st.scale = 1.0f / (float)F; emu_segments(logF, P, tw, ld, st, false); }
+    { Ld ld; ld.mode = LD_OLS_MAC; ld.logF = logF; ld.a = X.data() + s_lo * F; ld.b = H.data(); ld.nz = nz.data(); ld.P = P;
+      ld.lookback = s_lo;
+      St st; st.mode = ST_OLS_CHIRP; st.logF = logF; st.a = Pout.data(); st.chirp = chirp.data(); st.N = N; st.seg0 = s_lo;
+      st.frame0 = D; emu_segments(logF, s_hi - s_lo, tw, ld, st, true); }
+    double maxerr = 0, peak = 0;
+    const i64 step = std::max<i64>(1, N / 61);
+    for (i64 k = 0; k < N; k += step) {
+        cd acc = 0;
+        for (i64 n = 0; n < L; ++n) {
+            if (h0[n] == 0.f && h1[n] == 0.f) continue;
+            const i64 e = (n * k) % N;
+            const double a = -2 * PI * (double)e / (double)N;
+            acc += cd(h0[n], h1[n]) * cd(cos(a), sin(a));
+        }
+        peak = std::max(peak, std::abs(acc));
+        maxerr = std::max(maxerr, std::abs(acc - cd(Pout[k].x, Pout[k].y)));
+    }
+    printf("irs N=%lld L=%lld: max err %.3e (peak %.2f) rel %.3e\n", (long long)N, (long long)L, maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "irs")) {
+        int bad = check_irs(100003, 30000) + check_irs(65536, 9000) + check_irs(40001, 40000) + check_irs(5000, 300);
+        printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
+        return bad ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "ols")) {
         int bad = 0;
         bad += check_ols(12, 20000, 5000, false, 0, -1);

@@ -522,3 +522,33 @@ def test_ir_resampling_matches_scipy(rs, tmp_path):
                       layout="5.1 (Standard)")
     d = np.abs(np.round(pcm * 32768).astype(np.int32) - want["pcm"].astype(np.int32))
     assert pcm.shape == want["pcm"].shape and d.max() <= 1
+
+
+def test_sparse_ir_spectrum_route_matches_full_transform(rs, golden):
+    """The IR spectrum of a procedural IR is taken through the overlap-save route (cached chirp delay line);
+    it must agree with the two-M-point-transform route and with the goldens."""
+    from ars_b200 import _capi
+    g = golden("convolve")
+    keys = [str(k) for k in g["x_keys"]]
+    x = (0.3 * np.random.default_rng(3).standard_normal((50000, 2))).astype(np.float32)
+    kw = dict(hall_type="Cathedral", room_size=600., air_absorption=.3, bass_gain=1.4, treble_gain=.8, dry_wet=.55,
+              target_channel_layout="5.1 (Standard)")
+    out = []
+    try:
+        for use in (1, 0):
+            _capi.set_option("sparse_ir", use)
+            for i, p in enumerate(g["split_par"]):
+                el, ll, dw, b, t, ks, air = p[1:8]
+                got = rs.convolve_audio_split_3d(g["x_" + keys[int(p[0])]], g["early"], g["late"], el, ll, dw, b, t, 48000,
+                                                 ks, air)
+                assert rel_err(got, g[f"split{i}"]) <= TOL, (use, i, rel_err(got, g[f"split{i}"]))
+            np.random.seed(8)
+            out.append(rs.render_array(x, 48000, want_stereo=True, **kw))
+    finally:
+        _capi.set_option("sparse_ir", 1)
+    np.random.seed(8)
+    want = orc.render(x, 48000, hall="Cathedral", room_size=600., air=.3, bass=1.4, treble=.8, dry_wet_amount=.55,
+                      layout="5.1 (Standard)")
+    for r in out:
+        assert rel_err(r["stereo"], want["stereo"]) <= TOL and rel_err(r["final"], want["final"]) <= TOL
+    assert rel_err(out[0]["final"], out[1]["final"]) <= 2e-6

@@ -54,6 +54,8 @@ def test_fft_engine_host_emulation():
     assert r.returncode == 0, r.stdout[-2000:]
     r = subprocess.run([exe, "ols"], capture_output=True, text=True)      # overlap-save wiring incl. block ranges
     assert r.returncode == 0, r.stdout[-2000:]
+    r = subprocess.run([exe, "irs"], capture_output=True, text=True)      # short-IR spectrum route
+    assert r.returncode == 0, r.stdout[-2000:]
     env = dict(os.environ, ARS_FFT_PLAN="6,6,7")
     r = subprocess.run([exe, "19"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-2000:]

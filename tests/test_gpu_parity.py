@@ -552,3 +552,49 @@ def test_sparse_ir_spectrum_route_matches_full_transform(rs, golden):
     for r in out:
         assert rel_err(r["stereo"], want["stereo"]) <= TOL and rel_err(r["final"], want["final"]) <= TOL
     assert rel_err(out[0]["final"], out[1]["final"]) <= 2e-6
+
+
+def test_cfg2_full_size_vs_oracle(rs):
+    """BASELINE configs[1] at full size: 60 s mono -> 5.1, Room / Holz / 200 m^3, air 0.1, bass 1.5 / treble 0.8;
+    N = 2 970 503 is prime (the reference's FFTs fall back to Bluestein there, and so do ours)."""
+    rate = 48000
+    x = (0.3 * np.random.default_rng(0).standard_normal(60 * rate)).astype(np.float32)
+    np.random.seed(11)
+    want = orc.render(x, rate, hall="Room", room_size=200., diffusion=.5, air=.1, early=.8, late=.6, dry_wet_amount=.6,
+                      kill_start=.5, bass=1.5, treble=.8, x=.3, y=.4, z=.6, material="Holz", layout="5.1 (Standard)")
+    np.random.seed(11)
+    got = rs.render_array(x, rate, hall_type="Room", room_size=200., diffusion=.5, air_absorption=.1, base_early_level=.8,
+                          base_late_level=.6, dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.5, treble_gain=.8, x_pos=.3,
+                          y_pos=.4, z_pos=.6, material="Holz", target_channel_layout="5.1 (Standard)")
+    assert got["final"].shape == (2970503, 6)
+    assert rel_err(got["final"], want["final"]) <= TOL
+    assert snr_db(got["final"], want["final"]) >= 100.0
+    d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) < 1e-2
+    assert abs(got["metrics"]["lufs"] - want["metrics"]["lufs"]) <= 5e-3
+
+
+def test_cfg3_full_size_properties(rs):
+    """BASELINE configs[2] at full size (300 s, 8 s procedural IR, air 0.1, 5.1.2): N = 14 783 999, 2^25-point FFTs.
+    Size-independent properties: linearity (every guard idle), and agreement of the two IR-spectrum routes."""
+    from ars_b200 import _capi
+    rate = 48000
+    x = (0.02 * np.random.default_rng(2).standard_normal((300 * rate, 2), dtype=np.float32)).astype(np.float32)
+    kw = dict(hall_type="Cathedral", room_size=20000., ir_duration=8.0, material="Stein", air_absorption=.1, dry_wet=.5,
+              target_channel_layout="5.1.2 (Atmos Light)", want_metrics=False, want_pcm=False)
+    np.random.seed(3)
+    a = rs.render_array(x, rate, **kw)["final"]
+    assert a.shape == (14783999, 8) and np.max(np.abs(a)) < 0.9
+    np.random.seed(3)
+    b = rs.render_array((2.0 * x).astype(np.float32), rate, **kw)["final"]
+    assert rel_err(b, 2.0 * a) <= 2e-6
+    del b
+    try:
+        _capi.set_option("sparse_ir", 0)
+        np.random.seed(3)
+        c = rs.render_array(x, rate, **kw)["final"]
+    finally:
+        _capi.set_option("sparse_ir", 1)
+    assert rel_err(c, a) <= 2e-6
+    # the 18 ms height pair is the rear pair delayed and scaled by 0.6 * z (rs.py:549-554)
+    assert np.array_equal(a[864:, 6], (a[:-864, 4].astype(np.float64) * (0.5 * 0.6)).astype(np.float32))

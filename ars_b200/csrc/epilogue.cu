@@ -69,7 +69,7 @@ __device__ __forceinline__ void block_atomic_max(unsigned m, unsigned* dst) {
     if (threadIdx.x < 32) {
         m = (threadIdx.x < (blockDim.x + 31) / 32) ? s_m[threadIdx.x] : 0u;
         m = warp_max(m);
-        if (threadIdx.x == 0 && m) atomicMax(dst, m);
+        if (threadIdx.x == 0 && m > *reinterpret_cast<volatile unsigned*>(dst)) atomicMax(dst, m);
     }
     __syncthreads();      // the staging array is reused by the next reduction of the same block
 }

@@ -415,7 +415,9 @@ struct St {
             for (int q = 0; q < 4; ++q) {
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m[q] = max(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
-                if ((threadIdx.x & 31) == 0 && m[q]) atomicMax(maxbits + q, m[q]);
+                // thousands of tiles update the same four words: look first, only a new maximum pays for the atomic
+                if ((threadIdx.x & 31) == 0 && m[q] > *reinterpret_cast<volatile unsigned*>(maxbits + q))
+                    atomicMax(maxbits + q, m[q]);
             }
 #else
             const unsigned m[4] = {local_max, local_l, local_r, local_lr};

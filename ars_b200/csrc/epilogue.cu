@@ -112,6 +112,22 @@ __global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__
         }
         return;
     }
+    if (g1.mode == 1) {
+        // Stereo guard active: |L'| and |R'| maxima still follow in closed form (x / m is monotone), only the mono
+        // term max |float32(L' + R')| does not.  The pan maximum is used for nothing but its guard decision (> 1:
+        // divide; < 1e-9: flush), so when an upper bound of the mono term keeps every channel <= 1 and an exact
+        // L / R channel is >= 1e-9 the guard is provably idle and the pass over the signal is skipped; the exact
+        // L / R maximum is stored as a stand-in inside (1e-9, 1].
+        const float l = __fdiv_rn(__uint_as_float(st->max_l), g1.m), r = __fdiv_rn(__uint_as_float(st->max_r), g1.m);
+        const float mono_ub = __fmul_rn(__fadd_rn(l, r), 0.707f);
+        const float lr = fmaxf(fmaxf(__double2float_rn(__dmul_rn((double)l, ts.g_fl)), __double2float_rn(__dmul_rn((double)r, ts.g_fr))),
+                               fmaxf(__double2float_rn(__dmul_rn((double)l, ts.g_rl)), __double2float_rn(__dmul_rn((double)r, ts.g_rr))));
+        const float ub = fmaxf(fmaxf(fabsf(__double2float_rn(__dmul_rn((double)mono_ub, ts.g_c))), __fmul_rn(mono_ub, ts.g_lfe)), fabsf(lr));
+        if (ub <= 1.0f && fabsf(lr) >= 1e-9f) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) st->max_pan = abs_bits(lr);
+            return;
+        }
+    }
     unsigned m = 0;
     for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
         const float2 v = __ldg(y + (i - ts.y0));
@@ -210,7 +226,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
             }
         }
         if (mono) {
-            const float mv = __fdiv_rn(__fadd_rn(o[0], o[1]), 2.0f);    // np.mean(data[:, :2], axis=1), rs.py:688
+            const float mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);    // np.mean(data[:, :2], axis=1) (rs.py:688); x / 2 == x * 0.5 exactly
             mono[i - ts.out0] = mv;
             mm = max(mm, abs_bits(mv));
         }

@@ -211,9 +211,14 @@ struct Ld {
                                 : make_float2(0.f, 0.f);
         } else if constexpr (MODE == LD_CHIRP_XC) {    // (frames, cin) floats: cin == 1 duplicates, cin > 2 keeps the first two
             if (idx >= nvalid) return make_float2(0.f, 0.f);
-            const float l = ARS_LDG(f0 + idx * cin);
-            const float r = cin > 1 ? ARS_LDG(f0 + idx * cin + 1) : l;
-            return cmul(make_float2(l, r), ARS_LDG(b + idx));
+            float2 v;
+            if ((cin & 1) == 0) {                      // even channel count: the first two channels are one aligned 8-byte load
+                v = ARS_LDG(reinterpret_cast<const float2*>(f0 + idx * cin));
+            } else {
+                v.x = ARS_LDG(f0 + idx * cin);
+                v.y = cin > 1 ? ARS_LDG(f0 + idx * cin + 1) : v.x;
+            }
+            return cmul(v, ARS_LDG(b + idx));
         } else if constexpr (MODE == LD_CHIRP_PAIR) {  // two real arrays packed as re + i*im (each may be absent / shorter)
             const float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
             const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;

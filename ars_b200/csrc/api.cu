@@ -581,6 +581,22 @@ int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t w
     ARS_API_END
 }
 
+int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, float* side_rms_out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && rms_out && n > 0 && ch >= 1 && ch <= 8, "ars_channel_rms: needs (n > 0, 1..8 channels)");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", data, (size_t)n * ch);
+    double* d_s = c.buf("chan.sums", sizeof(double) * 9).as<double>();
+    ARS_CUDA(cudaMemsetAsync(d_s, 0, sizeof(double) * 9, c.stream));
+    channel_sums(d_x, n, ch, d_s);
+    double h[9];
+    download(h, d_s, (size_t)ch + 1);
+    sync();
+    for (int k = 0; k < ch; ++k) rms_out[k] = (float)std::sqrt(h[k] / (double)n);       // np.sqrt(np.mean(x**2)), float32
+    if (side_rms_out) *side_rms_out = ch >= 2 ? (float)std::sqrt(h[ch] / (double)n) : 0.f;
+    ARS_API_END
+}
+
 int ars_pcm16(const float* data, int64_t count, int16_t* out) {
     ARS_API_BEGIN
     ARS_CHECK(data && out && count > 0, "ars_pcm16: bad arguments");

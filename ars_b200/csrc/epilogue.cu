@@ -452,6 +452,31 @@ void sums_stage(const float* d_x, i64 N, int C, RenderState* d_state, float* d_m
     count_launch();
 }
 
+// per-channel sum of squares and the side signal's ((ch0 - ch1) * 0.5) sum of squares: the numerics of the
+// reference's A/B report (rs.py:769-798); sums[c] for c < C, sums[C] = side
+__global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restrict__ x, i64 N, int C, double* sums) {
+    double acc[9];
+    #pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (i64)gridDim.x * blockDim.x) {
+        const float* p = x + i * C;
+        #pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < C) { const float v = __ldg(p + c); acc[c] += (double)__fmul_rn(v, v); }
+        if (C >= 2) { const float sd = __fmul_rn(__fsub_rn(__ldg(p), __ldg(p + 1)), 0.5f); acc[8] += (double)__fmul_rn(sd, sd); }
+    }
+    #pragma unroll
+    for (int c = 0; c < 9; ++c)
+        if (c < C || c == 8) block_atomic_add(acc[c], sums + (c == 8 ? C : c));
+}
+void channel_sums(const float* d_x, i64 N, int C, double* d_sums) {
+    if (N <= 0 || C <= 0) return;
+    ARS_CHECK(C <= 8, "channel_sums: at most 8 channels");
+    channel_sums_kernel<<<stream_grid(N), 256, 0, ctx().stream>>>(d_x, N, C, d_sums);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
 __global__ void __launch_bounds__(256) stereo_from_kernel(const float* __restrict__ x, i64 n, int cin, float2* __restrict__ out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         const float l = x[i * cin];

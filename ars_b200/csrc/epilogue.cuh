@@ -48,6 +48,7 @@ void map_stage(const float* d_six, i64 N, const TailSpec& ts, float* d_out);    
 void delay_stage(const float* d_in, i64 N, int ch, i64 delay, float* d_out);                     // rs.py:507-515
 void pcm16_stage(const float* d_x, i64 count, short* d_pcm);                                     // rs.py:1082-1084
 void sums_stage(const float* d_x, i64 N, int C, RenderState* d_state, float* d_mono);           // peak, sum x^2, mono feed
-void stereo_from(const float* d_x, i64 n, int cin, float* d_out);            // rs.py:343-346 mono dup / first two
+void stereo_from(const float* d_x, i64 n, int cin, float* d_out);
+void channel_sums(const float* d_x, i64 N, int C, double* d_sums);          // C + 1 doubles, pre-zeroed (rs.py:769-798)            // rs.py:343-346 mono dup / first two
 
 }  // namespace ars

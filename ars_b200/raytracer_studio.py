@@ -403,6 +403,21 @@ def calculate_audio_metrics(data, rate):
         return metrics
 
 
+def channel_levels(data):
+    """Numerics of the reference's A/B report (rs.py:769-798): -> (per-channel RMS dBFS list, side-signal RMS of the
+    first two channels -- the report's "stereo width" metric; 0.0 for mono)."""
+    x = np.ascontiguousarray(data, dtype=_F32)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, ch = x.shape
+    if n == 0 or ch == 0:
+        return [], 0.0
+    rms = np.empty(ch, _F32)
+    side = _capi.C.c_float(0)
+    _capi.check(_lib().ars_channel_rms(_capi.ptr(x), n, ch, _capi.ptr(rms), _capi.C.byref(side)), "ars_channel_rms")
+    return [20 * math.log10(float(v)) if v > 1e-15 else -np.inf for v in rms], float(side.value)
+
+
 def float_to_pcm16(data):
     """clip +-0.9999, scrub non-finite, float -> int16 (rs.py:1082-1084 + libsndfile's rule)."""
     x = np.ascontiguousarray(data, dtype=_F32)

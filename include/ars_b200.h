@@ -154,6 +154,10 @@ ARS_API int ars_map_channels(const float* six, int64_t n, int32_t layout, double
 /* calculate_audio_metrics, rs.py:674-698.  data: (n, ch). */
 ARS_API int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t want_lufs, ArsMetrics* out);
 
+/* Numerics of the A/B report (run_audio_profiler_v4, rs.py:769-798): per-channel RMS sqrt(mean(x^2)) of an
+ * (n, ch <= 8) array and the RMS of the side signal (ch0 - ch1) * 0.5 (0 for mono).  rms_out: ch floats. */
+ARS_API int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, float* side_rms_out);
+
 /* clip + scrub + float->PCM16, rs.py:1082-1084 (libsndfile rule lrintf(x * 32767)). */
 ARS_API int ars_pcm16(const float* data, int64_t count, int16_t* out);
 

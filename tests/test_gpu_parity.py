@@ -598,3 +598,49 @@ def test_cfg3_full_size_properties(rs):
     assert rel_err(c, a) <= 2e-6
     # the 18 ms height pair is the rear pair delayed and scaled by 0.6 * z (rs.py:549-554)
     assert np.array_equal(a[864:, 6], (a[:-864, 4].astype(np.float64) * (0.5 * 0.6)).astype(np.float32))
+
+
+def test_channel_levels_match_numpy(rs):
+    """rs.py:769-798: per-channel RMS dBFS and the side-signal RMS ("stereo width")."""
+    g = np.random.default_rng(77)
+    for n, ch in ((48000, 6), (12345, 2), (999, 1), (30000, 8)):
+        d = (0.3 * g.standard_normal((n, ch)) * g.uniform(0.01, 1.0, ch)).astype(np.float32)
+        levels, side = rs.channel_levels(d)
+        for c in range(ch):
+            want = 20 * np.log10(float(np.sqrt(np.mean(d[:, c] ** 2))))
+            assert abs(levels[c] - want) <= 1e-4
+        want_side = float(np.sqrt(np.mean(((d[:, 0] - d[:, 1]) * 0.5) ** 2))) if ch >= 2 else 0.0
+        assert abs(side - want_side) <= 1e-6 * max(1.0, want_side)
+
+
+def test_device_pointer_render_equals_host_render(rs):
+    """ars_render_dev (device buffers, what bench.py times) must produce exactly what ars_render does."""
+    import torch
+    from ars_b200 import _capi
+    lib = _capi.init()
+    g = np.random.default_rng(5)
+    rate = 48000
+    x = (0.4 * g.standard_normal((70001, 2))).astype(np.float32)
+    kw = dict(hall_type="Room", room_size=250., air_absorption=.2, bass_gain=1.3, treble_gain=.9, dry_wet=.5,
+              target_channel_layout="7.1 (Surround)")
+    np.random.seed(17)
+    host = rs.render_array(x, rate, **kw)
+    p, refl = rs.make_render_params(rate, want_lufs=True, **kw)
+    np.random.seed(17)
+    taps, bases, noise = rs.draw_ir_randoms(rate, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+    N = int(lib.ars_render_out_len(p, x.shape[0], 0))
+    d_x = torch.from_numpy(x).cuda()
+    d_noise = torch.from_numpy(noise).cuda()
+    d_pcm = torch.empty((N, 8), dtype=torch.int16, device="cuda")
+    d_f32 = torch.empty((N, 8), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    keep = []
+    draws = _capi.make_draws(taps, bases, int(d_noise.data_ptr()), keep)
+    draws.noise_len = int(noise.size)
+    m = _capi.ArsMetrics()
+    _capi.check(lib.ars_render_dev(p, d_x.data_ptr(), x.shape[0], 2, None, 0, draws, None, d_f32.data_ptr(),
+                                   d_pcm.data_ptr(), m), "ars_render_dev")
+    _capi.check(lib.ars_sync(), "ars_sync")
+    assert np.array_equal(d_pcm.cpu().numpy(), host["pcm"])
+    assert np.array_equal(d_f32.cpu().numpy(), host["final"])
+    assert rs._metrics_dict(m) == host["metrics"]

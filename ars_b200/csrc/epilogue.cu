@@ -139,19 +139,26 @@ __global__ void __launch_bounds__(256) pan_max_kernel(const float2* __restrict__
     block_atomic_max(m, &st->max_pan);
 }
 
+// A = false compiles the guard away (the caller has checked that its mode is 0)
+template <bool A> __device__ __forceinline__ float guardT(float v, const Guard& g) {
+    if constexpr (A) return guard1(v, g);
+    else return v;
+}
+
+template <bool A1 = true, bool A2 = true>
 __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
                                           const Guard& g2, float (&o)[8]) {
     const float2 v = __ldg(y + (i - ts.y0));
     float s[6];
-    pan6(guard1(v.x, g1), guard1(v.y, g1), ts, s);
+    pan6(guardT<A1>(v.x, g1), guardT<A1>(v.y, g1), ts, s);
     #pragma unroll
-    for (int c = 0; c < 6; ++c) s[c] = guard1(s[c], g2);
+    for (int c = 0; c < 6; ++c) s[c] = guardT<A2>(s[c], g2);
     float rl_d = 0.f, rr_d = 0.f;
     if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
         // a delay <= 0 leaves the signal where it is (rs.py:510-511)
         const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0) - ts.y0));
-        rl_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.x, g1), ts.g_rl)), g2);
-        rr_d = guard1(__double2float_rn(__dmul_rn((double)guard1(w.y, g1), ts.g_rr)), g2);
+        rl_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(w.x, g1), ts.g_rl)), g2);
+        rr_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(w.y, g1), ts.g_rr)), g2);
     }
     map_frame(s, rl_d, rr_d, ts, o);
 }
@@ -169,32 +176,30 @@ __global__ void __launch_bounds__(256) map_max_kernel(const float2* __restrict__
 }
 
 __device__ __forceinline__ short pcm_of(float v) {
-    // np.clip(+-0.9999) in float32, NaN -> 0, then lrintf(x * 32767.0f)   (rs.py:1082-1084)
-    if (v != v) v = 0.f;
-    v = fminf(fmaxf(v, -0.9999f), 0.9999f);
-    return (short)__float2int_rn(__fmul_rn(v, 32767.0f));
+    // np.clip(+-0.9999) in float32, NaN -> 0, then lrintf(x * 32767.0f)   (rs.py:1082-1084).
+    // Evaluated as clamp(rint(x * 32767), +-32764): rounding is monotone and rint(0.9999f * 32767) = 32764, so
+    // clamping after the conversion gives the same integers; cvt.rni maps NaN to 0 and +-inf to the clamp.
+    const int q = __float2int_rn(__fmul_rn(v, 32767.0f));
+    return (short)min(max(q, -32764), 32764);
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st,
-                                                    float* __restrict__ out, short* __restrict__ pcm,
-                                                    float* __restrict__ mono) {
-    const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
-    // 5.1 / 7.1 / 5.1.2 carry the six channels through unchanged and add only attenuated (x0.7, x<=0.6) delayed
-    // copies, so their maximum is the guarded six-channel maximum (<= 1, or >= 1e-9): that guard never fires
-    const Guard g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
-    unsigned pk = 0, mm = 0;
-    double ss = 0.0;
+// The frame loop of the final pass; A1 / A2 / A3 say which peak guards are active (checked once per thread, so
+// idle guards cost nothing per sample).
+template <int C, bool A1, bool A2, bool A3>
+__device__ __forceinline__ void final_body(const float2* __restrict__ y, const TailSpec& ts, const Guard& g1, const Guard& g2,
+                                           const Guard& g3, float* __restrict__ out, short* __restrict__ pcm,
+                                           float* __restrict__ mono, float& pkf, bool& nan_seen, unsigned& mm, double& ss) {
     for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
         float o[8];
-        frame_out(y, i, ts, g1, g2, o);
+        frame_out<A1, A2>(y, i, ts, g1, g2, o);
         float fs = 0.f;        // one frame's squares in float32 (numpy squares in float32 too), then one conversion
         #pragma unroll
         for (int c = 0; c < C; ++c) {
-            o[c] = guard1(o[c], g3);
-            pk = max(pk, abs_bits(o[c]));
+            o[c] = guardT<A3>(o[c], g3);
+            pkf = fmaxf(pkf, fabsf(o[c]));
             fs = __fmaf_rn(o[c], o[c], fs);
         }
+        nan_seen |= (fs != fs);                       // a NaN sample makes the frame's sum NaN (np.max would return NaN)
         ss += (double)fs;
         if (out) {
             float* p = out + (i - ts.out0) * C;
@@ -231,6 +236,27 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
             mm = max(mm, abs_bits(mv));
         }
     }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st,
+                                                    float* __restrict__ out, short* __restrict__ pcm,
+                                                    float* __restrict__ mono) {
+    const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
+    // 5.1 / 7.1 / 5.1.2 carry the six channels through unchanged and add only attenuated (x0.7, x<=0.6) delayed
+    // copies, so their maximum is the guarded six-channel maximum (<= 1, or >= 1e-9): that guard never fires
+    const Guard g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
+    float pkf = 0.f;
+    bool nan_seen = false;
+    unsigned mm = 0;
+    double ss = 0.0;
+    if (g2.mode == 0 && g3.mode == 0) {
+        if (g1.mode == 0) final_body<C, false, false, false>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        else final_body<C, true, false, false>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+    } else {
+        final_body<C, true, true, true>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+    }
+    const unsigned pk = nan_seen ? 0x7fc00000u : __float_as_uint(pkf);
     block_atomic_max(pk, &st->peak_final);
     block_atomic_max(mm, &st->mono_max);
     block_atomic_add(ss, &st->sumsq);

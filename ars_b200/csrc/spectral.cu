@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(256) transfer_kernel(float2* __restrict__ Z, c
         const float2 h1 = make_float2(0.5f * (pk.y + pm.y), -0.5f * (pk.x - pm.x));
         const float dg = (float)fs.dry_gain, dw = (float)fs.dw;
         if (fs.mode == FILT_SPLIT) {
-            const float c0 = state->ir_any0 ? (float)fs.level0 : 0.f;
-            const float c1 = state->ir_any1 ? (float)fs.level1 * gain_air(fs, k) : 0.f;
+            const float c0 = (float)fs.level0;
+            const float c1 = (float)fs.level1 * gain_air(fs, k);
             float2 t = make_float2(c0 * h0.x + c1 * h1.x, c0 * h0.y + c1 * h1.y);
             t = make_float2((dg + dw * t.x) * geq, (dw * t.y) * geq);
             tl = tr = t;
@@ -424,9 +424,8 @@ void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L
             ld.mode = LD_CHIRP_PAIR;
             ld.f0 = d_ir0; ld.nvalid = L0;
             ld.f1 = d_ir1; ld.nvalid1 = L1;
-            ir_flags_kernel<<<64, 256, 0, c.stream>>>(d_ir0, L0, 1, d_ir1, L1, 1, d_state);
-            ARS_LAUNCH_CHECK();
-            count_launch();
+            // np.any(ir) gates each branch in the reference (rs.py:360,369); an all-zero part has an all-zero
+            // spectrum, so the gate changes nothing numerically and needs no pass over the IR here
         } else {
             ARS_CHECK(d_ir0 != nullptr && L0 >= 1, "spectral_filter: external IR missing");
             ld.mode = LD_CHIRP_X2;

@@ -345,9 +345,10 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = pbytes.value / (pms.value * 1e-3) / 1e9 if pms.value > 0 else 0.0
-    traffic = None
+    traffic = traffic_src = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        traffic, traffic_src = float(t["dram_bytes_per_launch_mean"]), t["source"]
     except Exception:
         pass
     step_ms = dev_ms / args.steps
@@ -374,7 +375,10 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "launches_per_step": int(pl.value), "ms_per_step_in_kernel": pms.value,
-                     "share_of_step": pms.value / step_ms if step_ms else None, "traffic": traffic},
+                     "share_of_step": pms.value / step_ms if step_ms else None,
+                     "algorithmic_bytes_per_launch": pbytes.value / max(1, pl.value),
+                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                     "traffic_source": traffic_src},
         "roofline_whole_render": {"algorithmic_bytes_per_step": int(out_bytes_per_frame * N),
                                   "achieved": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9, "unit": "GB/s",
                                   "frac": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9 / peak,
@@ -498,7 +502,7 @@ def main():
     ap.add_argument("--clips", type=int, default=128, help="cfg4: clips in the batch (BASELINE: 1024)")
     ap.add_argument("--seconds", type=float, default=0.0, help="override the clip length (default: the config's)")
     ap.add_argument("--ir-seconds", type=float, default=0.0, help="external-IR length for cfg5")
-    ap.add_argument("--cpu-sample-seconds", type=float, default=60.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=300.0)
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -644,3 +644,30 @@ def test_device_pointer_render_equals_host_render(rs):
     assert np.array_equal(d_pcm.cpu().numpy(), host["pcm"])
     assert np.array_equal(d_f32.cpu().numpy(), host["final"])
     assert rs._metrics_dict(m) == host["metrics"]
+
+
+def test_large_transform_2pow28_properties(rs):
+    """A 25-minute clip with the EQ mask on: N = 72 000 000 + L - 1, Bluestein length 2^28 (three passes of 2^8 /
+    2^8 / 2^12 points, two-level twiddle tables, 64-bit indices).  Linearity plus a direct time-domain spot check of
+    the convolution at a handful of output frames."""
+    rate = 48000
+    n = 25 * 60 * rate
+    g = np.random.default_rng(9)
+    x = (0.05 * g.standard_normal((n, 2), dtype=np.float32)).astype(np.float32)
+    ir = (g.standard_normal((4000, 2)) * np.exp(-np.arange(4000) / 800.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir)) * 10
+    kw = dict(external_ir_data=ir, dry_wet=.5, dry_wet_kill_start=1.0, bass_gain=1.0, treble_gain=1.00002,
+              target_channel_layout="Stereo", want_metrics=False, want_pcm=False, want_stereo=True)
+    a = rs.render_array(x, rate, **kw)                      # treble 1.00002 is outside np.isclose -> N-point path
+    assert a["stereo"].shape == (n + 3999, 2) and np.max(np.abs(a["stereo"])) < 1.0
+    # spot check: with gains this close to 1 the EQ changes the result by < 2e-5 * |y|, far below the tolerance used
+    for f in (0, 1234, 3999, n // 2 + 17, n - 1, n + 3000):
+        lo = max(0, f - 3999)
+        wl = sum(float(ir[f - m, 0]) * float(x[m, 0]) for m in range(lo, min(n, f + 1)))
+        wr = sum(float(ir[f - m, 1]) * float(x[m, 1]) for m in range(lo, min(n, f + 1)))
+        dl = float(x[f, 0]) if f < n else 0.0
+        dr = float(x[f, 1]) if f < n else 0.0
+        assert abs(a["stereo"][f, 0] - (0.5 * dl + 0.5 * wl)) <= 3e-5
+        assert abs(a["stereo"][f, 1] - (0.5 * dr + 0.5 * wr)) <= 3e-5
+    b = rs.render_array((2.0 * x).astype(np.float32), rate, **kw)
+    assert rel_err(b["stereo"], 2.0 * a["stereo"]) <= 2e-6

@@ -199,7 +199,7 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
     Ld ld;
     ld.logF = logF;
     if (tiled) {
-        constexpr int JT = 16;
+        constexpr int JT = 8;      // measured: 8 -> 4.81 ms, 12 -> 4.80, 16 -> 5.20, 32 -> 5.28 (600 s clip, 8 s stereo IR)
         float2* Y = c.buf("ols.Y", sizeof(float2) * (size_t)(run * F)).as<float2>();
         const dim3 grid((unsigned)((F + 255) / 256), (unsigned)((run + JT - 1) / JT));
         ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, X + (size_t)nseg * F + skip * F,

@@ -283,7 +283,8 @@ void ir_spectrum_short(BluesteinPlan* bp, const float* d_ir0, i64 L0, const floa
         const size_t need = sizeof(float2) * (size_t)(s_hi * F);
         if (bp->ols_x.cap < need) {
             const size_t old = bp->ols_x.cap;
-            bp->ols_x.reserve(need);
+            if (bp->ols_x.p) g_plan_pool.push_back(bp->ols_x);    // recycled like the other plan buffers (no free / malloc per clip)
+            bp->ols_x = take_buffer(need);
             bp->bytes += bp->ols_x.cap - old;
             c.blue_bytes += bp->ols_x.cap - old;
         }

@@ -671,3 +671,33 @@ def test_large_transform_2pow28_properties(rs):
         assert abs(a["stereo"][f, 1] - (0.5 * dr + 0.5 * wr)) <= 3e-5
     b = rs.render_array((2.0 * x).astype(np.float32), rate, **kw)
     assert rel_err(b["stereo"], 2.0 * a["stereo"]) <= 2e-6
+
+
+def test_concurrent_callers_are_serialised(rs):
+    """The reference is called from Gradio worker threads: concurrent calls into the library must
+    give the same results as sequential ones (one mutex, one stream)."""
+    import threading
+    g = np.random.default_rng(66)
+    ir = (g.standard_normal((3000, 2)) * np.exp(-np.arange(3000) / 700.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir)) * 5
+    jobs = [((0.3 * g.standard_normal((20000 + 1111 * i, 2))).astype(np.float32),
+             dict(external_ir_data=ir, dry_wet=.3 + .1 * i, bass_gain=1.0 + .1 * (i % 3), treble_gain=1.0,
+                  target_channel_layout=["Stereo", "5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)"][i % 4]))
+            for i in range(8)]
+    want = [rs.render_array(x, 48000, **kw) for x, kw in jobs]
+    got = [None] * len(jobs)
+
+    def work(i):
+        x, kw = jobs[i]
+        got[i] = rs.render_array(x, 48000, **kw)
+        rs.apply_surround_panning_3d(x, .3, .4, .5)          # interleave other entry points too
+        rs.calculate_audio_metrics(x, 48000)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for a, b in zip(want, got):
+        assert np.array_equal(a["final"], b["final"]) and np.array_equal(a["pcm"], b["pcm"])
+        assert a["metrics"] == b["metrics"]

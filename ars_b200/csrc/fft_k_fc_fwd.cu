@@ -1,0 +1,21 @@
+// One slice of the FFT pass-kernel instantiations (see fft_launch.cuh).
+#include "fft_launch.cuh"
+
+namespace ars {
+namespace fftk {
+
+bool fast_contig_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa) {
+    const int lm = ld.mode, sm = st.mode;
+    if (sm != ST_PLAIN) return false;
+#define F_CASE(R, C)                                                                                          \
+    if (ps.logR == R && ps.logT == C) {                                                                       \
+        if (lm == LD_PLAIN) { launch_contig<R, C, false, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; }    \
+        if (lm == LD_OLS_X) { launch_contig<R, C, false, LD_OLS_X, ST_PLAIN>(ld, st, pa); return true; }    \
+    }
+    ARS_FAST_CONTIG(F_CASE)
+#undef F_CASE
+    return false;
+}
+
+}  // namespace fftk
+}  // namespace ars

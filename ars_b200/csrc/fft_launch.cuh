@@ -1,0 +1,56 @@
+// Launchers of the FFT pass kernels, split over several translation units so that the ~130 kernel
+// instantiations compile in parallel (fft_k_*.cu); fft_plan.cu only dispatches.
+#pragma once
+#include "fft.cuh"
+
+namespace ars {
+namespace fftk {
+
+using namespace fft;
+
+constexpr int NT = 512;
+
+template <int LOGR, int LOGT, bool INV, int LDM, int STM>
+static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = StridedLayout<LOGR, LOGT>;
+    static bool attr_done = false;
+    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
+    auto k = pass_strided_kernel<LOGR, LOGT, INV, NT, LDM, STM>;
+    if (!attr_done && smem > 48 * 1024) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const i64 tiles = pa.M >> (LOGR + LOGT);
+    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+template <int LOGR, int LOGC, bool INV, int LDM, int STM>
+static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = ContigLayout<LOGR, LOGC>;
+    static bool attr_done = false;
+    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
+    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT, LDM, STM>;
+    if (!attr_done && smem > 48 * 1024) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const i64 tiles = pa.M >> (LOGR + LOGC);
+    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+// each returns false when it has no instantiation for the request (defined in fft_k_*.cu)
+bool fast_strided_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool fast_strided_inv(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool fast_contig_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool fast_contig_inv(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool generic_strided_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool generic_strided_inv(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool generic_contig_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+bool generic_contig_inv(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);
+
+}  // namespace fftk
+}  // namespace ars

@@ -1,5 +1,5 @@
 // FFT plans (pass decomposition + twiddle tables) and the launchers for fft.cuh.
-#include "fft.cuh"
+#include "fft_launch.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -186,81 +186,7 @@ static cudaEvent_t prof_event() {
 }
 
 // --------------------------------------------------------------- launchers ---
-constexpr int NT = 512;
-
-template <int LOGR, int LOGT, bool INV, int LDM, int STM>
-static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
-    using L = StridedLayout<LOGR, LOGT>;
-    static bool attr_done = false;
-    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
-    auto k = pass_strided_kernel<LOGR, LOGT, INV, NT, LDM, STM>;
-    if (!attr_done && smem > 48 * 1024) {
-        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const i64 tiles = pa.M >> (LOGR + LOGT);
-    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
-    ARS_LAUNCH_CHECK();
-    count_launch();
-}
-
-template <int LOGR, int LOGC, bool INV, int LDM, int STM>
-static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
-    using L = ContigLayout<LOGR, LOGC>;
-    static bool attr_done = false;
-    const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
-    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT, LDM, STM>;
-    if (!attr_done && smem > 48 * 1024) {
-        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const i64 tiles = pa.M >> (LOGR + LOGC);
-    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
-    ARS_LAUNCH_CHECK();
-    count_launch();
-}
-
-
-// Compile-time (load mode, store mode) pairs that occur in big transforms:
-//   forward first pass : LD_CHIRP_* -> ST_PLAIN (strided)      forward other passes: PLAIN -> PLAIN
-//   inverse first pass : LD_MULSPEC -> ST_PLAIN (contiguous)   inverse last pass   : PLAIN -> ST_CHIRP | ST_FINAL (strided)
-template <bool INV>
-static bool launch_fast(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa) {
-    if (!g_fast) return false;
-    const int lm = ld.mode, sm = st.mode;
-    if (ps.strided) {
-#define F_CASE(R, T)                                                                                              \
-        if (ps.logR == R && ps.logT == T) {                                                                       \
-            if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_strided<R, T, INV, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; } \
-            if constexpr (!INV) {                                                                                 \
-                if (sm == ST_PLAIN && lm == LD_CHIRP_X2) { launch_strided<R, T, false, LD_CHIRP_X2, ST_PLAIN>(ld, st, pa); return true; } \
-                if (sm == ST_PLAIN && lm == LD_CHIRP_XC) { launch_strided<R, T, false, LD_CHIRP_XC, ST_PLAIN>(ld, st, pa); return true; } \
-                if (sm == ST_PLAIN && lm == LD_CHIRP_PAIR) { launch_strided<R, T, false, LD_CHIRP_PAIR, ST_PLAIN>(ld, st, pa); return true; } \
-                if (sm == ST_PLAIN && lm == LD_CHIRP_C) { launch_strided<R, T, false, LD_CHIRP_C, ST_PLAIN>(ld, st, pa); return true; } \
-            } else {                                                                                              \
-                if (lm == LD_PLAIN && sm == ST_CHIRP) { launch_strided<R, T, true, LD_PLAIN, ST_CHIRP>(ld, st, pa); return true; } \
-                if (lm == LD_PLAIN && sm == ST_FINAL) { launch_strided<R, T, true, LD_PLAIN, ST_FINAL>(ld, st, pa); return true; } \
-            }                                                                                                     \
-        }
-        ARS_FAST_STRIDED(F_CASE)
-#undef F_CASE
-    } else {
-#define F_CASE(R, C)                                                                                              \
-        if (ps.logR == R && ps.logT == C) {                                                                       \
-            if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_contig<R, C, INV, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; } \
-            if constexpr (INV) {                                                                                  \
-                if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
-                if (lm == LD_OLS_MAC && sm == ST_OLS) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS>(ld, st, pa); return true; } \
-                if (lm == LD_OLS_MAC && sm == ST_OLS_CHIRP) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS_CHIRP>(ld, st, pa); return true; } \
-            } else {                                                                                              \
-                if (lm == LD_OLS_X && sm == ST_PLAIN) { launch_contig<R, C, false, LD_OLS_X, ST_PLAIN>(ld, st, pa); return true; } \
-            }                                                                                                     \
-        }
-        ARS_FAST_CONTIG(F_CASE)
-#undef F_CASE
-    }
-    return false;
-}
+using namespace fftk;
 
 template <bool INV>
 static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const St& st) {
@@ -280,18 +206,16 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
         ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
     } prof_scope(ld, st, p->M);
     if (ps.strided) ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
-    if (launch_fast<INV>(ps, ld, st, pa)) return;
-    if (ps.strided) {
-#define S_CASE(R, T) if (ps.logR == R && ps.logT == T) return launch_strided<R, T, INV, -1, -1>(ld, st, pa);
-        ARS_STRIDED_CASES(S_CASE)
-#undef S_CASE
-        ARS_CHECK(false, "no strided FFT pass kernel for this (logR, logT)");
-    } else {
-#define C_CASE(R, C) if (ps.logR == R && ps.logT == C) return launch_contig<R, C, INV, -1, -1>(ld, st, pa);
-        ARS_CONTIG_CASES(C_CASE)
-#undef C_CASE
-        ARS_CHECK(false, "no contiguous FFT pass kernel for this (logR, logC)");
+    bool done = false;
+    if (g_fast) {
+        if (ps.strided) done = INV ? fast_strided_inv(ps, ld, st, pa) : fast_strided_fwd(ps, ld, st, pa);
+        else done = INV ? fast_contig_inv(ps, ld, st, pa) : fast_contig_fwd(ps, ld, st, pa);
     }
+    if (!done) {
+        if (ps.strided) done = INV ? generic_strided_inv(ps, ld, st, pa) : generic_strided_fwd(ps, ld, st, pa);
+        else done = INV ? generic_contig_inv(ps, ld, st, pa) : generic_contig_fwd(ps, ld, st, pa);
+    }
+    ARS_CHECK(done, "no FFT pass kernel for this (logR, logT)");
 }
 
 int fft_segment_tile(int logF) { return logF == 12 ? 2 : 1; }

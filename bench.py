@@ -134,6 +134,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask), so that pinned host buffers are
+    allocated on the GPU's own NUMA node; with several ranks per box the host side of the copies otherwise crosses
+    sockets.  Best effort: silently does nothing when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ----------------------------------------------------------------------------- CPU arms -----
 def _oracle_render(args):
     w_name, seconds, seed_offset = args
@@ -213,6 +231,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _capi.init(local)
     w = WORKLOADS[args.workload]

@@ -701,3 +701,26 @@ def test_concurrent_callers_are_serialised(rs):
     for a, b in zip(want, got):
         assert np.array_equal(a["final"], b["final"]) and np.array_equal(a["pcm"], b["pcm"])
         assert a["metrics"] == b["metrics"]
+
+
+def test_batch_with_many_distinct_lengths_recycles_plans_correctly(rs):
+    """More distinct output lengths than the plan cache holds (16): evicted plans hand their buffers to new ones.
+    Every clip must still equal its single-call render bit for bit."""
+    g = np.random.default_rng(91)
+    rate = 16000
+    halls = ["Plate", "Room", "Cathedral"]
+    jobs = []
+    for i in range(22):
+        n = int(g.integers(4000, 40000))
+        jobs.append(dict(samples=(0.3 * g.standard_normal((n, 2))).astype(np.float32), rate=rate, seed=300 + i,
+                         hall_type=halls[i % 3], room_size=float(10 * g.integers(1, 101)),
+                         air_absorption=float(g.uniform()), bass_gain=float(g.uniform(.5, 2)), dry_wet=float(g.uniform()),
+                         target_channel_layout=["Stereo", "7.1 (Surround)", "5.1.2 (Atmos Light)"][i % 3]))
+    for rep in range(2):                      # second round: every plan of round one has been evicted in between
+        got = rs.render_batch(jobs, want_float=True)
+        for job, b in zip(jobs, got):
+            job = dict(job)
+            np.random.seed(job.pop("seed"))
+            a = rs.render_array(job.pop("samples"), job.pop("rate"), **job)
+            assert np.array_equal(a["final"], b["final"]) and np.array_equal(a["pcm"], b["pcm"])
+            assert a["metrics"] == b["metrics"]

@@ -32,6 +32,10 @@ void fft_profile_end(long long* launches, double* ms, double* bytes);
 static int g_opt_upols = 1;        // 1: use overlap-save whenever no exact-N mask is active; 0: always the N-point path
 static int g_opt_upols_logf = 13;  // 2B = 2^logF points per overlap-save transform (12 or 13)
 static int g_opt_sparse_ir = 1;    // 1: IR spectrum of sparse (procedural) IRs through the overlap-save route
+static unsigned long long g_air_fold_count = 0;   // convolution stages that took the folded-air route
+static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
+static int g_opt_air_fold_eps_e9 = 1000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
+static int g_opt_air_fold_max_taps = 32768;  // longest kept half-length of the air kernel; beyond: the exact N-point path
 
 // number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
 static int nonzero_partitions(const float* a, i64 na, const float* b, i64 nb) {
@@ -47,9 +51,19 @@ static int nonzero_partitions(const float* a, i64 na, const float* b, i64 nb) {
 }
 
 // the convolution stage: overlap-save when the render has no spectral mask, else the exact N-point filter
+// Non-zero extent of the IR parts as far as the host knows it (folded-air form, upols.cuh); late_hi < 0: unknown.
+struct IrExtent { i64 early_end = 0, late_lo = 0, late_hi = -1; };
+
 static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
-                              const FilterSpec& fs, float2* d_y, RenderState* st) {
-    if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK)
+                              const FilterSpec& fs, float2* d_y, RenderState* st, double rate = 0.0,
+                              const IrExtent& ext = IrExtent()) {
+    AirFold af;
+    if (g_opt_upols && g_opt_air_fold && ext.late_hi >= 0 && fs.level1 != 0.0 && d_ir1 &&
+        air_fold_plan(fs, ext.early_end, ext.late_lo, ext.late_hi, rate, 1e-9 * g_opt_air_fold_eps_e9,
+                      g_opt_air_fold_max_taps, &af)) {
+        ++g_air_fold_count;
+        upols_filter_airfold(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, af, d_y, st, g_opt_upols_logf);
+    } else if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK)
         upols_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, g_opt_upols_logf);
     else
         spectral_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st);
@@ -244,7 +258,16 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         // a procedural IR is a few dozen taps before the split plus a tail that decays by >= 1 % per sample and is
         // exactly zero in float32 some 10^4 samples later: a handful of non-zero partitions
         fs.sparse_ir = g_opt_sparse_ir;
-        convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st);
+        IrExtent ex;               // taps sit below the split; the tail starts there and underflows float32 to exact zeros
+        ex.early_end = g.split;
+        ex.late_lo = g.split;
+        ex.late_hi = g.split;
+        if (g.late_len > 0 && sp.amp > 0.0 && sp.decay > 0.0 && sp.decay < 1.0) {
+            // |tail[j]| <= 1e3 * amp * decay^j (the re-scaled boxcar mean of noise in [-1, 1]); float32 stores 0 below 2^-150
+            const double j0 = std::log(7.0e-46 / (1.0e3 * sp.amp)) / std::log(sp.decay);
+            ex.late_hi = g.split + (i64)std::min((double)g.late_len, std::max(0.0, std::ceil(j0) + 1.0));
+        }
+        convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st, p->rate, ex);
     }
     if (d_out_stereo) {
         ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
@@ -328,6 +351,7 @@ int ars_sync(void) {
 const char* ars_last_error(void) { return last_error_cstr(); }
 const char* ars_version(void) { return "ars_b200 0.1 (sm_100a)"; }
 uint64_t ars_launch_count(void) { return ctx_ready() ? ctx().launches : 0; }
+uint64_t ars_air_fold_count(void) { return g_air_fold_count; }
 void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
 
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -354,6 +378,10 @@ int ars_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "upols")) g_opt_upols = value ? 1 : 0;
     else if (!strcmp(key, "sparse_ir")) g_opt_sparse_ir = value ? 1 : 0;
     else if (!strcmp(key, "upols_logf")) { ARS_CHECK(value == 12 || value == 13, "upols_logf must be 12 or 13"); g_opt_upols_logf = value; }
+    else if (!strcmp(key, "air_fold")) g_opt_air_fold = value ? 1 : 0;
+    else if (!strcmp(key, "air_fold_eps_e9")) { ARS_CHECK(value >= 1, "air_fold_eps_e9 must be >= 1"); g_opt_air_fold_eps_e9 = value; }
+    else if (!strcmp(key, "air_fold_max_taps")) { ARS_CHECK(value >= 64, "air_fold_max_taps must be >= 64"); g_opt_air_fold_max_taps = value; }
+    else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END
 }
@@ -491,7 +519,14 @@ int ars_convolve_split(const float* data, int64_t n, int32_t cin, const float* e
     if (air_absorption > 0.01 && N >= 2) fill_air(fs, N, rate, air_absorption);     // rs.py:378
     fs.sparse_ir = (g_opt_sparse_ir && nonzero_partitions(early, len_early, late, len_late) <= 12) ? 1 : 0;
     float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
-    convolution_stage(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st);
+    IrExtent ex;
+    for (i64 i = len_early; i > 0 && ex.early_end == 0; --i) if (early[i - 1] != 0.f) ex.early_end = i;
+    ex.late_lo = len_late;
+    ex.late_hi = 0;
+    for (i64 i = 0; i < len_late; ++i) if (late[i] != 0.f) { ex.late_lo = i; break; }
+    for (i64 i = len_late; i > ex.late_lo; --i) if (late[i - 1] != 0.f) { ex.late_hi = i; break; }
+    if (ex.late_hi < ex.late_lo) ex.late_lo = ex.late_hi = 0;
+    convolution_stage(d_x, n, cin, d_e, len_early, d_l, len_late, fs, y, st, rate, ex);
     guard_apply(reinterpret_cast<float*>(y), N * 2, &st->max_stereo);               // rs.py:402-404
     download(out, reinterpret_cast<const float*>(y), (size_t)N * 2);
     sync();

@@ -201,6 +201,8 @@ struct Ld {
     i64 seg0 = 0;                   // LD_OLS_X: absolute block index of the launch's segment 0
     i64 frame0 = 0;                 // LD_OLS_X: absolute frame index of f0[0] (a rank may hold a slice of the signal)
     i64 lookback = 0;               // LD_OLS_MAC: delay-line segments that exist before the launch's segment 0
+    i64 adv = 0;                    // LD_OLS_X: the windows start `adv` frames later (IR with taps at negative times)
+    i64 circ = 0;                   // LD_OLS_X: > 0: the signal is the circ-periodic extension of the zero-padded frames
     // MODE >= 0: compile-time access mode (fast kernels); MODE < 0: runtime switch on `mode` (generic kernels)
     template <int MODE> ARS_HD float2 get(i64 idx) const {
         if constexpr (MODE < 0) return (*this)(idx);
@@ -232,10 +234,17 @@ struct Ld {
             return idx < nvalid ? cmul(ARS_LDG(a + idx), ARS_LDG(b + idx)) : make_float2(0.f, 0.f);
         } else if constexpr (MODE == LD_OLS_X) {       // overlap-save window s: frames [(s-1)B, (s+1)B) of the zero-padded signal
             const i64 seg = seg0 + (idx >> logF);
-            const i64 fr = ((seg - 1) << (logF - 1)) + (idx & (((i64)1 << logF) - 1)) - frame0;
+            i64 fr = (seg - 1) * ((i64)1 << (logF - 1)) + (idx & (((i64)1 << logF) - 1)) + adv - frame0;
+            if (circ > 0) { if (fr < 0) fr += circ; else if (fr >= circ) fr -= circ; }      // |fr| < 2 circ (upols.cu)
             if (fr < 0 || fr >= nvalid) return make_float2(0.f, 0.f);      // nvalid = frames held at f0
-            const float l = ARS_LDG(f0 + fr * cin);
-            const float r = cin > 1 ? ARS_LDG(f0 + fr * cin + 1) : l;
+            float l, r;
+            if ((cin & 1) == 0) {                      // even channel count: the first two channels are one aligned 8-byte load
+                const float2 v = ARS_LDG(reinterpret_cast<const float2*>(f0 + fr * cin));
+                l = v.x; r = v.y;
+            } else {
+                l = ARS_LDG(f0 + fr * cin);
+                r = cin > 1 ? ARS_LDG(f0 + fr * cin + 1) : l;
+            }
             return make_float2(l, c1 < 0.f ? -r : r);
         } else if constexpr (MODE == LD_OLS_IR) {      // IR partition p: taps [pB, (p+1)B), zero-padded to 2B, real
             const i64 seg = idx >> logF;

@@ -4,13 +4,14 @@
 namespace ars {
 namespace fftk {
 
-// inverse first pass: LD_MULSPEC -> ST_PLAIN ; overlap-save: fused MAC -> ST_OLS | ST_OLS_CHIRP
+// inverse first pass: LD_MULSPEC -> ST_PLAIN ; overlap-save: fused MAC (or the tiled MAC kernel's output) -> ST_OLS | ST_OLS_CHIRP
 bool fast_contig_inv(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa) {
     const int lm = ld.mode, sm = st.mode;
 #define F_CASE(R, C)                                                                                                            \
     if (ps.logR == R && ps.logT == C) {                                                                                         \
         if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_contig<R, C, true, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; }     \
         if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
+        if (lm == LD_PLAIN && sm == ST_OLS) { launch_contig<R, C, true, LD_PLAIN, ST_OLS>(ld, st, pa); return true; }           \
         if (lm == LD_OLS_MAC && sm == ST_OLS) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS>(ld, st, pa); return true; }     \
         if (lm == LD_OLS_MAC && sm == ST_OLS_CHIRP) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS_CHIRP>(ld, st, pa); return true; } \
     }

@@ -90,6 +90,9 @@ __global__ void __launch_bounds__(256) ols_mac_kernel(const float2* __restrict__
         if (j0 + q < run) Y[(j0 + q) * F + t] = acc[q];
 }
 
+static int g_mac_tiled_min = 8;    // partitions above which the register-tiled MAC kernel replaces the fused prologue
+void upols_set_mac_tiled_min(int p) { g_mac_tiled_min = p; }
+
 __global__ void or_flags_kernel(unsigned char* a, const unsigned char* b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] |= b[i];
@@ -102,10 +105,12 @@ __global__ void compact_partition_flags_kernel(const unsigned char* nz, int P, i
     plist[P] = n;
 }
 
-void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
-                  const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg) {
+// adv > 0 (with circ = N): the taps handed in start at time -adv (a multiple of B) and the signal is the N-periodic
+// extension of the zero-padded frames -- the folded-air form; dense: every partition carries taps.
+static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                      const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg, i64 adv,
+                      i64 circ, bool dense) {
     Ctx& c = ctx();
-    ARS_CHECK(upols_applicable(fs), "upols_filter: an exact-N spectral mask is active");
     ARS_CHECK(fs.mode == FILT_SPLIT || fs.mode == FILT_EXT, "upols_filter: needs an IR");
     const i64 N = fs.N;
     const int logB = logF - 1;
@@ -123,11 +128,14 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
     ARS_CHECK(block_lo >= 0 && block_lo < block_hi, "upols_filter: empty block range");
     const i64 x_frames = rg.x_frames < 0 ? n - rg.x_frame0 : rg.x_frames;
     // stored delay-line segments: absolute blocks [seg0, seg0 + nseg); blocks before 0 do not exist
-    const i64 seg0 = std::max<i64>(0, block_lo - (P - 1));
+    const i64 seg0 = circ > 0 ? block_lo - (P - 1) : std::max<i64>(0, block_lo - (P - 1));
     const i64 skip = block_lo - seg0;                         // halo segments in front of the computed range
     const i64 run = ((block_hi - block_lo + tile - 1) / tile) * tile;
     const i64 nseg = ((skip + run + tile - 1) / tile) * tile;
-    {   // the slice handed in must cover every existing frame the stored windows read
+    if (circ > 0) {
+        ARS_CHECK(adv % B == 0 && rg.x_frame0 == 0 && x_frames == n, "upols_filter: the circular form takes the whole signal");
+        ARS_CHECK((P + 1) * B < circ && adv + 2 * B < circ, "upols_filter: folded IR too long for the period");
+    } else {   // the slice handed in must cover every existing frame the stored windows read
         const i64 need_lo = std::max<i64>(0, (seg0 - 1) * B), need_hi = std::min<i64>(n, (seg0 + nseg) * B);
         ARS_CHECK(rg.x_frame0 <= need_lo && rg.x_frame0 + x_frames >= std::min(need_hi, std::min<i64>(n, block_hi * B)),
                   "upols_filter: the input slice does not cover the block range plus its halo");
@@ -186,6 +194,8 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
         ld.cin = cin;
         ld.seg0 = seg0;
         ld.c1 = k == 0 ? 0.f : -1.f;                                 // second spectrum: the conjugated signal
+        ld.adv = adv;
+        ld.circ = circ;
         St st;
         st.mode = ST_PLAIN;
         st.a = X + (size_t)k * nseg * F;
@@ -195,15 +205,15 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
     // ---- K4: MAC over the partitions + inverse transform; dry/wet + maxima fused into the last store ----
     // Short IRs (and procedural ones, whose tail partitions are all zero and skipped): the MAC runs inside the first
     // load of the inverse transform.  Long dense IRs: the register-tiled MAC kernel writes Y, the inverse reads it.
-    const bool tiled = ext && P > 8;
+    const bool tiled = (ext || dense) && P > g_mac_tiled_min;
     Ld ld;
     ld.logF = logF;
     if (tiled) {
         constexpr int JT = 8;      // measured: 8 -> 4.81 ms, 12 -> 4.80, 16 -> 5.20, 32 -> 5.28 (600 s clip, 8 s stereo IR)
         float2* Y = c.buf("ols.Y", sizeof(float2) * (size_t)(run * F)).as<float2>();
         const dim3 grid((unsigned)((F + 255) / 256), (unsigned)((run + JT - 1) / JT));
-        ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, X + (size_t)nseg * F + skip * F,
-                                                       H + (size_t)Ppad * F, Y, logF, P, skip, run);
+        ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, ext ? X + (size_t)nseg * F + skip * F : nullptr,
+                                                       ext ? H + (size_t)Ppad * F : nullptr, Y, logF, P, skip, run);
         ARS_LAUNCH_CHECK();
         count_launch();
         ld.mode = LD_PLAIN;
@@ -234,6 +244,167 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
     st.dw = (float)fs.dw;
     st.maxbits = &d_state->max_stereo;
     fft_segments(logF, run, ld, st, true);
+}
+
+void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                  const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg) {
+    ARS_CHECK(upols_applicable(fs), "upols_filter: an exact-N spectral mask is active");
+    upols_run(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, d_state, logF, rg, 0, 0, false);
+}
+
+// ------------------------------------------------------------------ folded air absorption (see upols.cuh) -----
+static __device__ __forceinline__ double air_gain(i64 k, i64 ka, double val, double ftop, double depth) {
+    if (k < ka) return 1.0;                                               // rs.py:321-329 in float64
+    double r = ((double)k * val - 2000.0) / (ftop - 2000.0);
+    r = fmin(fmax(r, 0.0), 1.0);
+    return 1.0 - r * depth;
+}
+
+// g[m] = (1/N) sum_k gain[min(k, N-k)] cos(2 pi k m / N), 0 <= m <= K.  With D = the second difference of the
+// (N-periodic, even) gain sequence, sum_k D[k] e^{i th k} = -4 sin^2(th/2) N g[m]; D is non-zero only at the knee
+// (bins ka-1, ka and their mirrors) and at the top of the ramp (bin N/2, or the pair (N-1)/2, (N+1)/2).
+__global__ void __launch_bounds__(256) air_kernel_table_kernel(double* __restrict__ g, i64 K, i64 N, i64 ka, double val,
+                                                               double ftop, double depth) {
+    const i64 m = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > K) return;
+    const i64 Kb = N / 2;
+    const double slope = -depth * val / (ftop - 2000.0);                  // gain[k+1] - gain[k] on the ramp
+    if (m == 0) {                                                         // the mean of the gain: an arithmetic series
+        const double cnt = (double)(Kb - ka + 1);
+        const double ramp_sum = (val * (double)(ka + Kb) * cnt * 0.5 - 2000.0 * cnt) / (ftop - 2000.0);
+        const double lost = 2.0 * depth * ramp_sum - ((N & 1) ? 0.0 : depth);     // the Nyquist bin counts once
+        g[0] = 1.0 - lost / (double)N;
+        return;
+    }
+    const double ga = air_gain(ka, ka, val, ftop, depth), gb = air_gain(ka + 1, ka, val, ftop, depth);
+    const double Da = ga - 1.0, Db = gb - 2.0 * ga + 1.0;
+    const double invN = 1.0 / (double)N;
+    const double c0 = cospi(2.0 * (double)(((ka - 1) * m) % N) * invN);
+    const double c1 = cospi(2.0 * (double)((ka * m) % N) * invN);
+    const double c2 = cospi(2.0 * (double)((Kb * m) % N) * invN);
+    const double num = 2.0 * Da * c0 + 2.0 * Db * c1 - 2.0 * slope * c2;
+    const double sn = sinpi((double)m * invN);
+    g[m] = -(num * invN) / (4.0 * sn * sn);
+}
+
+// The fold  h[m] = level0 * early[m] + level1 * sum_j late[j] g[m - j]  splits the air kernel at |d| = AIR_NEAR:
+//   near taps (|d| <= AIR_NEAR, the only ones above ~1e-6) are applied directly in float64;
+//   far taps (each below 1e-6, l2 norm ~1e-6) go through one float32 FFT convolution of length M2 >= span + 2K on the
+//   FFT engine -- its rounding error scales with |late| * |g_far| * 2^-23, i.e. ~1e-13 per tap.
+constexpr int AIR_NEAR = 64;
+
+// A = the non-zero stretch of the late part, B = the far taps wrapped modulo M2 (both as complex, zero imaginary part)
+__global__ void __launch_bounds__(256) air_far_pack_kernel(const float* __restrict__ late, i64 late_lo, i64 S,
+                                                           const double* __restrict__ g, i64 K, i64 M2,
+                                                           float2* __restrict__ A, float2* __restrict__ Bk) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M2) return;
+    A[i] = make_float2(i < S ? __ldg(late + late_lo + i) : 0.f, 0.f);
+    const i64 d = i <= M2 / 2 ? i : M2 - i;
+    Bk[i] = make_float2((d > AIR_NEAR && d <= K) ? (float)__ldg(g + d) : 0.f, 0.f);
+}
+
+// taps[m + adv] = float32( level0 * early[m] + level1 * (near sum in float64 + far[m]) ),  -adv <= m < Lf - adv
+__global__ void __launch_bounds__(128) air_fold_kernel(const float* __restrict__ early, i64 L0, const float* __restrict__ late,
+                                                       i64 late_lo, i64 late_hi, const double* __restrict__ g, i64 K,
+                                                       const float2* __restrict__ far, i64 M2, double level0,
+                                                       double level1, i64 adv, i64 Lf, float* __restrict__ taps) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lf) return;
+    const i64 m = i - adv;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (level1 != 0.0 && late_hi > late_lo) {
+        const i64 near = K < AIR_NEAR ? K : AIR_NEAR;
+        const i64 jlo = max(late_lo, m - near), jhi = min(late_hi, m + near + 1);
+        i64 j = jlo;
+        for (; j + 2 <= jhi; j += 2) {
+            acc0 = fma((double)__ldg(late + j), __ldg(g + llabs(m - j)), acc0);
+            acc1 = fma((double)__ldg(late + j + 1), __ldg(g + llabs(m - j - 1)), acc1);
+        }
+        if (j < jhi) acc0 = fma((double)__ldg(late + j), __ldg(g + llabs(m - j)), acc0);
+        const i64 q = m - late_lo;                                // far[q mod M2]: q in [-K, S + K)
+        if (far && q >= -K && q < (late_hi - late_lo) + K) acc1 += (double)__ldg(far + (q < 0 ? q + M2 : q)).x;
+    }
+    const double e = (early && m >= 0 && m < L0) ? (double)__ldg(early + m) : 0.0;
+    taps[i] = (float)(level0 * e + level1 * (acc0 + acc1));
+}
+
+bool air_fold_plan(const FilterSpec& fs, i64 early_end, i64 late_lo, i64 late_hi, double rate, double eps, i64 max_taps,
+                   AirFold* af) {
+    if (fs.mode != FILT_SPLIT || !fs.air_on || fs.eq_on || !(eps > 0.0)) return false;
+    const i64 N = fs.N, Kb = N / 2;
+    if (fs.ka < 2 || fs.ka + 2 > Kb || !(fs.ftop > 2000.0) || !(fs.depth > 0.0)) return false;
+    const double k = std::ceil(fs.depth * rate / ((fs.ftop - 2000.0) * 9.869604401089358 * eps));
+    if (!(k >= 1.0) || k > (double)max_taps) return false;
+    const i64 K = std::max<i64>(64, (i64)k);
+    late_lo = std::max<i64>(0, late_lo);
+    if (late_hi < late_lo) late_hi = late_lo;
+    const i64 span = std::max(early_end, late_hi + K) + K;           // folded taps live on [-K, span - K)
+    if (span + K + 3 * 8192 >= N || span > 8 * max_taps) return false;   // one wrap at most (upols_run)
+    af->K = K;
+    af->early_end = early_end;
+    af->late_lo = late_lo;
+    af->late_hi = late_hi;
+    return true;
+}
+
+void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early, i64 L0, const float* d_late, i64 L1,
+                          const FilterSpec& fs, const AirFold& af, float2* d_y, RenderState* d_state, int logF) {
+    Ctx& c = ctx();
+    ARS_CHECK(fs.mode == FILT_SPLIT && fs.air_on && !fs.eq_on, "upols_filter_airfold: needs the air ramp and no EQ mask");
+    if (!d_early) L0 = 0;
+    if (!d_late) L1 = 0;
+    const i64 B = (i64)1 << (logF - 1), K = af.K;
+    const i64 adv = ((K + B - 1) / B) * B;
+    const i64 late_lo = std::min(af.late_lo, L1), late_hi = std::min(af.late_hi, L1);
+    const i64 Lf = adv + std::max(std::min(af.early_end, L0), late_hi + K);
+    double* g = c.buf("fold.g", sizeof(double) * (size_t)(K + 1)).as<double>();
+    float* taps = c.buf("fold.taps", sizeof(float) * (size_t)Lf).as<float>();
+    air_kernel_table_kernel<<<ceil_div(K + 1, 256), 256, 0, c.stream>>>(g, K, fs.N, fs.ka, fs.val, fs.ftop, fs.depth);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    const i64 S = late_hi - late_lo;
+    float2* far = nullptr;
+    i64 M2 = 0;
+    if (K > AIR_NEAR && S > 0 && fs.level1 != 0.0) {
+        int logM2 = 10;
+        while (((i64)1 << logM2) < S + 2 * K + 1) ++logM2;
+        M2 = (i64)1 << logM2;
+        float2* A = c.buf("fold.A", sizeof(float2) * (size_t)M2).as<float2>();
+        float2* Bk = c.buf("fold.B", sizeof(float2) * (size_t)M2).as<float2>();
+        air_far_pack_kernel<<<ceil_div(M2, 256), 256, 0, c.stream>>>(d_late, late_lo, S, g, K, M2, A, Bk);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        FftPlan* fp = get_fft_plan(logM2);
+        for (float2* buf : {A, Bk}) {
+            Ld ld;
+            ld.mode = LD_PLAIN;
+            ld.a = buf;
+            St st;
+            st.mode = ST_PLAIN;
+            st.a = buf;
+            fft_forward(fp, ld, buf, st);
+        }
+        Ld ld;
+        ld.mode = LD_MULSPEC;
+        ld.a = A;
+        ld.b = Bk;
+        St st;
+        st.mode = ST_SCALE;
+        st.a = A;
+        st.scale = 1.0f / (float)M2;
+        fft_inverse(fp, ld, A, st);
+        far = A;
+    }
+    air_fold_kernel<<<ceil_div(Lf, 128), 128, 0, c.stream>>>(d_early, L0, d_late, late_lo, late_hi, g, K, far, M2, fs.level0,
+                                                              S > 0 ? fs.level1 : 0.0, adv, Lf, taps);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    FilterSpec f2 = fs;
+    f2.air_on = 0;
+    f2.level0 = 1.0;
+    f2.level1 = 0.0;
+    upols_run(d_x, n, cin, taps, Lf, nullptr, 0, f2, d_y, d_state, logF, OlsRange(), adv, fs.N, true);
 }
 
 }  // namespace ars

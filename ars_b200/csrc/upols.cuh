@@ -26,4 +26,27 @@ void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, 
 // true when the render has no exact-N spectral mask, i.e. UPOLS reproduces the reference
 inline bool upols_applicable(const FilterSpec& fs) { return !fs.eq_on && !fs.air_on; }
 
+// ---- air absorption folded into the impulse response (BASELINE north_star, subsystem 1) ----
+// The reference low-passes the late wet signal with a gain ramp on its exact N-point rfft (rs.py:316-332, 378-380):
+// a circular convolution of period N with the real, even kernel g = IDFT_N(gain).  The gain is piecewise linear in
+// the bin index, so g has a closed form (second differences of the gain are non-zero at <= 6 bins) and decays like
+// 1/m^2.  Keeping g on [-K, K] changes the late path's transfer function by at most
+//     eps(K) = depth * rate / ((f_top - 2000) * pi^2 * K)        (sup over frequency = the l1 norm of the dropped tail)
+// so  h = level0 * early + level1 * (late (*) g_K)  -- taps on [-K, L + K) -- turns the whole stage into ONE
+// overlap-save convolution over the N-periodic extension of the zero-padded signal.  The fold runs in float64.
+struct AirFold {
+    i64 K = 0;                  // taps kept on each side of the air kernel
+    i64 early_end = 0;          // early taps at index >= early_end are zero (bound known on the host)
+    i64 late_lo = 0, late_hi = 0;   // late taps outside [late_lo, late_hi) are zero (bound known on the host)
+};
+// K for a transfer-function error <= eps, or false when the fold does not apply (mask other than the air ramp, K or the
+// folded IR too long against max_taps / N): the caller then takes the exact N-point route.
+bool air_fold_plan(const FilterSpec& fs, i64 early_end, i64 late_lo, i64 late_hi, double rate, double eps, i64 max_taps,
+                   AirFold* af);
+// y = dry_gain * x_pad + dw * (x_pad (*)_N h), h as above; same outputs / maxima as upols_filter.
+void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early, i64 L0, const float* d_late, i64 L1,
+                          const FilterSpec& fs, const AirFold& af, float2* d_y, RenderState* d_state, int logF = 13);
+
+void upols_set_mac_tiled_min(int p);   // partitions above which dense IRs use the register-tiled MAC kernel
+
 }  // namespace ars

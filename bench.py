@@ -234,6 +234,8 @@ def run_ours(args):
         bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _capi.init(local)
+    for kv in args.opt:
+        _capi.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     w = WORKLOADS[args.workload]
     seconds = args.seconds or w["seconds"]
     x = make_clip(w, seconds, rank)
@@ -443,6 +445,8 @@ def run_cfg4(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _capi.init(local)
+    for kv in args.opt:
+        _capi.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     total = args.clips
     mine = sh.partition_clips([1] * total, world)[rank]
     presets = cfg4_presets(total)
@@ -524,6 +528,8 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=300.0)
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
+                    help="library option for experiments (ars_set_option), e.g. --opt air_fold=0")
     args = ap.parse_args()
     if args.workload == "cfg4" and args.impl != "reference":
         run_cfg4(args)

@@ -90,12 +90,18 @@ ARS_API int ars_sync(void);                       /* wait for everything enqueue
 ARS_API const char* ars_last_error(void);
 ARS_API const char* ars_version(void);
 ARS_API uint64_t ars_launch_count(void);          /* kernels this library has launched so far           */
+ARS_API uint64_t ars_air_fold_count(void);        /* convolution stages that took the folded-air route  */
 ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
 /* Options: "upols" (1 = use the partitioned overlap-save convolution whenever a render has no exact-N
  * spectral mask, i.e. air <= 0.01 and both EQ gains ~ 1 [default]; 0 = always the N-point spectral filter),
  * "upols_logf" (12 | 13: points per overlap-save transform = 2^logf, hop = half of it),
  * "sparse_ir" (1 = IR spectra of procedural / sparse IRs through the cached overlap-save route [default]; 0 = always
- * two M-point transforms). */
+ * two M-point transforms),
+ * "air_fold" (1 = a render whose only spectral mask is the air-absorption ramp [air > 0.01, EQ gains ~ 1] folds the
+ * ramp into the impulse response and runs as one overlap-save convolution [default]; 0 = exact N-point filter),
+ * "air_fold_eps_e9" (bound on the late path's transfer-function error the fold may introduce, in 1e-9; default 1000),
+ * "air_fold_max_taps" (longest half-length of the truncated air kernel; a longer one falls back to the N-point path),
+ * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);

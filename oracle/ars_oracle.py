@@ -519,8 +519,10 @@ def pcm16(data: np.ndarray):
 def render(samples, rate, *, external_ir=None, hall="Room", room_size=100.0, diffusion=0.5,
            air=0.1, early=0.8, late=0.6, dry_wet_amount=0.5, kill_start=0.5, bass=1.0,
            treble=1.0, x=0.5, y=0.5, z=0.5, material="Holz", layout=FALLBACK_LAYOUT,
-           rng=np.random, with_lufs=True):
-    """-> dict(stereo, final, names, metrics, pcm).  rs.py:1020-1084."""
+           rng=np.random, with_lufs=True, ir_duration=None):
+    """-> dict(stereo, final, names, metrics, pcm).  rs.py:1020-1084.
+    ir_duration: overrides the duration a2 derives (the "8 s IR" benchmark variant) -- the one
+    knob here that the reference's entry point does not have; everything downstream is the reference's call chain."""
     s = np.asarray(samples, F32)
     if s.ndim == 1:
         s = s[:, None]
@@ -532,6 +534,8 @@ def render(samples, rate, *, external_ir=None, hall="Room", room_size=100.0, dif
         stereo = convolve_external(s, external_ir, dry_wet_amount, bass, treble, rate, kill_start)
     else:
         dur, refl, mdel, split = shape_params(hall, room_size, z)
+        if ir_duration is not None:
+            dur = float(ir_duration)
         d = directionality(x, y, z, hall, diffusion, dry_wet_amount)
         e_ir, l_ir = generate_ir(rate, dur, refl, mdel, material, d, split, diffusion, rng)
         e_lvl, l_lvl = adapt_levels(dry_wet_amount, early, late)

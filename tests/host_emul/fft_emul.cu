@@ -336,6 +336,62 @@ static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_h
     return (maxerr / peak < 2e-5 && maxbits[0] != 0) ? 0 : 1;
 }
 
+// The folded-air form of the overlap-save stage (upols.cu: upols_filter_airfold): taps that start at time -adv over the
+// N-periodic extension of the zero-padded signal == the N-point circular convolution.
+static int check_ols_circ(int logF, i64 n, i64 N, i64 Lf, i64 adv) {
+    Tw tw;
+    make_tables(logF, tw);
+    const i64 B = (i64)1 << (logF - 1), F = (i64)1 << logF;
+    const int tile = logF == 12 ? 2 : 1;
+    std::mt19937 rng((unsigned)(n * 17 + Lf));
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<float> x(2 * n), h(Lf);
+    for (auto& v : x) v = U(rng);
+    for (i64 i = 0; i < Lf; ++i) h[i] = U(rng) * expf(-fabsf((float)(i - adv)) / (0.2f * Lf));
+    const int P = (int)((Lf + B - 1) / B), Ppad = ((P + tile - 1) / tile) * tile;
+    const i64 nblk = (N + B - 1) / B;
+    const i64 seg0 = -(P - 1), skip = P - 1;
+    const i64 run = ((nblk + tile - 1) / tile) * tile;
+    const i64 nseg = ((skip + run + tile - 1) / tile) * tile;
+    std::vector<float2> H((size_t)Ppad * F), X((size_t)nseg * F), y(N, make_float2(0, 0));
+    {
+        Ld ld; ld.mode = LD_OLS_IR; ld.logF = logF; ld.f0 = h.data(); ld.f1 = nullptr; ld.cin = 1; ld.nvalid = Lf; ld.c0 = 1.f;
+        St st; st.mode = ST_SCALE; st.a = H.data(); st.scale = 1.0f / (float)F;
+        emu_segments(logF, Ppad, tw, ld, st, false);
+    }
+    {
+        Ld ld; ld.mode = LD_OLS_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = 2;
+        ld.seg0 = seg0; ld.adv = adv; ld.circ = N;
+        St st; st.mode = ST_PLAIN; st.a = X.data();
+        emu_segments(logF, nseg, tw, ld, st, false);
+    }
+    unsigned maxbits[4] = {0, 0, 0, 0};
+    {
+        Ld ld; ld.mode = LD_OLS_MAC; ld.logF = logF; ld.a = X.data() + skip * F; ld.b = H.data(); ld.P = P; ld.lookback = skip;
+        St st; st.mode = ST_OLS; st.logF = logF; st.seg0 = 0; st.a = y.data(); st.frame0 = 0; st.N = N; st.dry = x.data();
+        st.dry_frame0 = 0; st.n = n; st.cin = 2; st.dg = 0.25f; st.dw = 0.5f; st.maxbits = maxbits;
+        emu_segments(logF, run, tw, ld, st, true);
+    }
+    double maxerr = 0, peak = 0;
+    const i64 stepf = std::max<i64>(1, N / 300);
+    for (i64 q = 0; q < N + 40; ++q) {
+        const i64 f = q < 20 ? q : (q < 40 ? N - 1 - (q - 20) : (q - 40));      // both ends densely, the rest sampled
+        if (q >= 40 && (q - 40) % stepf) continue;
+        double wl = 0, wr = 0;
+        for (i64 m = 0; m < Lf; ++m) {
+            i64 t = (f + adv - m) % N;
+            if (t < 0) t += N;
+            if (t < n) { wl += (double)h[m] * x[2 * t]; wr += (double)h[m] * x[2 * t + 1]; }
+        }
+        const double rl = 0.25 * (f < n ? x[2 * f] : 0) + 0.5 * wl, rr = 0.25 * (f < n ? x[2 * f + 1] : 0) + 0.5 * wr;
+        peak = std::max(peak, std::max(fabs(rl), fabs(rr)));
+        maxerr = std::max(maxerr, std::max(fabs(rl - y[f].x), fabs(rr - y[f].y)));
+    }
+    printf("ols-circ logF=%d n=%lld N=%lld Lf=%lld adv=%lld: max err %.3e (peak %.2f) rel %.3e\n", logF, (long long)n,
+           (long long)N, (long long)Lf, (long long)adv, maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5 && maxbits[0] != 0) ? 0 : 1;
+}
+
 // Short-IR spectrum route (spectral.cu: ir_spectrum_short): P[k] = DFT_N(h0 + i h1) through overlap-save over the
 // shifted Bluestein kernel.
 static int check_irs(i64 N, i64 L) {
@@ -402,6 +458,9 @@ int main(int argc, char** argv) {
         bad += check_ols(12, 60000, 7000, false, 5, 12);
         bad += check_ols(12, 60000, 7000, false, 12, -1);
         bad += check_ols(13, 3000, 100, false, 0, -1);
+        bad += check_ols_circ(12, 60000, 60000 + 5000 - 1, 9000, 4096);       // zero tail longer than the pre-ring
+        bad += check_ols_circ(13, 90000, 90000 + 100 - 1, 20000, 8192);       // pre- and post-ring wrap around the period
+        bad += check_ols_circ(12, 50000, 50000 + 3000 - 1, 2048 + 700, 2048);
         printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
         return bad ? 1 : 0;
     }

@@ -596,6 +596,16 @@ def test_cfg3_full_size_properties(rs):
     finally:
         _capi.set_option("sparse_ir", 1)
     assert rel_err(c, a) <= 2e-6
+    del c
+    # ... and of the two convolution routes: `a` took the folded-air overlap-save route, this one the N-point filter
+    try:
+        _capi.set_option("air_fold", 0)
+        np.random.seed(3)
+        e = rs.render_array(x, rate, **kw)["final"]
+    finally:
+        _capi.set_option("air_fold", 1)
+    assert rel_err(e, a) <= 3e-6, rel_err(e, a)
+    del e
     # the 18 ms height pair is the rear pair delayed and scaled by 0.6 * z (rs.py:549-554)
     assert np.array_equal(a[864:, 6], (a[:-864, 4].astype(np.float64) * (0.5 * 0.6)).astype(np.float32))
 
@@ -724,3 +734,118 @@ def test_batch_with_many_distinct_lengths_recycles_plans_correctly(rs):
             a = rs.render_array(job.pop("samples"), job.pop("rate"), **job)
             assert np.array_equal(a["final"], b["final"]) and np.array_equal(a["pcm"], b["pcm"])
             assert a["metrics"] == b["metrics"]
+
+
+# ------------------------------------------------------------------ air absorption folded into the IR ----------
+def _fold_opts(**kw):
+    from ars_b200 import _capi
+    for k, v in kw.items():
+        _capi.set_option(k, v)
+
+
+def _fold_defaults():
+    _fold_opts(air_fold=1, air_fold_eps_e9=1000, air_fold_max_taps=32768, mac_tiled_min=8)
+
+
+def _fold_count():
+    from ars_b200 import _capi
+    return int(_capi.init().ars_air_fold_count())
+
+
+def test_air_fold_stage_matches_exact_path_and_oracle(rs):
+    """A render whose only spectral mask is the air ramp (air > 0.01, EQ flat) folds the ramp into the IR and runs as
+    one overlap-save convolution (upols.cuh).  Against the exact N-point route and against the oracle, both MAC forms."""
+    rate = 48000
+    rng = np.random.default_rng(21)
+    np.random.seed(5)
+    early, late = rs.generate_impulse_response_split_3d(rate, 1.5, 30, 0.06, "Holz", 0.5, 0.08, 0.5)
+    cases = [((rng.standard_normal((70001, 2)) * 0.3).astype(np.float32), 0.1),
+             ((rng.standard_normal(40000) * 0.3).astype(np.float32), 0.15),
+             ((rng.standard_normal((52000, 3)) * 0.3).astype(np.float32), 0.05)]
+    try:
+        for x, air in cases:
+            want = orc.convolve_split(x, early, late, 0.7, 0.9, 0.6, 1.0, 1.0, rate, 0.5, air)
+            outs = {}
+            for name, opts in (("exact", dict(air_fold=0)), ("fold", dict(air_fold=1, mac_tiled_min=8)),
+                               ("fold_prologue", dict(air_fold=1, mac_tiled_min=1000))):
+                _fold_opts(**opts)
+                c0 = _fold_count()
+                outs[name] = rs.convolve_audio_split_3d(x, early, late, 0.7, 0.9, 0.6, 1.0, 1.0, rate, 0.5, air)
+                assert (_fold_count() - c0 == 1) == (name != "exact"), name
+                assert rel_err(outs[name], want) <= TOL, (name, air, rel_err(outs[name], want))
+                assert snr_db(outs[name], want) >= 100.0, (name, air, snr_db(outs[name], want))
+            assert rel_err(outs["fold"], outs["exact"]) <= 3e-6, rel_err(outs["fold"], outs["exact"])
+            assert rel_err(outs["fold_prologue"], outs["fold"]) <= 1e-6
+    finally:
+        _fold_defaults()
+
+
+def test_air_fold_wraps_around_the_period_like_the_n_point_filter(rs):
+    """The reference's ramp acts on the N-point rfft, i.e. circularly: with an IR much shorter than the kept air
+    kernel and energy at both ends of the signal the pre- and post-ring wrap around.  Pure tones at the two kinks of
+    the ramp (2 kHz, Nyquist) are the worst case of the truncation bound."""
+    rate = 48000
+    n = 90000
+    t = np.arange(n)
+    late = np.zeros(600, np.float32)
+    late[100:600] = (np.random.default_rng(2).standard_normal(500) * np.exp(-np.arange(500) / 80.0)).astype(np.float32)
+    late *= 0.7 / np.max(np.abs(late))
+    early = np.zeros(600, np.float32)
+    early[[3, 40, 77]] = [0.9, -0.4, 0.2]
+    sigs = {"noise": (np.random.default_rng(3).standard_normal((n, 2)) * 0.3).astype(np.float32),
+            "tone2k": np.stack([0.5 * np.sin(2 * np.pi * 2000.0 * t / rate), 0.5 * np.cos(np.pi * t)], 1).astype(np.float32)}
+    try:
+        for name, x in sigs.items():
+            want = orc.convolve_split(x, early, late, 0.8, 1.0, 0.7, 1.0, 1.0, rate, 0.5, 0.12)
+            _fold_opts(air_fold=1)
+            c0 = _fold_count()
+            got = rs.convolve_audio_split_3d(x, early, late, 0.8, 1.0, 0.7, 1.0, 1.0, rate, 0.5, 0.12)
+            assert _fold_count() == c0 + 1
+            assert rel_err(got, want) <= TOL, (name, rel_err(got, want))
+    finally:
+        _fold_defaults()
+
+
+def test_air_fold_error_bound_option_and_fallback(rs):
+    """air_fold_eps_e9 / air_fold_max_taps pick the kept kernel length; a ramp too deep for the bound falls back to the
+    exact N-point filter."""
+    rate = 48000
+    x = (np.random.default_rng(8).standard_normal((160000, 2)) * 0.3).astype(np.float32)
+    np.random.seed(6)
+    early, late = rs.generate_impulse_response_split_3d(rate, 1.0, 20, 0.05, "Teppich", 0.4, 0.06, 0.3)
+    try:
+        want = orc.convolve_split(x, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.6)
+        _fold_defaults()
+        c0 = _fold_count()
+        got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.6)
+        assert _fold_count() == c0, "air 0.6 needs > 32768 taps at 1e-6: must take the exact route"
+        assert rel_err(got, want) <= TOL
+        _fold_opts(air_fold_eps_e9=4000, air_fold_max_taps=65536)
+        got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.6)
+        assert _fold_count() == c0 + 1
+        assert rel_err(got, want) <= TOL, rel_err(got, want)
+        # EQ on: the brick-wall mask cannot be folded
+        got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.3, 0.8, rate, 0.5, 0.1)
+        assert _fold_count() == c0 + 1
+    finally:
+        _fold_defaults()
+
+
+def test_air_fold_whole_render_vs_oracle(rs):
+    """cfg3-like render (Cathedral / Stein, 8 s IR, air 0.1, EQ flat, 5.1.2, metrics + PCM), 20 s clip."""
+    rate = 48000
+    x = (0.2 * np.random.default_rng(2).standard_normal((20 * rate, 6))).astype(np.float32)
+    np.random.seed(3)
+    want = orc.render(x, rate, hall="Cathedral", room_size=20000., ir_duration=8.0, material="Stein", air=.1,
+                      dry_wet_amount=.5, layout="5.1.2 (Atmos Light)")
+    c0 = _fold_count()
+    np.random.seed(3)
+    got = rs.render_array(x, rate, hall_type="Cathedral", room_size=20000., ir_duration=8.0, material="Stein",
+                          air_absorption=.1, dry_wet=.5, target_channel_layout="5.1.2 (Atmos Light)")
+    assert _fold_count() == c0 + 1
+    assert rel_err(got["final"], want["final"]) <= TOL
+    assert snr_db(got["final"], want["final"]) >= 100.0
+    d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) < 1e-2
+    assert abs(got["metrics"]["lufs"] - want["metrics"]["lufs"]) <= 5e-3
+    assert abs(got["metrics"]["rms_dbfs"] - want["metrics"]["rms_dbfs"]) <= 1e-3

@@ -21,9 +21,11 @@ void fft_profile_end(long long* launches, double* ms, double* bytes);
 #define ARS_API_END                                                     \
         return ARS_OK;                                                  \
     } catch (const Error& e) {                                          \
+        side_abort();                                                   \
         set_last_error(e.what());                                       \
         return e.code;                                                  \
     } catch (const std::exception& e) {                                 \
+        side_abort();                                                   \
         set_last_error(e.what());                                       \
         return ARS_ERR_INTERNAL;                                        \
     }
@@ -34,7 +36,8 @@ static int g_opt_upols_logf = 13;  // 2B = 2^logF points per overlap-save transf
 static int g_opt_sparse_ir = 1;    // 1: IR spectrum of sparse (procedural) IRs through the overlap-save route
 static unsigned long long g_air_fold_count = 0;   // convolution stages that took the folded-air route
 static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
-static int g_opt_air_fold_eps_e9 = 1000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
+static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
+static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
 static int g_opt_air_fold_max_taps = 32768;  // longest kept half-length of the air kernel; beyond: the exact N-point path
 
 // number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
@@ -54,13 +57,18 @@ static int nonzero_partitions(const float* a, i64 na, const float* b, i64 nb) {
 // Non-zero extent of the IR parts as far as the host knows it (folded-air form, upols.cuh); late_hi < 0: unknown.
 struct IrExtent { i64 early_end = 0, late_lo = 0, late_hi = -1; };
 
+static bool folds_air(const FilterSpec& fs, const IrExtent& ext, double rate, AirFold* af) {
+    AirFold tmp;
+    return g_opt_upols && g_opt_air_fold && ext.late_hi >= 0 && fs.level1 != 0.0 &&
+           air_fold_plan(fs, ext.early_end, ext.late_lo, ext.late_hi, rate, 1e-9 * g_opt_air_fold_eps_e9,
+                         g_opt_air_fold_max_taps, af ? af : &tmp);
+}
+
 static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                               const FilterSpec& fs, float2* d_y, RenderState* st, double rate = 0.0,
                               const IrExtent& ext = IrExtent()) {
     AirFold af;
-    if (g_opt_upols && g_opt_air_fold && ext.late_hi >= 0 && fs.level1 != 0.0 && d_ir1 &&
-        air_fold_plan(fs, ext.early_end, ext.late_lo, ext.late_hi, rate, 1e-9 * g_opt_air_fold_eps_e9,
-                      g_opt_air_fold_max_taps, &af)) {
+    if (d_ir1 && folds_air(fs, ext, rate, &af)) {
         ++g_air_fold_count;
         upols_filter_airfold(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, af, d_y, st, g_opt_upols_logf);
     } else if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK)
@@ -241,16 +249,6 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
                   "render: noise length does not match the IR geometry");
         ARS_CHECK(g.late_len == 0 || (draws && draws->noise), "render: tail noise missing");
         IrSpec sp = ir_spec(p->rate, p->ir_duration, p->absorption, p->directionality, p->diffusion, g, ntaps);
-        std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
-        std::vector<i64> tap_pos;
-        std::vector<double> tap_val;
-        sp.ntaps = ir_early_taps(draws ? (const i64*)draws->tap_delay : nullptr, strength.data(), ntaps, g.length, tap_pos, tap_val);
-        // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, so the vectors may die)
-        const i64* d_delay = upload("ir.delay", tap_pos.data(), tap_pos.size());
-        const double* d_strength = upload("ir.strength", tap_val.data(), tap_val.size());
-        float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();
-        float* d_late = c.buf("ir.late", sizeof(float) * (size_t)g.length).as<float>();
-        ir_synth(sp, d_delay, d_strength, draws ? draws->noise : nullptr, d_early, d_late);
         fs.mode = FILT_SPLIT;
         fs.level0 = (g.length > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;     // rs.py:360
         fs.level1 = (g.length > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;       // rs.py:369
@@ -267,7 +265,21 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
             const double j0 = std::log(7.0e-46 / (1.0e3 * sp.amp)) / std::log(sp.decay);
             ex.late_hi = g.split + (i64)std::min((double)g.late_len, std::max(0.0, std::ceil(j0) + 1.0));
         }
+        // the folded-air route: IR synthesis, the fold and the IR partition spectra are a chain of small latency-bound
+        // kernels that does not depend on the signal -- it runs on the side stream, next to the delay-line transform
+        if (g_opt_side_stream && folds_air(fs, ex, p->rate, nullptr)) side_begin();
+        std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
+        std::vector<i64> tap_pos;
+        std::vector<double> tap_val;
+        sp.ntaps = ir_early_taps(draws ? (const i64*)draws->tap_delay : nullptr, strength.data(), ntaps, g.length, tap_pos, tap_val);
+        // (pageable host memory: cudaMemcpyAsync returns once the bytes are staged, so the vectors may die)
+        const i64* d_delay = upload("ir.delay", tap_pos.data(), tap_pos.size());
+        const double* d_strength = upload("ir.strength", tap_val.data(), tap_val.size());
+        float* d_early = c.buf("ir.early", sizeof(float) * (size_t)g.length).as<float>();
+        float* d_late = c.buf("ir.late", sizeof(float) * (size_t)g.length).as<float>();
+        ir_synth(sp, d_delay, d_strength, draws ? draws->noise : nullptr, d_early, d_late);
         convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st, p->rate, ex);
+        side_join();               // (no-op unless the stage left the side stream open)
     }
     if (d_out_stereo) {
         ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
@@ -381,6 +393,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "air_fold")) g_opt_air_fold = value ? 1 : 0;
     else if (!strcmp(key, "air_fold_eps_e9")) { ARS_CHECK(value >= 1, "air_fold_eps_e9 must be >= 1"); g_opt_air_fold_eps_e9 = value; }
     else if (!strcmp(key, "air_fold_max_taps")) { ARS_CHECK(value >= 64, "air_fold_max_taps must be >= 64"); g_opt_air_fold_max_taps = value; }
+    else if (!strcmp(key, "side_stream")) g_opt_side_stream = value ? 1 : 0;
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END

@@ -73,6 +73,11 @@ struct Ctx {
     unsigned long long launches = 0;                  // kernels launched by this library
     void* pinned = nullptr;                           // small pinned scratch for D2H scalars
     size_t pinned_cap = 0;
+    // side stream (side_begin / side_to_main / side_join): a stretch of small, latency-bound kernels -- IR synthesis,
+    // the air fold, the IR partition spectra -- runs next to the delay-line transform instead of in front of it
+    cudaStream_t aux = nullptr, main_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int side_state = 0;                               // 0: none, 1: enqueuing on aux, 2: back on main, join pending
 
     DevBuf& buf(const char* name, size_t bytes) {
         DevBuf& b = ws[name];
@@ -86,6 +91,14 @@ Ctx& ctx();                 // throws if ars_init was not called
 bool ctx_ready();
 void ctx_init(int device);
 void ctx_shutdown();
+
+// What is enqueued between side_begin() and side_to_main() goes to the auxiliary stream (ordered after everything
+// already on the main stream); what follows goes to the main stream again and runs concurrently with it until
+// side_join(), which makes the main stream wait for the side work.  side_abort() restores the main stream (errors).
+void side_begin();
+void side_to_main();
+void side_join();
+void side_abort();
 
 inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
 

@@ -70,6 +70,42 @@ void ctx_init(int device) {
     g_ctx = c;
 }
 
+void side_begin() {
+    Ctx& c = ctx();
+    if (c.side_state != 0) return;
+    if (!c.aux) {
+        ARS_CUDA(cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking));
+        ARS_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        ARS_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    }
+    ARS_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+    ARS_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+    c.main_stream = c.stream;
+    c.stream = c.aux;
+    c.side_state = 1;
+}
+void side_to_main() {
+    Ctx& c = ctx();
+    if (c.side_state != 1) return;
+    ARS_CUDA(cudaEventRecord(c.ev_join, c.aux));
+    c.stream = c.main_stream;
+    c.side_state = 2;
+}
+void side_join() {
+    Ctx& c = ctx();
+    if (c.side_state == 1) side_to_main();
+    if (c.side_state != 2) return;
+    ARS_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+    c.side_state = 0;
+}
+void side_abort() {
+    if (!ctx_ready()) return;
+    Ctx& c = ctx();
+    if (c.side_state == 1) c.stream = c.main_stream;
+    if (c.side_state != 0 && c.aux) cudaStreamSynchronize(c.aux);
+    c.side_state = 0;
+}
+
 void fft_release_plans();       // fft_plan.cu
 void bluestein_release_plans(); // bluestein.cu
 
@@ -82,6 +118,12 @@ void ctx_shutdown() {
     fft_release_plans();
     for (auto& kv : g_ctx->ws) kv.second.release();
     if (g_ctx->pinned) cudaFreeHost(g_ctx->pinned);
+    if (g_ctx->aux) {
+        cudaStreamSynchronize(g_ctx->aux);
+        cudaStreamDestroy(g_ctx->aux);
+        cudaEventDestroy(g_ctx->ev_fork);
+        cudaEventDestroy(g_ctx->ev_join);
+    }
     cudaStreamDestroy(g_ctx->stream);
     delete g_ctx;
     g_ctx = nullptr;

@@ -145,22 +145,36 @@ template <bool A> __device__ __forceinline__ float guardT(float v, const Guard& 
     else return v;
 }
 
+// the frame's two loads: the stereo frame itself and, for the layouts with a delayed pair, the frame `delay` earlier
+struct FrameIn { float2 v, w; };
+__device__ __forceinline__ FrameIn frame_load(const float2* __restrict__ y, i64 i, const TailSpec& ts) {
+    FrameIn f;
+    f.v = __ldg(y + (i - ts.y0));
+    f.w = make_float2(0.f, 0.f);
+    // a delay <= 0 leaves the signal where it is (rs.py:510-511)
+    if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) f.w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0) - ts.y0));
+    return f;
+}
+
 template <bool A1 = true, bool A2 = true>
-__device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
-                                          const Guard& g2, float (&o)[8]) {
-    const float2 v = __ldg(y + (i - ts.y0));
+__device__ __forceinline__ void frame_math(const FrameIn& f, i64 i, const TailSpec& ts, const Guard& g1, const Guard& g2,
+                                           float (&o)[8]) {
     float s[6];
-    pan6(guardT<A1>(v.x, g1), guardT<A1>(v.y, g1), ts, s);
+    pan6(guardT<A1>(f.v.x, g1), guardT<A1>(f.v.y, g1), ts, s);
     #pragma unroll
     for (int c = 0; c < 6; ++c) s[c] = guardT<A2>(s[c], g2);
     float rl_d = 0.f, rr_d = 0.f;
     if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) {
-        // a delay <= 0 leaves the signal where it is (rs.py:510-511)
-        const float2 w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0) - ts.y0));
-        rl_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(w.x, g1), ts.g_rl)), g2);
-        rr_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(w.y, g1), ts.g_rr)), g2);
+        rl_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(f.w.x, g1), ts.g_rl)), g2);
+        rr_d = guardT<A2>(__double2float_rn(__dmul_rn((double)guardT<A1>(f.w.y, g1), ts.g_rr)), g2);
     }
     map_frame(s, rl_d, rr_d, ts, o);
+}
+
+template <bool A1 = true, bool A2 = true>
+__device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
+                                          const Guard& g2, float (&o)[8]) {
+    frame_math<A1, A2>(frame_load(y, i, ts), i, ts, g1, g2, o);
 }
 
 __global__ void __launch_bounds__(256) map_max_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st) {
@@ -189,9 +203,15 @@ template <int C, bool A1, bool A2, bool A3>
 __device__ __forceinline__ void final_body(const float2* __restrict__ y, const TailSpec& ts, const Guard& g1, const Guard& g2,
                                            const Guard& g3, float* __restrict__ out, short* __restrict__ pcm,
                                            float* __restrict__ mono, float& pkf, bool& nan_seen, unsigned& mm, double& ss) {
-    for (i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ts.i_hi; i += (i64)gridDim.x * blockDim.x) {
+    // the loads of the next frame are issued before the arithmetic of this one: the pass is bound by load latency
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    i64 i = ts.i_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    FrameIn cur = i < ts.i_hi ? frame_load(y, i, ts) : FrameIn();
+    for (; i < ts.i_hi; i += stride) {
+        const FrameIn f = cur;
+        if (i + stride < ts.i_hi) cur = frame_load(y, i + stride, ts);
         float o[8];
-        frame_out<A1, A2>(y, i, ts, g1, g2, o);
+        frame_math<A1, A2>(f, i, ts, g1, g2, o);
         float fs = 0.f;        // one frame's squares in float32 (numpy squares in float32 too), then one conversion
         #pragma unroll
         for (int c = 0; c < C; ++c) {

@@ -281,6 +281,24 @@ struct Ld {
             return make_float2(l, r);
         }
     }
+    // LD_OLS_X: ask the L2 for the new half (B frames) of the windows of `nsegs` segments starting at launch segment
+    // `seg` -- the pass waits on its first loads (DRAM at a third of its bandwidth), so a hint a couple of waves
+    // ahead turns DRAM latency into L2 latency.  Only a hint: a stretch that wraps around the period is clipped.
+    ARS_HD void prefetch_x(i64 seg, int nsegs, int tid, int nthreads) const {
+#ifdef __CUDA_ARCH__
+        const i64 B = (i64)1 << (logF - 1);
+        i64 lo = (seg0 + seg) * B + adv - frame0;
+        if (circ > 0) { if (lo < 0) lo += circ; else if (lo >= circ) lo -= circ; }
+        i64 hi = lo + (i64)nsegs * B;
+        if (lo < 0) lo = 0;
+        if (hi > nvalid) hi = nvalid;
+        if (hi <= lo) return;
+        const char* p0 = reinterpret_cast<const char*>(f0 + lo * cin);
+        const char* p1 = reinterpret_cast<const char*>(f0 + hi * cin);
+        for (const char* p = p0 + (i64)tid * 128; p < p1; p += (i64)nthreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+    }
     // The complex multiply-accumulate over the partitions, fused into the loads of the inverse transform:
     // r spectrum bins of one butterfly at a time, so 2r (4r) independent loads are in flight per partition.
     template <int r> ARS_HD void get_mac(i64 idx0, i64 step, float2 (&v)[r]) const {
@@ -801,7 +819,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_strided_kernel(Ld 
 
 // Contiguous pass: tile = C whole segments of R adjacent elements.
 template <int LOGR, int LOGC, bool INV, int NT, int LDM, int STM>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : (NT == 256 ? 3 : 1)) pass_contig_kernel(Ld ld, St st, PassArgs pa) {
     extern __shared__ float2 sm[];
     if constexpr (LDM == LD_PLAIN || LDM == LD_MULSPEC) {
         if (pa.prefetch > 0 && (i64)blockIdx.x + pa.prefetch < (i64)gridDim.x) {
@@ -809,6 +827,10 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_contig_kernel(Ld l
             prefetch_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>>(
                 ld.a, LDM == LD_MULSPEC ? ld.b : nullptr, ContigFirst<LOGR>{base2}, ContigLast<LOGR>{base2});
         }
+    }
+    if constexpr (LDM == LD_OLS_X) {
+        if (pa.prefetch > 0 && (i64)blockIdx.x + pa.prefetch < (i64)gridDim.x)
+            ld.prefetch_x(((i64)blockIdx.x + pa.prefetch) << LOGC, 1 << LOGC, threadIdx.x, NT);
     }
     const i64 base = (i64)blockIdx.x << (LOGR + LOGC);
     run_tile<LOGR, INV, false, NT, ContigLayout<LOGR, LOGC>, LDM, STM>(sm, ld, st, pa, ContigFirst<LOGR>{base},

@@ -11,6 +11,8 @@ bool fast_contig_inv(const FftPass& ps, const Ld& ld, const St& st, const PassAr
     if (ps.logR == R && ps.logT == C) {                                                                                         \
         if (lm == LD_PLAIN && sm == ST_PLAIN) { launch_contig<R, C, true, LD_PLAIN, ST_PLAIN>(ld, st, pa); return true; }     \
         if (lm == LD_MULSPEC && sm == ST_PLAIN) { launch_contig<R, C, true, LD_MULSPEC, ST_PLAIN>(ld, st, pa); return true; } \
+        if (lm == LD_PLAIN && sm == ST_OLS && ols_threads() == 256) { launch_contig<R, C, true, LD_PLAIN, ST_OLS, 256>(ld, st, pa); return true; } \
+        if (lm == LD_OLS_MAC && sm == ST_OLS && ols_threads() == 256) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS, 256>(ld, st, pa); return true; } \
         if (lm == LD_PLAIN && sm == ST_OLS) { launch_contig<R, C, true, LD_PLAIN, ST_OLS>(ld, st, pa); return true; }           \
         if (lm == LD_OLS_MAC && sm == ST_OLS) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS>(ld, st, pa); return true; }     \
         if (lm == LD_OLS_MAC && sm == ST_OLS_CHIRP) { launch_contig<R, C, true, LD_OLS_MAC, ST_OLS_CHIRP>(ld, st, pa); return true; } \

@@ -26,21 +26,25 @@ static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     count_launch();
 }
 
-template <int LOGR, int LOGC, bool INV, int LDM, int STM>
+// NTC = 256: three 8192-point tiles (and 768 threads) per SM instead of two -- the overlap-save block transforms wait
+// on their first loads, and a third tile in flight hides more of that latency than the fourth warp per scheduler
+template <int LOGR, int LOGC, bool INV, int LDM, int STM, int NTC = NT>
 static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = ContigLayout<LOGR, LOGC>;
     static bool attr_done = false;
     const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
-    auto k = pass_contig_kernel<LOGR, LOGC, INV, NT, LDM, STM>;
+    auto k = pass_contig_kernel<LOGR, LOGC, INV, NTC, LDM, STM>;
     if (!attr_done && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const i64 tiles = pa.M >> (LOGR + LOGC);
-    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
+    k<<<(unsigned)tiles, NTC, smem, ctx().stream>>>(ld, st, pa);
     ARS_LAUNCH_CHECK();
     count_launch();
 }
+
+int ols_threads();     // 512 | 256: CTA size of the overlap-save block transforms (ARS_OLS_NT, fft_plan.cu)
 
 // each returns false when it has no instantiation for the request (defined in fft_k_*.cu)
 bool fast_strided_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassArgs& pa);

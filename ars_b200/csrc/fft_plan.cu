@@ -196,7 +196,8 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     pa.logLg = ps.logLg;
     pa.tw = p->tw;
     static const int pf = env_int("ARS_FFT_PREFETCH", 0);
-    pa.prefetch = pf;
+    static const int pf_x = env_int("ARS_OLS_PREFETCH", 296);      // delay-line transform: tiles ahead (2 per SM resident)
+    pa.prefetch = ld.mode == LD_OLS_X ? pf_x : pf;
     pa.ptab = ps.ptab;
     struct ProfScope {
         bool on;
@@ -218,6 +219,13 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     ARS_CHECK(done, "no FFT pass kernel for this (logR, logT)");
 }
 
+namespace fftk {
+int ols_threads() {
+    static const int nt = env_int("ARS_OLS_NT", 512) == 256 ? 256 : 512;
+    return nt;
+}
+}  // namespace fftk
+
 int fft_segment_tile(int logF) { return logF == 12 ? 2 : 1; }
 
 void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) {
@@ -229,10 +237,10 @@ void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) 
     tmp.tw.stage = local_table();
     tmp.tw.lo = tmp.tw.hi = nullptr;
     const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
-    // the per-launch profile (ars_profile_*) is about the M-point passes, the dominant kernels; block transforms
-    // with a fused multiply-accumulate have a different byte / flop balance and are left out of it
+    // the per-launch profile (ars_profile_*) covers the passes that move the signal: the M-point passes and the
+    // overlap-save block transforms over the whole delay line; the handful of IR-partition transforms are left out
     const bool prof = g_prof.on;
-    g_prof.on = false;
+    if (nseg < 64) g_prof.on = false;
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);
     else launch_pass<false>(&tmp, ps, ld, st);
     g_prof.on = prof;

@@ -16,6 +16,8 @@
 // Zc = FFT(L - iR).
 #include "upols.cuh"
 
+#include <cstdlib>
+
 namespace ars {
 
 using namespace fft;
@@ -162,25 +164,32 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         st.scale = 1.0f / (float)F;
         fft_segments(logF, Ppad, ld, st, false);
     }
-    ARS_CUDA(cudaMemsetAsync(nz, 0, (size_t)Ppad, c.stream));
-    if (ext) {              // a partition is skipped only when both channels' taps vanish there
-        unsigned char* nz2 = c.buf("ols.nz2", (size_t)Ppad).as<unsigned char>();
-        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz, P);
-        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0 + 1, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz2, P);
-        or_flags_kernel<<<ceil_div(P, 256), 256, 0, c.stream>>>(nz, nz2, P);
-        ARS_LAUNCH_CHECK();
-        count_launch(3);
+    int* plist = nullptr;
+    if (dense) {
+        nz = nullptr;              // folded taps fill every partition: nothing to skip, no flag kernels
     } else {
-        partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, d_ir1, L1, 1, (float)fs.level0, (float)fs.level1, logB,
-                                                        nz, P);
+        ARS_CUDA(cudaMemsetAsync(nz, 0, (size_t)Ppad, c.stream));
+        if (ext) {              // a partition is skipped only when both channels' taps vanish there
+            unsigned char* nz2 = c.buf("ols.nz2", (size_t)Ppad).as<unsigned char>();
+            partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz, P);
+            partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0 + 1, L0, nullptr, 0, 2, 1.f, 0.f, logB, nz2, P);
+            or_flags_kernel<<<ceil_div(P, 256), 256, 0, c.stream>>>(nz, nz2, P);
+            ARS_LAUNCH_CHECK();
+            count_launch(3);
+        } else {
+            partition_flags_kernel<<<P, 256, 0, c.stream>>>(d_ir0, L0, d_ir1, L1, 1, (float)fs.level0, (float)fs.level1, logB,
+                                                            nz, P);
+            ARS_LAUNCH_CHECK();
+            count_launch();
+        }
+
+        plist = c.buf("ols.plist", sizeof(int) * (size_t)(P + 1)).as<int>();
+        compact_partition_flags_kernel<<<1, 32, 0, c.stream>>>(nz, P, plist);
         ARS_LAUNCH_CHECK();
         count_launch();
     }
 
-    int* plist = c.buf("ols.plist", sizeof(int) * (size_t)(P + 1)).as<int>();
-    compact_partition_flags_kernel<<<1, 32, 0, c.stream>>>(nz, P, plist);
-    ARS_LAUNCH_CHECK();
-    count_launch();
+    side_to_main();    // (folded-air renders: everything up to here ran on the side stream; the delay line does not need it)
 
     // ---- K3: frequency-domain delay line ----
     float2* X = c.buf("ols.X", sizeof(float2) * (size_t)(nseg * F) * nspec).as<float2>();
@@ -202,6 +211,8 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         fft_segments(logF, nseg, ld, st, false);
     }
 
+    side_join();
+
     // ---- K4: MAC over the partitions + inverse transform; dry/wet + maxima fused into the last store ----
     // Short IRs (and procedural ones, whose tail partitions are all zero and skipped): the MAC runs inside the first
     // load of the inverse transform.  Long dense IRs: the register-tiled MAC kernel writes Y, the inverse reads it.
@@ -212,8 +223,10 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         constexpr int JT = 8;      // measured: 8 -> 4.81 ms, 12 -> 4.80, 16 -> 5.20, 32 -> 5.28 (600 s clip, 8 s stereo IR)
         float2* Y = c.buf("ols.Y", sizeof(float2) * (size_t)(run * F)).as<float2>();
         const dim3 grid((unsigned)((F + 255) / 256), (unsigned)((run + JT - 1) / JT));
+        // (a packed FFMA2 form of this kernel was measured: 5.83 ms against 4.82 ms on cfg5 -- the extra operand pairs
+        // cost more registers and moves than the halved FMA count saves)
         ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, ext ? X + (size_t)nseg * F + skip * F : nullptr,
-                                                       ext ? H + (size_t)Ppad * F : nullptr, Y, logF, P, skip, run);
+                                        ext ? H + (size_t)Ppad * F : nullptr, Y, logF, P, skip, run);
         ARS_LAUNCH_CHECK();
         count_launch();
         ld.mode = LD_PLAIN;
@@ -288,26 +301,64 @@ __global__ void __launch_bounds__(256) air_kernel_table_kernel(double* __restric
 }
 
 // The fold  h[m] = level0 * early[m] + level1 * sum_j late[j] g[m - j]  splits the air kernel at |d| = AIR_NEAR:
-//   near taps (|d| <= AIR_NEAR, the only ones above ~1e-6) are applied directly in float64;
-//   far taps (each below 1e-6, l2 norm ~1e-6) go through one float32 FFT convolution of length M2 >= span + 2K on the
-//   FFT engine -- its rounding error scales with |late| * |g_far| * 2^-23, i.e. ~1e-13 per tap.
+//   near taps (|d| <= AIR_NEAR, the only ones above ~1e-6) are applied in float64 by air_fold_kernel;
+//   far taps (each below 1e-6, l1 norm ~1e-4) are a float32 Toeplitz product in air_far_kernel -- its rounding error
+//   is relative to partial sums of ~1e-5, i.e. ~1e-11 per tap.
 constexpr int AIR_NEAR = 64;
+constexpr int FAR_R = 8;                 // outputs per thread (32 apart), = unroll depth of the sliding window
+constexpr int FAR_WARPS = 4;             // warps per CTA; a warp owns 32 * FAR_R consecutive outputs
+constexpr int FAR_OUT = 32 * FAR_R * FAR_WARPS;
 
-// A = the non-zero stretch of the late part, B = the far taps wrapped modulo M2 (both as complex, zero imaginary part)
-__global__ void __launch_bounds__(256) air_far_pack_kernel(const float* __restrict__ late, i64 late_lo, i64 S,
-                                                           const double* __restrict__ g, i64 K, i64 M2,
-                                                           float2* __restrict__ A, float2* __restrict__ Bk) {
+// G2[d + half] = float32(g[|d|]) for AIR_NEAR < |d| <= K, else 0: the far taps with zero aprons, so that the product
+// below needs no bounds checks
+__global__ void __launch_bounds__(256) air_far_table_kernel(const double* __restrict__ g, i64 K, i64 half,
+                                                            float* __restrict__ G2) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M2) return;
-    A[i] = make_float2(i < S ? __ldg(late + late_lo + i) : 0.f, 0.f);
-    const i64 d = i <= M2 / 2 ? i : M2 - i;
-    Bk[i] = make_float2((d > AIR_NEAR && d <= K) ? (float)__ldg(g + d) : 0.f, 0.f);
+    if (i > 2 * half) return;
+    const i64 d = llabs(i - half);
+    G2[i] = (d > AIR_NEAR && d <= K) ? (float)__ldg(g + d) : 0.f;
+}
+
+// part[split][q + K] = sum over the split's stretch of j of late[late_lo + j] * G2[q - j],  -K <= q < S + K.
+// A thread owns FAR_R outputs 32 apart and walks j in steps of 32 (for each of the 32 phases), so the FAR_R taps it
+// needs slide through registers: one coalesced tap load and one broadcast signal load per FAR_R multiply-adds.
+__global__ void __launch_bounds__(32 * FAR_WARPS) air_far_kernel(const float* __restrict__ late, i64 late_lo, i64 S,
+                                                                 const float* __restrict__ G2c, i64 K, i64 chunk, i64 nout,
+                                                                 float* __restrict__ part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 q0 = -K + (i64)blockIdx.x * FAR_OUT + warp * (32 * FAR_R) + lane;   // output of slot r: q0 + 32 r
+    const i64 jc0 = (i64)blockIdx.y * chunk;
+    const float* x = late + late_lo;
+    float acc[FAR_R];
+    #pragma unroll
+    for (int r = 0; r < FAR_R; ++r) acc[r] = 0.f;
+    for (int ph = 0; ph < 32; ++ph) {
+        const i64 j0 = jc0 + ph;
+        const float* gp = G2c + (q0 - j0);                  // tap of (slot r, step s): gp[32 (r - s)]
+        float w[FAR_R];
+        #pragma unroll
+        for (int r = 0; r < FAR_R; ++r) w[r] = __ldg(gp + 32 * r);
+        for (i64 s0 = 0; s0 * 32 < chunk; s0 += FAR_R) {
+            #pragma unroll
+            for (int u = 0; u < FAR_R; ++u) {
+                const i64 s = s0 + u, j = j0 + 32 * s;
+                const float xv = j < S ? __ldg(x + j) : 0.f;
+                const float nw = __ldg(gp - 32 * (s + 1));
+                #pragma unroll
+                for (int r = 0; r < FAR_R; ++r) acc[r] = fmaf(xv, w[(r - u + FAR_R) % FAR_R], acc[r]);
+                w[(FAR_R - 1 - u) % FAR_R] = nw;           // slot of r = 0 at step s + 1
+            }
+        }
+    }
+    float* dst = part + (i64)blockIdx.y * nout + (q0 + K);
+    #pragma unroll
+    for (int r = 0; r < FAR_R; ++r) dst[32 * r] = acc[r];
 }
 
 // taps[m + adv] = float32( level0 * early[m] + level1 * (near sum in float64 + far[m]) ),  -adv <= m < Lf - adv
 __global__ void __launch_bounds__(128) air_fold_kernel(const float* __restrict__ early, i64 L0, const float* __restrict__ late,
                                                        i64 late_lo, i64 late_hi, const double* __restrict__ g, i64 K,
-                                                       const float2* __restrict__ far, i64 M2, double level0,
+                                                       const float* __restrict__ part, int nsplit, i64 nout, double level0,
                                                        double level1, i64 adv, i64 Lf, float* __restrict__ taps) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Lf) return;
@@ -322,8 +373,9 @@ __global__ void __launch_bounds__(128) air_fold_kernel(const float* __restrict__
             acc1 = fma((double)__ldg(late + j + 1), __ldg(g + llabs(m - j - 1)), acc1);
         }
         if (j < jhi) acc0 = fma((double)__ldg(late + j), __ldg(g + llabs(m - j)), acc0);
-        const i64 q = m - late_lo;                                // far[q mod M2]: q in [-K, S + K)
-        if (far && q >= -K && q < (late_hi - late_lo) + K) acc1 += (double)__ldg(far + (q < 0 ? q + M2 : q)).x;
+        const i64 q = m - late_lo;                                // far part: q in [-K, S + K)
+        if (part && q >= -K && q < (late_hi - late_lo) + K)
+            for (int sp = 0; sp < nsplit; ++sp) acc1 += (double)__ldg(part + (i64)sp * nout + (q + K));   // fixed order
     }
     const double e = (early && m >= 0 && m < L0) ? (double)__ldg(early + m) : 0.0;
     taps[i] = (float)(level0 * e + level1 * (acc0 + acc1));
@@ -355,8 +407,9 @@ void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early
     if (!d_early) L0 = 0;
     if (!d_late) L1 = 0;
     const i64 B = (i64)1 << (logF - 1), K = af.K;
-    const i64 adv = ((K + B - 1) / B) * B;
     const i64 late_lo = std::min(af.late_lo, L1), late_hi = std::min(af.late_hi, L1);
+    // the folded late part starts at late_lo - K: only the stretch before time zero needs the advance
+    const i64 adv = ((std::max<i64>(0, K - late_lo) + B - 1) / B) * B;
     const i64 Lf = adv + std::max(std::min(af.early_end, L0), late_hi + K);
     double* g = c.buf("fold.g", sizeof(double) * (size_t)(K + 1)).as<double>();
     float* taps = c.buf("fold.taps", sizeof(float) * (size_t)Lf).as<float>();
@@ -364,40 +417,28 @@ void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early
     ARS_LAUNCH_CHECK();
     count_launch();
     const i64 S = late_hi - late_lo;
-    float2* far = nullptr;
-    i64 M2 = 0;
+    float* part = nullptr;
+    int nsplit = 0;
+    i64 nout = 0;
     if (K > AIR_NEAR && S > 0 && fs.level1 != 0.0) {
-        int logM2 = 10;
-        while (((i64)1 << logM2) < S + 2 * K + 1) ++logM2;
-        M2 = (i64)1 << logM2;
-        float2* A = c.buf("fold.A", sizeof(float2) * (size_t)M2).as<float2>();
-        float2* Bk = c.buf("fold.B", sizeof(float2) * (size_t)M2).as<float2>();
-        air_far_pack_kernel<<<ceil_div(M2, 256), 256, 0, c.stream>>>(d_late, late_lo, S, g, K, M2, A, Bk);
+        const int nx = ceil_div(S + 2 * K, FAR_OUT);
+        nout = (i64)nx * FAR_OUT;
+        nsplit = std::max(1, std::min(32, ceil_div(2 * c.sm_count, nx)));
+        const i64 step = 32 * FAR_R;                                         // a stretch of j is whole unrolled sweeps
+        const i64 chunk = ((ceil_div(S, nsplit) + step - 1) / step) * step;
+        nsplit = ceil_div(S, chunk);
+        const i64 half = K + (i64)nsplit * chunk + nout + 64;                // |q - j| never leaves the table
+        float* G2 = c.buf("fold.G2", sizeof(float) * (size_t)(2 * half + 1)).as<float>();
+        part = c.buf("fold.part", sizeof(float) * (size_t)(nsplit * nout)).as<float>();
+        air_far_table_kernel<<<ceil_div(2 * half + 1, 256), 256, 0, c.stream>>>(g, K, half, G2);
         ARS_LAUNCH_CHECK();
-        count_launch();
-        FftPlan* fp = get_fft_plan(logM2);
-        for (float2* buf : {A, Bk}) {
-            Ld ld;
-            ld.mode = LD_PLAIN;
-            ld.a = buf;
-            St st;
-            st.mode = ST_PLAIN;
-            st.a = buf;
-            fft_forward(fp, ld, buf, st);
-        }
-        Ld ld;
-        ld.mode = LD_MULSPEC;
-        ld.a = A;
-        ld.b = Bk;
-        St st;
-        st.mode = ST_SCALE;
-        st.a = A;
-        st.scale = 1.0f / (float)M2;
-        fft_inverse(fp, ld, A, st);
-        far = A;
+        air_far_kernel<<<dim3((unsigned)nx, (unsigned)nsplit), 32 * FAR_WARPS, 0, c.stream>>>(d_late, late_lo, S, G2 + half, K,
+                                                                                           chunk, nout, part);
+        ARS_LAUNCH_CHECK();
+        count_launch(2);
     }
-    air_fold_kernel<<<ceil_div(Lf, 128), 128, 0, c.stream>>>(d_early, L0, d_late, late_lo, late_hi, g, K, far, M2, fs.level0,
-                                                              S > 0 ? fs.level1 : 0.0, adv, Lf, taps);
+    air_fold_kernel<<<ceil_div(Lf, 128), 128, 0, c.stream>>>(d_early, L0, d_late, late_lo, late_hi, g, K, part, nsplit, nout,
+                                                              fs.level0, S > 0 ? fs.level1 : 0.0, adv, Lf, taps);
     ARS_LAUNCH_CHECK();
     count_launch();
     FilterSpec f2 = fs;

@@ -349,8 +349,10 @@ def run_ours(args):
     barrier()
 
     # ---- roofline of the dominant kernels (FFT passes), separate untimed run with per-launch events ----
+    folds0 = int(lib.ars_air_fold_count())
     _capi.check(lib.ars_profile_begin(), "profile")
     step_dev()
+    air_folds = int(lib.ars_air_fold_count()) > folds0
     pl, pms, pbytes = _capi.C.c_int64(0), _capi.C.c_double(0), _capi.C.c_double(0)
     _capi.check(lib.ars_profile_end(_capi.C.byref(pl), _capi.C.byref(pms), _capi.C.byref(pbytes)), "profile")
     barrier()
@@ -383,8 +385,9 @@ def run_ours(args):
         "config": {"workload": w["desc"], "clip_seconds": seconds, "frames_in": n, "frames_out": N,
                    "channels_out": C, "clips_per_step": world, "parallelism": f"clip-sharded x{world}",
                    "ir_frames": L if ext else int(p.ir_duration * RATE),
-                   "l2": "working set (input 8*n B, 8*M B FFT buffers, M = 2^%d) exceeds the 126 MB L2; no flush needed"
-                         % int(np.ceil(np.log2(2 * N - 1)))},
+                   "route": "folded-air overlap-save" if air_folds else "see DESIGN.md section 2",
+                   "l2": "working set (input %d MB, delay-line / FFT work buffers >= %d MB, output %d MB) exceeds the "
+                         "126 MB L2; no flush needed" % (n * cin * 4 >> 20, 8 * N >> 19, N * C * 2 >> 20)},
         "e2e": {"value": total_seconds / (e2e_ms * 1e-3), "unit": "audio-seconds/s", "ms_per_step": e2e_ms / args.steps,
                 "call": "ars_render_batch (host buffers, copy/compute pipelined across the steps' clips)",
                 "single_call_ms": single_ms,
@@ -392,7 +395,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(h_pcm.numel() * 2 + 56)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "fft pass kernels (pass_strided_kernel / pass_contig_kernel)",
+        "roofline": {"bound": "hbm", "kernel": "fft pass kernels (pass_contig_kernel block transforms of the overlap-save "
+                                               "route / pass_strided_kernel + pass_contig_kernel M-point passes)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "launches_per_step": int(pl.value), "ms_per_step_in_kernel": pms.value,
@@ -403,8 +407,8 @@ def run_ours(args):
         "roofline_whole_render": {"algorithmic_bytes_per_step": int(out_bytes_per_frame * N),
                                   "achieved": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9, "unit": "GB/s",
                                   "frac": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9 / peak,
-                                  "note": "SURVEY 8(d) compulsory bytes of an ideal single fused pass; the exact "
-                                          "N-point DFT the reference's EQ/air masks require needs 6 multi-pass FFTs"},
+                                  "note": "SURVEY 8(d) compulsory bytes of an ideal single fused pass (8 B in + 2 B per "
+                                          "output channel per frame) over the whole step, all kernels included"},
         "metrics_of_last_render": metrics_dev,
     }
     if world == 1 and not args.no_cpu and not ext:

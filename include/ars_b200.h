@@ -99,8 +99,10 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * two M-point transforms),
  * "air_fold" (1 = a render whose only spectral mask is the air-absorption ramp [air > 0.01, EQ gains ~ 1] folds the
  * ramp into the impulse response and runs as one overlap-save convolution [default]; 0 = exact N-point filter),
- * "air_fold_eps_e9" (bound on the late path's transfer-function error the fold may introduce, in 1e-9; default 1000),
+ * "air_fold_eps_e9" (bound on the late path's transfer-function error the fold may introduce, in 1e-9; default 2000),
  * "air_fold_max_taps" (longest half-length of the truncated air kernel; a longer one falls back to the N-point path),
+ * "side_stream" (1 = folded-air renders run IR synthesis, fold and IR spectra on a second stream next to the delay-line
+ * transform [default]),
  * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */

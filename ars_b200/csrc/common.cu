@@ -74,7 +74,10 @@ void side_begin() {
     Ctx& c = ctx();
     if (c.side_state != 0) return;
     if (!c.aux) {
-        ARS_CUDA(cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking));
+        // highest priority: the side chain's small CTAs must get in between the CTAs of the big transform next to it
+        int least = 0, greatest = 0;
+        ARS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        ARS_CUDA(cudaStreamCreateWithPriority(&c.aux, cudaStreamNonBlocking, greatest));
         ARS_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         ARS_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     }

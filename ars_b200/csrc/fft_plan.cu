@@ -196,7 +196,7 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     pa.logLg = ps.logLg;
     pa.tw = p->tw;
     static const int pf = env_int("ARS_FFT_PREFETCH", 0);
-    static const int pf_x = env_int("ARS_OLS_PREFETCH", 296);      // delay-line transform: tiles ahead (2 per SM resident)
+    static const int pf_x = env_int("ARS_OLS_PREFETCH", 0);        // delay-line transform: tiles ahead (measured: 148 -> -2 %, 296 / 592 -> +1..4 %; off)
     pa.prefetch = ld.mode == LD_OLS_X ? pf_x : pf;
     pa.ptab = ps.ptab;
     struct ProfScope {

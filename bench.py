@@ -237,6 +237,8 @@ def run_ours(args):
     for kv in args.opt:
         _capi.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     w = WORKLOADS[args.workload]
+    if args.cin:
+        w = dict(w, cin=args.cin, desc=w["desc"] + " [input channels overridden: %d]" % args.cin)
     seconds = args.seconds or w["seconds"]
     x = make_clip(w, seconds, rank)
     x2 = x if x.ndim == 2 else x[:, None]
@@ -532,6 +534,7 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=300.0)
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cin", type=int, default=0, help="experiments: override the clip's channel count")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="library option for experiments (ars_set_option), e.g. --opt air_fold=0")
     args = ap.parse_args()

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) ols_mac_kernel(const float2* __restrict__
         if (j0 + q < run) Y[(j0 + q) * F + t] = acc[q];
 }
 
-static int g_mac_tiled_min = 8;    // partitions above which the register-tiled MAC kernel replaces the fused prologue
+static int g_mac_tiled_min = 4;    // partitions above which the register-tiled MAC kernel replaces the fused prologue
 void upols_set_mac_tiled_min(int p) { g_mac_tiled_min = p; }
 
 __global__ void or_flags_kernel(unsigned char* a, const unsigned char* b, int n) {
@@ -224,9 +224,11 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         float2* Y = c.buf("ols.Y", sizeof(float2) * (size_t)(run * F)).as<float2>();
         const dim3 grid((unsigned)((F + 255) / 256), (unsigned)((run + JT - 1) / JT));
         // (a packed FFMA2 form of this kernel was measured: 5.83 ms against 4.82 ms on cfg5 -- the extra operand pairs
-        // cost more registers and moves than the halved FMA count saves)
+        // cost more registers and moves than the halved FMA count saves;
+        // and a form that requests all P coefficients and JT + P - 1 delay-line values up front (117 registers): 143 us
+        // against 102 us for this sliding form at P = 7 on cfg3)
         ols_mac_kernel<JT><<<grid, 256, 0, c.stream>>>(X + skip * F, H, ext ? X + (size_t)nseg * F + skip * F : nullptr,
-                                        ext ? H + (size_t)Ppad * F : nullptr, Y, logF, P, skip, run);
+                                                       ext ? H + (size_t)Ppad * F : nullptr, Y, logF, P, skip, run);
         ARS_LAUNCH_CHECK();
         count_launch();
         ld.mode = LD_PLAIN;

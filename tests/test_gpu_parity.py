@@ -744,7 +744,7 @@ def _fold_opts(**kw):
 
 
 def _fold_defaults():
-    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=32768, mac_tiled_min=8)
+    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=32768, mac_tiled_min=4)
 
 
 def _fold_count():
@@ -766,7 +766,7 @@ def test_air_fold_stage_matches_exact_path_and_oracle(rs):
         for x, air in cases:
             want = orc.convolve_split(x, early, late, 0.7, 0.9, 0.6, 1.0, 1.0, rate, 0.5, air)
             outs = {}
-            for name, opts in (("exact", dict(air_fold=0)), ("fold", dict(air_fold=1, mac_tiled_min=8)),
+            for name, opts in (("exact", dict(air_fold=0)), ("fold", dict(air_fold=1, mac_tiled_min=4)),
                                ("fold_prologue", dict(air_fold=1, mac_tiled_min=1000))):
                 _fold_opts(**opts)
                 c0 = _fold_count()

@@ -267,7 +267,10 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         }
         // the folded-air route: IR synthesis, the fold and the IR partition spectra are a chain of small latency-bound
         // kernels that does not depend on the signal -- it runs on the side stream, next to the delay-line transform
-        if (g_opt_side_stream && folds_air(fs, ex, p->rate, nullptr)) side_begin();
+        if (g_opt_side_stream && folds_air(fs, ex, p->rate, nullptr)) {
+            fft_touch_tables();    // (built once, on the main stream, before both streams read them)
+            side_begin();
+        }
         std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
         std::vector<i64> tap_pos;
         std::vector<double> tap_val;
@@ -394,6 +397,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "air_fold_eps_e9")) { ARS_CHECK(value >= 1, "air_fold_eps_e9 must be >= 1"); g_opt_air_fold_eps_e9 = value; }
     else if (!strcmp(key, "air_fold_max_taps")) { ARS_CHECK(value >= 64, "air_fold_max_taps must be >= 64"); g_opt_air_fold_max_taps = value; }
     else if (!strcmp(key, "side_stream")) g_opt_side_stream = value ? 1 : 0;
+    else if (!strcmp(key, "ols_r2")) upols_set_r2(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END

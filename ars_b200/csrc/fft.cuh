@@ -177,8 +177,8 @@ template <bool INV> struct Dft<16, INV> {
 
 // ------------------------------------------------------------- Ld / St functors
 enum LdMode { LD_PLAIN = 0, LD_MULSPEC, LD_CHIRP_X2, LD_CHIRP_XC, LD_CHIRP_PAIR, LD_CHIRP_B, LD_CHIRP_C,
-              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC, LD_OLS_CHIRPSIG, LD_OLS_IRC };
-enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP };
+              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC, LD_OLS_CHIRPSIG, LD_OLS_IRC, LD_OLS_X2, LD_OLS_IR2 };
+enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP, ST_OLS2 };
 
 struct Ld {
     int mode = LD_PLAIN;
@@ -203,6 +203,11 @@ struct Ld {
     i64 lookback = 0;               // LD_OLS_MAC: delay-line segments that exist before the launch's segment 0
     i64 adv = 0;                    // LD_OLS_X: the windows start `adv` frames later (IR with taps at negative times)
     i64 circ = 0;                   // LD_OLS_X: > 0: the signal is the circ-periodic extension of the zero-padded frames
+    // LD_OLS_X2 / LD_OLS_IR2 (and ST_OLS2): the 2B-point overlap-save transform as a radix-2 stage folded into the
+    // load (store) plus two B-point transforms -- sub-segment 0 of a segment holds the even bins, sub-segment 1 the odd
+    // ones.  The two halves of an overlap-save window are exactly the operands of that stage: a = w[i] + w[i+B],
+    // b = (w[i] - w[i+B]) w_2B^i; an IR partition has an empty second half: a = h[i], b = h[i] w_2B^i.
+    const float2* tw2 = nullptr;    // w_2B^i, i < B
     // MODE >= 0: compile-time access mode (fast kernels); MODE < 0: runtime switch on `mode` (generic kernels)
     template <int MODE> ARS_HD float2 get(i64 idx) const {
         if constexpr (MODE < 0) return (*this)(idx);
@@ -271,6 +276,23 @@ struct Ld {
             const float u = (f0 && i < nvalid) ? ARS_LDG(f0 + i * cin) : 0.f;
             const float v = (f1 && i < nvalid1) ? ARS_LDG(f1 + i * cin) : 0.f;
             return cmul(make_float2(u, v), ARS_LDG(b + i));
+        } else if constexpr (MODE == LD_OLS_X2) {      // radix-2 stage over the window of segment s (see tw2)
+            const i64 B = (i64)1 << (logF - 1);
+            const i64 seg = seg0 + (idx >> logF);
+            const i64 i = idx & (B - 1);
+            const float2 x0 = frame_at((seg - 1) * B + i + adv - frame0), x1 = frame_at(seg * B + i + adv - frame0);
+            if ((idx & B) == 0) return make_float2(x0.x + x1.x, x0.y + x1.y);
+            return cmul(make_float2(x0.x - x1.x, x0.y - x1.y), ARS_LDG(tw2 + i));
+        } else if constexpr (MODE == LD_OLS_IR2) {     // IR partition p, radix-2 stage over [taps | zeros]
+            const i64 B = (i64)1 << (logF - 1);
+            const i64 t = idx & (B - 1);
+            const i64 i = ((idx >> logF) << (logF - 1)) + t;
+            const float u = (f0 && i < nvalid) ? ARS_LDG(f0 + i * cin) : 0.f;
+            const float v = (f1 && i < nvalid1) ? ARS_LDG(f1 + i * cin) : 0.f;
+            const float h = c0 * u + c1 * v;
+            if ((idx & B) == 0) return make_float2(h, 0.f);
+            const float2 w = ARS_LDG(tw2 + t);
+            return make_float2(h * w.x, h * w.y);
         } else if constexpr (MODE == LD_OLS_MAC) {     // Y_s = sum_p X_{s-p} H_p (+ Xc_{s-p} Hc_p)
             float2 acc[1];
             get_mac<1>(idx, 0, acc);
@@ -280,6 +302,20 @@ struct Ld {
             const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
             return make_float2(l, r);
         }
+    }
+    // one stereo frame of the (periodically extended, zero-padded) signal as L + iR; c1 < 0 conjugates
+    ARS_HD float2 frame_at(i64 fr) const {
+        if (circ > 0) { if (fr < 0) fr += circ; else if (fr >= circ) fr -= circ; }
+        if (fr < 0 || fr >= nvalid) return make_float2(0.f, 0.f);
+        float l, r;
+        if ((cin & 1) == 0) {
+            const float2 v = ARS_LDG(reinterpret_cast<const float2*>(f0 + fr * cin));
+            l = v.x; r = v.y;
+        } else {
+            l = ARS_LDG(f0 + fr * cin);
+            r = cin > 1 ? ARS_LDG(f0 + fr * cin + 1) : l;
+        }
+        return make_float2(l, c1 < 0.f ? -r : r);
     }
     // LD_OLS_X: ask the L2 for the new half (B frames) of the windows of `nsegs` segments starting at launch segment
     // `seg` -- the pass waits on its first loads (DRAM at a third of its bandwidth), so a hint a couple of waves
@@ -354,6 +390,8 @@ struct Ld {
             case LD_OLS_MAC: return get<LD_OLS_MAC>(idx);
             case LD_OLS_CHIRPSIG: return get<LD_OLS_CHIRPSIG>(idx);
             case LD_OLS_IRC: return get<LD_OLS_IRC>(idx);
+            case LD_OLS_X2: return get<LD_OLS_X2>(idx);
+            case LD_OLS_IR2: return get<LD_OLS_IR2>(idx);
         }
         return make_float2(0.f, 0.f);
     }
@@ -375,6 +413,33 @@ struct St {
     i64 frame0 = 0, dry_frame0 = 0;  // absolute frame index of a[0] / dry[0]; N = absolute end frame (exclusive)
     unsigned* maxbits = nullptr;     // ST_FINAL: 4 words: bits of max |x|, max |x.re|, max |x.im|, max |f32(re + im)|
     unsigned local_max = 0, local_l = 0, local_r = 0, local_lr = 0;
+    const float2* tw2 = nullptr;     // ST_OLS2: w_2B^i, i < B (see Ld::tw2)
+    // one overlap-save output frame: mix with the dry frame, store, track the maxima
+    ARS_HD void ols_out(i64 fr, float2 v) {
+        if (fr >= N) return;
+        float l = 0.f, r = 0.f;
+        const i64 df = fr - dry_frame0;
+        if (df >= 0 && df < n) {                                           // n = dry frames held at `dry`
+            if ((cin & 1) == 0) {
+                const float2 d = ARS_LDG(reinterpret_cast<const float2*>(dry + df * cin));
+                l = d.x; r = d.y;
+            } else {
+                l = ARS_LDG(dry + df * cin);
+                r = cin > 1 ? ARS_LDG(dry + df * cin + 1) : l;
+            }
+        }
+        const float2 y = make_float2(dg * l + dw * v.x, dg * r + dw * v.y);
+        a[fr - frame0] = y;
+        const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
+        if (m0 > local_l) local_l = m0;
+        if (m1 > local_r) local_r = m1;
+        if (m2 > local_lr) local_lr = m2;
+    }
+    // ST_OLS2: the radix-2 stage that ends the 2B-point inverse, second half only: y[i + B] = ya[i] - conj(w^i) yb[i]
+    ARS_HD void put_ols2(i64 seg, int i, float2 ya, float2 yb) {
+        const float2 t = cmulc(yb, ARS_LDG(tw2 + i));
+        ols_out(((seg0 + seg) << (logF - 1)) + i, make_float2(ya.x - t.x, ya.y - t.y));
+    }
     // chirp operand of the store, fetched early so its latency overlaps the butterfly
     template <int MODE> ARS_HD float2 pre(i64 idx) const {
         if constexpr (MODE < 0) {
@@ -395,6 +460,7 @@ struct St {
                 case ST_FINAL: put<ST_FINAL>(idx, v, aux); break;
                 case ST_OLS: put<ST_OLS>(idx, v, aux); break;
                 case ST_OLS_CHIRP: put<ST_OLS_CHIRP>(idx, v, aux); break;
+                case ST_OLS2: break;      // fast instantiations only
             }
         } else if constexpr (MODE == ST_PLAIN) {
             a[idx] = v;
@@ -410,21 +476,9 @@ struct St {
         } else if constexpr (MODE == ST_OLS) {
             const i64 F = (i64)1 << logF, B = F >> 1;
             const i64 t = idx & (F - 1);
-            const i64 fr = ((seg0 + (idx >> logF)) << (logF - 1)) + (t - B);       // absolute output frame
-            if (t >= B && fr < N) {
-                float l = 0.f, r = 0.f;
-                const i64 df = fr - dry_frame0;
-                if (df >= 0 && df < n) {                                           // n = dry frames held at `dry`
-                    l = ARS_LDG(dry + df * cin);
-                    r = cin > 1 ? ARS_LDG(dry + df * cin + 1) : l;
-                }
-                const float2 y = make_float2(dg * l + dw * v.x, dg * r + dw * v.y);
-                a[fr - frame0] = y;
-                const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
-                if (m0 > local_l) local_l = m0;
-                if (m1 > local_r) local_r = m1;
-                if (m2 > local_lr) local_lr = m2;
-            }
+            if (t >= B) ols_out(((seg0 + (idx >> logF)) << (logF - 1)) + (t - B), v);      // absolute output frame
+        } else if constexpr (MODE == ST_OLS2) {
+            // (stored by run_tile through put_ols2 once both sub-segments are back in shared memory)
         } else {
             if (idx < N) {
                 float2 y = cmul(v, aux);
@@ -439,7 +493,7 @@ struct St {
     }
     template <int MODE> ARS_HD void put(i64 idx, float2 v) { put<MODE>(idx, v, pre<MODE>(idx)); }
     ARS_HD void finish() {
-        if ((mode == ST_FINAL || mode == ST_OLS) && maxbits) {
+        if ((mode == ST_FINAL || mode == ST_OLS || mode == ST_OLS2) && maxbits) {
             local_max = local_l > local_r ? local_l : local_r;
 #ifdef __CUDA_ARCH__
             unsigned m[4] = {local_max, local_l, local_r, local_lr};
@@ -672,7 +726,11 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 #pragma unroll
                 for (int k = 1; k < r; ++k) v[k] = cmul(v[k], w[k]);
             }
-            if constexpr (first) {
+            if constexpr (first && STM == ST_OLS2) {
+                Dft<r, true>::run(v);
+                #pragma unroll
+                for (int t = 0; t < r; ++t) ARS_SM(t) = v[t];
+            } else if constexpr (first) {
                 float2 aux[r];
                 const i64 idx0 = gfirst(row0, c);
                 #pragma unroll
@@ -707,6 +765,12 @@ __device__ __forceinline__ void run_tile(float2* sm, LD& ld, ST& st, const PassA
         if constexpr (n > 2) { ARS_STAGE(2); __syncthreads(); }
         if constexpr (n > 1) { ARS_STAGE(1); __syncthreads(); }
         ARS_STAGE(0);
+        if constexpr (STM == ST_OLS2) {            // closing radix-2 stage across the tile's two sub-segments
+            static_assert(STM != ST_OLS2 || (LAYOUT::C == 2 && !STRIDED), "ST_OLS2: a tile is the two halves of one segment");
+            __syncthreads();
+            const i64 seg = gfirst(0, 0) >> (LOGR + 1);
+            for (int i = tid; i < (1 << LOGR); i += NT) st.put_ols2(seg, i, sm[LAYOUT::sidx(i, 0)], sm[LAYOUT::sidx(i, 1)]);
+        }
     }
     st.finish();
 }
@@ -755,6 +819,10 @@ inline void emulate_tile(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfir
         if constexpr (n > 2) { ARS_ALL(2); }
         if constexpr (n > 1) { ARS_ALL(1); }
         ARS_ALL(0);
+        if constexpr (STM == ST_OLS2) {
+            const i64 seg = gfirst(0, 0) >> (LOGR + 1);
+            for (int i = 0; i < (1 << LOGR); ++i) st.put_ols2(seg, i, sm[LAYOUT::sidx(i, 0)], sm[LAYOUT::sidx(i, 1)]);
+        }
     }
 #undef ARS_ALL
     st.finish();
@@ -889,6 +957,10 @@ void fft_forward(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st)
 // Inverse transform: first pass reads through `ld` (permuted order), last pass writes natural
 // order through `st`.  Unnormalised.
 void fft_inverse(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st);
+// `nseg` independent 8192-point overlap-save transforms as a radix-2 stage folded into the load / store plus two
+// 4096-point transforms per segment (LD_OLS_X2 | LD_OLS_IR2 forward, ST_OLS2 inverse; fills in Ld::tw2 / St::tw2)
+void fft_segments_r2(i64 nseg, fft::Ld ld, fft::St st, bool inverse);
+void fft_touch_tables();      // builds the shared stage table on the current stream if it does not exist yet
 // One contiguous pass over `nseg` independent 2^logF-point segments (logF = 12 or 13; nseg a multiple of
 // fft_segment_tile(logF)): the block transforms of the overlap-save convolution.
 int fft_segment_tile(int logF);

@@ -10,6 +10,10 @@ bool fast_contig_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassAr
         launch_contig<13, 0, false, LD_OLS_IR, ST_SCALE>(ld, st, pa);
         return true;
     }
+    if (ps.logR == 12 && ps.logT == 1) {          // radix-2-folded overlap-save transforms (fft_segments_r2)
+        if (lm == LD_OLS_X2 && sm == ST_PLAIN) { launch_contig<12, 1, false, LD_OLS_X2, ST_PLAIN>(ld, st, pa); return true; }
+        if (lm == LD_OLS_IR2 && sm == ST_SCALE) { launch_contig<12, 1, false, LD_OLS_IR2, ST_SCALE>(ld, st, pa); return true; }
+    }
     if (sm != ST_PLAIN) return false;
 #define F_CASE(R, C)                                                                                          \
     if (ps.logR == R && ps.logT == C) {                                                                       \

@@ -139,8 +139,8 @@ static double ld_bytes(const Ld& ld, i64 M) {
         case LD_CHIRP_B: return 8.0 * (double)(2 * ld.N - 1);
         case LD_CHIRP_C: return 16.0 * (double)ld.nvalid;
         case LD_REAL_PAIR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
-        case LD_OLS_X: return 8.0 * (double)ld.nvalid;
-        case LD_OLS_IR: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
+        case LD_OLS_X: case LD_OLS_X2: return 8.0 * (double)ld.nvalid;
+        case LD_OLS_IR: case LD_OLS_IR2: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
         case LD_OLS_MAC: return 8.0 * (double)M;       // compulsory: each delay-line spectrum once
         case LD_OLS_CHIRPSIG: return 8.0 * (double)ld.N;
         case LD_OLS_IRC: return 4.0 * (double)(ld.nvalid + ld.nvalid1) + 8.0 * (double)std::max(ld.nvalid, ld.nvalid1);
@@ -151,7 +151,7 @@ static double st_bytes(const St& st, i64 M) {
     switch (st.mode) {
         case ST_PLAIN: case ST_SCALE: return 8.0 * (double)M;
         case ST_CHIRP: case ST_FINAL: return 16.0 * (double)st.N;
-        case ST_OLS: return 16.0 * (double)st.N;
+        case ST_OLS: case ST_OLS2: return 16.0 * (double)st.N;
         case ST_OLS_CHIRP: return 16.0 * (double)st.N;
     }
     return 0.0;
@@ -213,6 +213,7 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
         else done = INV ? fast_contig_inv(ps, ld, st, pa) : fast_contig_fwd(ps, ld, st, pa);
     }
     if (!done) {
+        ARS_CHECK(st.mode != ST_OLS2, "ST_OLS2 has compile-time-mode instantiations only");
         if (ps.strided) done = INV ? generic_strided_inv(ps, ld, st, pa) : generic_strided_fwd(ps, ld, st, pa);
         else done = INV ? generic_contig_inv(ps, ld, st, pa) : generic_contig_fwd(ps, ld, st, pa);
     }
@@ -239,6 +240,25 @@ void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) 
     const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
     // the per-launch profile (ars_profile_*) covers the passes that move the signal: the M-point passes and the
     // overlap-save block transforms over the whole delay line; the handful of IR-partition transforms are left out
+    const bool prof = g_prof.on;
+    if (nseg < 64) g_prof.on = false;
+    if (inverse) launch_pass<true>(&tmp, ps, ld, st);
+    else launch_pass<false>(&tmp, ps, ld, st);
+    g_prof.on = prof;
+}
+
+void fft_touch_tables() { local_table(); }
+
+void fft_segments_r2(i64 nseg, Ld ld, St st, bool inverse) {
+    ARS_CHECK(nseg > 0, "fft_segments_r2: no segments");
+    FftPlan tmp;
+    tmp.logM = 0;
+    tmp.M = nseg << 13;
+    tmp.tw.stage = local_table();
+    tmp.tw.lo = tmp.tw.hi = nullptr;
+    ld.logF = st.logF = 13;
+    ld.tw2 = st.tw2 = local_table() + stage_off(13);      // w_8192^i, i < 4096
+    const FftPass ps = {false, 12, 1, 12};
     const bool prof = g_prof.on;
     if (nseg < 64) g_prof.on = false;
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256) ols_mac_kernel(const float2* __restrict__
         if (j0 + q < run) Y[(j0 + q) * F + t] = acc[q];
 }
 
+static int g_ols_r2 = 0;           // 1: 8192-point transforms as a folded radix-2 stage + two 4096-point transforms (measured slower, below)
+void upols_set_r2(int on) { g_ols_r2 = on ? 1 : 0; }
 static int g_mac_tiled_min = 4;    // partitions above which the register-tiled MAC kernel replaces the fused prologue
 void upols_set_mac_tiled_min(int p) { g_mac_tiled_min = p; }
 
@@ -121,6 +123,11 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
     if (!d_ir1) L1 = 0;
     const bool ext = fs.mode == FILT_EXT;
     const i64 L = ext ? L0 : std::max(L0, L1);
+    // logF = 13, optional: a radix-2 stage folded into the window load / the output store + two 4096-point transforms per
+    // segment (the three-stage tile of the M-point passes) instead of the four-stage 8192-point tile (fft.cuh, Ld::tw2).
+    // Measured on cfg3: inverse 182 us against 191 us, but the delay-line transform 292 us against 192 us -- every
+    // window frame is then requested by both sub-segments' threads, and that pass is bound by its loads.  Off.
+    const bool r2 = logF == 13 && g_ols_r2;
     const int tile = fft_segment_tile(logF);
     const int P = (int)std::max<i64>(1, (L + B - 1) / B);
     const int Ppad = ((P + tile - 1) / tile) * tile;
@@ -162,7 +169,8 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         st.mode = ST_SCALE;
         st.a = H + (size_t)k * Ppad * F;
         st.scale = 1.0f / (float)F;
-        fft_segments(logF, Ppad, ld, st, false);
+        if (r2) { ld.mode = LD_OLS_IR2; fft_segments_r2(Ppad, ld, st, false); }
+        else fft_segments(logF, Ppad, ld, st, false);
     }
     int* plist = nullptr;
     if (dense) {
@@ -208,7 +216,8 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
         St st;
         st.mode = ST_PLAIN;
         st.a = X + (size_t)k * nseg * F;
-        fft_segments(logF, nseg, ld, st, false);
+        if (r2) { ld.mode = LD_OLS_X2; fft_segments_r2(nseg, ld, st, false); }
+        else fft_segments(logF, nseg, ld, st, false);
     }
 
     side_join();
@@ -258,7 +267,8 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
     st.dg = (float)fs.dry_gain;
     st.dw = (float)fs.dw;
     st.maxbits = &d_state->max_stereo;
-    fft_segments(logF, run, ld, st, true);
+    if (r2) { st.mode = ST_OLS2; fft_segments_r2(run, ld, st, true); }
+    else fft_segments(logF, run, ld, st, true);
 }
 
 void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,

@@ -47,6 +47,7 @@ bool air_fold_plan(const FilterSpec& fs, i64 early_end, i64 late_lo, i64 late_hi
 void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early, i64 L0, const float* d_late, i64 L1,
                           const FilterSpec& fs, const AirFold& af, float2* d_y, RenderState* d_state, int logF = 13);
 
+void upols_set_r2(int on);             // 1: 8192-point transforms through the folded radix-2 form (default 0: measured slower)
 void upols_set_mac_tiled_min(int p);   // partitions above which dense IRs use the register-tiled MAC kernel
 
 }  // namespace ars

@@ -271,6 +271,18 @@ static void emu_segments(int logF, i64 nseg, const Tw& tw, const Ld& ld, const S
     (void)ps;
 }
 
+// the radix-2-folded form of the 8192-point overlap-save transforms (fft_plan.cu: fft_segments_r2)
+static void emu_segments_r2(i64 nseg, const Tw& tw, Ld ld, St st, bool inverse) {
+    PassArgs pa;
+    pa.M = nseg << 13; pa.logM = 0; pa.logLg = 12; pa.prefetch = 0; pa.ptab = nullptr; pa.tw = tw;
+    ld.logF = st.logF = 13;
+    ld.tw2 = st.tw2 = tw.stage + stage_off(13);
+    if (!inverse && ld.mode == LD_OLS_IR2) emu_contig<12, 1, false, LD_OLS_IR2, ST_SCALE>(ld, st, pa);
+    else if (!inverse) emu_contig<12, 1, false, LD_OLS_X2, ST_PLAIN>(ld, st, pa);
+    else emu_contig<12, 1, true, LD_OLS_MAC, ST_OLS2>(ld, st, pa);
+}
+static bool g_r2 = false;     // check_ols / check_ols_circ: run the logF = 13 cases through the folded form
+
 static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_hi) {
     Tw tw;
     make_tables(logF, tw);
@@ -300,13 +312,13 @@ static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_h
         ld.nvalid = ld.nvalid1 = L;
         if (ext) { ld.c0 = 0.5f; ld.c1 = k == 0 ? 0.5f : -0.5f; } else { ld.c0 = 1.f; ld.c1 = 0.f; }
         St st; st.mode = ST_SCALE; st.a = H.data() + (size_t)k * Ppad * F; st.scale = 1.0f / (float)F;
-        emu_segments(logF, Ppad, tw, ld, st, false);
+        if (g_r2 && logF == 13) { ld.mode = LD_OLS_IR2; emu_segments_r2(Ppad, tw, ld, st, false); } else emu_segments(logF, Ppad, tw, ld, st, false);
     }
     for (int k = 0; k < nspec; ++k) {
         Ld ld; ld.mode = LD_OLS_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = 2;
         ld.seg0 = seg0; ld.c1 = k == 0 ? 0.f : -1.f;
         St st; st.mode = ST_PLAIN; st.a = X.data() + (size_t)k * nseg * F;
-        emu_segments(logF, nseg, tw, ld, st, false);
+        if (g_r2 && logF == 13) { ld.mode = LD_OLS_X2; emu_segments_r2(nseg, tw, ld, st, false); } else emu_segments(logF, nseg, tw, ld, st, false);
     }
     unsigned maxbits[4] = {0, 0, 0, 0};
     {
@@ -316,7 +328,7 @@ static int check_ols(int logF, i64 n, i64 L, bool ext, i64 block_lo, i64 block_h
         St st; st.mode = ST_OLS; st.logF = logF; st.seg0 = block_lo; st.a = y.data(); st.frame0 = 0;
         st.N = std::min<i64>(N, block_hi * B); st.dry = x.data(); st.dry_frame0 = 0; st.n = n; st.cin = 2;
         st.dg = 0.25f; st.dw = 0.5f; st.maxbits = maxbits;
-        emu_segments(logF, run, tw, ld, st, true);
+        if (g_r2 && logF == 13) { st.mode = ST_OLS2; emu_segments_r2(run, tw, ld, st, true); } else emu_segments(logF, run, tw, ld, st, true);
     }
     double maxerr = 0, peak = 0;
     const i64 f_lo = block_lo * B, f_hi = std::min<i64>(N, block_hi * B);
@@ -357,20 +369,20 @@ static int check_ols_circ(int logF, i64 n, i64 N, i64 Lf, i64 adv) {
     {
         Ld ld; ld.mode = LD_OLS_IR; ld.logF = logF; ld.f0 = h.data(); ld.f1 = nullptr; ld.cin = 1; ld.nvalid = Lf; ld.c0 = 1.f;
         St st; st.mode = ST_SCALE; st.a = H.data(); st.scale = 1.0f / (float)F;
-        emu_segments(logF, Ppad, tw, ld, st, false);
+        if (g_r2 && logF == 13) { ld.mode = LD_OLS_IR2; emu_segments_r2(Ppad, tw, ld, st, false); } else emu_segments(logF, Ppad, tw, ld, st, false);
     }
     {
         Ld ld; ld.mode = LD_OLS_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = 2;
         ld.seg0 = seg0; ld.adv = adv; ld.circ = N;
         St st; st.mode = ST_PLAIN; st.a = X.data();
-        emu_segments(logF, nseg, tw, ld, st, false);
+        if (g_r2 && logF == 13) { ld.mode = LD_OLS_X2; emu_segments_r2(nseg, tw, ld, st, false); } else emu_segments(logF, nseg, tw, ld, st, false);
     }
     unsigned maxbits[4] = {0, 0, 0, 0};
     {
         Ld ld; ld.mode = LD_OLS_MAC; ld.logF = logF; ld.a = X.data() + skip * F; ld.b = H.data(); ld.P = P; ld.lookback = skip;
         St st; st.mode = ST_OLS; st.logF = logF; st.seg0 = 0; st.a = y.data(); st.frame0 = 0; st.N = N; st.dry = x.data();
         st.dry_frame0 = 0; st.n = n; st.cin = 2; st.dg = 0.25f; st.dw = 0.5f; st.maxbits = maxbits;
-        emu_segments(logF, run, tw, ld, st, true);
+        if (g_r2 && logF == 13) { st.mode = ST_OLS2; emu_segments_r2(run, tw, ld, st, true); } else emu_segments(logF, run, tw, ld, st, true);
     }
     double maxerr = 0, peak = 0;
     const i64 stepf = std::max<i64>(1, N / 300);
@@ -461,6 +473,12 @@ int main(int argc, char** argv) {
         bad += check_ols_circ(12, 60000, 60000 + 5000 - 1, 9000, 4096);       // zero tail longer than the pre-ring
         bad += check_ols_circ(13, 90000, 90000 + 100 - 1, 20000, 8192);       // pre- and post-ring wrap around the period
         bad += check_ols_circ(12, 50000, 50000 + 3000 - 1, 2048 + 700, 2048);
+        g_r2 = true;
+        bad += check_ols(13, 50001, 20000, false, 0, -1);
+        bad += check_ols(13, 70000, 9000, true, 3, 9);
+        bad += check_ols(13, 3000, 100, false, 0, -1);
+        bad += check_ols_circ(13, 90000, 90000 + 100 - 1, 20000, 8192);
+        g_r2 = false;
         printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
         return bad ? 1 : 0;
     }

@@ -744,7 +744,7 @@ def _fold_opts(**kw):
 
 
 def _fold_defaults():
-    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=32768, mac_tiled_min=4)
+    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=32768, mac_tiled_min=4, ols_r2=0)
 
 
 def _fold_count():
@@ -767,7 +767,9 @@ def test_air_fold_stage_matches_exact_path_and_oracle(rs):
             want = orc.convolve_split(x, early, late, 0.7, 0.9, 0.6, 1.0, 1.0, rate, 0.5, air)
             outs = {}
             for name, opts in (("exact", dict(air_fold=0)), ("fold", dict(air_fold=1, mac_tiled_min=4)),
-                               ("fold_prologue", dict(air_fold=1, mac_tiled_min=1000))):
+                               ("fold_prologue", dict(air_fold=1, mac_tiled_min=1000)),
+                               ("fold_r2", dict(air_fold=1, mac_tiled_min=4, ols_r2=1)),
+                               ("fold_r2_prologue", dict(air_fold=1, mac_tiled_min=1000, ols_r2=1))):
                 _fold_opts(**opts)
                 c0 = _fold_count()
                 outs[name] = rs.convolve_audio_split_3d(x, early, late, 0.7, 0.9, 0.6, 1.0, 1.0, rate, 0.5, air)
@@ -776,6 +778,7 @@ def test_air_fold_stage_matches_exact_path_and_oracle(rs):
                 assert snr_db(outs[name], want) >= 100.0, (name, air, snr_db(outs[name], want))
             assert rel_err(outs["fold"], outs["exact"]) <= 3e-6, rel_err(outs["fold"], outs["exact"])
             assert rel_err(outs["fold_prologue"], outs["fold"]) <= 1e-6
+            assert rel_err(outs["fold_r2"], outs["fold"]) <= 1e-6 and rel_err(outs["fold_r2_prologue"], outs["fold"]) <= 1e-6
     finally:
         _fold_defaults()
 

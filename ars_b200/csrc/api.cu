@@ -398,6 +398,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "air_fold_max_taps")) { ARS_CHECK(value >= 64, "air_fold_max_taps must be >= 64"); g_opt_air_fold_max_taps = value; }
     else if (!strcmp(key, "side_stream")) g_opt_side_stream = value ? 1 : 0;
     else if (!strcmp(key, "ols_r2")) upols_set_r2(value);
+    else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END

@@ -171,6 +171,140 @@ __global__ void __launch_bounds__(256) gate_energy_kernel(const float* __restric
     }
 }
 
+// ---- fused form of the loudness chain (hop >= 4096 samples, i.e. rate >= 40 960 Hz) ------------------------------
+// The chain above touches the signal seven times (2 x [aggregate, apply] + energies, with two filtered copies written
+// and re-read).  Fused: the kernel that applies stage 1 also forms stage 2's block aggregates from the float32-rounded
+// samples it holds, and the kernel that applies stage 2 squares its output straight into the 100 ms hops
+// [lo_h, lo_{h+1}) the 400 ms gating blocks are made of (hi_j == lo_{j+4} exactly: both are int(0.4 * (0.25 j + 1) *
+// rate) with 0.25 j + 1 exact) instead of writing it.  Same arithmetic per sample, same float32 rounding between the
+// stages; only the order in which the squares of a gating block are added differs.
+__device__ __forceinline__ i64 hop_lo(i64 h, double rate) {        // int(T_g * (h * step) * rate), pyloudnorm's order
+    return (i64)__dmul_rn(__dmul_rn(0.4, __dmul_rn((double)h, 0.25)), rate);
+}
+__device__ __forceinline__ i64 hop_of(i64 i, double rate) {         // largest h with hop_lo(h) <= i
+    i64 h = (i64)((double)i / (0.1 * rate));
+    while (h > 0 && hop_lo(h, rate) > i) --h;
+    while (hop_lo(h + 1, rate) <= i) ++h;
+    return h;
+}
+
+// MODE 0: y = stage cf applied to x (float32), agg2 = block aggregates of stage cf2 over y.
+// MODE 1: stage cf applied to x, squared into hop energies: part[4 b + k] = energy of block b inside hop hop_of(b BS) + k.
+template <int MODE>
+__global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restrict__ x, i64 N, ScanCoef cf,
+                                                           const double2* __restrict__ block_state, float* __restrict__ y,
+                                                           ScanCoef cf2, double2* __restrict__ agg2, double rate,
+                                                           double* __restrict__ part) {
+    __shared__ float sx[NTB * (CH + 1)];
+    __shared__ double2 sv[NTB];
+    const i64 base = (i64)blockIdx.x * BS;
+    const int t = threadIdx.x;
+    for (int i = t; i < BS; i += NTB) {
+        const i64 g = base + i;
+        sx[(i / CH) * (CH + 1) + (i % CH)] = g < N ? x[g] : 0.f;
+    }
+    __syncthreads();
+    float* mine = sx + t * (CH + 1);
+    double2 z = make_double2(0.0, 0.0);
+    #pragma unroll 8
+    for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
+    double2 v = z;
+    if (t == 0) {
+        const double2 ps = mat_vec(cf.pw[0], block_state[blockIdx.x]);
+        v.x += ps.x; v.y += ps.y;
+    }
+    sv[t] = v;
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int off = 1 << k;
+        double2 add = make_double2(0.0, 0.0);
+        if (t >= off) add = mat_vec(cf.pw[k], sv[t - off]);
+        __syncthreads();
+        v.x += add.x; v.y += add.y;
+        sv[t] = v;
+        __syncthreads();
+    }
+    double2 s = (t == 0) ? block_state[blockIdx.x] : sv[t - 1];
+    if (MODE == 0) {
+        double2 z2 = make_double2(0.0, 0.0);
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) {
+            const float o = (float)df2t(cf.q, (double)mine[j], s);     // float32 store, as pyloudnorm
+            mine[j] = o;
+            df2t(cf2.q, (double)o, z2);                                   // stage 2 from a zero state
+        }
+        __syncthreads();                                                 // everybody is done with sv
+        double2 w = z2;
+        sv[t] = w;
+        __syncthreads();
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int off = 1 << k;
+            double2 add = make_double2(0.0, 0.0);
+            if (t >= off) add = mat_vec(cf2.pw[k], sv[t - off]);
+            __syncthreads();
+            w.x += add.x; w.y += add.y;
+            sv[t] = w;
+            __syncthreads();
+        }
+        if (t == NTB - 1) agg2[blockIdx.x] = w;
+        for (int i = t; i < BS; i += NTB) {
+            const i64 g = base + i;
+            if (g < N) y[g] = sx[(i / CH) * (CH + 1) + (i % CH)];
+        }
+    } else {
+        const i64 g0 = base + (i64)t * CH;
+        const i64 hb = hop_of(base, rate);
+        const i64 h0 = hop_of(g0, rate);
+        const i64 next = hop_lo(h0 + 1, rate);
+        double e0 = 0.0, e1 = 0.0;
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) {
+            const float o = (float)df2t(cf.q, (double)mine[j], s);
+            const double sq = (double)__fmul_rn(o, o);
+            const i64 g = g0 + j;
+            if (g < N) { if (g < next) e0 += sq; else e1 += sq; }
+        }
+        const int k0 = (int)(h0 - hb);
+        __shared__ double se[4][NTB / 32];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((t & 31) == 0) se[k][t >> 5] = c;
+        }
+        __syncthreads();
+        if (t < 4) {
+            double tot = 0.0;
+            for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
+            part[(i64)blockIdx.x * 4 + t] = tot;
+        }
+    }
+}
+
+// z_j = (E_j + E_{j+1} + E_{j+2} + E_{j+3}) / (T_g * rate), E_h gathered from the per-block partial sums in block order
+__global__ void __launch_bounds__(256) hop_combine_kernel(const double* __restrict__ part, i64 N, double rate, int nblocks,
+                                                          double* __restrict__ z) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nblocks) return;
+    double tot = 0.0;
+    for (int q = 0; q < 4; ++q) {
+        const i64 h = j + q;
+        const i64 lo = min(hop_lo(h, rate), N), hi = min(hop_lo(h + 1, rate), N);
+        if (hi <= lo) continue;
+        for (i64 b = lo / BS; b <= (hi - 1) / BS; ++b) {
+            const i64 k = h - hop_of(b * BS, rate);
+            if (k >= 0 && k < 4) tot += part[b * 4 + k];
+        }
+    }
+    z[j] = __dmul_rn(1.0 / __dmul_rn(0.4, rate), tot);
+}
+
+static int g_lufs_fused = 1;
+void loudness_set_fused(int on) { g_lufs_fused = on ? 1 : 0; }
+
 static void k_weighting(double rate, Biquad out[2]) {
     // pyloudnorm IIRfilter coefficients: high shelf +4 dB @1500 Hz Q=1/sqrt2, high pass 38 Hz Q=0.5
     const double PI = 3.14159265358979323846;
@@ -271,16 +405,37 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     if (nb <= 0) return 1;
     Biquad q[2];
     k_weighting(rate, q);
-    float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
-    float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
-    run_biquad(d_mono, y1, N, q[0]);
-    run_biquad(y1, y2, N, q[1]);
     double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
-    gate_energy_kernel<<<nb, 256, 0, c.stream>>>(y2, N, rate, nb, dz);
-    ARS_LAUNCH_CHECK();
+    float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
+    if (g_lufs_fused && 0.1 * rate >= 4096.0) {
+        const int nblocks = (int)((N + BS - 1) / BS);
+        const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
+        double2* st1 = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
+        double2* st2 = c.buf("lufs.state2", sizeof(double2) * (size_t)nblocks).as<double2>();
+        double* part = c.buf("lufs.part", sizeof(double) * 4 * (size_t)nblocks).as<double>();
+        BlockPow bp1, bp2;
+        bp1.p[0] = c1.pw[8];
+        bp2.p[0] = c2.pw[8];
+        for (int k = 1; k < 10; ++k) { bp1.p[k] = mat_mul(bp1.p[k - 1], bp1.p[k - 1]); bp2.p[k] = mat_mul(bp2.p[k - 1], bp2.p[k - 1]); }
+        biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, nullptr);
+        block_scan_kernel<<<1, 1024, 0, c.stream>>>(st1, nblocks, bp1);
+        biquad_fused_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, y1, c2, st2, rate, nullptr);
+        block_scan_kernel<<<1, 1024, 0, c.stream>>>(st2, nblocks, bp2);
+        biquad_fused_kernel<1><<<nblocks, NTB, 0, c.stream>>>(y1, N, c2, st2, nullptr, c2, nullptr, rate, part);
+        hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(part, N, rate, nb, dz);
+        ARS_LAUNCH_CHECK();
+        count_launch(6);
+    } else {
+        float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
+        run_biquad(d_mono, y1, N, q[0]);
+        run_biquad(y1, y2, N, q[1]);
+        gate_energy_kernel<<<nb, 256, 0, c.stream>>>(y2, N, rate, nb, dz);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+    }
     gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs);
     ARS_LAUNCH_CHECK();
-    count_launch(2);
+    count_launch();
     return 0;
 }
 

@@ -10,4 +10,6 @@ int loudness_blocks(i64 N, double rate);
 // the loudness (-inf for silence).  Returns 1 without enqueuing when the signal is shorter than one 400 ms block.
 int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs);
 
+void loudness_set_fused(int on);     // 1 (default): fused chain at rates >= 40 960 Hz; 0: one pass per stage and step
+
 }  // namespace ars

@@ -105,6 +105,7 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * transform [default]),
  * "ols_r2" (1 = the 8192-point overlap-save transforms run as a radix-2 stage folded into the window load / output
  * store plus two 4096-point transforms; 0 = one four-stage 8192-point tile [default: measured faster]),
+ * "lufs_fused" (1 = loudness chain in three passes over the signal instead of seven [default]),
  * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */

@@ -187,6 +187,26 @@ def test_lufs_matches_oracle_restatement(rs):
     assert rs.calculate_audio_metrics(np.zeros((48000, 2), np.float32), 48000)["lufs"] == -np.inf
 
 
+def test_lufs_fused_chain_equals_stagewise_chain(rs):
+    """The fused loudness chain (three passes, hop energies) against the pass-per-stage chain: same per-sample arithmetic,
+    only the summation order of a gating block's squares differs.  Lengths that end inside / at a hop or block edge."""
+    from ars_b200 import _capi
+    g = np.random.default_rng(17)
+    try:
+        for n, rate in ((48000 * 7 + 311, 48000), (44100 * 5, 44100), (8192 * 12, 48000), (19200 + 4800 * 3, 48000),
+                        (96000 * 3 + 7, 96000), (19200, 48000)):
+            d = (0.2 * g.standard_normal((n, 2))).astype(np.float32)
+            d[n // 4: n // 2] *= 0.003
+            out = []
+            for fused in (1, 0):
+                _capi.set_option("lufs_fused", fused)
+                out.append(rs.calculate_audio_metrics(d, rate)["lufs"])
+            assert abs(out[0] - out[1]) <= 1e-9, (n, rate, out)
+            assert abs(out[0] - orc.metrics(d, rate)["lufs"]) <= 2e-3
+    finally:
+        _capi.set_option("lufs_fused", 1)
+
+
 def test_pcm16_bit_exact(rs):
     g = np.random.default_rng(8)
     x = (0.6 * g.standard_normal((20001, 6))).astype(np.float32)

@@ -453,6 +453,34 @@ struct St {
         if (m1 > local_r) local_r = m1;
         if (m2 > local_lr) local_lr = m2;
     }
+    // ST_OLS for the r outputs of one last-stage butterfly (`step` apart inside one segment): when the segment's whole
+    // second half is inside the output and has dry frames, frame index, bounds and addresses are formed once
+    template <int r> ARS_HD void put_ols(i64 idx0, i64 step, const float2 (&v)[r]) {
+        const i64 F = (i64)1 << logF, B = F >> 1;
+        const i64 t0 = idx0 & (F - 1);
+        const i64 fr0 = ((seg0 + (idx0 >> logF)) << (logF - 1)) + t0 - B;      // frame of element 0 (first half: < block start)
+        const i64 blk = fr0 - t0 + B;                                          // first output frame of the segment
+        if ((cin & 1) == 0 && blk + B <= N && blk >= dry_frame0 && blk + B - dry_frame0 <= n) {
+            const float2* dp = reinterpret_cast<const float2*>(dry + (fr0 - dry_frame0) * cin);
+            const i64 ds = step * (cin >> 1);
+            float2* ap = a + (fr0 - frame0);
+            #pragma unroll
+            for (int k = 0; k < r; ++k) {
+                if (t0 + k * step >= B) {
+                    const float2 d = ARS_LDG(dp + k * ds);
+                    const float2 y = make_float2(dg * d.x + dw * v[k].x, dg * d.y + dw * v[k].y);
+                    ap[k * step] = y;
+                    const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
+                    if (m0 > local_l) local_l = m0;
+                    if (m1 > local_r) local_r = m1;
+                    if (m2 > local_lr) local_lr = m2;
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < r; ++k) put<ST_OLS>(idx0 + k * step, v[k], make_float2(1.f, 0.f));
+        }
+    }
     // ST_OLS2: the radix-2 stage that ends the 2B-point inverse, second half only: y[i + B] = ya[i] - conj(w^i) yb[i]
     ARS_HD void put_ols2(i64 seg, int i, float2 ya, float2 yb) {
         const float2 t = cmulc(yb, ARS_LDG(tw2 + i));
@@ -757,6 +785,9 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
                 Dft<r, true>::run(v);
                 #pragma unroll
                 for (int t = 0; t < r; ++t) ARS_SM(t) = v[t];
+            } else if constexpr (first && STM == ST_OLS) {
+                Dft<r, true>::run(v);
+                st.template put_ols<r>(gfirst(row0, c), fstep, v);
             } else if constexpr (first) {
                 float2 aux[r];
                 const i64 idx0 = gfirst(row0, c);

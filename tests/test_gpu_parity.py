@@ -872,3 +872,39 @@ def test_air_fold_whole_render_vs_oracle(rs):
     assert d.max() <= 1 and np.mean(d != 0) < 1e-2
     assert abs(got["metrics"]["lufs"] - want["metrics"]["lufs"]) <= 5e-3
     assert abs(got["metrics"]["rms_dbfs"] - want["metrics"]["rms_dbfs"]) <= 1e-3
+
+
+def test_preset_manifest_batch_equals_single_renders(rs, tmp_path):
+    """The reference's preset JSON as a batch-job description (ars_b200/presets.py): a manifest of WAV + preset pairs
+    rendered in one pipelined batch writes the same PCM_16 payload as rendering each clip on its own."""
+    from ars_b200 import presets, wavio
+    rate = 48000
+    g = np.random.default_rng(31)
+    a = (0.3 * g.standard_normal((30000, 2))).astype(np.float32)
+    b = (0.3 * g.standard_normal(41000)).astype(np.float32)
+    ir = (g.standard_normal((6000, 2)) * np.exp(-np.arange(6000) / 900.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir))
+    wavio.write_float32(str(tmp_path / "a.wav"), a, rate)
+    wavio.write_float32(str(tmp_path / "b.wav"), b, rate)
+    wavio.write_float32(str(tmp_path / "ir.wav"), ir, rate)
+    p1 = {"hall_type": "Cathedral", "material": "Stein", "room_size": 900, "air_absorption": 0.1, "dry_wet": 0.6,
+          "target_layout": "5.1.2 (Atmos Light)", "z_pos": 0.8}
+    presets.save_preset(str(tmp_path / "dom_v4.json"), presets.settings_to_preset(presets.preset_to_settings(p1)[0]))
+    manifest = {"jobs": [{"audio": "a.wav", "preset": "dom_v4.json", "seed": 5, "out": "a_out.wav"},
+                         {"audio": "b.wav", "preset": {"hall_type": "Plate", "bass_gain": 1.4, "target_layout": "Stereo"},
+                          "seed": 6, "out": "b_out.wav"},
+                         {"audio": "a.wav", "preset": {"use_external_ir": True, "dry_wet": 0.4}, "external_ir": "ir.wav"}]}
+    (tmp_path / "jobs.json").write_text(__import__("json").dumps(manifest))
+    res = presets.render_manifest(str(tmp_path / "jobs.json"))
+    assert [r["pcm"].shape[1] for r in res] == [8, 2, 6] and res[2]["out"] is None
+    np.random.seed(5)
+    one = rs.render_array(a, rate, **presets.preset_to_settings(p1)[0])
+    assert np.array_equal(one["pcm"], res[0]["pcm"])
+    back, r2 = wavio.read(str(tmp_path / "a_out.wav"))
+    assert r2 == rate and np.array_equal((back * 32768.0).astype(np.int16), one["pcm"])
+    np.random.seed(6)
+    two = rs.render_array(b, rate, hall_type="Plate", bass_gain=1.4, target_channel_layout="Stereo")
+    assert np.array_equal(two["pcm"], res[1]["pcm"])
+    three = rs.render_array(a, rate, external_ir_data=ir, dry_wet=0.4)
+    assert np.array_equal(three["pcm"], res[2]["pcm"])
+    assert abs(three["metrics"]["lufs"] - res[2]["metrics"]["lufs"]) <= 1e-9

@@ -149,3 +149,28 @@ def test_sharding_over_gloo_world_size_2():
         assert sorted(allm) == [0, 1, 2, 3, 4]            # every rank sees every clip's metrics
         assert allm[3][0] == -23.0
         assert peak == 1.25                               # max over ranks
+
+
+def test_preset_schema_follows_the_reference_loader(tmp_path):
+    """ars_b200/presets.py: the reference's preset JSON (rs.py:883-896, 913-927) as a batch-job description --
+    defaults for missing / null / unparsable values, bool coercion, key renaming, save/load round trip."""
+    from ars_b200 import presets
+
+    s, ext = presets.preset_to_settings({})
+    assert ext is False
+    assert s == {"hall_type": "Room", "material": "Holz", "room_size": 100.0, "diffusion": 0.5, "air_absorption": 0.1,
+                 "base_early_level": 0.8, "base_late_level": 0.6, "dry_wet": 0.5, "dry_wet_kill_start": 0.5,
+                 "bass_gain": 1.0, "treble_gain": 1.0, "x_pos": 0.5, "y_pos": 0.5, "z_pos": 0.5,
+                 "target_channel_layout": "5.1 (Standard)"}
+    raw = {"use_external_ir": 1, "hall_type": "Cathedral", "room_size": "250", "diffusion": None, "dry_wet": "viel",
+           "late_level": 1, "target_layout": "7.1 (Surround)", "_version": "4.1", "unknown": 3}
+    s, ext = presets.preset_to_settings(raw)
+    assert ext is True and s["hall_type"] == "Cathedral" and s["room_size"] == 250.0 and s["diffusion"] == 0.5
+    assert s["dry_wet"] == 0.5 and s["base_late_level"] == 1.0 and isinstance(s["base_late_level"], float)
+    assert s["target_channel_layout"] == "7.1 (Surround)" and "unknown" not in s
+    back = presets.settings_to_preset(s, use_external_ir=ext, name="Dom")
+    assert list(back)[:16] == list(presets.PRESET_KEYS) and back["_source_name"] == "Dom"
+    p = tmp_path / "Dom_v4.json"
+    presets.save_preset(str(p), back)
+    s2, ext2 = presets.preset_to_settings(presets.load_preset(str(p)))
+    assert (s2, ext2) == (s, ext)

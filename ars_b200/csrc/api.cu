@@ -38,7 +38,7 @@ static unsigned long long g_air_fold_count = 0;   // convolution stages that too
 static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
-static int g_opt_air_fold_max_taps = 32768;  // longest kept half-length of the air kernel; beyond: the exact N-point path
+static int g_opt_air_fold_max_taps = 131072;  // longest kept half-length of the air kernel; beyond: the exact N-point path
 
 // number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
 static int nonzero_partitions(const float* a, i64 na, const float* b, i64 nb) {

@@ -403,6 +403,10 @@ bool air_fold_plan(const FilterSpec& fs, i64 early_end, i64 late_lo, i64 late_hi
     const i64 K = std::max<i64>(64, (i64)k);
     late_lo = std::max<i64>(0, late_lo);
     if (late_hi < late_lo) late_hi = late_lo;
+    // beyond 32768 taps the float32 far product (work ~ late span x K, on the side stream) starts to show: fold only
+    // while it stays well under the N-point route's cost (~ N).  Measured at N = 14.8 M: air 1.0 (K = 88 k) 1.33 ms
+    // folded against 1.99 ms exact; a 30 s clip breaks even there.
+    if (K > 32768 && (double)(late_hi - late_lo) * (double)K > 128.0 * (double)N) return false;
     const i64 span = std::max(early_end, late_hi + K) + K;           // folded taps live on [-K, span - K)
     if (span + K + 3 * 8192 >= N || span > 8 * max_taps) return false;   // one wrap at most (upols_run)
     af->K = K;

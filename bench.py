@@ -239,6 +239,8 @@ def run_ours(args):
     w = WORKLOADS[args.workload]
     if args.cin:
         w = dict(w, cin=args.cin, desc=w["desc"] + " [input channels overridden: %d]" % args.cin)
+    if args.air is not None:
+        w = dict(w, settings=dict(w["settings"], air_absorption=args.air), desc=w["desc"] + " [air overridden: %g]" % args.air)
     seconds = args.seconds or w["seconds"]
     x = make_clip(w, seconds, rank)
     x2 = x if x.ndim == 2 else x[:, None]
@@ -535,6 +537,7 @@ def main():
     ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cin", type=int, default=0, help="experiments: override the clip's channel count")
+    ap.add_argument("--air", type=float, default=None, help="experiments: override the air-absorption setting")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="library option for experiments (ars_set_option), e.g. --opt air_fold=0")
     args = ap.parse_args()

@@ -100,7 +100,8 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * "air_fold" (1 = a render whose only spectral mask is the air-absorption ramp [air > 0.01, EQ gains ~ 1] folds the
  * ramp into the impulse response and runs as one overlap-save convolution [default]; 0 = exact N-point filter),
  * "air_fold_eps_e9" (bound on the late path's transfer-function error the fold may introduce, in 1e-9; default 2000),
- * "air_fold_max_taps" (longest half-length of the truncated air kernel; a longer one falls back to the N-point path),
+ * "air_fold_max_taps" (longest half-length of the truncated air kernel [default 131072: every air value at 2e-6];
+ * a longer one -- or, above 32768 taps, one whose fold would cost more than half the N-point route -- takes that route),
  * "side_stream" (1 = folded-air renders run IR synthesis, fold and IR spectra on a second stream next to the delay-line
  * transform [default]),
  * "ols_r2" (1 = the 8192-point overlap-save transforms run as a radix-2 stage folded into the window load / output

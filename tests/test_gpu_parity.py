@@ -764,7 +764,7 @@ def _fold_opts(**kw):
 
 
 def _fold_defaults():
-    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=32768, mac_tiled_min=4, ols_r2=0)
+    _fold_opts(air_fold=1, air_fold_eps_e9=2000, air_fold_max_taps=131072, mac_tiled_min=4, ols_r2=0)
 
 
 def _fold_count():
@@ -841,12 +841,23 @@ def test_air_fold_error_bound_option_and_fallback(rs):
         _fold_defaults()
         c0 = _fold_count()
         got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.6)
-        assert _fold_count() == c0, "air 0.6 needs > 32768 taps at 2e-6: must take the exact route"
+        assert _fold_count() == c0, "air 0.6 needs 53 k taps at 2e-6, too much fold work for a 4 s clip: must take the exact route"
         assert rel_err(got, want) <= TOL
         _fold_opts(air_fold_eps_e9=4000, air_fold_max_taps=65536)
         got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.6)
         assert _fold_count() == c0 + 1
         assert rel_err(got, want) <= TOL, rel_err(got, want)
+        # beyond 32768 taps the fold is taken when the clip is long enough for it to pay (late span x K <= 128 N)
+        _fold_defaults()
+        xl = (np.random.default_rng(9).standard_normal((80 * rate, 2)) * 0.3).astype(np.float32)
+        want_l = orc.convolve_split(xl, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.5)
+        c1 = _fold_count()
+        got_l = rs.convolve_audio_split_3d(xl, early, late, 0.8, 0.6, 0.5, 1.0, 1.0, rate, 0.5, 0.5)
+        assert _fold_count() == c1 + 1, "air 0.5 (44 k taps) on an 80 s clip folds"
+        assert rel_err(got_l, want_l) <= TOL, rel_err(got_l, want_l)
+        assert snr_db(got_l, want_l) >= 100.0
+        del xl, want_l, got_l
+        c0 = _fold_count() - 1
         # EQ on: the brick-wall mask cannot be folded
         got = rs.convolve_audio_split_3d(x, early, late, 0.8, 0.6, 0.5, 1.3, 0.8, rate, 0.5, 0.1)
         assert _fold_count() == c0 + 1

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "ars_map_channels": (C.c_int, [_p, _i64, _i32, _d, _d, _p]),
     "ars_metrics": (C.c_int, [_p, _i64, _i32, _d, _i32, C.POINTER(ArsMetrics)]),
     "ars_channel_rms": (C.c_int, [_p, _i64, _i32, _p, C.POINTER(C.c_float)]),
+    "ars_spectrogram_segments": (_i64, [_i64, _i32]),
+    "ars_spectrogram": (C.c_int, [_p, _i64, _i32, _d, _i32, _p]),
     "ars_pcm16": (C.c_int, [_p, _i64, _p]),
     "ars_render_out_len": (_i64, [C.POINTER(ArsRenderParams), _i64, _i64]),
     "ars_render": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),

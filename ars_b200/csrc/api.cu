@@ -650,6 +650,26 @@ int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, fl
     ARS_API_END
 }
 
+int64_t ars_spectrogram_segments(int64_t n, int32_t nperseg) {
+    if (nperseg < 2 || n < nperseg) return 0;
+    return (n - nperseg / 2) / (nperseg - nperseg / 2);
+}
+
+int ars_spectrogram(const float* data, int64_t n, int32_t ch, double rate, int32_t nperseg, float* sxx_out) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && sxx_out && n > 0 && ch >= 1 && rate > 0, "ars_spectrogram: bad arguments");
+    Ctx& c = ctx();
+    const float* d_x = upload("in.x", data, (size_t)n * ch);
+    const i64 nseg = ars_spectrogram_segments(n, nperseg);
+    ARS_CHECK(nseg >= 1, "ars_spectrogram: signal shorter than one segment");
+    const size_t count = (size_t)(nperseg / 2 + 1) * (size_t)nseg;
+    float* d_s = c.buf("spec.sxx", sizeof(float) * count).as<float>();
+    spectrogram_psd(d_x, n, ch, rate, nperseg, d_s, nullptr);      // first channel (rs.py:621)
+    download(sxx_out, d_s, count);
+    sync();
+    ARS_API_END
+}
+
 int ars_pcm16(const float* data, int64_t count, int16_t* out) {
     ARS_API_BEGIN
     ARS_CHECK(data && out && count > 0, "ars_pcm16: bad arguments");

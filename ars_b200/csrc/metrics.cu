@@ -439,4 +439,85 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     return 0;
 }
 
+// ---- spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(x, fs, window='hann', nperseg,
+// noverlap = nperseg // 2) with scipy's defaults -- detrend='constant' (each segment's mean removed), one-sided power
+// spectral density: Sxx[k, j] = c_k |FFT(w (x_j - mean x_j))[k]|^2 / (fs sum w^2), c_k = 2 except at DC and Nyquist.
+// One CTA per segment: mean, periodic Hann window, an in-shared-memory Stockham radix-2 FFT in natural order (this is
+// plotting support, far off the render path: the pass kernels' permuted order would need an extra reordering pass).
+__global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restrict__ x, i64 n, int stride, int logN, int hop,
+                                                          int nseg, float scale, float* __restrict__ out) {
+    extern __shared__ float2 sbuf[];
+    const int N = 1 << logN, t = threadIdx.x, j = blockIdx.x;
+    float2* a = sbuf;
+    float2* b = sbuf + N;
+    const float* seg = x + (i64)j * hop * stride;
+    float part = 0.f;
+    for (int i = t; i < N; i += blockDim.x) {
+        const float v = seg[(i64)i * stride];
+        a[i] = make_float2(v, 0.f);
+        part += v;
+    }
+    __shared__ float red[8];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((t & 31) == 0) red[t >> 5] = part;
+    __syncthreads();
+    float mean = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mean += red[w];
+    mean /= (float)N;
+    for (int i = t; i < N; i += blockDim.x) {
+        float s, c;
+        sincospif(2.0f * (float)i / (float)N, &s, &c);
+        a[i].x = (a[i].x - mean) * (0.5f - 0.5f * c);                 // scipy get_window('hann', N): periodic
+    }
+    __syncthreads();
+    // Stockham autosort, decimation in frequency: after stage q (L = N >> q) the output is in natural order at the end
+    for (int L = N, m = 1; L > 1; L >>= 1, m <<= 1) {
+        const int half = L >> 1;
+        for (int i = t; i < (N >> 1); i += blockDim.x) {
+            const int p = i / m, q = i % m;                            // p < half
+            float s, c;
+            sincospif(-2.0f * (float)p / (float)L, &s, &c);
+            const float2 u = a[q + m * p], v = a[q + m * (p + half)];
+            b[q + m * (2 * p)] = make_float2(u.x + v.x, u.y + v.y);
+            const float2 d = make_float2(u.x - v.x, u.y - v.y);
+            b[q + m * (2 * p + 1)] = make_float2(d.x * c - d.y * s, d.x * s + d.y * c);
+        }
+        __syncthreads();
+        float2* tmp = a; a = b; b = tmp;
+    }
+    const int nf = (N >> 1) + 1;
+    for (int k = t; k < nf; k += blockDim.x) {
+        const float2 X = a[k];
+        const float onesided = (k == 0 || k == (N >> 1)) ? 1.f : 2.f;
+        out[(i64)k * nseg + j] = (X.x * X.x + X.y * X.y) * scale * onesided;
+    }
+}
+
+void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out) {
+    Ctx& c = ctx();
+    int logN = 0;
+    while ((1 << logN) < nperseg) ++logN;
+    ARS_CHECK(nperseg >= 2 && (1 << logN) == nperseg && nperseg <= 8192, "spectrogram: nperseg must be a power of two in 2..8192");
+    ARS_CHECK(n >= nperseg, "spectrogram: signal shorter than one segment");
+    const int hop = nperseg - nperseg / 2;
+    const int nseg = (int)((n - nperseg / 2) / hop);                  // scipy: (n - noverlap) // (nperseg - noverlap)
+    double wsum = 0.0;
+    for (int i = 0; i < nperseg; ++i) {
+        const float w = 0.5f - 0.5f * (float)std::cos(2.0 * 3.14159265358979323846 * i / nperseg);
+        wsum += (double)w * (double)w;
+    }
+    const float scale = (float)(1.0 / (rate * wsum));
+    const size_t smem = sizeof(float2) * 2 * (size_t)nperseg;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ARS_CUDA(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * 2 * 8192)));
+        attr_done = true;
+    }
+    spectrogram_kernel<<<nseg, 256, smem, c.stream>>>(d_x, n, stride, logN, hop, nseg, scale, d_out);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+    if (nseg_out) *nseg_out = nseg;
+}
+
 }  // namespace ars

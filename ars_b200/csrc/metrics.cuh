@@ -10,6 +10,8 @@ int loudness_blocks(i64 N, double rate);
 // the loudness (-inf for silence).  Returns 1 without enqueuing when the signal is shorter than one 400 ms block.
 int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs);
 
+// scipy.signal.spectrogram(x[:, 0], fs, window='hann', nperseg, noverlap=nperseg//2) -> d_out[(nperseg/2+1) x nseg], row-major
+void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out);
 void loudness_set_fused(int on);     // 1 (default): fused chain at rates >= 40 960 Hz; 0: one pass per stage and step
 
 }  // namespace ars

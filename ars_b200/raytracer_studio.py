@@ -418,6 +418,29 @@ def channel_levels(data):
     return [20 * math.log10(float(v)) if v > 1e-15 else -np.inf for v in rms], float(side.value)
 
 
+def spectrogram(data, rate):
+    """Numerics of the visualiser's spectrogram (rs.py:621-634): first channel, nperseg 4096 / 2048 / 1024 by duration
+    (> 30 s / > 5 s / else), 50 % overlap, Hann, scipy's defaults -> (f, t, Sxx) as scipy.signal.spectrogram returns them.
+    The dB scaling and colour limits (rs.py:636-639) are plotting and stay with the reference."""
+    x = np.ascontiguousarray(data, dtype=_F32)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, ch = x.shape
+    duration = n / rate if rate > 0 else 0
+    nperseg = 4096 if duration > 30 else 2048 if duration > 5 else 1024
+    nperseg = min(nperseg, n)
+    if nperseg < 2:
+        raise ValueError("Signal zu kurz für Spektrogramm.")
+    if nperseg & (nperseg - 1):
+        raise ValueError("Spektrogramm: Segmentlänge muss eine Zweierpotenz sein (Signal kürzer als 1024 Samples).")
+    nseg = int(_lib().ars_spectrogram_segments(n, nperseg))
+    sxx = np.empty((nperseg // 2 + 1, nseg), _F32)
+    _capi.check(_lib().ars_spectrogram(_capi.ptr(x), n, ch, float(rate), nperseg, _capi.ptr(sxx)), "ars_spectrogram")
+    f = np.fft.rfftfreq(nperseg, 1.0 / rate)
+    t = (np.arange(nseg) * (nperseg - nperseg // 2) + nperseg / 2) / float(rate)
+    return f, t, sxx
+
+
 def float_to_pcm16(data):
     """clip +-0.9999, scrub non-finite, float -> int16 (rs.py:1082-1084 + libsndfile's rule)."""
     x = np.ascontiguousarray(data, dtype=_F32)

@@ -169,6 +169,11 @@ ARS_API int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, i
 /* Numerics of the A/B report (run_audio_profiler_v4, rs.py:769-798): per-channel RMS sqrt(mean(x^2)) of an
  * (n, ch <= 8) array and the RMS of the side signal (ch0 - ch1) * 0.5 (0 for mono).  rms_out: ch floats. */
 ARS_API int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, float* side_rms_out);
+/* Spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(data[:, 0], fs=rate, window='hann', nperseg,
+ * noverlap = nperseg / 2) with scipy's defaults (constant detrend, one-sided density).  nperseg: a power of two in
+ * 2..8192.  sxx_out: (nperseg / 2 + 1) rows x ars_spectrogram_segments(n, nperseg) columns, row-major float32. */
+ARS_API int64_t ars_spectrogram_segments(int64_t n, int32_t nperseg);
+ARS_API int ars_spectrogram(const float* data, int64_t n, int32_t ch, double rate, int32_t nperseg, float* sxx_out);
 
 /* clip + scrub + float->PCM16, rs.py:1082-1084 (libsndfile rule lrintf(x * 32767)). */
 ARS_API int ars_pcm16(const float* data, int64_t count, int16_t* out);

@@ -919,3 +919,24 @@ def test_preset_manifest_batch_equals_single_renders(rs, tmp_path):
     three = rs.render_array(a, rate, external_ir_data=ir, dry_wet=0.4)
     assert np.array_equal(three["pcm"], res[2]["pcm"])
     assert abs(three["metrics"]["lufs"] - res[2]["metrics"]["lufs"]) <= 1e-9
+
+
+def test_spectrogram_matches_scipy(rs):
+    """Numerics of the visualiser's spectrogram (rs.py:621-634) against scipy.signal.spectrogram with the reference's
+    arguments: segment length by duration, 50 % overlap, Hann, constant detrend, one-sided density."""
+    from scipy.signal import spectrogram
+    g = np.random.default_rng(41)
+    for seconds, ch, rate in ((2.0, 1, 48000), (7.5, 2, 44100), (31.0, 6, 48000)):
+        n = int(seconds * rate)
+        t = np.arange(n) / rate
+        x = (0.2 * g.standard_normal((n, ch)) + 0.5 * np.sin(2 * np.pi * 1000.0 * t)[:, None] + 0.1).astype(np.float32)
+        nperseg = 4096 if seconds > 30 else 2048 if seconds > 5 else 1024
+        f0, t0, s0 = spectrogram(x[:, 0].astype(np.float64), fs=rate, nperseg=nperseg, noverlap=nperseg // 2, window="hann")
+        f1, t1, s1 = rs.spectrogram(x if ch > 1 else x[:, 0], rate)
+        assert s1.shape == s0.shape and s1.dtype == np.float32
+        assert np.allclose(f1, f0) and np.allclose(t1, t0)
+        assert np.max(np.abs(s1 - s0)) <= 2e-5 * np.max(s0)
+        db0, db1 = 10 * np.log10(np.maximum(s0, 1e-10)), 10 * np.log10(np.maximum(s1, 1e-10))
+        assert abs(np.median(db1) - np.median(db0)) <= 1e-2 and abs(db1.max() - db0.max()) <= 1e-3
+    with pytest.raises(ValueError):
+        rs.spectrogram(np.zeros(700, np.float32), 48000)

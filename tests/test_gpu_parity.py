@@ -338,6 +338,13 @@ def test_batch_pipeline_equals_single_renders(rs):
     ir = (g.standard_normal((3000, 2)) * np.exp(-np.arange(3000) / 600.0)[:, None]).astype(np.float32)
     jobs.append(dict(samples=(0.3 * g.standard_normal((20000, 2))).astype(np.float32), rate=rate,
                      external_ir_data=ir, bass_gain=1.3, target_channel_layout="5.1 (Standard)"))
+    # clips with more than two channels (the reference reads channels 0-1 only, rs.py:345)
+    jobs.append(dict(samples=(0.3 * g.standard_normal((150001, 6))).astype(np.float32), rate=rate, seed=300,
+                     hall_type="Cathedral", air_absorption=0.1, target_channel_layout="5.1.2 (Atmos Light)"))
+    jobs.append(dict(samples=(0.3 * g.standard_normal((90000, 3))).astype(np.float32), rate=rate, seed=301,
+                     hall_type="Room", bass_gain=1.2, target_channel_layout="Stereo"))
+    jobs.append(dict(samples=(0.3 * g.standard_normal((140000, 6))).astype(np.float32), rate=rate, seed=302,
+                     hall_type="Plate", air_absorption=0.0, target_channel_layout="7.1 (Surround)"))
     got = rs.render_batch(jobs, want_float=True)
     for job, b in zip(jobs, got):
         job = dict(job)

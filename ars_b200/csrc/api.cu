@@ -261,8 +261,9 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         ex.late_lo = g.split;
         ex.late_hi = g.split;
         if (g.late_len > 0 && sp.amp > 0.0 && sp.decay > 0.0 && sp.decay < 1.0) {
-            // |tail[j]| <= 1e3 * amp * decay^j (the re-scaled boxcar mean of noise in [-1, 1]); float32 stores 0 below 2^-150
-            const double j0 = std::log(7.0e-46 / (1.0e3 * sp.amp)) / std::log(sp.decay);
+            // |tail[j]| <= 1e6 * amp * decay^j: the boxcar mean of noise in [-1, 1] is re-scaled by std_raw / std_smooth,
+            // and the reference only does that while std_smooth > 1e-6 (rs.py:289-291); float32 stores 0 below 2^-150
+            const double j0 = std::log(7.0e-46 / (1.0e6 * sp.amp)) / std::log(sp.decay);
             ex.late_hi = g.split + (i64)std::min((double)g.late_len, std::max(0.0, std::ceil(j0) + 1.0));
         }
         // the folded-air route: IR synthesis, the fold and the IR partition spectra are a chain of small latency-bound

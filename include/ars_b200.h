@@ -64,7 +64,8 @@ typedef struct ArsIrDraws {
     const double* tap_base;     /* ntaps base strengths, uniform(0.3, 0.8)                    */
     int32_t ntaps;
     int32_t reserved;
-    const double* noise;        /* late_len raw tail noise, uniform(-1, 1)                    */
+    const double* noise;        /* late_len raw tail noise, uniform(-1, 1); values must lie in [-1, 1]: the folded-air
+                                 * route bounds the non-zero extent of the tail from that range                 */
     int64_t noise_len;          /* = length - split                                            */
 } ArsIrDraws;
 

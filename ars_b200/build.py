@@ -23,6 +23,8 @@ SOURCES = ["fft_k_gc_fwd.cu", "fft_k_gc_inv.cu", "fft_k_gs_fwd.cu", "fft_k_gs_in
            "api.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Wno-deprecated-gpu-targets"]
+if os.environ.get("ARS_EXTRA_NVCC_FLAGS"):          # experiments, e.g. -DARS_RAD13=1
+    NVCC_FLAGS += os.environ["ARS_EXTRA_NVCC_FLAGS"].split()
 
 
 def _nvcc() -> str:

@@ -51,6 +51,8 @@ ARS_RAD(9, 3, 8, 8, 8, 1)
 ARS_RAD(10, 3, 16, 8, 8, 1)
 ARS_RAD(11, 3, 16, 16, 8, 1)
 ARS_RAD(12, 3, 16, 16, 16, 1)
+// (other four-stage splits of 13 measured on the overlap-save route: 16.16.16.2 -0.4 %, 16.16.8.4 +0.3 %, 8.8.8.16 +0.8 %,
+// 2.16.16.16 +8 % -- the stage count and its barriers set the pace of this tile, not the radix mix)
 ARS_RAD(13, 4, 16, 8, 8, 8)
 #undef ARS_RAD
 

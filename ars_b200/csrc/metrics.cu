@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) gate_energy_kernel(const float* __restric
 
 // ---- fused form of the loudness chain (hop >= 4096 samples, i.e. rate >= 40 960 Hz) ------------------------------
 // The chain above touches the signal seven times (2 x [aggregate, apply] + energies, with two filtered copies written
-// and re-read).  Fused: the kernel that applies stage 1 also forms stage 2's block aggregates from the float32-rounded
+// and re-read) and runs two single-CTA scans over the block aggregates.  Fused (three passes, no scan -- lookback_state): the kernel that applies stage 1 also forms stage 2's block aggregates from the float32-rounded
 // samples it holds, and the kernel that applies stage 2 squares its output straight into the 100 ms hops
 // [lo_h, lo_{h+1}) the 400 ms gating blocks are made of (hi_j == lo_{j+4} exactly: both are int(0.4 * (0.25 j + 1) *
 // rate) with 0.25 j + 1 exact) instead of writing it.  Same arithmetic per sample, same float32 rounding between the
@@ -188,11 +188,25 @@ __device__ __forceinline__ i64 hop_of(i64 i, double rate) {         // largest h
     return h;
 }
 
+// Start state of block b from the aggregates of the blocks before it: s_b = agg[b-1] + M (agg[b-2] + M (agg[b-3] + ...)),
+// M = A^BS, cut after `depth` terms -- the K-weighting filters forget fast (|M| ~ 1e-17 at 48 kHz), so the host picks the
+// depth at which the dropped terms are below 1e-25 of the kept ones and no scan over the blocks is needed.
+__device__ __forceinline__ double2 lookback_state(const double2* __restrict__ agg, int b, const Mat2& M, int depth) {
+    double2 s = make_double2(0.0, 0.0);
+    const int d0 = b < depth ? b : depth;
+    for (int d = d0; d >= 1; --d) {
+        const double2 a = agg[b - d];
+        const double2 ms = mat_vec(M, s);
+        s = make_double2(a.x + ms.x, a.y + ms.y);
+    }
+    return s;
+}
+
 // MODE 0: y = stage cf applied to x (float32), agg2 = block aggregates of stage cf2 over y.
 // MODE 1: stage cf applied to x, squared into hop energies: part[4 b + k] = energy of block b inside hop hop_of(b BS) + k.
 template <int MODE>
 __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restrict__ x, i64 N, ScanCoef cf,
-                                                           const double2* __restrict__ block_state, float* __restrict__ y,
+                                                           const double2* __restrict__ agg, int depth, float* __restrict__ y,
                                                            ScanCoef cf2, double2* __restrict__ agg2, double rate,
                                                            double* __restrict__ part) {
     __shared__ float sx[NTB * (CH + 1)];
@@ -209,8 +223,10 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
     #pragma unroll 8
     for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
     double2 v = z;
+    double2 s0 = make_double2(0.0, 0.0);
     if (t == 0) {
-        const double2 ps = mat_vec(cf.pw[0], block_state[blockIdx.x]);
+        s0 = lookback_state(agg, (int)blockIdx.x, cf.pw[8], depth);
+        const double2 ps = mat_vec(cf.pw[0], s0);
         v.x += ps.x; v.y += ps.y;
     }
     sv[t] = v;
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
         sv[t] = v;
         __syncthreads();
     }
-    double2 s = (t == 0) ? block_state[blockIdx.x] : sv[t - 1];
+    double2 s = (t == 0) ? s0 : sv[t - 1];
     if (MODE == 0) {
         double2 z2 = make_double2(0.0, 0.0);
         #pragma unroll 8
@@ -285,10 +301,7 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
 }
 
 // z_j = (E_j + E_{j+1} + E_{j+2} + E_{j+3}) / (T_g * rate), E_h gathered from the per-block partial sums in block order
-__global__ void __launch_bounds__(256) hop_combine_kernel(const double* __restrict__ part, i64 N, double rate, int nblocks,
-                                                          double* __restrict__ z) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nblocks) return;
+__device__ __forceinline__ double hop_block_energy(const double* __restrict__ part, i64 N, double rate, int j) {
     double tot = 0.0;
     for (int q = 0; q < 4; ++q) {
         const i64 h = j + q;
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(256) hop_combine_kernel(const double* __restri
             if (k >= 0 && k < 4) tot += part[b * 4 + k];
         }
     }
-    z[j] = __dmul_rn(1.0 / __dmul_rn(0.4, rate), tot);
+    return __dmul_rn(1.0 / __dmul_rn(0.4, rate), tot);
 }
 
 static int g_lufs_fused = 1;
@@ -372,11 +385,16 @@ __device__ __forceinline__ void block_sum_dc(double& v, int& n) {
 // BS.1770-4 gating exactly as pyloudnorm implements it (mono => channel gain 1), one CTA over the block
 // energies: absolute gate at -70 LUFS, relative gate 10 LU under the abs-gated mean, loudness of the survivors.
 // Also applies the reference's silence test (rs.py:689): peak of the mono feed < 1e-6 -> -inf.
-__global__ void __launch_bounds__(1024) gate_kernel(const double* __restrict__ z, int nb, const unsigned* __restrict__ mono_max,
-                                                    double* lufs_out) {
+// part != nullptr (fused chain): the block energies z are first gathered here from the hop partial sums.
+__global__ void __launch_bounds__(1024) gate_kernel(double* __restrict__ z, int nb, const unsigned* __restrict__ mono_max,
+                                                    double* lufs_out, const double* __restrict__ part, i64 N, double rate) {
     if (__uint_as_float(*mono_max) < 1e-6f) {
         if (threadIdx.x == 0) *lufs_out = -CUDART_INF;
         return;
+    }
+    if (part) {
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) z[j] = hop_block_energy(part, N, rate, j);
+        __syncthreads();
     }
     double s = 0.0;
     int n = 0;
@@ -407,24 +425,26 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     k_weighting(rate, q);
     double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
     float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
-    if (g_lufs_fused && 0.1 * rate >= 4096.0) {
+    const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
+    // look-back depth at which the dropped start-state terms are below 1e-25 of the kept ones (0: use the block scan)
+    auto depth_of = [](const Mat2& M) {
+        const double nrm = std::sqrt(M.m00 * M.m00 + M.m01 * M.m01 + M.m10 * M.m10 + M.m11 * M.m11);
+        if (!(nrm < 0.05)) return 0;
+        return std::max(2, (int)std::ceil(-25.0 * std::log(10.0) / std::log(nrm)));
+    };
+    const int dep1 = depth_of(c1.pw[8]), dep2 = depth_of(c2.pw[8]);
+    const double* part = nullptr;
+    if (g_lufs_fused && 0.1 * rate >= 4096.0 && dep1 > 0 && dep2 > 0) {
         const int nblocks = (int)((N + BS - 1) / BS);
-        const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
         double2* st1 = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
         double2* st2 = c.buf("lufs.state2", sizeof(double2) * (size_t)nblocks).as<double2>();
-        double* part = c.buf("lufs.part", sizeof(double) * 4 * (size_t)nblocks).as<double>();
-        BlockPow bp1, bp2;
-        bp1.p[0] = c1.pw[8];
-        bp2.p[0] = c2.pw[8];
-        for (int k = 1; k < 10; ++k) { bp1.p[k] = mat_mul(bp1.p[k - 1], bp1.p[k - 1]); bp2.p[k] = mat_mul(bp2.p[k - 1], bp2.p[k - 1]); }
+        double* d_part = c.buf("lufs.part", sizeof(double) * 4 * (size_t)nblocks).as<double>();
         biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, nullptr);
-        block_scan_kernel<<<1, 1024, 0, c.stream>>>(st1, nblocks, bp1);
-        biquad_fused_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, y1, c2, st2, rate, nullptr);
-        block_scan_kernel<<<1, 1024, 0, c.stream>>>(st2, nblocks, bp2);
-        biquad_fused_kernel<1><<<nblocks, NTB, 0, c.stream>>>(y1, N, c2, st2, nullptr, c2, nullptr, rate, part);
-        hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(part, N, rate, nb, dz);
+        biquad_fused_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, dep1, y1, c2, st2, rate, nullptr);
+        biquad_fused_kernel<1><<<nblocks, NTB, 0, c.stream>>>(y1, N, c2, st2, dep2, nullptr, c2, nullptr, rate, d_part);
         ARS_LAUNCH_CHECK();
-        count_launch(6);
+        count_launch(3);
+        part = d_part;
     } else {
         float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
         run_biquad(d_mono, y1, N, q[0]);
@@ -433,7 +453,7 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
         ARS_LAUNCH_CHECK();
         count_launch();
     }
-    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs);
+    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs, part, N, rate);
     ARS_LAUNCH_CHECK();
     count_launch();
     return 0;

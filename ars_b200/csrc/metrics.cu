@@ -314,6 +314,12 @@ __device__ __forceinline__ double hop_block_energy(const double* __restrict__ pa
     }
     return __dmul_rn(1.0 / __dmul_rn(0.4, rate), tot);
 }
+// (one thread per gating block over many CTAs: gathered inside the single-CTA gate kernel this took 16 us longer)
+__global__ void __launch_bounds__(256) hop_combine_kernel(const double* __restrict__ part, i64 N, double rate, int nblocks,
+                                                          double* __restrict__ z) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nblocks) z[j] = hop_block_energy(part, N, rate, j);
+}
 
 static int g_lufs_fused = 1;
 void loudness_set_fused(int on) { g_lufs_fused = on ? 1 : 0; }
@@ -385,16 +391,11 @@ __device__ __forceinline__ void block_sum_dc(double& v, int& n) {
 // BS.1770-4 gating exactly as pyloudnorm implements it (mono => channel gain 1), one CTA over the block
 // energies: absolute gate at -70 LUFS, relative gate 10 LU under the abs-gated mean, loudness of the survivors.
 // Also applies the reference's silence test (rs.py:689): peak of the mono feed < 1e-6 -> -inf.
-// part != nullptr (fused chain): the block energies z are first gathered here from the hop partial sums.
-__global__ void __launch_bounds__(1024) gate_kernel(double* __restrict__ z, int nb, const unsigned* __restrict__ mono_max,
-                                                    double* lufs_out, const double* __restrict__ part, i64 N, double rate) {
+__global__ void __launch_bounds__(1024) gate_kernel(const double* __restrict__ z, int nb, const unsigned* __restrict__ mono_max,
+                                                    double* lufs_out) {
     if (__uint_as_float(*mono_max) < 1e-6f) {
         if (threadIdx.x == 0) *lufs_out = -CUDART_INF;
         return;
-    }
-    if (part) {
-        for (int j = threadIdx.x; j < nb; j += blockDim.x) z[j] = hop_block_energy(part, N, rate, j);
-        __syncthreads();
     }
     double s = 0.0;
     int n = 0;
@@ -433,7 +434,6 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
         return std::max(2, (int)std::ceil(-25.0 * std::log(10.0) / std::log(nrm)));
     };
     const int dep1 = depth_of(c1.pw[8]), dep2 = depth_of(c2.pw[8]);
-    const double* part = nullptr;
     if (g_lufs_fused && 0.1 * rate >= 4096.0 && dep1 > 0 && dep2 > 0) {
         const int nblocks = (int)((N + BS - 1) / BS);
         double2* st1 = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
@@ -442,9 +442,9 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
         biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, nullptr);
         biquad_fused_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, dep1, y1, c2, st2, rate, nullptr);
         biquad_fused_kernel<1><<<nblocks, NTB, 0, c.stream>>>(y1, N, c2, st2, dep2, nullptr, c2, nullptr, rate, d_part);
+        hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(d_part, N, rate, nb, dz);
         ARS_LAUNCH_CHECK();
-        count_launch(3);
-        part = d_part;
+        count_launch(4);
     } else {
         float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
         run_biquad(d_mono, y1, N, q[0]);
@@ -453,7 +453,7 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
         ARS_LAUNCH_CHECK();
         count_launch();
     }
-    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs, part, N, rate);
+    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs);
     ARS_LAUNCH_CHECK();
     count_launch();
     return 0;

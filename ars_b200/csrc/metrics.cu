@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
                                                            double* __restrict__ part) {
     __shared__ float sx[NTB * (CH + 1)];
     __shared__ double2 sv[NTB];
+    __shared__ i64 s_lo[3];
     const i64 base = (i64)blockIdx.x * BS;
     const int t = threadIdx.x;
+    if (MODE == 1 && t < 3) s_lo[t] = hop_lo(hop_of(base, rate) + 1 + t, rate);
     for (int i = t; i < BS; i += NTB) {
         const i64 g = base + i;
         sx[(i / CH) * (CH + 1) + (i % CH)] = g < N ? x[g] : 0.f;
@@ -270,10 +272,10 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
             if (g < N) y[g] = sx[(i / CH) * (CH + 1) + (i % CH)];
         }
     } else {
+        // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
         const i64 g0 = base + (i64)t * CH;
-        const i64 hb = hop_of(base, rate);
-        const i64 h0 = hop_of(g0, rate);
-        const i64 next = hop_lo(h0 + 1, rate);
+        const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
+        const i64 next = s_lo[k0 < 3 ? k0 : 2];
         double e0 = 0.0, e1 = 0.0;
         #pragma unroll 8
         for (int j = 0; j < CH; ++j) {
@@ -282,7 +284,6 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
             const i64 g = g0 + j;
             if (g < N) { if (g < next) e0 += sq; else e1 += sq; }
         }
-        const int k0 = (int)(h0 - hb);
         __shared__ double se[4][NTB / 32];
         #pragma unroll
         for (int k = 0; k < 4; ++k) {

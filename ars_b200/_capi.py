@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ars_version": (C.c_char_p, []),
     "ars_launch_count": (C.c_uint64, []),
     "ars_air_fold_count": (C.c_uint64, []),
+    "ars_olsb_count": (C.c_uint64, []),
     "ars_stream": (C.c_void_p, []),
     "ars_ir_synth": (C.c_int, [_d, _d, _d, _d, _d, _d, _d, C.POINTER(ArsIrDraws), _p, _p, _i64]),
     "ars_ir_geometry": (C.c_int, [_d, _d, _d, _d, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),

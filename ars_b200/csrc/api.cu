@@ -38,6 +38,7 @@ static unsigned long long g_air_fold_count = 0;   // convolution stages that too
 static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
+static int g_opt_lufs_from_stage = 1;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array)
 static int g_opt_air_fold_max_taps = 131072;  // longest kept half-length of the air kernel; beyond: the exact N-point path
 
 // number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
@@ -71,9 +72,15 @@ static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_i
     if (d_ir1 && folds_air(fs, ext, rate, &af)) {
         ++g_air_fold_count;
         upols_filter_airfold(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, af, d_y, st, g_opt_upols_logf);
-    } else if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK)
-        upols_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, g_opt_upols_logf);
-    else
+    } else if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK) {
+        // taps beyond the host-known extent are zero (procedural IRs): they neither cost partitions nor block length
+        i64 taps = fs.mode == FILT_EXT ? L0 : std::max(d_ir0 ? L0 : 0, d_ir1 ? L1 : 0);
+        if (fs.mode == FILT_SPLIT && ext.late_hi >= 0) taps = std::min(taps, std::max<i64>(1, std::max(ext.early_end, ext.late_hi)));
+        OlsbPlan pl;
+        if (olsb_plan(fs.N, taps, 0, 0, &pl)) olsb_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, pl);
+        else
+            upols_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, g_opt_upols_logf);
+    } else
         spectral_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st);
 }
 
@@ -292,6 +299,17 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
     if (!d_out_f32 && !d_out_pcm && !want_metrics) return;
     const TailSpec ts = make_tail(N, p->layout, p->rate, p->x, p->y, p->z);
     tail_maxes(y, ts, st);
+    if (want_metrics && p->want_lufs && g_opt_lufs_from_stage && loudness_from_stage_possible(p->rate)) {
+        // the loudness meter recomputes its feed from the stage output, so it needs nothing from the final pass: it runs
+        // on the side stream NEXT TO it (one is bound by issue slots and conversions, the other by float64 latency)
+        if (g_opt_side_stream) side_begin();
+        const int s = integrated_loudness_from_stage(y, ts, p->rate, st);
+        if (lufs_status) *lufs_status = s == 0 ? ARS_LUFS_OK : ARS_LUFS_NONE;
+        side_to_main();
+        tail_final(y, ts, st, d_out_f32, d_out_pcm, nullptr);
+        side_join();
+        return;
+    }
     float* d_mono = nullptr;
     if (want_metrics && p->want_lufs) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
     tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
@@ -368,6 +386,7 @@ const char* ars_last_error(void) { return last_error_cstr(); }
 const char* ars_version(void) { return "ars_b200 0.1 (sm_100a)"; }
 uint64_t ars_launch_count(void) { return ctx_ready() ? ctx().launches : 0; }
 uint64_t ars_air_fold_count(void) { return g_air_fold_count; }
+uint64_t ars_olsb_count(void) { return olsb_count(); }
 void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
 
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -399,7 +418,13 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "air_fold_max_taps")) { ARS_CHECK(value >= 64, "air_fold_max_taps must be >= 64"); g_opt_air_fold_max_taps = value; }
     else if (!strcmp(key, "side_stream")) g_opt_side_stream = value ? 1 : 0;
     else if (!strcmp(key, "ols_r2")) upols_set_r2(value);
+    else if (!strcmp(key, "olsb")) olsb_set_options(value ? 1 : 0, -1, -1);
+    else if (!strcmp(key, "olsb_logf")) { ARS_CHECK(value == 0 || (value >= 18 && value <= 22), "olsb_logf must be 0 (automatic) or 18..22"); olsb_set_options(-1, value, -1); }
+    else if (!strcmp(key, "olsb_lanes") || !strcmp(key, "olsb_first_all") || !strcmp(key, "olsb_reverse") ||
+             !strcmp(key, "olsb_dryfold")) olsb_set_tuning(key, value);
+    else if (!strcmp(key, "olsb_stripe")) { ARS_CHECK(value >= 0, "olsb_stripe must be >= 0"); olsb_set_options(-1, -1, value); }
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
+    else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END

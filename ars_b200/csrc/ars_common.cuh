@@ -78,6 +78,15 @@ struct Ctx {
     cudaStream_t aux = nullptr, main_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int side_state = 0;                               // 0: none, 1: enqueuing on aux, 2: back on main, join pending
+    // lanes (lane_fork / lane_use / lane_join): independent stretches of one stage -- the stripes of the big-block
+    // overlap-save convolution -- are enqueued round-robin on a few streams so that one stripe's loads run under another's
+    // arithmetic; every lane starts after what the main stream holds at the fork and the main stream waits for all
+    static constexpr int MAX_LANES = 4;
+    cudaStream_t lanes[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_lane_fork = nullptr;
+    int lanes_open = 0;
+    cudaStream_t lane_saved = nullptr;
 
     DevBuf& buf(const char* name, size_t bytes) {
         DevBuf& b = ws[name];
@@ -99,6 +108,14 @@ void side_begin();
 void side_to_main();
 void side_join();
 void side_abort();
+
+// lane_fork(n): n lanes start behind the main stream's current position; lane_use(i) makes lane i the library's current
+// stream (i < 0: back to the main stream); lane_wait_side(i): lane i waits for the side stream's work (a pending
+// side_to_main); lane_join(): the main stream waits for every lane.
+void lane_fork(int n);
+void lane_use(int i);
+void lane_wait_side(int i);
+void lane_join();
 
 inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
 

@@ -1,6 +1,8 @@
 // Context, workspace cache and error plumbing of libars_b200.
 #include "ars_common.cuh"
 
+#include <algorithm>
+
 namespace ars {
 
 static Ctx* g_ctx = nullptr;
@@ -104,9 +106,50 @@ void side_join() {
 void side_abort() {
     if (!ctx_ready()) return;
     Ctx& c = ctx();
+    if (c.lanes_open) {
+        c.stream = c.lane_saved;
+        for (int i = 0; i < c.lanes_open; ++i) cudaStreamSynchronize(c.lanes[i]);
+        c.lanes_open = 0;
+    }
     if (c.side_state == 1) c.stream = c.main_stream;
     if (c.side_state != 0 && c.aux) cudaStreamSynchronize(c.aux);
     c.side_state = 0;
+}
+
+void lane_fork(int n) {
+    Ctx& c = ctx();
+    if (c.lanes_open) return;
+    n = std::max(1, std::min(n, (int)Ctx::MAX_LANES));
+    if (!c.ev_lane_fork) ARS_CUDA(cudaEventCreateWithFlags(&c.ev_lane_fork, cudaEventDisableTiming));
+    for (int i = 0; i < n; ++i)
+        if (!c.lanes[i]) {
+            ARS_CUDA(cudaStreamCreateWithFlags(&c.lanes[i], cudaStreamNonBlocking));
+            ARS_CUDA(cudaEventCreateWithFlags(&c.lane_done[i], cudaEventDisableTiming));
+        }
+    ARS_CUDA(cudaEventRecord(c.ev_lane_fork, c.stream));
+    for (int i = 0; i < n; ++i) ARS_CUDA(cudaStreamWaitEvent(c.lanes[i], c.ev_lane_fork, 0));
+    c.lane_saved = c.stream;
+    c.lanes_open = n;
+}
+void lane_use(int i) {
+    Ctx& c = ctx();
+    if (!c.lanes_open) return;
+    c.stream = i < 0 ? c.lane_saved : c.lanes[i % c.lanes_open];
+}
+void lane_wait_side(int i) {
+    Ctx& c = ctx();
+    if (!c.lanes_open || c.side_state != 2) return;
+    ARS_CUDA(cudaStreamWaitEvent(c.lanes[i % c.lanes_open], c.ev_join, 0));
+}
+void lane_join() {
+    Ctx& c = ctx();
+    if (!c.lanes_open) return;
+    c.stream = c.lane_saved;
+    for (int i = 0; i < c.lanes_open; ++i) {
+        ARS_CUDA(cudaEventRecord(c.lane_done[i], c.lanes[i]));
+        ARS_CUDA(cudaStreamWaitEvent(c.stream, c.lane_done[i], 0));
+    }
+    c.lanes_open = 0;
 }
 
 void fft_release_plans();       // fft_plan.cu
@@ -127,6 +170,13 @@ void ctx_shutdown() {
         cudaEventDestroy(g_ctx->ev_fork);
         cudaEventDestroy(g_ctx->ev_join);
     }
+    for (int i = 0; i < Ctx::MAX_LANES; ++i)
+        if (g_ctx->lanes[i]) {
+            cudaStreamSynchronize(g_ctx->lanes[i]);
+            cudaStreamDestroy(g_ctx->lanes[i]);
+            cudaEventDestroy(g_ctx->lane_done[i]);
+        }
+    if (g_ctx->ev_lane_fork) cudaEventDestroy(g_ctx->ev_lane_fork);
     cudaStreamDestroy(g_ctx->stream);
     delete g_ctx;
     g_ctx = nullptr;

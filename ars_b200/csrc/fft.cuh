@@ -179,8 +179,9 @@ template <bool INV> struct Dft<16, INV> {
 
 // ------------------------------------------------------------- Ld / St functors
 enum LdMode { LD_PLAIN = 0, LD_MULSPEC, LD_CHIRP_X2, LD_CHIRP_XC, LD_CHIRP_PAIR, LD_CHIRP_B, LD_CHIRP_C,
-              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC, LD_OLS_CHIRPSIG, LD_OLS_IRC, LD_OLS_X2, LD_OLS_IR2 };
-enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP, ST_OLS2 };
+              LD_REAL_PAIR, LD_OLS_X, LD_OLS_IR, LD_OLS_MAC, LD_OLS_CHIRPSIG, LD_OLS_IRC, LD_OLS_X2, LD_OLS_IR2,
+              LD_OLSB_X, LD_TAPS };
+enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP, ST_OLS2, ST_OLSB };
 
 struct Ld {
     int mode = LD_PLAIN;
@@ -210,6 +211,17 @@ struct Ld {
     // ones.  The two halves of an overlap-save window are exactly the operands of that stage: a = w[i] + w[i+B],
     // b = (w[i] - w[i+B]) w_2B^i; an IR partition has an empty second half: a = h[i], b = h[i] w_2B^i.
     const float2* tw2 = nullptr;    // w_2B^i, i < B
+    // LD_OLSB_X (big-block overlap-save, upols.cu): transform j of 2^logF points is the window of the signal that
+    // starts `skip` frames before output frame (seg0 + j) * hop; skip = taps - 1 aliased outputs are dropped, hop <= F - skip.
+    // seg0 / frame0 / nvalid / cin / adv / circ / c1 as for LD_OLS_X.  stash (optional): the dry frame of every output
+    // frame of the launch, compact stereo, at [j * hop + (frame - (seg0 + j) * hop)] -- the inverse's last pass mixes from it
+    // instead of re-reading a (frames, cin > 2) clip at 4 cin bytes per frame.
+    i64 hop = 0, skip = 0;
+    float2* stash = nullptr;
+    // LD_TAPS: real taps c0 * f0[i * cin] + c1 * f1[i * cin] (+ delta at index delta_at: the dry path of the mix folded
+    // into the impulse response, y = dg x + dw (x * h) = x * (dg delta + dw h))
+    i64 delta_at = -1;
+    float delta = 0.f;
     // MODE >= 0: compile-time access mode (fast kernels); MODE < 0: runtime switch on `mode` (generic kernels)
     template <int MODE> ARS_HD float2 get(i64 idx) const {
         if constexpr (MODE < 0) return (*this)(idx);
@@ -299,6 +311,17 @@ struct Ld {
             float2 acc[1];
             get_mac<1>(idx, 0, acc);
             return acc[0];
+        } else if constexpr (MODE == LD_OLSB_X) {      // big-block overlap-save window (see hop / skip above)
+            const i64 j = idx >> logF;
+            const i64 t = idx & (((i64)1 << logF) - 1);
+            const float2 v = frame_at((seg0 + j) * hop - skip + t + adv - frame0);
+            const i64 o = t - skip + adv;              // the window element that is the dry frame of output o of transform j
+            if (stash && o >= 0 && o < hop) stash[j * hop + o] = make_float2(v.x, c1 < 0.f ? -v.y : v.y);
+            return v;
+        } else if constexpr (MODE == LD_TAPS) {        // real taps c0 * f0[i * cin] + c1 * f1[i * cin], zero-padded
+            const float u = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx * cin) : 0.f;
+            const float v = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx * cin) : 0.f;
+            return make_float2(c0 * u + c1 * v + (idx == delta_at ? delta : 0.f), 0.f);
         } else {                                       // LD_REAL_PAIR: plain zero-padded packing
             const float l = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx) : 0.f;
             const float r = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx) : 0.f;
@@ -324,6 +347,45 @@ struct Ld {
         } else {
             #pragma unroll
             for (int k = 0; k < r; ++k) v[k] = get<LD_OLS_X>(idx0 + k * step);
+        }
+    }
+    // LD_OLSB_X for the r elements of one first-stage butterfly (`step` apart, all inside one transform): same idea
+    template <int r> ARS_HD void get_xb(i64 idx0, i64 step, float2 (&v)[r]) const {
+        const i64 j = idx0 >> logF;
+        const i64 t0 = idx0 & (((i64)1 << logF) - 1);
+        const i64 fr = (seg0 + j) * hop - skip + t0 + adv - frame0;
+        const i64 last = fr + (r - 1) * step;
+        if (fr >= 0 && last < nvalid && (circ <= 0 || last < circ)) {
+            if ((cin & 1) == 0) {
+                const float2* p = reinterpret_cast<const float2*>(f0 + fr * cin);
+                const i64 ps = step * (cin >> 1);
+                #pragma unroll
+                for (int k = 0; k < r; ++k) v[k] = ARS_LDG(p + k * ps);
+            } else {
+                const float* p = f0 + fr * cin;
+                const i64 ps = step * cin;
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const float l = ARS_LDG(p + k * ps);
+                    v[k] = make_float2(l, cin > 1 ? ARS_LDG(p + k * ps + 1) : l);
+                }
+            }
+            if (stash) {
+                const i64 o0 = t0 - skip + adv;
+                float2* sp = stash + j * hop + o0;
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const i64 o = o0 + k * step;
+                    if (o >= 0 && o < hop) sp[k * step] = v[k];
+                }
+            }
+            if (c1 < 0.f) {
+                #pragma unroll
+                for (int k = 0; k < r; ++k) v[k].y = -v[k].y;
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < r; ++k) v[k] = get<LD_OLSB_X>(idx0 + k * step);
         }
     }
     // one stereo frame of the (periodically extended, zero-padded) signal as L + iR; c1 < 0 conjugates
@@ -415,6 +477,8 @@ struct Ld {
             case LD_OLS_IRC: return get<LD_OLS_IRC>(idx);
             case LD_OLS_X2: return get<LD_OLS_X2>(idx);
             case LD_OLS_IR2: return get<LD_OLS_IR2>(idx);
+            case LD_OLSB_X: return get<LD_OLSB_X>(idx);
+            case LD_TAPS: return get<LD_TAPS>(idx);
         }
         return make_float2(0.f, 0.f);
     }
@@ -437,6 +501,10 @@ struct St {
     unsigned* maxbits = nullptr;     // ST_FINAL: 4 words: bits of max |x|, max |x.re|, max |x.im|, max |f32(re + im)|
     unsigned local_max = 0, local_l = 0, local_r = 0, local_lr = 0;
     const float2* tw2 = nullptr;     // ST_OLS2: w_2B^i, i < B (see Ld::tw2)
+    // ST_OLSB (big-block overlap-save): element t of transform j is output frame (seg0 + j) * hop + t - skip when
+    // skip <= t < skip + hop; stash (optional, see Ld::stash): compact stereo dry frames of the launch's outputs
+    i64 hop = 0, skip = 0;
+    const float2* stash = nullptr;
     // the dry frame that goes with overlap-save output frame `fr` (zero outside the slice held at `dry`)
     ARS_HD float2 dry_at(i64 fr) const {
         const i64 df = fr - dry_frame0;
@@ -483,6 +551,44 @@ struct St {
             for (int k = 0; k < r; ++k) put<ST_OLS>(idx0 + k * step, v[k], make_float2(1.f, 0.f));
         }
     }
+    // ST_OLSB for the r outputs of one last-stage butterfly (`step` apart inside one transform)
+    template <int r> ARS_HD void put_olsb(i64 idx0, i64 step, const float2 (&v)[r]) {
+        const i64 j = idx0 >> logF;
+        const i64 t0 = idx0 & (((i64)1 << logF) - 1);
+        const i64 o0 = t0 - skip;                                   // output index inside the transform's hop
+        const i64 blk = (seg0 + j) * hop;                           // first output frame of the transform
+        const i64 olast = o0 + (r - 1) * step;
+        const bool mix = dg != 0.f;                                 // (dg == 0: the dry path is part of the taps, Ld::delta)
+        const bool dry_ok = (stash || !mix) ? true : ((cin & 1) == 0 && blk + (o0 < 0 ? 0 : o0) >= dry_frame0 &&
+                                                      blk + olast - dry_frame0 < n);
+        if (dry_ok && blk + (olast < hop ? olast : hop - 1) < N) {
+            const float2* dp = stash ? stash + (j * hop + o0)
+                                     : reinterpret_cast<const float2*>(dry + (blk + o0 - dry_frame0) * cin);
+            const i64 ds = stash ? step : step * (cin >> 1);
+            float2* ap = a + (blk + o0 - frame0);
+            #pragma unroll
+            for (int k = 0; k < r; ++k) {
+                const i64 o = o0 + k * step;
+                if (o >= 0 && o < hop) {
+                    float2 y;
+                    if (mix) {
+                        const float2 d = ARS_LDG(dp + k * ds);
+                        y = make_float2(dg * d.x + dw * v[k].x, dg * d.y + dw * v[k].y);
+                    } else {
+                        y = make_float2(dw * v[k].x, dw * v[k].y);
+                    }
+                    ap[k * step] = y;
+                    const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
+                    if (m0 > local_l) local_l = m0;
+                    if (m1 > local_r) local_r = m1;
+                    if (m2 > local_lr) local_lr = m2;
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < r; ++k) put<ST_OLSB>(idx0 + k * step, v[k], make_float2(1.f, 0.f));
+        }
+    }
     // ST_OLS2: the radix-2 stage that ends the 2B-point inverse, second half only: y[i + B] = ya[i] - conj(w^i) yb[i]
     ARS_HD void put_ols2(i64 seg, int i, float2 ya, float2 yb) {
         const float2 t = cmulc(yb, ARS_LDG(tw2 + i));
@@ -510,6 +616,7 @@ struct St {
                 case ST_OLS: put<ST_OLS>(idx, v, aux); break;
                 case ST_OLS_CHIRP: put<ST_OLS_CHIRP>(idx, v, aux); break;
                 case ST_OLS2: break;      // fast instantiations only
+                case ST_OLSB: put<ST_OLSB>(idx, v, aux); break;
             }
         } else if constexpr (MODE == ST_PLAIN) {
             a[idx] = v;
@@ -531,6 +638,14 @@ struct St {
                 const i64 fr = ((seg0 + (idx >> logF)) << (logF - 1)) + (t - B);               // absolute output frame
                 ols_out(fr, v, dry_at(fr));
             }
+        } else if constexpr (MODE == ST_OLSB) {
+            const i64 j = idx >> logF;
+            const i64 o = (idx & (((i64)1 << logF) - 1)) - skip;
+            if (o >= 0 && o < hop) {
+                const i64 fr = (seg0 + j) * hop + o;
+                ols_out(fr, v, dg == 0.f ? make_float2(0.f, 0.f)
+                                         : (stash ? (fr < N ? ARS_LDG(stash + j * hop + o) : make_float2(0.f, 0.f)) : dry_at(fr)));
+            }
         } else if constexpr (MODE == ST_OLS2) {
             // (stored by run_tile through put_ols2 once both sub-segments are back in shared memory)
         } else {
@@ -547,7 +662,7 @@ struct St {
     }
     template <int MODE> ARS_HD void put(i64 idx, float2 v) { put<MODE>(idx, v, pre<MODE>(idx)); }
     ARS_HD void finish() {
-        if ((mode == ST_FINAL || mode == ST_OLS || mode == ST_OLS2) && maxbits) {
+        if ((mode == ST_FINAL || mode == ST_OLS || mode == ST_OLS2 || mode == ST_OLSB) && maxbits) {
             local_max = local_l > local_r ? local_l : local_r;
 #ifdef __CUDA_ARCH__
             unsigned m[4] = {local_max, local_l, local_r, local_lr};
@@ -625,6 +740,7 @@ template <int LOGR, int LOGC> struct ContigLayout {
 };
 
 struct PassArgs {
+    i64 total = 0;  // > 0: points of the whole launch -- a batch of total / M independent M-point transforms (0: one transform)
     i64 M;          // transform length
     int logM;
     int logLg;      // strided: segment length of this pass (Lg); contiguous: == LOGR
@@ -726,6 +842,7 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
             if constexpr (first) {
                 i64 idx = gfirst(row0, c);
                 if constexpr (LDM == LD_OLS_X) ld.template get_x<r>(idx, fstep, v);
+                else if constexpr (LDM == LD_OLSB_X) ld.template get_xb<r>(idx, fstep, v);
                 else {
                     #pragma unroll
                     for (int t = 0; t < r; ++t) { v[t] = ld.template get<LDM>(idx); idx += fstep; }
@@ -790,6 +907,9 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
             } else if constexpr (first && STM == ST_OLS) {
                 Dft<r, true>::run(v);
                 st.template put_ols<r>(gfirst(row0, c), fstep, v);
+            } else if constexpr (first && STM == ST_OLSB) {
+                Dft<r, true>::run(v);
+                st.template put_olsb<r>(gfirst(row0, c), fstep, v);
             } else if constexpr (first) {
                 float2 aux[r];
                 const i64 idx0 = gfirst(row0, c);
@@ -965,6 +1085,184 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : (NT == 256 ? 3 : 1)) pass_
                                                              ContigLast<LOGR>{base}, 0u);
 }
 
+
+// ------------------------------------------------- fused middle pass (big-block overlap-save, upols.cu) ---
+// The last forward pass and the first inverse pass of an M-point transform are both the contiguous pass over the
+// same tile, with the spectrum product in between -- so they run as ONE kernel: forward stages, product with the IR
+// spectrum in registers (the forward's last butterfly leaves exactly the values the inverse's first butterfly takes),
+// inverse stages; one trip through shared memory instead of two through HBM, and no launch in between.
+//   plain  : Y = Z H                                   (one real IR for both channels of Z = FFT(L + iR))
+//   MIRROR : Y = Z A + conj(Z[F - k]) Bc               (stereo IR: A = (H_L + H_R)/2, Bc = (H_L - H_R)/2, upols.cu)
+// The mirror bin F - k of (first-pass digit k1, second-pass digit k2) is (R1 - k1, R2 - 1 - k2) for k1 != 0: it lives in
+// the segment of digit R1 - k1, and complementing every digit of k2 reverses the position inside the segment, whatever the
+// parking order.  A MIRROR tile therefore holds the two segments of a digit pair (k1, R1 - k1); the pair (0, R1/2) is its
+// own mirror: segment R1/2 reverses in itself, segment 0 maps k2 -> (R2 - k2) mod R2 through the digit maps below.
+struct MidArgs {
+    const float2* h0 = nullptr;     // H (plain) or A (MIRROR): permuted order, pre-scaled by 1/F, F points
+    const float2* h1 = nullptr;     // MIRROR: Bc
+    i64 fmask = 0;                  // F - 1
+    const int* rho = nullptr;       // MIRROR: row (segment) that holds first-pass digit k1, R1 entries
+    int logR1 = 0;                  // MIRROR: log2 of the first (strided) pass's length
+};
+
+// slot (row inside the tile column, in-place order b * rl + k) of second-pass output digit kf: inverse of kfull_of
+template <int LOGR> ARS_HD int inplace_row_of(int kf) {
+    constexpr int n = Rad<LOGR>::n;
+    constexpr int R = 1 << LOGR;
+    constexpr int rl = Rad<LOGR>::r(n - 1);
+    int b = 0;
+    #pragma unroll
+    for (int s = 0; s < n - 1; ++s) {
+        const int rs = Rad<LOGR>::r(s);
+        const int W = R / (Prod<LOGR>::before(s + 1) * rl);
+        b += (kf % rs) * W;
+        kf /= rs;
+    }
+    return b * rl + kf;
+}
+
+template <int LOGR> struct PairFirst {          // a tile made of two arbitrary segments
+    i64 b0, b1;
+    ARS_HD i64 operator()(int row, int c) const { return (c ? b1 : b0) + row; }
+    ARS_HD constexpr i64 step() const { return 1; }
+};
+template <int LOGR> struct PairLast {
+    i64 b0, b1;
+    ARS_HD i64 operator()(int b, int c) const { return (c ? b1 : b0) + b; }
+    ARS_HD constexpr i64 step() const { return (1 << LOGR) / Rad<LOGR>::r(Rad<LOGR>::n - 1); }
+};
+
+template <int LOGR, int LOGC, bool MIRROR> struct MidStage {
+    using LAYOUT = ContigLayout<LOGR, LOGC>;
+    static constexpr int n = Rad<LOGR>::n;
+    static constexpr int R = 1 << LOGR;
+    static constexpr int r = Rad<LOGR>::r(n - 1);
+    static constexpr int NB = R / r;
+    static constexpr int TOTAL = NB * LAYOUT::C;
+    // forward last stage of butterfly q; MIRROR: the spectrum goes back to the butterfly's own rows for the partners to read
+    static ARS_HD void fwd(float2* sm, int q, float2 (&v)[r]) {
+        const int b = q % NB, c = q / NB;
+        #pragma unroll
+        for (int t = 0; t < r; ++t) v[t] = sm[LAYOUT::sidx(b * r + t, c)];
+        Dft<r, false>::run(v);
+        if constexpr (MIRROR) {
+            #pragma unroll
+            for (int k = 0; k < r; ++k) sm[LAYOUT::sidx(b * r + k, c)] = v[k];
+        }
+    }
+    // spectrum product (v <- Y)
+    template <class GL> static ARS_HD void mul(const float2* sm, const MidArgs& ma, GL glast, int q, bool selfm, float2 (&v)[r]) {
+        const int b = q % NB, c = q / NB;
+        i64 idx = glast(b, c);
+        #pragma unroll
+        for (int k = 0; k < r; ++k) {
+            const i64 h = idx & ma.fmask;
+            if constexpr (!MIRROR) {
+                v[k] = cmul(v[k], ARS_LDG(ma.h0 + h));
+            } else {
+                int prow = R - 1 - (b * r + k), pc = 1 - c;
+                if (selfm) {
+                    pc = c;
+                    if (c == 0) prow = inplace_row_of<LOGR>((R - kfull_of<LOGR>(b, k)) & (R - 1));
+                }
+                const float2 zm = sm[LAYOUT::sidx(prow, pc)];
+                const float2 t0 = cmul(v[k], ARS_LDG(ma.h0 + h));
+                const float2 t1 = cmul(cconj(zm), ARS_LDG(ma.h1 + h));
+                v[k] = make_float2(t0.x + t1.x, t0.y + t1.y);
+            }
+            idx += glast.step();
+        }
+    }
+    // inverse last stage (no twiddle: its sub-transforms have length r)
+    static ARS_HD void inv(float2* sm, int q, float2 (&v)[r]) {
+        const int b = q % NB, c = q / NB;
+        Dft<r, true>::run(v);
+        #pragma unroll
+        for (int t = 0; t < r; ++t) sm[LAYOUT::sidx(b * r + t, c)] = v[t];
+    }
+};
+
+// tile -> segment bases of the middle pass
+template <int LOGR, int LOGC, bool MIRROR> struct MidTile {
+    i64 b0, b1;
+    bool selfm;
+    ARS_HD MidTile(i64 tile, const MidArgs& ma) {
+        if constexpr (!MIRROR) {
+            b0 = tile << (LOGR + LOGC);
+            b1 = b0 + ((i64)1 << LOGR);
+            selfm = false;
+        } else {
+            static_assert(!MIRROR || LOGC == 1, "a mirror tile is a pair of segments");
+            const int half = 1 << (ma.logR1 - 1);
+            const int tau = (int)(tile & (half - 1));
+            const i64 j = tile >> (ma.logR1 - 1);
+            selfm = tau == 0;
+            const int sa = ma.rho[tau], sb = ma.rho[selfm ? half : 2 * half - tau];
+            b0 = ((j << ma.logR1) + sa) << LOGR;
+            b1 = ((j << ma.logR1) + sb) << LOGR;
+        }
+    }
+};
+
+#define ARS_MID_STAGE(S_, INV_, LDM_, STM_) \
+    run_stage<LOGR, S_, INV_, false, NT, LAYOUT, LDM_, STM_>(sm, ld, st, pa, gfirst, glast, 0u, tid)
+template <int LOGR, int LOGC, int NT, bool MIRROR>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_mid_kernel(Ld ld, St st, PassArgs pa, MidArgs ma) {
+    extern __shared__ float2 sm[];
+    using LAYOUT = ContigLayout<LOGR, LOGC>;
+    using MS = MidStage<LOGR, LOGC, MIRROR>;
+    constexpr int n = Rad<LOGR>::n;
+    static_assert(n == 3 && MS::TOTAL == NT, "middle pass: three-stage tile, one last-stage butterfly per thread");
+    const int tid = (int)threadIdx.x;
+    const MidTile<LOGR, LOGC, MIRROR> mt((i64)blockIdx.x, ma);
+    const PairFirst<LOGR> gfirst{mt.b0, mt.b1};
+    const PairLast<LOGR> glast{mt.b0, mt.b1};
+    ARS_MID_STAGE(0, false, LD_PLAIN, ST_PLAIN);
+    __syncthreads();
+    ARS_MID_STAGE(1, false, LD_PLAIN, ST_PLAIN);
+    __syncthreads();
+    float2 v[MS::r];
+    MS::fwd(sm, tid, v);
+    if constexpr (MIRROR) __syncthreads();
+    MS::mul(sm, ma, glast, tid, mt.selfm, v);
+    if constexpr (MIRROR) __syncthreads();
+    MS::inv(sm, tid, v);
+    __syncthreads();
+    ARS_MID_STAGE(1, true, LD_PLAIN, ST_PLAIN);
+    __syncthreads();
+    ARS_MID_STAGE(0, true, LD_PLAIN, ST_PLAIN);
+}
+
+// host emulation of one middle-pass tile (tests/host_emul): per-"thread" registers live in `regs` across the barriers
+template <int LOGR, int LOGC, int NT, bool MIRROR>
+inline void emulate_mid_tile(float2* sm, float2* regs, Ld& ld, St& st, const PassArgs& pa, const MidArgs& ma, i64 tile) {
+    using LAYOUT = ContigLayout<LOGR, LOGC>;
+    using MS = MidStage<LOGR, LOGC, MIRROR>;
+    const MidTile<LOGR, LOGC, MIRROR> mt(tile, ma);
+    const PairFirst<LOGR> gfirst{mt.b0, mt.b1};
+    const PairLast<LOGR> glast{mt.b0, mt.b1};
+    typedef float2 (&VR)[MS::r];
+    for (int tid = 0; tid < NT; ++tid) ARS_MID_STAGE(0, false, LD_PLAIN, ST_PLAIN);
+    for (int tid = 0; tid < NT; ++tid) ARS_MID_STAGE(1, false, LD_PLAIN, ST_PLAIN);
+    for (int q = 0; q < MS::TOTAL; ++q) MS::fwd(sm, q, reinterpret_cast<VR>(*(regs + (size_t)q * MS::r)));
+    for (int q = 0; q < MS::TOTAL; ++q) MS::mul(sm, ma, glast, q, mt.selfm, reinterpret_cast<VR>(*(regs + (size_t)q * MS::r)));
+    for (int q = 0; q < MS::TOTAL; ++q) MS::inv(sm, q, reinterpret_cast<VR>(*(regs + (size_t)q * MS::r)));
+    for (int tid = 0; tid < NT; ++tid) ARS_MID_STAGE(1, true, LD_PLAIN, ST_PLAIN);
+    for (int tid = 0; tid < NT; ++tid) ARS_MID_STAGE(0, true, LD_PLAIN, ST_PLAIN);
+}
+#undef ARS_MID_STAGE
+
+// row (segment) in which a strided first pass of 2^logR1 points leaves its output digit k1 (StridedLast: b * rl + k)
+inline int strided_row_of(int logR1, int k1) {
+    switch (logR1) {
+#define ARS_ROW(L) case L: return inplace_row_of<L>(k1);
+        ARS_ROW(1) ARS_ROW(2) ARS_ROW(3) ARS_ROW(4) ARS_ROW(5) ARS_ROW(6) ARS_ROW(7) ARS_ROW(8) ARS_ROW(9) ARS_ROW(10)
+        ARS_ROW(11) ARS_ROW(12) ARS_ROW(13)
+#undef ARS_ROW
+    }
+    return k1;
+}
+
 }  // namespace fft
 
 // instantiated (logR, logT|logC) pass variants; the launcher and the host emulator share the list
@@ -1005,6 +1303,7 @@ struct FftPlan {
     std::vector<FftPass> passes;   // forward order
     DevBuf tw_lo, tw_hi;
     std::vector<DevBuf> pass_tabs;  // per strided pass: PassArgs::ptab
+    DevBuf rho;                     // big-block overlap-save, stereo IR: MidArgs::rho (built on first use)
     fft::Tw tw{};
 };
 
@@ -1020,6 +1319,12 @@ void fft_inverse(FftPlan* p, const fft::Ld& ld, float2* work, const fft::St& st)
 // `nseg` independent 8192-point overlap-save transforms as a radix-2 stage folded into the load / store plus two
 // 4096-point transforms per segment (LD_OLS_X2 | LD_OLS_IR2 forward, ST_OLS2 inverse; fills in Ld::tw2 / St::tw2)
 void fft_segments_r2(i64 nseg, fft::Ld ld, fft::St st, bool inverse);
+// Big-block overlap-save (upols.cu): `nbatch` M-point transforms back to back in `work`; first = the strided forward
+// pass (reads through ld), mid = contiguous forward pass x spectrum (h1: the mirror form for stereo IRs) x contiguous
+// inverse pass in place, last = the strided inverse pass (writes through st).
+void fft_batch_first(FftPlan* p, i64 nbatch, const fft::Ld& ld, const fft::St& st);
+void fft_batch_mid(FftPlan* p, i64 nbatch, float2* work, const float2* h0, const float2* h1);
+void fft_batch_last(FftPlan* p, i64 nbatch, const fft::Ld& ld, const fft::St& st);
 void fft_touch_tables();      // builds the shared stage table on the current stream if it does not exist yet
 // One contiguous pass over `nseg` independent 2^logF-point segments (logF = 12 or 13; nseg a multiple of
 // fft_segment_tile(logF)): the block transforms of the overlap-save convolution.

@@ -14,6 +14,10 @@ bool fast_contig_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassAr
         if (lm == LD_OLS_X2 && sm == ST_PLAIN) { launch_contig<12, 1, false, LD_OLS_X2, ST_PLAIN>(ld, st, pa); return true; }
         if (lm == LD_OLS_IR2 && sm == ST_SCALE) { launch_contig<12, 1, false, LD_OLS_IR2, ST_SCALE>(ld, st, pa); return true; }
     }
+    if (sm == ST_SCALE && lm == LD_PLAIN && ps.logR == 12 && ps.logT == 1) {       // IR spectrum of the big-block route
+        launch_contig<12, 1, false, LD_PLAIN, ST_SCALE>(ld, st, pa);
+        return true;
+    }
     if (sm != ST_PLAIN) return false;
 #define F_CASE(R, C)                                                                                          \
     if (ps.logR == R && ps.logT == C) {                                                                       \

@@ -15,9 +15,14 @@ bool fast_strided_fwd(const FftPass& ps, const Ld& ld, const St& st, const PassA
         if (lm == LD_CHIRP_XC) { launch_strided<R, T, false, LD_CHIRP_XC, ST_PLAIN>(ld, st, pa); return true; }     \
         if (lm == LD_CHIRP_PAIR) { launch_strided<R, T, false, LD_CHIRP_PAIR, ST_PLAIN>(ld, st, pa); return true; } \
         if (lm == LD_CHIRP_C) { launch_strided<R, T, false, LD_CHIRP_C, ST_PLAIN>(ld, st, pa); return true; }       \
+        if (lm == LD_OLSB_X) { launch_strided<R, T, false, LD_OLSB_X, ST_PLAIN>(ld, st, pa); return true; }         \
+        if (lm == LD_TAPS) { launch_strided<R, T, false, LD_TAPS, ST_PLAIN>(ld, st, pa); return true; }             \
     }
     ARS_FAST_STRIDED(F_CASE)
 #undef F_CASE
+    // 2^22-point big-block overlap-save transforms: 2^10 x 2^12
+    if (ps.logR == 10 && ps.logT == 3 && lm == LD_OLSB_X) { launch_strided<10, 3, false, LD_OLSB_X, ST_PLAIN>(ld, st, pa); return true; }
+    if (ps.logR == 10 && ps.logT == 3 && lm == LD_TAPS) { launch_strided<10, 3, false, LD_TAPS, ST_PLAIN>(ld, st, pa); return true; }
     return false;
 }
 

@@ -20,7 +20,7 @@ static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    const i64 tiles = pa.M >> (LOGR + LOGT);
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGT);
     k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
     ARS_LAUNCH_CHECK();
     count_launch();
@@ -38,11 +38,29 @@ static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    const i64 tiles = pa.M >> (LOGR + LOGC);
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
     k<<<(unsigned)tiles, NTC, smem, ctx().stream>>>(ld, st, pa);
     ARS_LAUNCH_CHECK();
     count_launch();
 }
+
+// fused middle pass of the big-block overlap-save transforms (fft.cuh: pass_mid_kernel)
+template <int LOGR, int LOGC, bool MIRROR>
+static void launch_mid(const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma) {
+    using L = ContigLayout<LOGR, LOGC>;
+    static bool attr_done = false;
+    const size_t smem = sizeof(float2) * L::SMEM_ELEMS;
+    auto k = pass_mid_kernel<LOGR, LOGC, NT, MIRROR>;
+    if (!attr_done) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
+    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa, ma);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+void mid_pass(bool mirror, const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma);    // fft_k_mid.cu
 
 int ols_threads();     // 512 | 256: CTA size of the overlap-save block transforms (ARS_OLS_NT, fft_plan.cu)
 

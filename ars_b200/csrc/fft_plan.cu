@@ -63,6 +63,7 @@ void fft_release_plans() {
             kv.second->tw_lo.release();
             kv.second->tw_hi.release();
             for (auto& t : kv.second->pass_tabs) t.release();
+            kv.second->rho.release();
             delete kv.second;
         }
         ctx().fft_plans.clear();
@@ -115,6 +116,9 @@ FftPlan* get_fft_plan(int logM) {
         count_launch();
         ps.ptab = p->pass_tabs[i].as<float2>();
     }
+    // a plan may be created while the library is enqueuing on its side stream and be used from the main stream
+    // right after: finish the tables here, once per plan, instead of tracking which stream built them
+    ARS_CUDA(cudaStreamSynchronize(c.stream));
     c.fft_plans[logM] = p;
     return p;
 }
@@ -144,6 +148,8 @@ static double ld_bytes(const Ld& ld, i64 M) {
         case LD_OLS_MAC: return 8.0 * (double)M;       // compulsory: each delay-line spectrum once
         case LD_OLS_CHIRPSIG: return 8.0 * (double)ld.N;
         case LD_OLS_IRC: return 4.0 * (double)(ld.nvalid + ld.nvalid1) + 8.0 * (double)std::max(ld.nvalid, ld.nvalid1);
+        case LD_OLSB_X: return 8.0 * (double)M;        // (the windows overlap: an upper bound of the frames one launch reads)
+        case LD_TAPS: return 4.0 * (double)(ld.nvalid + ld.nvalid1);
     }
     return 0.0;
 }
@@ -153,6 +159,7 @@ static double st_bytes(const St& st, i64 M) {
         case ST_CHIRP: case ST_FINAL: return 16.0 * (double)st.N;
         case ST_OLS: case ST_OLS2: return 16.0 * (double)st.N;
         case ST_OLS_CHIRP: return 16.0 * (double)st.N;
+        case ST_OLSB: return 16.0 * (double)M;
     }
     return 0.0;
 }
@@ -189,8 +196,9 @@ static cudaEvent_t prof_event() {
 using namespace fftk;
 
 template <bool INV>
-static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const St& st) {
+static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const St& st, i64 total = 0) {
     PassArgs pa;
+    pa.total = total;
     pa.M = p->M;
     pa.logM = p->logM;
     pa.logLg = ps.logLg;
@@ -205,7 +213,7 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
             if (on) { g_prof.bytes += ld_bytes(l, M) + st_bytes(s, M); ARS_CUDA(cudaEventRecord(prof_event(), ctx().stream)); }
         }
         ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
-    } prof_scope(ld, st, p->M);
+    } prof_scope(ld, st, total > 0 ? total : p->M);
     if (ps.strided) ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
     bool done = false;
     if (g_fast) {
@@ -264,6 +272,63 @@ void fft_segments_r2(i64 nseg, Ld ld, St st, bool inverse) {
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);
     else launch_pass<false>(&tmp, ps, ld, st);
     g_prof.on = prof;
+}
+
+// ---- batched two-pass transforms of the big-block overlap-save route (upols.cu) ----
+// `nbatch` independent M-point transforms laid out back to back in one buffer; the plan must be strided + contiguous(12).
+static void check_two_pass(const FftPlan* p) {
+    ARS_CHECK(p->passes.size() == 2 && p->passes[0].strided && !p->passes[1].strided && p->passes[1].logR == 12 &&
+                  p->passes[1].logT == 1,
+              "big-block overlap-save needs a two-pass plan (strided + 2 x 4096 contiguous)");
+}
+void fft_batch_first(FftPlan* p, i64 nbatch, const Ld& ld, const St& st) {
+    check_two_pass(p);
+    launch_pass<false>(p, p->passes[0], ld, st, nbatch * p->M);
+}
+void fft_batch_last(FftPlan* p, i64 nbatch, const Ld& ld, const St& st) {
+    check_two_pass(p);
+    launch_pass<true>(p, p->passes[0], ld, st, nbatch * p->M);
+}
+void fft_batch_mid(FftPlan* p, i64 nbatch, float2* work, const float2* h0, const float2* h1) {
+    check_two_pass(p);
+    const int logR1 = p->passes[0].logR;
+    MidArgs ma;
+    ma.h0 = h0;
+    ma.h1 = h1;
+    ma.fmask = p->M - 1;
+    ma.logR1 = logR1;
+    if (h1) {
+        if (!p->rho.p) {            // segment of every first-pass digit (the mirror tiles pair digit k1 with R1 - k1)
+            std::vector<int> rho((size_t)1 << logR1);
+            for (int k1 = 0; k1 < (1 << logR1); ++k1) rho[(size_t)k1] = strided_row_of(logR1, k1);
+            p->rho.reserve(sizeof(int) * rho.size());
+            ARS_CUDA(cudaMemcpyAsync(p->rho.p, rho.data(), sizeof(int) * rho.size(), cudaMemcpyHostToDevice, ctx().stream));
+            ARS_CUDA(cudaStreamSynchronize(ctx().stream));       // (once per plan: the host vector dies here)
+        }
+        ma.rho = p->rho.as<int>();
+    }
+    PassArgs pa;
+    pa.total = nbatch * p->M;
+    pa.M = p->M;
+    pa.logM = p->logM;
+    pa.logLg = 12;
+    pa.prefetch = 0;
+    pa.ptab = nullptr;
+    pa.tw = p->tw;
+    Ld ld;
+    ld.mode = LD_PLAIN;
+    ld.a = work;
+    St st;
+    st.mode = ST_PLAIN;
+    st.a = work;
+    struct ProfScope {
+        bool on;
+        ProfScope(i64 pts, bool two) : on(g_prof.on) {
+            if (on) { g_prof.bytes += (two ? 32.0 : 24.0) * (double)pts; ARS_CUDA(cudaEventRecord(prof_event(), ctx().stream)); }
+        }
+        ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
+    } prof_scope(pa.total, h1 != nullptr);
+    mid_pass(h1 != nullptr, ld, st, pa, ma);
 }
 
 void fft_forward(FftPlan* p, const Ld& ld_first, float2* work, const St& st_last) {

@@ -10,6 +10,7 @@
 // re-filters every chunk from its true start state.  As in pyloudnorm, the stage output is
 // rounded to float32 before the next stage reads it.
 #include "metrics.cuh"
+#include "tail_math.cuh"
 
 #include <cmath>
 #include <math_constants.h>
@@ -171,13 +172,10 @@ __global__ void __launch_bounds__(256) gate_energy_kernel(const float* __restric
     }
 }
 
-// ---- fused form of the loudness chain (hop >= 4096 samples, i.e. rate >= 40 960 Hz) ------------------------------
-// The chain above touches the signal seven times (2 x [aggregate, apply] + energies, with two filtered copies written
-// and re-read) and runs two single-CTA scans over the block aggregates.  Fused (three passes, no scan -- lookback_state): the kernel that applies stage 1 also forms stage 2's block aggregates from the float32-rounded
-// samples it holds, and the kernel that applies stage 2 squares its output straight into the 100 ms hops
-// [lo_h, lo_{h+1}) the 400 ms gating blocks are made of (hi_j == lo_{j+4} exactly: both are int(0.4 * (0.25 j + 1) *
-// rate) with 0.25 j + 1 exact) instead of writing it.  Same arithmetic per sample, same float32 rounding between the
-// stages; only the order in which the squares of a gating block are added differs.
+// ---- hop arithmetic of the one-pass meter (hop >= 4096 samples, i.e. rate >= 40 960 Hz) ----------------------------
+// The 400 ms gating blocks are made of 100 ms hops [lo_h, lo_{h+1}) (hi_j == lo_{j+4} exactly: both are
+// int(0.4 * (0.25 j + 1) * rate) with 0.25 j + 1 exact), so the squares go straight into hop sums; only the order in
+// which the squares of a gating block are added differs from the stage-wise chain.
 __device__ __forceinline__ i64 hop_lo(i64 h, double rate) {        // int(T_g * (h * step) * rate), pyloudnorm's order
     return (i64)__dmul_rn(__dmul_rn(0.4, __dmul_rn((double)h, 0.25)), rate);
 }
@@ -188,49 +186,61 @@ __device__ __forceinline__ i64 hop_of(i64 i, double rate) {         // largest h
     return h;
 }
 
-// Start state of block b from the aggregates of the blocks before it: s_b = agg[b-1] + M (agg[b-2] + M (agg[b-3] + ...)),
-// M = A^BS, cut after `depth` terms -- the K-weighting filters forget fast (|M| ~ 1e-17 at 48 kHz), so the host picks the
-// depth at which the dropped terms are below 1e-25 of the kept ones and no scan over the blocks is needed.
-__device__ __forceinline__ double2 lookback_state(const double2* __restrict__ agg, int b, const Mat2& M, int depth) {
-    double2 s = make_double2(0.0, 0.0);
-    const int d0 = b < depth ? b : depth;
-    for (int d = d0; d >= 1; --d) {
-        const double2 a = agg[b - d];
-        const double2 ms = mat_vec(M, s);
-        s = make_double2(a.x + ms.x, a.y + ms.y);
+// ---- one-pass loudness meter ------------------------------------------------------------------------------------
+// One kernel reads the meter's input ONCE and leaves the hop energies: per block of BS samples it filters stage 1 and
+// stage 2 (each: chunk end states from a zero state, block scan, true start states, second sweep), rounding stage 1's
+// output to float32 in shared memory as pyloudnorm does in its array, and squares stage 2's output straight into the
+// 100 ms hops.  Blocks are handed out in ticket order; a block publishes its zero-start aggregate of a stage BEFORE it
+// waits for the aggregates of the few blocks in front of it (the K-weighting filters forget fast: |A^BS| ~ 1e-17 at
+// 48 kHz, so `depth` terms of the look-back suffice), so no block ever waits on a block behind it and there is no serial
+// chain through the blocks.  Same arithmetic per sample as the stage-wise chain; the filtered signals never leave the SM.
+struct SrcMono {                       // a materialised feed (ars_metrics, block-sharded renders)
+    const float* x;
+    __device__ __forceinline__ void prepare() {}
+    __device__ __forceinline__ float at(i64 i) const { return __ldg(x + i); }
+};
+struct SrcStage {                      // mean(ch0, ch1) of the final frame (rs.py:687-688), recomputed from the convolution stage's
+    const float2* y;                   // output exactly as final_kernel forms it -- the meter then needs no feed array and can
+    TailSpec ts;                       // run next to the final pass instead of behind it
+    const RenderState* st;
+    Guard g1, g2, g3;
+    __device__ __forceinline__ void prepare() {
+        g1 = make_guard(st->max_stereo);
+        g2 = make_guard(st->max_pan);
+        g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
     }
-    return s;
-}
+    __device__ __forceinline__ float at(i64 i) const {
+        FrameIn f;
+        f.v = __ldg(y + (i - ts.y0));
+        f.w = make_float2(0.f, 0.f);
+        float o[8];
+        frame_math<true, true>(f, -1, ts, g1, g2, o);          // (frame index -1: the delayed pair is not needed)
+        return __fmul_rn(__fadd_rn(guard1(o[0], g3), guard1(o[1], g3)), 0.5f);
+    }
+};
 
-// MODE 0: y = stage cf applied to x (float32), agg2 = block aggregates of stage cf2 over y.
-// MODE 1: stage cf applied to x, squared into hop energies: part[4 b + k] = energy of block b inside hop hop_of(b BS) + k.
-template <int MODE>
-__global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restrict__ x, i64 N, ScanCoef cf,
-                                                           const double2* __restrict__ agg, int depth, float* __restrict__ y,
-                                                           ScanCoef cf2, double2* __restrict__ agg2, double rate,
-                                                           double* __restrict__ part) {
-    __shared__ float sx[NTB * (CH + 1)];
-    __shared__ double2 sv[NTB];
-    __shared__ i64 s_lo[3];
-    const i64 base = (i64)blockIdx.x * BS;
+struct LoudArgs {
+    i64 N;
+    double rate;
+    ScanCoef c1, c2;
+    int dep1, dep2;
+    double2* agg1;                     // per block: zero-start end state of stage 1 / stage 2
+    double2* agg2;
+    int* flag1;                        // per block: aggregate published (zeroed before the launch)
+    int* flag2;
+    unsigned* ticket;                  // block counter (zeroed before the launch)
+    double* part;                      // [4 b + k]: energy of block b inside hop hop_of(b BS) + k
+    unsigned* mono_max;                // bits of max |feed| (null: the caller has it already)
+};
+
+// True start state of this thread's chunk for one stage: zero-state sweep, block scan, publish, look back, propagate.
+__device__ __forceinline__ double2 chunk_start_state(const float* mine, const ScanCoef& cf, double2* __restrict__ agg,
+                                                     int* __restrict__ flag, int depth, int b, double2* sv, double2* s_start) {
     const int t = threadIdx.x;
-    if (MODE == 1 && t < 3) s_lo[t] = hop_lo(hop_of(base, rate) + 1 + t, rate);
-    for (int i = t; i < BS; i += NTB) {
-        const i64 g = base + i;
-        sx[(i / CH) * (CH + 1) + (i % CH)] = g < N ? x[g] : 0.f;
-    }
-    __syncthreads();
-    float* mine = sx + t * (CH + 1);
     double2 z = make_double2(0.0, 0.0);
     #pragma unroll 8
     for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
     double2 v = z;
-    double2 s0 = make_double2(0.0, 0.0);
-    if (t == 0) {
-        s0 = lookback_state(agg, (int)blockIdx.x, cf.pw[8], depth);
-        const double2 ps = mat_vec(cf.pw[0], s0);
-        v.x += ps.x; v.y += ps.y;
-    }
     sv[t] = v;
     __syncthreads();
     #pragma unroll
@@ -243,61 +253,92 @@ __global__ void __launch_bounds__(NTB) biquad_fused_kernel(const float* __restri
         sv[t] = v;
         __syncthreads();
     }
-    double2 s = (t == 0) ? s0 : sv[t - 1];
-    if (MODE == 0) {
-        double2 z2 = make_double2(0.0, 0.0);
-        #pragma unroll 8
-        for (int j = 0; j < CH; ++j) {
-            const float o = (float)df2t(cf.q, (double)mine[j], s);     // float32 store, as pyloudnorm
-            mine[j] = o;
-            df2t(cf2.q, (double)o, z2);                                   // stage 2 from a zero state
+    if (t == NTB - 1) {                                    // publish first ...
+        agg[b] = v;
+        __threadfence();
+        *reinterpret_cast<volatile int*>(flag + b) = 1;
+    }
+    if (t == 0) {                                          // ... then look back: s_b = agg[b-1] + M (agg[b-2] + M (...))
+        double2 s = make_double2(0.0, 0.0);
+        const int d0 = b < depth ? b : depth;
+        for (int d = d0; d >= 1; --d) {
+            while (*reinterpret_cast<volatile int*>(flag + (b - d)) == 0) __nanosleep(40);
+            __threadfence();
+            const double2 a = __ldcg(agg + (b - d));
+            const double2 ms = mat_vec(cf.pw[8], s);
+            s = make_double2(a.x + ms.x, a.y + ms.y);
         }
-        __syncthreads();                                                 // everybody is done with sv
-        double2 w = z2;
-        sv[t] = w;
-        __syncthreads();
+        *s_start = s;
+    }
+    __syncthreads();
+    double2 w = *s_start;                                  // A^(CH t) s_b by binary powering with the tabulated A^(CH 2^k)
+    #pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if ((t >> k) & 1) w = mat_vec(cf.pw[k], w);
+    if (t > 0) { const double2 p = sv[t - 1]; w.x += p.x; w.y += p.y; }
+    __syncthreads();                                       // sv / s_start are reused by the next stage
+    return w;
+}
+
+template <class SRC>
+__global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a) {
+    __shared__ float sx[NTB * (CH + 1)];
+    __shared__ double2 sv[NTB];
+    __shared__ double2 s_start;
+    __shared__ i64 s_lo[3];
+    __shared__ unsigned s_b;
+    __shared__ double se[4][NTB / 32];
+    const int t = threadIdx.x;
+    if (t == 0) s_b = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int b = (int)s_b;
+    const i64 base = (i64)b * BS;
+    if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
+    src.prepare();
+    unsigned mm = 0;
+    for (int i = t; i < BS; i += NTB) {
+        const i64 g = base + i;
+        const float v = g < a.N ? src.at(g) : 0.f;
+        sx[(i / CH) * (CH + 1) + (i % CH)] = v;
+        mm = max(mm, abs_bits(v));
+    }
+    if (a.mono_max) {
         #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int off = 1 << k;
-            double2 add = make_double2(0.0, 0.0);
-            if (t >= off) add = mat_vec(cf2.pw[k], sv[t - off]);
-            __syncthreads();
-            w.x += add.x; w.y += add.y;
-            sv[t] = w;
-            __syncthreads();
-        }
-        if (t == NTB - 1) agg2[blockIdx.x] = w;
-        for (int i = t; i < BS; i += NTB) {
-            const i64 g = base + i;
-            if (g < N) y[g] = sx[(i / CH) * (CH + 1) + (i % CH)];
-        }
-    } else {
-        // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
-        const i64 g0 = base + (i64)t * CH;
-        const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
-        const i64 next = s_lo[k0 < 3 ? k0 : 2];
-        double e0 = 0.0, e1 = 0.0;
-        #pragma unroll 8
-        for (int j = 0; j < CH; ++j) {
-            const float o = (float)df2t(cf.q, (double)mine[j], s);
-            const double sq = (double)__fmul_rn(o, o);
-            const i64 g = g0 + j;
-            if (g < N) { if (g < next) e0 += sq; else e1 += sq; }
-        }
-        __shared__ double se[4][NTB / 32];
+        for (int o = 16; o > 0; o >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        if ((t & 31) == 0 && mm > *reinterpret_cast<volatile unsigned*>(a.mono_max)) atomicMax(a.mono_max, mm);
+    }
+    __syncthreads();
+    float* mine = sx + t * (CH + 1);
+    // stage 1 (high shelf): float32 store, as pyloudnorm
+    double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sv, &s_start);
+    #pragma unroll 8
+    for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(a.c1.q, (double)mine[j], s);
+    // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
+    s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sv, &s_start);
+    // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
+    const i64 g0 = base + (i64)t * CH;
+    const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
+    const i64 next = s_lo[k0 < 3 ? k0 : 2];
+    double e0 = 0.0, e1 = 0.0;
+    #pragma unroll 8
+    for (int j = 0; j < CH; ++j) {
+        const float o = (float)df2t(a.c2.q, (double)mine[j], s);
+        const double sq = (double)__fmul_rn(o, o);
+        const i64 g = g0 + j;
+        if (g < a.N) { if (g < next) e0 += sq; else e1 += sq; }
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
         #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if ((t & 31) == 0) se[k][t >> 5] = c;
-        }
-        __syncthreads();
-        if (t < 4) {
-            double tot = 0.0;
-            for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
-            part[(i64)blockIdx.x * 4 + t] = tot;
-        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((t & 31) == 0) se[k][t >> 5] = c;
+    }
+    __syncthreads();
+    if (t < 4) {
+        double tot = 0.0;
+        for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
+        a.part[(i64)b * 4 + t] = tot;
     }
 }
 
@@ -416,9 +457,9 @@ __global__ void __launch_bounds__(1024) gate_kernel(const double* __restrict__ z
     if (threadIdx.x == 0) *lufs_out = -0.691 + 10.0 * log10(n2 > 0 ? s2 / (double)n2 : 0.0);   // log10(0) = -inf, as numpy
 }
 
-// Enqueues the whole loudness measurement; *d_lufs receives the value.  Returns 1 (and enqueues nothing)
-// when the signal is shorter than one 400 ms block (pyloudnorm raises -> the reference reports None).
-int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs) {
+template <class SRC>
+static int loudness_run(SRC src, i64 N, double rate, unsigned* d_mono_max_out, const float* d_mono_stagewise,
+                        const unsigned* d_mono_max, double* d_lufs) {
     Ctx& c = ctx();
     if (!((double)N >= 0.4 * rate)) return 1;            // "Audio must have length greater than the block size"
     const int nb = loudness_blocks(N, rate);
@@ -426,7 +467,6 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     Biquad q[2];
     k_weighting(rate, q);
     double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
-    float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
     const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
     // look-back depth at which the dropped start-state terms are below 1e-25 of the kept ones (0: use the block scan)
     auto depth_of = [](const Mat2& M) {
@@ -437,18 +477,32 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     const int dep1 = depth_of(c1.pw[8]), dep2 = depth_of(c2.pw[8]);
     if (g_lufs_fused && 0.1 * rate >= 4096.0 && dep1 > 0 && dep2 > 0) {
         const int nblocks = (int)((N + BS - 1) / BS);
-        double2* st1 = c.buf("lufs.state", sizeof(double2) * (size_t)nblocks).as<double2>();
-        double2* st2 = c.buf("lufs.state2", sizeof(double2) * (size_t)nblocks).as<double2>();
-        double* d_part = c.buf("lufs.part", sizeof(double) * 4 * (size_t)nblocks).as<double>();
-        biquad_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, nullptr);
-        biquad_fused_kernel<0><<<nblocks, NTB, 0, c.stream>>>(d_mono, N, c1, st1, dep1, y1, c2, st2, rate, nullptr);
-        biquad_fused_kernel<1><<<nblocks, NTB, 0, c.stream>>>(y1, N, c2, st2, dep2, nullptr, c2, nullptr, rate, d_part);
-        hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(d_part, N, rate, nb, dz);
+        // [agg1 | agg2 | part | flag1 | flag2 | ticket]: the flags and the ticket are zeroed per launch
+        const size_t off_flags = sizeof(double2) * 2 * (size_t)nblocks + sizeof(double) * 4 * (size_t)nblocks;
+        const size_t bytes_flags = sizeof(int) * (2 * (size_t)nblocks + 4);
+        char* ws = c.buf("lufs.onepass", off_flags + bytes_flags).as<char>();
+        LoudArgs a;
+        a.N = N;
+        a.rate = rate;
+        a.c1 = c1; a.c2 = c2;
+        a.dep1 = dep1; a.dep2 = dep2;
+        a.agg1 = reinterpret_cast<double2*>(ws);
+        a.agg2 = a.agg1 + nblocks;
+        a.part = reinterpret_cast<double*>(a.agg2 + nblocks);
+        a.flag1 = reinterpret_cast<int*>(ws + off_flags);
+        a.flag2 = a.flag1 + nblocks;
+        a.ticket = reinterpret_cast<unsigned*>(a.flag2 + nblocks);
+        a.mono_max = d_mono_max_out;
+        ARS_CUDA(cudaMemsetAsync(ws + off_flags, 0, bytes_flags, c.stream));
+        loudness_kernel<SRC><<<nblocks, NTB, 0, c.stream>>>(src, a);
+        hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(a.part, N, rate, nb, dz);
         ARS_LAUNCH_CHECK();
-        count_launch(4);
+        count_launch(2);
     } else {
+        ARS_CHECK(d_mono_stagewise != nullptr, "loudness: the stage-wise chain needs a materialised feed");
+        float* y1 = c.buf("lufs.y1", sizeof(float) * (size_t)N).as<float>();
         float* y2 = c.buf("lufs.y2", sizeof(float) * (size_t)N).as<float>();
-        run_biquad(d_mono, y1, N, q[0]);
+        run_biquad(d_mono_stagewise, y1, N, q[0]);
         run_biquad(y1, y2, N, q[1]);
         gate_energy_kernel<<<nb, 256, 0, c.stream>>>(y2, N, rate, nb, dz);
         ARS_LAUNCH_CHECK();
@@ -458,6 +512,28 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
     ARS_LAUNCH_CHECK();
     count_launch();
     return 0;
+}
+
+// Enqueues the whole loudness measurement; *d_lufs receives the value.  Returns 1 (and enqueues nothing)
+// when the signal is shorter than one 400 ms block (pyloudnorm raises -> the reference reports None).
+int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs) {
+    SrcMono src;
+    src.x = d_mono;
+    return loudness_run(src, N, rate, nullptr, d_mono, d_mono_max, d_lufs);
+}
+
+bool loudness_from_stage_possible(double rate) { return g_lufs_fused && 0.1 * rate >= 4096.0; }
+
+// The same measurement fed straight from the convolution stage's output (mean of the first two final channels is
+// recomputed per sample): no feed array, so the meter can run next to the final pass.  Needs the guards' maxima in
+// *d_state (max_stereo, max_pan, and max_map for the Stereo layout); writes d_state->mono_max and d_state->lufs.
+int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state) {
+    ARS_CHECK(loudness_from_stage_possible(rate), "loudness: the one-pass meter needs rate >= 40 960 Hz");
+    SrcStage src;
+    src.y = d_y;
+    src.ts = ts;
+    src.st = d_state;
+    return loudness_run(src, ts.N, rate, &d_state->mono_max, nullptr, &d_state->mono_max, &d_state->lufs);
 }
 
 // ---- spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(x, fs, window='hann', nperseg,

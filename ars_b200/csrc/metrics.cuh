@@ -1,6 +1,6 @@
 // Loudness metric (K-weighted, gated, BS.1770-4 as pyloudnorm implements it) -- see metrics.cu.
 #pragma once
-#include "ars_common.cuh"
+#include "epilogue.cuh"
 
 namespace ars {
 
@@ -9,6 +9,11 @@ int loudness_blocks(i64 N, double rate);
 // max |mono|.  Enqueues biquads, block energies and the gate on the library stream; *d_lufs (device) receives
 // the loudness (-inf for silence).  Returns 1 without enqueuing when the signal is shorter than one 400 ms block.
 int integrated_loudness_async(const float* d_mono, i64 N, double rate, const unsigned* d_mono_max, double* d_lufs);
+
+// The same meter fed from the convolution stage's output (the mono feed is recomputed per sample exactly as the final
+// pass forms it); see metrics.cu.  Possible at rates >= 40 960 Hz with the one-pass meter enabled.
+bool loudness_from_stage_possible(double rate);
+int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state);
 
 // scipy.signal.spectrogram(x[:, 0], fs, window='hann', nperseg, noverlap=nperseg//2) -> d_out[(nperseg/2+1) x nseg], row-major
 void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out);

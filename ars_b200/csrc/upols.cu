@@ -271,6 +271,179 @@ static void upols_run(const float* d_x, i64 n, int cin, const float* d_ir0, i64 
     else fft_segments(logF, run, ld, st, true);
 }
 
+// ------------------------------------------------------------------ big-block overlap-save (see upols.cuh) -----
+static int g_olsb_on = 1, g_olsb_logf = 0, g_olsb_stripe = 0;
+static int g_olsb_lanes = 1, g_olsb_first_all = 0, g_olsb_reverse = 1, g_olsb_dryfold = 1;
+void olsb_set_tuning(const char* key, int value) {
+    if (!strcmp(key, "olsb_lanes")) g_olsb_lanes = std::max(1, value);
+    else if (!strcmp(key, "olsb_first_all")) g_olsb_first_all = value ? 1 : 0;
+    else if (!strcmp(key, "olsb_reverse")) g_olsb_reverse = value ? 1 : 0;
+    else if (!strcmp(key, "olsb_dryfold")) g_olsb_dryfold = value ? 1 : 0;
+}
+void olsb_set_options(int on, int logf, int stripe) {
+    if (on >= 0) g_olsb_on = on ? 1 : 0;
+    if (logf >= 0) g_olsb_logf = logf;
+    if (stripe >= 0) g_olsb_stripe = stripe;
+}
+bool olsb_enabled() { return g_olsb_on != 0; }
+static unsigned long long g_olsb_count = 0;
+unsigned long long olsb_count() { return g_olsb_count; }
+
+bool olsb_plan(i64 N, i64 taps, i64 adv, i64 circ, OlsbPlan* out) {
+    if (!g_olsb_on || taps < 1 || N < 1) return false;
+    const i64 skip = taps - 1;
+    int logF = g_olsb_logf;
+    if (logF == 0) {
+        logF = 18;
+        while (logF < 22 && ((i64)1 << logF) < 8 * taps) ++logF;              // hop efficiency >= 87.5 % where 2^22 allows
+        while (logF > 18 && ((i64)1 << (logF - 1)) >= 4 * taps && ((i64)1 << (logF - 1)) >= N + skip) --logF;   // short render
+    }
+    if (logF < 18 || logF > 22) return false;
+    const i64 F = (i64)1 << logF;
+    if (4 * skip > 3 * F) return false;                                       // hop efficiency < 25 %: taps too long
+    if (2 * (N + skip) < F) return false;                                     // less than half a block of work
+    const i64 hop = F - skip;
+    if (circ > 0 && (F + adv + hop >= circ || skip >= circ)) return false;    // |frame| < 2 circ (Ld::frame_at wraps once)
+    OlsbPlan p;
+    p.logF = logF;
+    p.F = F;
+    p.hop = hop;
+    p.skip = skip;
+    p.J = (N + hop - 1) / hop;
+    const i64 tiles = F >> 13;                                                // CTAs of a pass per transform
+    const i64 wave = 2 * (i64)(ctx_ready() ? ctx().sm_count : 148);
+    p.stripe = g_olsb_stripe > 0 ? g_olsb_stripe : (int)std::max<i64>(1, wave / tiles);
+    *out = p;
+    return true;
+}
+
+void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                 const FilterSpec& fs, float2* d_y, RenderState* d_state, const OlsbPlan& pl, const OlsRange& rg,
+                 i64 adv, i64 circ) {
+    Ctx& c = ctx();
+    ARS_CHECK(fs.mode == FILT_SPLIT || fs.mode == FILT_EXT, "olsb_filter: needs an IR");
+    ++g_olsb_count;
+    ARS_CHECK(!fs.eq_on && !fs.air_on, "olsb_filter: an exact-N spectral mask is active");
+    const i64 N = fs.N, F = pl.F, hop = pl.hop, skip = pl.skip;
+    const bool ext = fs.mode == FILT_EXT;
+    if (!d_ir0) L0 = 0;
+    if (!d_ir1) L1 = 0;
+    ARS_CHECK(std::max(L0, ext ? (i64)0 : L1) >= 1 && hop >= 1 && pl.J >= 1, "olsb_filter: bad plan");
+    const i64 taps = skip + 1;
+    FftPlan* fp = get_fft_plan(pl.logF);
+    const i64 j_lo = rg.block_lo;
+    const i64 j_hi = (rg.block_hi < 0 || rg.block_hi > pl.J) ? pl.J : rg.block_hi;
+    ARS_CHECK(j_lo >= 0 && j_lo < j_hi, "olsb_filter: empty block range");
+    const i64 x_frames = rg.x_frames < 0 ? n - rg.x_frame0 : rg.x_frames;
+    if (circ > 0) ARS_CHECK(rg.x_frame0 == 0 && x_frames == n, "olsb_filter: the circular form takes the whole signal");
+    else {
+        const i64 need_lo = std::max<i64>(0, j_lo * hop - skip), need_hi = std::min<i64>(n, j_hi * hop);
+        ARS_CHECK(rg.x_frame0 <= need_lo && rg.x_frame0 + x_frames >= need_hi,
+                  "olsb_filter: the input slice does not cover the block range plus its halo");
+    }
+
+    // ---- IR spectrum (spectra), pre-scaled by 1/F, in the engine's permuted order ----
+    // The dry path of the mix rides in the taps: y = dg x + dw (x * h) = x * (dg delta + dw h), so the last pass stores
+    // the inverse transform as it is and never touches the input again (the exact-N route forms the same sum per bin).
+    const bool dryfold = g_olsb_dryfold != 0;
+    const int nspec = ext ? 2 : 1;
+    float2* H = c.buf("olsb.H", sizeof(float2) * (size_t)F * nspec).as<float2>();
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld;
+        ld.mode = LD_TAPS;
+        const double wet = dryfold ? fs.dw : 1.0;
+        if (ext) {          // A = (hL + hR) / 2 ; Bc = (hL - hR) / 2 from the interleaved stereo IR
+            ld.f0 = d_ir0; ld.f1 = d_ir0 + 1; ld.cin = 2; ld.nvalid = ld.nvalid1 = std::min(L0, taps);
+            ld.c0 = (float)(0.5 * wet); ld.c1 = (float)(k == 0 ? 0.5 * wet : -0.5 * wet);
+        } else {            // h = level0 * early + level1 * late
+            ld.f0 = d_ir0; ld.f1 = d_ir1; ld.cin = 1; ld.nvalid = std::min(L0, taps); ld.nvalid1 = std::min(L1, taps);
+            ld.c0 = (float)(fs.level0 * wet); ld.c1 = (float)(fs.level1 * wet);
+        }
+        if (dryfold && k == 0) { ld.delta_at = adv; ld.delta = (float)fs.dry_gain; }
+        St st;
+        st.mode = ST_SCALE;
+        st.a = H + (size_t)k * F;
+        st.scale = 1.0f / (float)F;
+        fft_forward(fp, ld, H + (size_t)k * F, st);
+    }
+
+    side_to_main();    // (folded-air renders: everything up to here ran on the side stream)
+
+    // ---- the transforms, in stripes ----
+    // A stripe = `Js` transforms; first pass, middle pass and last pass of a stripe follow each other so that its work
+    // buffer is still in the L2 when the next pass reads it.  lanes > 1: stripes go round-robin to that many streams (each
+    // with its own work buffer), so one stripe's loads run under another's arithmetic and no pass is a single wave of CTAs
+    // in lockstep.  first_all: the first pass of EVERY stripe is enqueued ahead of the first middle pass -- the work the
+    // IR chain on the side stream hides behind -- at the price of a work buffer for the whole render.
+    const i64 nj = j_hi - j_lo;
+    const int Js = (int)std::min<i64>(pl.stripe, nj);
+    const i64 nstripes = (nj + Js - 1) / Js;
+    const int lanes = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(g_olsb_lanes, Ctx::MAX_LANES), nstripes));
+    const bool first_all = g_olsb_first_all != 0 && nstripes > 1;
+    const i64 wslots = first_all ? nj : (i64)Js * lanes;
+    float2* W = c.buf("olsb.W", sizeof(float2) * (size_t)F * (size_t)wslots).as<float2>();
+    const i64 nvalid = std::min<i64>(x_frames, n - rg.x_frame0);
+    auto first_pass = [&](i64 j0, i64 nb, float2* w) {
+        Ld ld;
+        ld.mode = LD_OLSB_X;
+        ld.logF = pl.logF;
+        ld.f0 = d_x;
+        ld.frame0 = rg.x_frame0;
+        ld.nvalid = nvalid;
+        ld.cin = cin;
+        ld.seg0 = j0;
+        ld.hop = hop;
+        ld.skip = skip;
+        ld.adv = adv;
+        ld.circ = circ;
+        St st;
+        st.mode = ST_PLAIN;
+        st.a = w;
+        fft_batch_first(fp, nb, ld, st);
+    };
+    auto last_pass = [&](i64 j0, i64 nb, float2* w) {
+        Ld ld;
+        ld.mode = LD_PLAIN;
+        ld.a = w;
+        St st;
+        st.mode = ST_OLSB;
+        st.logF = pl.logF;
+        st.seg0 = j0;
+        st.hop = hop;
+        st.skip = skip;
+        st.a = d_y;
+        st.frame0 = rg.y_frame0;
+        st.N = std::min<i64>(N, j_hi * hop);
+        st.dry = d_x;
+        st.dry_frame0 = rg.x_frame0;
+        st.n = nvalid;
+        st.cin = cin;
+        st.dg = dryfold ? 0.f : (float)fs.dry_gain;
+        st.dw = dryfold ? 1.f : (float)fs.dw;
+        st.maxbits = &d_state->max_stereo;
+        fft_batch_last(fp, nb, ld, st);
+    };
+    if (first_all) first_pass(j_lo, nj, W);
+    if (lanes > 1) lane_fork(lanes);
+    else if (first_all) side_join();
+    for (i64 si = 0; si < nstripes; ++si) {
+        const i64 sk = (first_all && g_olsb_reverse) ? nstripes - 1 - si : si;      // newest work buffer first: still in the L2
+        const i64 j0 = j_lo + sk * Js;
+        const i64 nb = std::min<i64>(Js, j_hi - j0);
+        const int lane = (int)(si % lanes);
+        float2* w = W + (size_t)F * (size_t)(first_all ? sk * Js : (i64)lane * Js);
+        if (lanes > 1) lane_use(lane);
+        if (!first_all) first_pass(j0, nb, w);
+        if (si < lanes) {                                   // the first product of a stream needs the IR spectrum
+            if (lanes > 1) lane_wait_side(lane);
+            else side_join();
+        }
+        fft_batch_mid(fp, nb, w, H, ext ? H + (size_t)F : nullptr);
+        last_pass(j0, nb, w);
+    }
+    if (lanes > 1) { lane_join(); side_join(); }
+}
+
 void upols_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                   const FilterSpec& fs, float2* d_y, RenderState* d_state, int logF, const OlsRange& rg) {
     ARS_CHECK(upols_applicable(fs), "upols_filter: an exact-N spectral mask is active");
@@ -461,7 +634,9 @@ void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early
     f2.air_on = 0;
     f2.level0 = 1.0;
     f2.level1 = 0.0;
-    upols_run(d_x, n, cin, taps, Lf, nullptr, 0, f2, d_y, d_state, logF, OlsRange(), adv, fs.N, true);
+    OlsbPlan pl;
+    if (olsb_plan(fs.N, Lf, adv, fs.N, &pl)) olsb_filter(d_x, n, cin, taps, Lf, nullptr, 0, f2, d_y, d_state, pl, OlsRange(), adv, fs.N);
+    else upols_run(d_x, n, cin, taps, Lf, nullptr, 0, f2, d_y, d_state, logF, OlsRange(), adv, fs.N, true);
 }
 
 }  // namespace ars

@@ -47,6 +47,31 @@ bool air_fold_plan(const FilterSpec& fs, i64 early_end, i64 late_lo, i64 late_hi
 void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early, i64 L0, const float* d_late, i64 L1,
                           const FilterSpec& fs, const AirFold& af, float2* d_y, RenderState* d_state, int logF = 13);
 
+// ---- big-block overlap-save: ONE partition, 2^18..2^22-point blocks through the two-pass M-point engine ----
+// When the taps fit a quarter of a two-pass transform the convolution runs as plain overlap-save with hop = F - (taps - 1):
+// strided forward pass over the signal windows, fused middle pass (contiguous forward x IR spectrum x contiguous inverse,
+// fft.cuh: pass_mid_kernel), strided inverse pass with the dry/wet mix and the maxima in its store -- three trips per point
+// at >= 75 % hop efficiency instead of the partitioned form's forward + MAC + inverse at 50 %.  The transforms of a
+// render are processed in stripes whose work buffer stays in the L2.
+struct OlsbPlan {
+    int logF = 0;
+    i64 F = 0, hop = 0, skip = 0;     // skip = taps - 1 aliased outputs per transform
+    i64 J = 0;                        // transforms of the whole render: ceil(N / hop)
+    int stripe = 1;                   // transforms per stripe
+};
+// false: the big-block form does not apply (taps too long for 2^22 points, render shorter than half a block, wrap
+// constraints of the circular form) -- the caller takes the partitioned route.
+bool olsb_plan(i64 N, i64 taps, i64 adv, i64 circ, OlsbPlan* out);
+// transforms [range.block_lo, range.block_hi) of the render (block = one transform = plan.hop output frames); taps_hi:
+// index beyond which every tap is known to be zero (< 0: unknown, the whole IR counts)
+void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
+                 const FilterSpec& fs, float2* d_y, RenderState* d_state, const OlsbPlan& plan,
+                 const OlsRange& range = OlsRange(), i64 adv = 0, i64 circ = 0);
+void olsb_set_options(int on, int logf, int stripe);     // -1 leaves a value unchanged; logf / stripe 0 = automatic
+void olsb_set_tuning(const char* key, int value);   // olsb_lanes | olsb_first_all | olsb_reverse | olsb_dryfold
+bool olsb_enabled();
+unsigned long long olsb_count();      // convolution stages that took the big-block route
+
 void upols_set_r2(int on);             // 1: 8192-point transforms through the folded radix-2 form (default 0: measured slower)
 void upols_set_mac_tiled_min(int p);   // partitions above which dense IRs use the register-tiled MAC kernel
 

@@ -92,6 +92,7 @@ ARS_API const char* ars_last_error(void);
 ARS_API const char* ars_version(void);
 ARS_API uint64_t ars_launch_count(void);          /* kernels this library has launched so far           */
 ARS_API uint64_t ars_air_fold_count(void);        /* convolution stages that took the folded-air route  */
+ARS_API uint64_t ars_olsb_count(void);            /* ... that took the big-block overlap-save route      */
 ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
 /* Options: "upols" (1 = use the partitioned overlap-save convolution whenever a render has no exact-N
  * spectral mask, i.e. air <= 0.01 and both EQ gains ~ 1 [default]; 0 = always the N-point spectral filter),
@@ -107,8 +108,15 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * transform [default]),
  * "ols_r2" (1 = the 8192-point overlap-save transforms run as a radix-2 stage folded into the window load / output
  * store plus two 4096-point transforms; 0 = one four-stage 8192-point tile [default: measured faster]),
- * "lufs_fused" (1 = loudness chain in three passes over the signal instead of seven [default]),
- * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel). */
+ * "lufs_fused" (1 = one-pass loudness meter: both K-weighting stages and the hop energies in one kernel [default];
+ * 0 = one pass per stage and step), "lufs_from_stage" (1 = inside a render the meter recomputes its feed from the
+ * convolution stage's output and runs next to the final pass [default]; 0 = the final pass writes a feed array),
+ * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel),
+ * "olsb" (1 = mask-free and folded-air convolutions whose taps fit a quarter of a two-pass transform run as ONE-partition
+ * overlap-save over 2^18..2^22-point blocks: strided forward pass, fused middle pass [contiguous forward x IR spectrum x
+ * contiguous inverse], strided inverse pass [default]; 0 = always the 4096-frame partitioned form),
+ * "olsb_logf" (0 = block length chosen from the tap count [default] | 18..22), "olsb_stripe" (0 = transforms per
+ * L2-resident stripe chosen from the SM count [default] | n). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);

@@ -58,7 +58,7 @@ constexpr int NT = 256;
 template <int LOGR, int LOGT, bool INV, int LDM = -1, int STM = -1> static void emu_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = StridedLayout<LOGR, LOGT>;
     std::vector<float2> sm(L::SMEM_ELEMS);
-    const i64 tiles = pa.M >> (LOGR + LOGT);
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGT);
     for (i64 tile = 0; tile < tiles; ++tile) {
         Ld l = ld;
         St s = st;
@@ -70,7 +70,7 @@ template <int LOGR, int LOGT, bool INV, int LDM = -1, int STM = -1> static void 
 template <int LOGR, int LOGC, bool INV, int LDM = -1, int STM = -1> static void emu_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = ContigLayout<LOGR, LOGC>;
     std::vector<float2> sm(L::SMEM_ELEMS);
-    const i64 tiles = pa.M >> (LOGR + LOGC);
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
     for (i64 tile = 0; tile < tiles; ++tile) {
         Ld l = ld;
         St s = st;
@@ -79,8 +79,9 @@ template <int LOGR, int LOGC, bool INV, int LDM = -1, int STM = -1> static void 
     }
 }
 
-template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& ps, const Ld& ld, const St& st) {
+template <bool INV> static void emu_pass(int logM, const Tw& tw, const FftPass& ps, const Ld& ld, const St& st, i64 total = 0) {
     PassArgs pa;
+    pa.total = total;
     pa.M = (i64)1 << logM;
     pa.logM = logM;
     pa.logLg = ps.logLg;
@@ -455,7 +456,108 @@ static int check_irs(i64 N, i64 L) {
     return (maxerr / peak < 2e-5) ? 0 : 1;
 }
 
+// Big-block overlap-save wiring (upols.cu: olsb_filter): strided forward pass over the windows, fused middle pass
+// (plain and mirror form), strided inverse pass with the dry/wet store; stripes, stash, circular form.
+static int check_olsb(int logF, i64 n, i64 Lf, bool ext, int cin, i64 adv, i64 circ, int stripe, bool dryfold = true) {
+    EmuPlan p;
+    p.logM = logF;
+    p.passes = fft_decompose(logF);
+    attach_pass_tables(p);
+    make_tables(logF, p.tw);
+    if (p.passes.size() != 2 || !p.passes[0].strided || p.passes[1].logR != 12 || p.passes[1].logT != 1) { printf("olsb: not a two-pass plan\n"); return 1; }
+    const i64 F = (i64)1 << logF, skip = Lf - 1, hop = F - skip;
+    const i64 N = circ > 0 ? circ : n + Lf - 1;
+    const i64 J = (N + hop - 1) / hop;
+    std::mt19937 rng((unsigned)(n * 13 + Lf + cin));
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<float> x((size_t)cin * n), ir(2 * Lf);
+    for (auto& v : x) v = U(rng);
+    for (i64 i = 0; i < Lf; ++i) {
+        const float d = expf(-fabsf((float)(i - adv)) / (0.3f * Lf));
+        ir[2 * i] = U(rng) * d;
+        ir[2 * i + 1] = ext ? U(rng) * d : ir[2 * i];
+    }
+    const int nspec = ext ? 2 : 1;
+    std::vector<float2> H((size_t)F * nspec), W((size_t)F * stripe), y(N, make_float2(0, 0)), stash;
+    if (cin != 2) stash.resize((size_t)hop * stripe);
+    for (int k = 0; k < nspec; ++k) {
+        Ld ld; ld.mode = LD_TAPS; ld.f0 = ir.data(); ld.f1 = ir.data() + 1; ld.cin = 2; ld.nvalid = ld.nvalid1 = Lf;
+        const float wet = dryfold ? 0.5f : 1.f;
+        if (ext) { ld.c0 = 0.5f * wet; ld.c1 = (k == 0 ? 0.5f : -0.5f) * wet; } else { ld.c0 = wet; ld.c1 = 0.f; }
+        if (dryfold && k == 0) { ld.delta_at = adv; ld.delta = 0.25f; }
+        St st; st.mode = ST_SCALE; st.a = H.data() + (size_t)k * F; st.scale = 1.0f / (float)F;
+        emu_forward(p, ld, H.data() + (size_t)k * F, st);
+    }
+    std::vector<int> rho((size_t)1 << p.passes[0].logR);
+    for (size_t k1 = 0; k1 < rho.size(); ++k1) rho[k1] = strided_row_of(p.passes[0].logR, (int)k1);
+    unsigned maxbits[4] = {0, 0, 0, 0};
+    std::vector<float2> smem(ContigLayout<12, 1>::SMEM_ELEMS), regs((size_t)512 * 16);
+    for (i64 j0 = 0; j0 < J; j0 += stripe) {
+        const i64 nb = std::min<i64>(stripe, J - j0);
+        {
+            Ld ld; ld.mode = LD_OLSB_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = cin; ld.seg0 = j0;
+            ld.hop = hop; ld.skip = skip; ld.adv = adv; ld.circ = circ; ld.stash = stash.empty() ? nullptr : stash.data();
+            St st; st.mode = ST_PLAIN; st.a = W.data();
+            emu_pass<false>(logF, p.tw, p.passes[0], ld, st, nb * F);
+        }
+        {
+            MidArgs ma; ma.h0 = H.data(); ma.h1 = ext ? H.data() + F : nullptr; ma.fmask = F - 1; ma.rho = rho.data(); ma.logR1 = p.passes[0].logR;
+            PassArgs pa; pa.total = nb * F; pa.M = F; pa.logM = logF; pa.logLg = 12; pa.prefetch = 0; pa.ptab = nullptr; pa.tw = p.tw;
+            Ld ld; ld.mode = LD_PLAIN; ld.a = W.data();
+            St st; st.mode = ST_PLAIN; st.a = W.data();
+            for (i64 tile = 0; tile < (pa.total >> 13); ++tile) {
+                Ld l = ld; St s = st;
+                if (ext) emulate_mid_tile<12, 1, 512, true>(smem.data(), regs.data(), l, s, pa, ma, tile);
+                else emulate_mid_tile<12, 1, 512, false>(smem.data(), regs.data(), l, s, pa, ma, tile);
+            }
+        }
+        {
+            Ld ld; ld.mode = LD_PLAIN; ld.a = W.data();
+            St st; st.mode = ST_OLSB; st.logF = logF; st.seg0 = j0; st.hop = hop; st.skip = skip; st.a = y.data(); st.frame0 = 0;
+            st.N = N; st.dry = x.data(); st.dry_frame0 = 0; st.n = n; st.cin = cin; st.stash = stash.empty() ? nullptr : stash.data();
+            st.dg = dryfold ? 0.f : 0.25f; st.dw = dryfold ? 1.f : 0.5f; st.maxbits = maxbits;
+            emu_pass<true>(logF, p.tw, p.passes[0], ld, st, nb * F);
+        }
+    }
+    double maxerr = 0, peak = 0;
+    const i64 stepf = std::max<i64>(1, N / 500);
+    for (i64 q = 0; q < N + 60; ++q) {
+        i64 f;
+        if (q < 20) f = q; else if (q < 40) f = N - 1 - (q - 20); else if (q < 60) f = std::min(N - 1, hop - 10 + (q - 40)); else f = q - 60;
+        if (q >= 60 && (q - 60) % stepf) continue;
+        double wl = 0, wr = 0;
+        for (i64 m = 0; m < Lf; ++m) {
+            i64 t = f + adv - m;
+            if (circ > 0) { t %= N; if (t < 0) t += N; }
+            if (t < 0 || t >= n) continue;
+            const double xl = x[(size_t)t * cin], xr = cin > 1 ? x[(size_t)t * cin + 1] : xl;
+            wl += (double)ir[2 * m] * xl;
+            wr += (double)ir[2 * m + 1] * xr;
+        }
+        const double dl = f < n ? x[(size_t)f * cin] : 0, dr = f < n ? (cin > 1 ? x[(size_t)f * cin + 1] : x[(size_t)f * cin]) : 0;
+        const double rl = 0.25 * dl + 0.5 * wl, rr = 0.25 * dr + 0.5 * wr;
+        peak = std::max(peak, std::max(fabs(rl), fabs(rr)));
+        maxerr = std::max(maxerr, std::max(fabs(rl - y[f].x), fabs(rr - y[f].y)));
+    }
+    printf("olsb logF=%d n=%lld Lf=%lld ext=%d cin=%d adv=%lld circ=%lld stripe=%d J=%lld: max err %.3e (peak %.2f) rel %.3e\n", logF,
+           (long long)n, (long long)Lf, (int)ext, cin, (long long)adv, (long long)circ, stripe, (long long)J, maxerr, peak, maxerr / peak);
+    return (maxerr / peak < 2e-5 && maxbits[0] != 0) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "olsb")) {
+        int bad = 0;
+        bad += check_olsb(18, 700000, 20000, false, 2, 0, 0, 2);
+        bad += check_olsb(18, 500000, 30000, true, 2, 0, 0, 3);
+        bad += check_olsb(18, 400000, 9000, false, 6, 0, 0, 1);
+        bad += check_olsb(18, 300000, 12000, true, 1, 0, 0, 2);
+        bad += check_olsb(18, 600000, 25000, false, 2, 8192, 600000 + 400 - 1, 2);     // circular form, taps before time zero
+        bad += check_olsb(19, 900000, 100000, true, 2, 0, 0, 1);
+        bad += check_olsb(18, 300000, 12000, true, 1, 0, 0, 2, false);
+        bad += check_olsb(18, 600000, 25000, false, 6, 8192, 600000 + 400 - 1, 2, false);
+        printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
+        return bad ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "irs")) {
         int bad = check_irs(100003, 30000) + check_irs(65536, 9000) + check_irs(40001, 40000) + check_irs(5000, 300);
         printf(bad ? "FAILED (%d)\n" : "OK\n", bad);

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "ars_timer_end": (C.c_int, [C.POINTER(C.c_float)]),
     "ars_profile_begin": (C.c_int, []),
     "ars_profile_end": (C.c_int, [C.POINTER(_i64), C.POINTER(_d), C.POINTER(_d)]),
+    "ars_profile_report": (C.c_char_p, []),
 }
 
 _lib = None

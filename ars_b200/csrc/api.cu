@@ -13,6 +13,7 @@ namespace ars {
 const char* last_error_cstr();
 void fft_profile_begin();
 void fft_profile_end(long long* launches, double* ms, double* bytes);
+const char* prof_last_report();
 
 #define ARS_API_BEGIN                                                   \
     try {                                                               \
@@ -65,6 +66,34 @@ static bool folds_air(const FilterSpec& fs, const IrExtent& ext, double rate, Ai
                          g_opt_air_fold_max_taps, af ? af : &tmp);
 }
 
+// taps of a mask-free convolution: those beyond the host-known extent are zero (procedural IRs) and cost neither
+// partitions nor block length
+static i64 mask_free_taps(const FilterSpec& fs, i64 L0, i64 L1, const IrExtent& ext) {
+    i64 taps = fs.mode == FILT_EXT ? L0 : std::max(L0, L1);
+    if (fs.mode == FILT_SPLIT && ext.late_hi >= 0) taps = std::min(taps, std::max<i64>(1, std::max(ext.early_end, ext.late_hi)));
+    return std::max<i64>(1, taps);
+}
+
+// The big-block route's first pass needs only the signal: enqueue it ahead of everything that makes the impulse
+// response.  -> true when it went out (the IR chain then runs on the side stream, next to it).
+static bool early_first_pass(const float* d_x, i64 n, int cin, i64 L0, i64 L1, const FilterSpec& fs, double rate,
+                             const IrExtent& ext) {
+    if (!g_opt_upols || !olsb_enabled() || fs.mode == FILT_MASK || fs.eq_on) return false;
+    AirFold af;
+    OlsbPlan pl;
+    if (fs.air_on) {
+        if (!(L1 > 0 && folds_air(fs, ext, rate, &af))) return false;
+        i64 adv = 0, taps = 0;
+        air_fold_geometry(af, L0, L1, g_opt_upols_logf, &adv, &taps);
+        if (!olsb_plan(fs.N, taps, adv, fs.N, &pl)) return false;
+        olsb_first_pass_early(d_x, n, cin, pl, adv, fs.N);
+        return true;
+    }
+    if (!olsb_plan(fs.N, mask_free_taps(fs, L0, L1, ext), 0, 0, &pl)) return false;
+    olsb_first_pass_early(d_x, n, cin, pl, 0, 0);
+    return true;
+}
+
 static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                               const FilterSpec& fs, float2* d_y, RenderState* st, double rate = 0.0,
                               const IrExtent& ext = IrExtent()) {
@@ -73,9 +102,7 @@ static void convolution_stage(const float* d_x, i64 n, int cin, const float* d_i
         ++g_air_fold_count;
         upols_filter_airfold(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, af, d_y, st, g_opt_upols_logf);
     } else if (g_opt_upols && upols_applicable(fs) && fs.mode != FILT_MASK) {
-        // taps beyond the host-known extent are zero (procedural IRs): they neither cost partitions nor block length
-        i64 taps = fs.mode == FILT_EXT ? L0 : std::max(d_ir0 ? L0 : 0, d_ir1 ? L1 : 0);
-        if (fs.mode == FILT_SPLIT && ext.late_hi >= 0) taps = std::min(taps, std::max<i64>(1, std::max(ext.early_end, ext.late_hi)));
+        const i64 taps = mask_free_taps(fs, d_ir0 ? L0 : 0, d_ir1 ? L1 : 0, ext);
         OlsbPlan pl;
         if (olsb_plan(fs.N, taps, 0, 0, &pl)) olsb_filter(d_x, n, cin, d_ir0, L0, d_ir1, L1, fs, d_y, st, pl);
         else
@@ -247,6 +274,7 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
     if (p->external_ir) {
         ARS_CHECK(d_ext_ir && ext_len >= 1, "render: external IR missing");
         fs.mode = FILT_EXT;
+        early_first_pass(d_in, n, cin, ext_len, 0, fs, p->rate, IrExtent());
         convolution_stage(d_in, n, cin, d_ext_ir, ext_len, nullptr, 0, fs, y, st);
     } else {
         ARS_CHECK(p->ir_duration > 0, "render: IR duration must be positive");
@@ -275,10 +303,9 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         }
         // the folded-air route: IR synthesis, the fold and the IR partition spectra are a chain of small latency-bound
         // kernels that does not depend on the signal -- it runs on the side stream, next to the delay-line transform
-        if (g_opt_side_stream && folds_air(fs, ex, p->rate, nullptr)) {
-            fft_touch_tables();    // (built once, on the main stream, before both streams read them)
-            side_begin();
-        }
+        fft_touch_tables();        // (built once, on the main stream, before both streams read them)
+        const bool early = early_first_pass(d_in, n, cin, g.length, g.length, fs, p->rate, ex);
+        if (g_opt_side_stream && (early || folds_air(fs, ex, p->rate, nullptr))) side_begin();
         std::vector<double> strength = tap_strengths(draws, p->absorption, p->directionality, g.tap_hi);
         std::vector<i64> tap_pos;
         std::vector<double> tap_val;
@@ -421,10 +448,11 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "olsb")) olsb_set_options(value ? 1 : 0, -1, -1);
     else if (!strcmp(key, "olsb_logf")) { ARS_CHECK(value == 0 || (value >= 18 && value <= 22), "olsb_logf must be 0 (automatic) or 18..22"); olsb_set_options(-1, value, -1); }
     else if (!strcmp(key, "olsb_lanes") || !strcmp(key, "olsb_first_all") || !strcmp(key, "olsb_reverse") ||
-             !strcmp(key, "olsb_dryfold")) olsb_set_tuning(key, value);
+             !strcmp(key, "olsb_dryfold") || !strcmp(key, "olsb_early")) olsb_set_tuning(key, value);
     else if (!strcmp(key, "olsb_stripe")) { ARS_CHECK(value >= 0, "olsb_stripe must be >= 0"); olsb_set_options(-1, -1, value); }
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
+    else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END
@@ -533,6 +561,8 @@ int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n
     sync();
     ARS_API_END
 }
+
+const char* ars_profile_report(void) { return prof_last_report(); }
 
 int64_t ars_convolve_out_len(int64_t n, int64_t len_early, int64_t len_late) {
     // rs.py:351-355 (a missing IR stands for zeros(1))

@@ -117,6 +117,23 @@ void lane_use(int i);
 void lane_wait_side(int i);
 void lane_join();
 
+// ---- per-kernel event timing (ars_profile_begin / ars_profile_end / ars_profile_report) ----
+// Between begin and end every launch site that opens a KernelScope brackets its kernel with two CUDA events on the
+// stream it launches on; the report groups the launches by name.  `bytes` = the launch's algorithmic (compulsory) bytes.
+// bench.py runs one untimed render this way, with the side stream and the lanes off, so that the kernels run one
+// after another as they do under ncu.
+struct KernelScope {
+    bool on;
+    size_t index = 0;
+    KernelScope(const char* name, double bytes);
+    ~KernelScope();
+};
+void prof_session_begin();
+// launches / ms / bytes: totals over the records whose name starts with `prefix` (null: all); json (optional): one
+// object per kernel name {"name", "launches", "ms", "bytes"}
+void prof_session_end(const char* prefix, long long* launches, double* ms, double* bytes, std::string* json);
+bool prof_session_on();
+
 inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
 
 // ------------------------------------------------------------ device math ---

@@ -152,6 +152,78 @@ void lane_join() {
     c.lanes_open = 0;
 }
 
+// ---------------------------------------------------------------- profiling ---
+struct ProfRec { const char* name; double bytes; cudaEvent_t e0, e1; };
+static struct {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::string last_json;
+} g_kprof;
+
+static cudaEvent_t kprof_event() {
+    if (g_kprof.used == g_kprof.pool.size()) {
+        cudaEvent_t e;
+        ARS_CUDA(cudaEventCreate(&e));
+        g_kprof.pool.push_back(e);
+    }
+    return g_kprof.pool[g_kprof.used++];
+}
+bool prof_session_on() { return g_kprof.on; }
+void prof_session_begin() {
+    g_kprof.on = true;
+    g_kprof.recs.clear();
+    g_kprof.used = 0;
+}
+KernelScope::KernelScope(const char* name, double bytes) : on(g_kprof.on) {
+    if (!on) return;
+    ProfRec r;
+    r.name = name;
+    r.bytes = bytes;
+    r.e0 = kprof_event();
+    r.e1 = kprof_event();
+    ARS_CUDA(cudaEventRecord(r.e0, ctx().stream));
+    index = g_kprof.recs.size();
+    g_kprof.recs.push_back(r);
+}
+KernelScope::~KernelScope() {
+    if (on && index < g_kprof.recs.size()) cudaEventRecord(g_kprof.recs[index].e1, ctx().stream);
+}
+void prof_session_end(const char* prefix, long long* launches, double* ms, double* bytes, std::string* json) {
+    ARS_CUDA(cudaDeviceSynchronize());
+    g_kprof.on = false;
+    struct Agg { long long n = 0; double ms = 0, bytes = 0; };
+    std::vector<std::pair<std::string, Agg>> order;
+    long long tl = 0;
+    double tm = 0, tb = 0;
+    for (const ProfRec& r : g_kprof.recs) {
+        float t = 0.f;
+        ARS_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        size_t k = 0;
+        for (; k < order.size(); ++k) if (order[k].first == r.name) break;
+        if (k == order.size()) order.push_back({r.name, Agg()});
+        order[k].second.n += 1;
+        order[k].second.ms += t;
+        order[k].second.bytes += r.bytes;
+        if (!prefix || !strncmp(r.name, prefix, strlen(prefix))) { tl += 1; tm += t; tb += r.bytes; }
+    }
+    if (launches) *launches = tl;
+    if (ms) *ms = tm;
+    if (bytes) *bytes = tb;
+    std::string js = "[";
+    for (size_t k = 0; k < order.size(); ++k) {
+        char b[512];
+        snprintf(b, sizeof b, "%s{\"name\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"bytes\": %.0f}", k ? ", " : "",
+                 order[k].first.c_str(), order[k].second.n, order[k].second.ms, order[k].second.bytes);
+        js += b;
+    }
+    js += "]";
+    g_kprof.last_json = js;
+    if (json) *json = js;
+}
+const char* prof_last_report() { return g_kprof.last_json.c_str(); }
+
 void fft_release_plans();       // fft_plan.cu
 void bluestein_release_plans(); // bluestein.cu
 

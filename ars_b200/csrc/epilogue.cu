@@ -208,6 +208,7 @@ static TailSpec with_window(const TailSpec& in) {
 void tail_pan_max(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) {
     const TailSpec ts = with_window(ts_in);
     if (ts.i_hi <= ts.i_lo) return;
+    KernelScope prof("pan_max_kernel", 0.0);
     pan_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, ctx().stream>>>(d_y, ts, d_state);
     ARS_LAUNCH_CHECK();
     count_launch();
@@ -216,6 +217,7 @@ void tail_pan_max(const float2* d_y, const TailSpec& ts_in, RenderState* d_state
 void tail_map_max(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) {
     const TailSpec ts = with_window(ts_in);
     if (ts.i_hi <= ts.i_lo || ts.layout != LAYOUT_STEREO) return;
+    KernelScope prof("map_max_kernel", 8.0 * (double)(ts.i_hi - ts.i_lo));
     map_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, ctx().stream>>>(d_y, ts, d_state);
     ARS_LAUNCH_CHECK();
     count_launch();
@@ -225,10 +227,14 @@ void tail_maxes(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) 
     const TailSpec ts = with_window(ts_in);
     if (ts.N <= 0) return;
     Ctx& c = ctx();
-    pan_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, c.stream>>>(d_y, ts, d_state);
+    {
+        KernelScope prof("pan_max_kernel", 0.0);
+        pan_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, c.stream>>>(d_y, ts, d_state);
+    }
     ARS_LAUNCH_CHECK();
     count_launch();
     if (ts.layout == LAYOUT_STEREO) {
+        KernelScope prof("map_max_kernel", 8.0 * (double)(ts.i_hi - ts.i_lo));
         map_max_kernel<<<stream_grid(ts.i_hi - ts.i_lo), 256, 0, c.stream>>>(d_y, ts, d_state);
         ARS_LAUNCH_CHECK();
         count_launch();
@@ -241,6 +247,8 @@ void tail_final(const float2* d_y, const TailSpec& ts_in, RenderState* d_state, 
     if (ts.N <= 0 || ts.i_hi <= ts.i_lo) return;
     Ctx& c = ctx();
     const int grid = stream_grid(ts.i_hi - ts.i_lo);
+    KernelScope prof("final_kernel (guards, pan, map, clip, PCM16, sums)",
+                     (double)(ts.i_hi - ts.i_lo) * (8.0 + (d_pcm ? 2.0 * ts.C : 0.0) + (d_out ? 4.0 * ts.C : 0.0) + (d_mono ? 4.0 : 0.0)));
     if (ts.C == 2) final_kernel<2><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
     else if (ts.C == 6) final_kernel<6><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
     else final_kernel<8><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);

@@ -552,41 +552,49 @@ struct St {
         }
     }
     // ST_OLSB for the r outputs of one last-stage butterfly (`step` apart inside one transform)
-    template <int r> ARS_HD void put_olsb(i64 idx0, i64 step, const float2 (&v)[r]) {
+    template <int r> ARS_HD void put_olsb(i64 idx0, i64 step64, const float2 (&v)[r]) {
+        // (offsets inside a transform fit 32 bits: F <= 2^22; one unsigned compare tells 0 <= o < hop)
         const i64 j = idx0 >> logF;
-        const i64 t0 = idx0 & (((i64)1 << logF) - 1);
-        const i64 o0 = t0 - skip;                                   // output index inside the transform's hop
+        const int t0 = (int)(idx0 & (((i64)1 << logF) - 1));
+        const int step = (int)step64, hp = (int)hop;
+        const int o0 = t0 - (int)skip;                              // output index inside the transform's hop
         const i64 blk = (seg0 + j) * hop;                           // first output frame of the transform
-        const i64 olast = o0 + (r - 1) * step;
+        const int olast = o0 + (r - 1) * step;
         const bool mix = dg != 0.f;                                 // (dg == 0: the dry path is part of the taps, Ld::delta)
         const bool dry_ok = (stash || !mix) ? true : ((cin & 1) == 0 && blk + (o0 < 0 ? 0 : o0) >= dry_frame0 &&
                                                       blk + olast - dry_frame0 < n);
-        if (dry_ok && blk + (olast < hop ? olast : hop - 1) < N) {
-            const float2* dp = stash ? stash + (j * hop + o0)
-                                     : reinterpret_cast<const float2*>(dry + (blk + o0 - dry_frame0) * cin);
-            const i64 ds = stash ? step : step * (cin >> 1);
+        if (dry_ok && blk + (olast < hp ? olast : hp - 1) < N) {
             float2* ap = a + (blk + o0 - frame0);
-            #pragma unroll
-            for (int k = 0; k < r; ++k) {
-                const i64 o = o0 + k * step;
-                if (o >= 0 && o < hop) {
-                    float2 y;
-                    if (mix) {
-                        const float2 d = ARS_LDG(dp + k * ds);
-                        y = make_float2(dg * d.x + dw * v[k].x, dg * d.y + dw * v[k].y);
-                    } else {
-                        y = make_float2(dw * v[k].x, dw * v[k].y);
+            if (!mix) {
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    if ((unsigned)(o0 + k * step) < (unsigned)hp) {
+                        const float2 y = make_float2(dw * v[k].x, dw * v[k].y);
+                        ap[k * step] = y;
+                        local_l = max(local_l, abs_bits(y.x));
+                        local_r = max(local_r, abs_bits(y.y));
+                        local_lr = max(local_lr, abs_bits(fadd_rn(y.x, y.y)));
                     }
-                    ap[k * step] = y;
-                    const unsigned m0 = abs_bits(y.x), m1 = abs_bits(y.y), m2 = abs_bits(fadd_rn(y.x, y.y));
-                    if (m0 > local_l) local_l = m0;
-                    if (m1 > local_r) local_r = m1;
-                    if (m2 > local_lr) local_lr = m2;
+                }
+            } else {
+                const float2* dp = stash ? stash + (j * hop + o0)
+                                         : reinterpret_cast<const float2*>(dry + (blk + o0 - dry_frame0) * cin);
+                const i64 ds = stash ? step : (i64)step * (cin >> 1);
+                #pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    if ((unsigned)(o0 + k * step) < (unsigned)hp) {
+                        const float2 d = ARS_LDG(dp + k * ds);
+                        const float2 y = make_float2(dg * d.x + dw * v[k].x, dg * d.y + dw * v[k].y);
+                        ap[k * step] = y;
+                        local_l = max(local_l, abs_bits(y.x));
+                        local_r = max(local_r, abs_bits(y.y));
+                        local_lr = max(local_lr, abs_bits(fadd_rn(y.x, y.y)));
+                    }
                 }
             }
         } else {
             #pragma unroll
-            for (int k = 0; k < r; ++k) put<ST_OLSB>(idx0 + k * step, v[k], make_float2(1.f, 0.f));
+            for (int k = 0; k < r; ++k) put<ST_OLSB>(idx0 + k * step64, v[k], make_float2(1.f, 0.f));
         }
     }
     // ST_OLS2: the radix-2 stage that ends the 2B-point inverse, second half only: y[i + B] = ya[i] - conj(w^i) yb[i]

@@ -124,15 +124,8 @@ FftPlan* get_fft_plan(int logM) {
 }
 
 // ---------------------------------------------------------------- profiling ---
-// Optional per-launch CUDA-event timing of the FFT pass kernels (the dominant kernels of a render);
-// bench.py turns it on for a separate, untimed run to get the roofline numerator and denominator.
-struct PassProf {
-    bool on = false;
-    std::vector<cudaEvent_t> ev;     // pairs (start, stop)
-    size_t used = 0;
-    double bytes = 0.0;              // algorithmic bytes of the recorded launches
-} g_prof;
-
+// Per-launch CUDA-event timing of the pass kernels goes through the library-wide KernelScope (common.cu); the names
+// start with "fft:" so that ars_profile_end can report the pass kernels' totals as before.
 static double ld_bytes(const Ld& ld, i64 M) {
     switch (ld.mode) {
         case LD_PLAIN: return 8.0 * (double)M;
@@ -164,32 +157,20 @@ static double st_bytes(const St& st, i64 M) {
     return 0.0;
 }
 
-void fft_profile_begin() {
-    g_prof.on = true;
-    g_prof.used = 0;
-    g_prof.bytes = 0.0;
-}
-// -> launches, total milliseconds, algorithmic bytes
+void fft_profile_begin() { prof_session_begin(); }
+// -> launches, total milliseconds, algorithmic bytes of the pass kernels
 void fft_profile_end(long long* launches, double* ms, double* bytes) {
-    ARS_CUDA(cudaStreamSynchronize(ctx().stream));
-    double tot = 0.0;
-    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
-        float t = 0.f;
-        ARS_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
-        tot += t;
-    }
-    *launches = (long long)(g_prof.used / 2);
-    *ms = tot;
-    *bytes = g_prof.bytes;
-    g_prof.on = false;
+    prof_session_end("fft:", launches, ms, bytes, nullptr);
 }
-static cudaEvent_t prof_event() {
-    if (g_prof.used == g_prof.ev.size()) {
-        cudaEvent_t e;
-        ARS_CUDA(cudaEventCreate(&e));
-        g_prof.ev.push_back(e);
-    }
-    return g_prof.ev[g_prof.used++];
+static const char* pass_name(const Ld& ld, const St& st, bool inv, bool strided) {
+    if (ld.mode == LD_OLSB_X) return "fft:olsb first pass (strided forward, signal windows in)";
+    if (st.mode == ST_OLSB) return "fft:olsb last pass (strided inverse, stereo frames + maxima out)";
+    if (ld.mode == LD_OLS_X || ld.mode == LD_OLS_X2) return "fft:ols delay-line transform";
+    if (st.mode == ST_OLS || st.mode == ST_OLS2) return "fft:ols inverse transform";
+    if (ld.mode == LD_TAPS || ld.mode == LD_OLS_IR || ld.mode == LD_OLS_IR2 || ld.mode == LD_OLS_IRC) return "ir spectrum pass";
+    if (st.mode == ST_SCALE) return "ir spectrum pass";
+    if (strided) return inv ? "fft:strided inverse pass" : "fft:strided forward pass";
+    return inv ? "fft:contiguous inverse pass" : "fft:contiguous forward pass";
 }
 
 // --------------------------------------------------------------- launchers ---
@@ -207,13 +188,8 @@ static void launch_pass(const FftPlan* p, const FftPass& ps, const Ld& ld, const
     static const int pf_x = env_int("ARS_OLS_PREFETCH", 0);        // delay-line transform: tiles ahead (measured: 148 -> -2 %, 296 / 592 -> +1..4 %; off)
     pa.prefetch = ld.mode == LD_OLS_X ? pf_x : pf;
     pa.ptab = ps.ptab;
-    struct ProfScope {
-        bool on;
-        ProfScope(const Ld& l, const St& s, i64 M) : on(g_prof.on) {
-            if (on) { g_prof.bytes += ld_bytes(l, M) + st_bytes(s, M); ARS_CUDA(cudaEventRecord(prof_event(), ctx().stream)); }
-        }
-        ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
-    } prof_scope(ld, st, total > 0 ? total : p->M);
+    const i64 pts = total > 0 ? total : p->M;
+    KernelScope prof_scope(pass_name(ld, st, INV, ps.strided), prof_session_on() ? ld_bytes(ld, pts) + st_bytes(st, pts) : 0.0);
     if (ps.strided) ARS_CHECK(ps.logLg - ps.logR >= ps.logT, "strided pass narrower than its tile");
     bool done = false;
     if (g_fast) {
@@ -246,13 +222,8 @@ void fft_segments(int logF, i64 nseg, const Ld& ld, const St& st, bool inverse) 
     tmp.tw.stage = local_table();
     tmp.tw.lo = tmp.tw.hi = nullptr;
     const FftPass ps = {false, logF, logF == 12 ? 1 : 0, logF};
-    // the per-launch profile (ars_profile_*) covers the passes that move the signal: the M-point passes and the
-    // overlap-save block transforms over the whole delay line; the handful of IR-partition transforms are left out
-    const bool prof = g_prof.on;
-    if (nseg < 64) g_prof.on = false;
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);
     else launch_pass<false>(&tmp, ps, ld, st);
-    g_prof.on = prof;
 }
 
 void fft_touch_tables() { local_table(); }
@@ -267,11 +238,8 @@ void fft_segments_r2(i64 nseg, Ld ld, St st, bool inverse) {
     ld.logF = st.logF = 13;
     ld.tw2 = st.tw2 = local_table() + stage_off(13);      // w_8192^i, i < 4096
     const FftPass ps = {false, 12, 1, 12};
-    const bool prof = g_prof.on;
-    if (nseg < 64) g_prof.on = false;
     if (inverse) launch_pass<true>(&tmp, ps, ld, st);
     else launch_pass<false>(&tmp, ps, ld, st);
-    g_prof.on = prof;
 }
 
 // ---- batched two-pass transforms of the big-block overlap-save route (upols.cu) ----
@@ -321,13 +289,8 @@ void fft_batch_mid(FftPlan* p, i64 nbatch, float2* work, const float2* h0, const
     St st;
     st.mode = ST_PLAIN;
     st.a = work;
-    struct ProfScope {
-        bool on;
-        ProfScope(i64 pts, bool two) : on(g_prof.on) {
-            if (on) { g_prof.bytes += (two ? 32.0 : 24.0) * (double)pts; ARS_CUDA(cudaEventRecord(prof_event(), ctx().stream)); }
-        }
-        ~ProfScope() { if (on) cudaEventRecord(prof_event(), ctx().stream); }
-    } prof_scope(pa.total, h1 != nullptr);
+    KernelScope prof_scope("fft:olsb middle pass (contiguous forward x IR spectrum x contiguous inverse)",
+                           (h1 ? 16.0 : 16.0) * (double)pa.total);
     mid_pass(h1 != nullptr, ld, st, pa, ma);
 }
 

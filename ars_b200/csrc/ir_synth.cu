@@ -143,6 +143,7 @@ void ir_synth(const IrSpec& sp, const i64* d_delay, const double* d_strength, co
               float* d_late) {
     Ctx& c = ctx();
     ARS_CHECK(sp.length >= 1 && sp.split >= 0 && sp.split <= sp.length, "ir_synth: bad geometry");
+    KernelScope prof("ir synthesis chain (taps, smoothed tail, envelope, normalisation)", 16.0 * (double)sp.length);
     ARS_CUDA(cudaMemsetAsync(d_early, 0, sizeof(float) * (size_t)sp.length, c.stream));
     ARS_CUDA(cudaMemsetAsync(d_late, 0, sizeof(float) * (size_t)sp.length, c.stream));
     if (sp.ntaps > 0) {       // d_delay / d_strength hold the merged, normalised taps (ir_early_taps)

@@ -196,26 +196,29 @@ __device__ __forceinline__ i64 hop_of(i64 i, double rate) {         // largest h
 // chain through the blocks.  Same arithmetic per sample as the stage-wise chain; the filtered signals never leave the SM.
 struct SrcMono {                       // a materialised feed (ars_metrics, block-sharded renders)
     const float* x;
-    __device__ __forceinline__ void prepare() {}
-    __device__ __forceinline__ float at(i64 i) const { return __ldg(x + i); }
+    __device__ __forceinline__ bool prepare() { return true; }
+    __device__ __forceinline__ float2 load(i64 i) const { return make_float2(__ldg(x + i), 0.f); }
+    template <bool G> __device__ __forceinline__ float value(float2 raw) const { return raw.x; }
 };
 struct SrcStage {                      // mean(ch0, ch1) of the final frame (rs.py:687-688), recomputed from the convolution stage's
     const float2* y;                   // output exactly as final_kernel forms it -- the meter then needs no feed array and can
     TailSpec ts;                       // run next to the final pass instead of behind it
     const RenderState* st;
     Guard g1, g2, g3;
-    __device__ __forceinline__ void prepare() {
+    __device__ __forceinline__ bool prepare() {             // -> every peak guard idle (the per-sample form without them)
         g1 = make_guard(st->max_stereo);
         g2 = make_guard(st->max_pan);
         g3 = make_guard(ts.layout == LAYOUT_STEREO ? st->max_map : 0u);
+        return g1.mode == 0 && g2.mode == 0 && g3.mode == 0;
     }
-    __device__ __forceinline__ float at(i64 i) const {
+    __device__ __forceinline__ float2 load(i64 i) const { return __ldg(y + (i - ts.y0)); }
+    template <bool G> __device__ __forceinline__ float value(float2 raw) const {
         FrameIn f;
-        f.v = __ldg(y + (i - ts.y0));
+        f.v = raw;
         f.w = make_float2(0.f, 0.f);
         float o[8];
-        frame_math<true, true>(f, -1, ts, g1, g2, o);          // (frame index -1: the delayed pair is not needed)
-        return __fmul_rn(__fadd_rn(guard1(o[0], g3), guard1(o[1], g3)), 0.5f);
+        frame_math<G, G>(f, -1, ts, g1, g2, o);             // (frame index -1: the delayed pair is not needed)
+        return __fmul_rn(__fadd_rn(guardT<G>(o[0], g3), guardT<G>(o[1], g3)), 0.5f);
     }
 };
 
@@ -280,8 +283,35 @@ __device__ __forceinline__ double2 chunk_start_state(const float* mine, const Sc
     return w;
 }
 
+// the block's samples into shared memory, eight loads in flight per thread (the feed's arithmetic would otherwise wait
+// for every load in turn)
+template <class SRC, bool G>
+__device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 base, i64 N) {
+    const int t = threadIdx.x;
+    unsigned mm = 0;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < CH; i0 += 8) {
+        float2 raw[8];
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const i64 g = base + (i64)(i0 + u) * NTB + t;
+            raw[u] = g < N ? src.load(g) : make_float2(0.f, 0.f);
+        }
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = (i0 + u) * NTB + t;
+            const float v = src.template value<G>(raw[u]);
+            sx[(i / CH) * (CH + 1) + (i % CH)] = v;
+            mm = max(mm, abs_bits(v));
+        }
+    }
+    return mm;
+}
+
+// Persistent CTAs: each takes the next block in ticket order until none is left (the coefficient tables in the
+// kernel's parameter space are then fetched once per CTA, not once per block).
 template <class SRC>
-__global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a) {
+__global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int nblocks) {
     __shared__ float sx[NTB * (CH + 1)];
     __shared__ double2 sv[NTB];
     __shared__ double2 s_start;
@@ -289,56 +319,56 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a) {
     __shared__ unsigned s_b;
     __shared__ double se[4][NTB / 32];
     const int t = threadIdx.x;
-    if (t == 0) s_b = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const int b = (int)s_b;
-    const i64 base = (i64)b * BS;
-    if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
-    src.prepare();
+    const bool idle = src.prepare();
     unsigned mm = 0;
-    for (int i = t; i < BS; i += NTB) {
-        const i64 g = base + i;
-        const float v = g < a.N ? src.at(g) : 0.f;
-        sx[(i / CH) * (CH + 1) + (i % CH)] = v;
-        mm = max(mm, abs_bits(v));
+    for (;;) {
+        if (t == 0) s_b = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int b = (int)s_b;
+        if (b >= nblocks) break;
+        const i64 base = (i64)b * BS;
+        if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
+        const unsigned m1 = idle ? loud_feed<SRC, false>(src, sx, base, a.N) : loud_feed<SRC, true>(src, sx, base, a.N);
+        mm = max(mm, m1);
+        __syncthreads();
+        float* mine = sx + t * (CH + 1);
+        // stage 1 (high shelf): float32 store, as pyloudnorm
+        double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sv, &s_start);
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(a.c1.q, (double)mine[j], s);
+        // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
+        s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sv, &s_start);
+        // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
+        const i64 g0 = base + (i64)t * CH;
+        const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
+        const i64 next = s_lo[k0 < 3 ? k0 : 2];
+        double e0 = 0.0, e1 = 0.0;
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) {
+            const float o = (float)df2t(a.c2.q, (double)mine[j], s);
+            const double sq = (double)__fmul_rn(o, o);
+            const i64 g = g0 + j;
+            if (g < a.N) { if (g < next) e0 += sq; else e1 += sq; }
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((t & 31) == 0) se[k][t >> 5] = c;
+        }
+        __syncthreads();
+        if (t < 4) {
+            double tot = 0.0;
+            for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
+            a.part[(i64)b * 4 + t] = tot;
+        }
+        __syncthreads();                                   // the block's shared arrays (and s_b) are rewritten next
     }
     if (a.mono_max) {
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, o));
         if ((t & 31) == 0 && mm > *reinterpret_cast<volatile unsigned*>(a.mono_max)) atomicMax(a.mono_max, mm);
-    }
-    __syncthreads();
-    float* mine = sx + t * (CH + 1);
-    // stage 1 (high shelf): float32 store, as pyloudnorm
-    double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sv, &s_start);
-    #pragma unroll 8
-    for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(a.c1.q, (double)mine[j], s);
-    // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
-    s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sv, &s_start);
-    // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
-    const i64 g0 = base + (i64)t * CH;
-    const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
-    const i64 next = s_lo[k0 < 3 ? k0 : 2];
-    double e0 = 0.0, e1 = 0.0;
-    #pragma unroll 8
-    for (int j = 0; j < CH; ++j) {
-        const float o = (float)df2t(a.c2.q, (double)mine[j], s);
-        const double sq = (double)__fmul_rn(o, o);
-        const i64 g = g0 + j;
-        if (g < a.N) { if (g < next) e0 += sq; else e1 += sq; }
-    }
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if ((t & 31) == 0) se[k][t >> 5] = c;
-    }
-    __syncthreads();
-    if (t < 4) {
-        double tot = 0.0;
-        for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
-        a.part[(i64)b * 4 + t] = tot;
     }
 }
 
@@ -364,7 +394,9 @@ __global__ void __launch_bounds__(256) hop_combine_kernel(const double* __restri
 }
 
 static int g_lufs_fused = 1;
+static int g_lufs_ctas_per_sm = 3;
 void loudness_set_fused(int on) { g_lufs_fused = on ? 1 : 0; }
+void loudness_set_ctas_per_sm(int n) { g_lufs_ctas_per_sm = n < 1 ? 1 : (n > 8 ? 8 : n); }
 
 static void k_weighting(double rate, Biquad out[2]) {
     // pyloudnorm IIRfilter coefficients: high shelf +4 dB @1500 Hz Q=1/sqrt2, high pass 38 Hz Q=0.5
@@ -494,7 +526,14 @@ static int loudness_run(SRC src, i64 N, double rate, unsigned* d_mono_max_out, c
         a.ticket = reinterpret_cast<unsigned*>(a.flag2 + nblocks);
         a.mono_max = d_mono_max_out;
         ARS_CUDA(cudaMemsetAsync(ws + off_flags, 0, bytes_flags, c.stream));
-        loudness_kernel<SRC><<<nblocks, NTB, 0, c.stream>>>(src, a);
+        {
+            KernelScope prof("loudness_kernel (K-weighting stages + hop energies, one pass)", (double)N * (d_mono_max_out ? 8.0 : 4.0));
+            // next to the final pass the meter takes a few CTAs per SM only, so that both kernels are resident together
+            const int per_sm = d_mono_max_out ? g_lufs_ctas_per_sm : 6;
+            const int grid = std::max(1, std::min(nblocks, c.sm_count * per_sm));
+            loudness_kernel<SRC><<<grid, NTB, 0, c.stream>>>(src, a, nblocks);
+        }
+        KernelScope prof("loudness gating (hop_combine + gate)", 0.0);
         hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(a.part, N, rate, nb, dz);
         ARS_LAUNCH_CHECK();
         count_launch(2);
@@ -508,6 +547,7 @@ static int loudness_run(SRC src, i64 N, double rate, unsigned* d_mono_max_out, c
         ARS_LAUNCH_CHECK();
         count_launch();
     }
+    KernelScope prof("loudness gating (hop_combine + gate)", 0.0);
     gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, d_mono_max, d_lufs);
     ARS_LAUNCH_CHECK();
     count_launch();

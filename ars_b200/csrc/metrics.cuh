@@ -17,6 +17,7 @@ int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double
 
 // scipy.signal.spectrogram(x[:, 0], fs, window='hann', nperseg, noverlap=nperseg//2) -> d_out[(nperseg/2+1) x nseg], row-major
 void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out);
+void loudness_set_ctas_per_sm(int n);   // CTAs per SM of the one-pass meter when it runs next to the final pass
 void loudness_set_fused(int on);     // 1 (default): fused chain at rates >= 40 960 Hz; 0: one pass per stage and step
 
 }  // namespace ars

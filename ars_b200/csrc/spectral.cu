@@ -449,7 +449,10 @@ void spectral_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L
         st.a = Z;
         bluestein_dft(bp, ld, work, st);
     }
-    transfer_kernel<<<ceil_div(N / 2 + 1, 256), 256, 0, c.stream>>>(Z, P, fs, d_state);
+    {
+        KernelScope prof("transfer_kernel (per-bin transfer function)", 24.0 * (double)N);
+        transfer_kernel<<<ceil_div(N / 2 + 1, 256), 256, 0, c.stream>>>(Z, P, fs, d_state);
+    }
     ARS_LAUNCH_CHECK();
     count_launch();
     {

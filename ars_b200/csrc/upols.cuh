@@ -67,6 +67,12 @@ bool olsb_plan(i64 N, i64 taps, i64 adv, i64 circ, OlsbPlan* out);
 void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, const float* d_ir1, i64 L1,
                  const FilterSpec& fs, float2* d_y, RenderState* d_state, const OlsbPlan& plan,
                  const OlsRange& range = OlsRange(), i64 adv = 0, i64 circ = 0);
+// The first pass needs nothing but the signal: a render enqueues it for every transform BEFORE the kernels that make the
+// impulse response (synthesis, air fold, IR spectrum -- a chain of small latency-bound launches that then runs next to
+// it on the side stream); the olsb_filter call that follows with the same signal, plan, adv and circ skips its own.
+void olsb_first_pass_early(const float* d_x, i64 n, int cin, const OlsbPlan& plan, i64 adv, i64 circ);
+// taps before time zero and total tap count of the folded-air impulse response (what upols_filter_airfold builds)
+void air_fold_geometry(const AirFold& af, i64 L0, i64 L1, int logF, i64* adv, i64* taps);
 void olsb_set_options(int on, int logf, int stripe);     // -1 leaves a value unchanged; logf / stripe 0 = automatic
 void olsb_set_tuning(const char* key, int value);   // olsb_lanes | olsb_first_all | olsb_reverse | olsb_dryfold
 bool olsb_enabled();

@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the render hot path (BASELINE.json metric: audio-seconds rendered per second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5|cfg4|long]
 
-One "step" = one complete render of the workload clip: procedural IR synthesis -> exact-N spectral
-filter (convolution + air absorption + dry/wet + EQ) -> pan -> layout map -> metrics -> int16 PCM.
+One "step" = one complete render of the workload clip: procedural IR synthesis (or an external stereo IR) ->
+convolution + air absorption + dry/wet + EQ -> pan -> layout map -> metrics -> int16 PCM.
 
-  value : clip-seconds rendered per second with the input clip already resident in HBM and the PCM
-          result left in HBM (ars_render_dev), timed with CUDA events on the library's stream.
-  e2e   : the same metric through the host-buffer C-ABI call (ars_render): pinned host input copied
-          to the device, PCM frames + metrics copied back, every step, inside the timed region.
-  N > 1 : one process per GPU (torchrun), every rank renders its own clip of the same shape
-          (clips are independent: no collective on the data path), barrier + max over ranks.
+  value     : clip-seconds rendered per second with the input clip already resident in HBM and the PCM result left in
+              HBM (ars_render_dev), timed with CUDA events on the library's stream.
+  e2e       : the same metric through the host-buffer C-ABI (ars_render_batch): pinned host input copied to the
+              device, PCM frames + metrics copied back, every step, inside the timed region.
+  e2e_numpy : the call the drop-in module exposes (raytracer_studio.render_array, pageable numpy in / numpy out).
+  roofline  : SURVEY 8(d): algorithmic bytes of one render (8 B in + 2 B per output channel per frame) / ms_per_step
+              against the measured HBM copy bandwidth; `kernels` lists every kernel >= 5 % of the step with its own
+              event-timed duration, algorithmic bytes and (from the committed ncu capture) DRAM bytes.
+  parity    : the GPU result of the timed workload against the CPU oracle's render of the same clip, same draws
+              (N = 1 only; the oracle render doubles as `cpu_baseline`).
+  N > 1     : one process per GPU (torchrun), every rank renders its own clip of the same shape (clips are
+              independent: no collective on the data path), barrier + max over ranks.       scaling = weak
+  --workload long --gpus N : ONE long mask-free render (BASELINE configs[4]) split by overlap-save block ranges over
+              the N ranks (ars_b200.sharding.render_long_sharded).                             scaling = strong
 
-`--impl reference` times the CPU oracle (oracle/ars_oracle.py: a numpy/scipy restatement of the
-reference, which is a Python file and cannot travel) on the host cores, one clip per process.
+`--impl reference` times the CPU oracle (oracle/ars_oracle.py: a numpy/scipy restatement of the reference, which is a
+Python file and cannot travel) on the host cores, one full-length clip per process, same config keys.
 """
 from __future__ import annotations
 
@@ -24,7 +32,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -33,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RATE = 48000
+METRIC = "audio-seconds rendered per second (x realtime) @48kHz, 8 s IR"
 WORKLOADS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on (48 kHz, 8 s IR, 5.1 bed)
     "cfg3": dict(desc="configs[2]: 5 min 48 kHz 6-ch clip (ch0-1 used, as the reference does), internal hall "
@@ -50,8 +58,8 @@ WORKLOADS = {
                                base_late_level=.6, dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.5, treble_gain=.8,
                                x_pos=.3, y_pos=.4, z_pos=.6, material="Holz",
                                target_channel_layout="5.1 (Standard)")),
-    # BASELINE.json configs[4] (single-GPU slice): long stereo render (x) dense stereo IR, EQ flat -> the
-    # partitioned overlap-save path; default 600 s (x) 8 s, override with --seconds / --ir-seconds
+    # BASELINE.json configs[4] (single-GPU slice): long stereo render (x) dense external stereo IR, EQ flat;
+    # default 600 s (x) 8 s, override with --seconds / --ir-seconds
     "cfg5": dict(desc="configs[4]: long 48 kHz stereo clip (x) dense external stereo IR, EQ flat, dw 0.5, 5.1 out "
                       "(overlap-save convolution path)",
                  seconds=600, cin=2, amp=0.1, data_seed=5, np_seed=0, ext_ir_seconds=8.0,
@@ -62,6 +70,7 @@ ORACLE_KW = {"hall_type": "hall", "room_size": "room_size", "diffusion": "diffus
              "base_early_level": "early", "base_late_level": "late", "dry_wet": "dry_wet_amount",
              "dry_wet_kill_start": "kill_start", "bass_gain": "bass", "treble_gain": "treble", "x_pos": "x",
              "y_pos": "y", "z_pos": "z", "material": "material", "target_channel_layout": "layout"}
+LAYOUT_CHANNELS = {"Stereo": 2, "5.1 (Standard)": 6, "7.1 (Surround)": 8, "5.1.2 (Atmos Light)": 8}
 
 
 def make_ir(seconds):
@@ -79,9 +88,24 @@ def make_clip(w, seconds, seed_offset=0):
     return (w["amp"] * g.standard_normal(shape, dtype=np.float32)).astype(np.float32)
 
 
+def workload_config(w, seconds, world, ext_ir_seconds=None):
+    """The config keys both arms print (so that the driver sees the same configuration on either side)."""
+    s = w["settings"]
+    n = int(seconds * RATE)
+    ext = "ext_ir_seconds" in w
+    L = int((ext_ir_seconds or w.get("ext_ir_seconds", 0)) * RATE) if ext else int(s["ir_duration"] * RATE) if "ir_duration" in s else None
+    cfg = {"workload": w["desc"], "clip_seconds": seconds, "frames_in": n,
+           "channels_out": LAYOUT_CHANNELS[s["target_channel_layout"]], "clips_per_step": world,
+           "parallelism": f"clip-sharded x{world}"}
+    if L is not None:
+        cfg["ir_frames"] = L
+        cfg["frames_out"] = n + L - 1
+    return cfg
+
+
 # ----------------------------------------------------------------------------- clocks ------
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampled every 100 ms while the timed region runs (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -136,8 +160,8 @@ class ClockSampler:
 
 def bind_to_gpu_numa_node(gpu_index):
     """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask), so that pinned host buffers are
-    allocated on the GPU's own NUMA node; with several ranks per box the host side of the copies otherwise crosses
-    sockets.  Best effort: silently does nothing when NVML is unavailable."""
+    allocated on the GPU's own NUMA node.  Best effort: silently does nothing when NVML is unavailable (and a no-op on
+    boxes that expose one NUMA node)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -152,19 +176,29 @@ def bind_to_gpu_numa_node(gpu_index):
         return 0
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 # ----------------------------------------------------------------------------- CPU arms -----
-def _oracle_render(args):
-    w_name, seconds, seed_offset = args
+def oracle_render(w_name, seconds, seed_offset=0, keep=False):
+    """One render of the workload clip by the CPU oracle.  -> (seconds taken, outputs or None)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ars_oracle as orc
     w = WORKLOADS[w_name]
     x = make_clip(w, seconds, seed_offset)
-    kw = {ORACLE_KW[k]: v for k, v in w["settings"].items() if k in ORACLE_KW}
-    np.random.seed(w["np_seed"])
+    s = w["settings"]
+    np.random.seed(w["np_seed"] + seed_offset)
     t0 = time.perf_counter()
-    if "ir_duration" in w["settings"]:
-        # same override the GPU arm uses: call the oracle stages with the forced IR duration
-        s = w["settings"]
+    if "ext_ir_seconds" in w:
+        kw = {ORACLE_KW[k]: v for k, v in s.items() if k in ORACLE_KW}
+        out = orc.render(x, RATE, external_ir=make_ir(w["ext_ir_seconds"]), **kw)
+        final, pcm, met = out["final"], out["pcm"], out["metrics"]
+    elif "ir_duration" in s:
+        # same override the GPU arm uses: the reference's stages called with the forced IR duration
         dur, refl, mdel, split = orc.shape_params(s["hall_type"], s["room_size"], s["z_pos"])
         dur = s["ir_duration"]
         d = orc.directionality(s["x_pos"], s["y_pos"], s["z_pos"], s["hall_type"], s["diffusion"], s["dry_wet"])
@@ -175,51 +209,212 @@ def _oracle_render(args):
                                     s["dry_wet_kill_start"], s["air_absorption"])
         six = orc.pan_5_1(stereo, s["x_pos"], s["y_pos"], s["z_pos"])
         final, _ = orc.map_layout(six, s["target_channel_layout"], RATE, s["z_pos"])
-        orc.metrics(final, RATE)
-        orc.pcm16(final)
+        met = orc.metrics(final, RATE)
+        pcm = orc.pcm16(final)
     else:
-        orc.render(x, RATE, **kw)
-    return time.perf_counter() - t0
+        kw = {ORACLE_KW[k]: v for k, v in s.items() if k in ORACLE_KW}
+        out = orc.render(x, RATE, **kw)
+        final, pcm, met = out["final"], out["pcm"], out["metrics"]
+    dt = time.perf_counter() - t0
+    return dt, ((final, pcm, met) if keep else None)
 
 
-def cpu_baseline(w_name, sample_seconds):
-    dt = _oracle_render((w_name, sample_seconds, 0))
-    return {"value": sample_seconds / dt, "unit": "audio-seconds/s", "cores": 1, "kind": "port",
-            "sample": f"first {sample_seconds} s of the {w_name} clip, same settings, oracle/ars_oracle.py "
-                      f"(numpy/scipy restatement of the reference; single-threaded like the reference), {dt:.2f} s"}
+def _oracle_job(args):
+    return oracle_render(*args)[0]
 
 
 def run_reference(args):
-    """--impl reference: the CPU oracle on every host core (one clip per process), bounded sample per step."""
+    """--impl reference: the CPU oracle on every host core (one FULL-LENGTH clip per process and step), the same
+    workload and config keys as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    w = WORKLOADS[args.workload]
+    name = "cfg3" if args.workload in ("cfg4", "long") else args.workload
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    sample = args.ref_sample_seconds
-    jobs = [(args.workload, sample, i) for i in range(cores)]
+    if args.ref_procs:
+        cores = min(cores, args.ref_procs)
+    seconds = args.ref_sample_seconds or args.seconds or w["seconds"]
+    jobs = [(name, seconds, i) for i in range(cores)]
+    warm = min(args.warmup, 1)          # one warm-up pass: a step is ~30 s of CPU work on every core
     with mp.get_context("fork").Pool(cores) as pool:
-        for _ in range(args.warmup if args.warmup < 2 else 1):
-            pool.map(_oracle_render, jobs)
+        for _ in range(warm):
+            pool.map(_oracle_job, jobs)
         t0 = time.perf_counter()
+        per_clip = []
         for _ in range(args.steps):
-            pool.map(_oracle_render, jobs)
+            per_clip += pool.map(_oracle_job, jobs)
         dt = time.perf_counter() - t0
-    value = cores * sample * args.steps / dt
-    line = {"impl": "reference", "metric": "audio-seconds rendered per second (x realtime) @48kHz, 8 s IR",
-            "value": value, "unit": "audio-seconds/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "sample": f"{sample} s clips, {cores} at a time"},
+    value = cores * seconds * args.steps / dt
+    cfg = workload_config(w, seconds, 1)
+    cfg.update({"clips_per_step": cores, "parallelism": f"{cores} host processes, one clip each (numpy/scipy FFTs are "
+                                                         "single-threaded)", "warmup_done": warm})
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-seconds/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "audio-seconds/s", "cores": cores, "kind": "port",
-                             "sample": f"{cores} processes x {sample} s clips per step (clip-parallel; numpy/scipy FFTs "
-                                       "are single-threaded), oracle/ars_oracle.py"},
+                             "sample": f"{cores} processes x one {seconds:g} s clip per step (the workload's own clip "
+                                       f"length), oracle/ars_oracle.py; mean {np.mean(per_clip):.1f} s per clip and core"},
             "e2e": {"value": value, "unit": "audio-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- GPU arm ------
+class Render:
+    """One workload set up for repeated rendering: device-resident and pinned-host copies of the inputs."""
+
+    def __init__(self, lib, capi, rs, w, seconds, rank, ir_seconds=None, torch=None):
+        self.lib, self.capi, self.rs, self.w, self.seconds, self.torch = lib, capi, rs, w, seconds, torch
+        x = make_clip(w, seconds, rank)
+        self.x_np = x
+        x2 = x if x.ndim == 2 else x[:, None]
+        self.n, self.cin = x2.shape
+        self.ext = "ext_ir_seconds" in w
+        self.p, refl = rs.make_render_params(RATE, want_lufs=True, external_ir=self.ext, **w["settings"])
+        self.L = 0
+        self.h_ir = self.d_ir = None
+        self.ir_np = None
+        if self.ext:
+            self.ir_np = make_ir(ir_seconds or w["ext_ir_seconds"])
+            self.L = self.ir_np.shape[0]
+            self.h_ir = torch.from_numpy(self.ir_np).pin_memory()
+            self.d_ir = self.h_ir.cuda()
+            self.taps, self.bases, self.noise = np.zeros(0, np.int64), np.zeros(0), np.zeros(0)
+        else:
+            np.random.seed(w["np_seed"] + rank)
+            self.taps, self.bases, self.noise = rs.draw_ir_randoms(RATE, self.p.ir_duration, refl, self.p.ir_max_delay,
+                                                                   self.p.ir_split_time)
+        self.N = int(lib.ars_render_out_len(self.p, self.n, self.L))
+        self.C = LAYOUT_CHANNELS[w["settings"]["target_channel_layout"]]
+        self.h_in = torch.from_numpy(np.ascontiguousarray(x2)).pin_memory()
+        self.h_noise = torch.from_numpy(self.noise).pin_memory()
+        self.h_pcm = [torch.empty((self.N, self.C), dtype=torch.int16).pin_memory() for _ in range(2)]
+        self.d_in = self.h_in.cuda()
+        self.d_noise = self.h_noise.cuda()
+        self.d_pcm = torch.empty((self.N, self.C), dtype=torch.int16, device="cuda")
+        torch.cuda.synchronize()
+        self.keep = []
+        self.draws_h = capi.make_draws(self.taps, self.bases, self.h_noise.numpy(), self.keep)
+        self.draws_d = capi.make_draws(self.taps, self.bases, int(self.d_noise.data_ptr()), self.keep)
+        self.draws_d.noise_len = int(self.noise.size)
+        self.m = capi.ArsMetrics()
+
+    def step_dev(self):
+        self.capi.check(self.lib.ars_render_dev(self.p, self.d_in.data_ptr(), self.n, self.cin,
+                                                self.d_ir.data_ptr() if self.ext else None, self.L,
+                                                None if self.ext else self.draws_d, None, None, self.d_pcm.data_ptr(),
+                                                self.m), "ars_render_dev")
+
+    def step_host(self, out_f32=None, out_pcm=None):
+        self.capi.check(self.lib.ars_render(self.p, self.h_in.data_ptr(), self.n, self.cin,
+                                            self.h_ir.data_ptr() if self.ext else None, self.L,
+                                            None if self.ext else self.draws_h, None, out_f32,
+                                            out_pcm if out_pcm is not None else self.h_pcm[0].data_ptr(), self.m),
+                        "ars_render")
+
+    def batch_host(self, count, metrics_list):
+        C = self.capi.C
+        clips = (self.capi.ArsClip * count)()
+        for i in range(count):
+            k = clips[i]
+            k.params = C.pointer(self.p)
+            k.in_ = self.h_in.data_ptr()
+            k.n, k.cin = self.n, self.cin
+            if self.ext:
+                k.ext_ir, k.ext_ir_len = self.h_ir.data_ptr(), self.L
+            else:
+                k.draws = C.pointer(self.draws_h)
+            k.out_pcm = self.h_pcm[i % 2].data_ptr()
+            k.metrics = C.pointer(metrics_list[i])
+        self.capi.check(self.lib.ars_render_batch(clips, count), "ars_render_batch")
+
+    def time_dev(self, steps, warmup):
+        for _ in range(warmup):
+            self.step_dev()
+        self.capi.check(self.lib.ars_sync(), "ars_sync")
+        ms = self.capi.C.c_float(0)
+        self.capi.check(self.lib.ars_timer_begin(), "timer")
+        for _ in range(steps):
+            self.step_dev()
+        self.capi.check(self.lib.ars_timer_end(self.capi.C.byref(ms)), "timer")
+        return float(ms.value) / steps
+
+    def h2d_bytes(self):
+        return int(self.h_in.numel() * 4 + self.noise.size * 8 + self.taps.size * 16 + self.L * 8)
+
+    def d2h_bytes(self):
+        return int(self.N * self.C * 2 + 56)
+
+    def algorithmic_bytes(self):
+        """compulsory traffic of an ideal fused pass: 8 B in + 2 B per output channel per frame."""
+        return int((8 + 2 * self.C) * self.N)
+
+
+def profile_kernels(lib, capi, r, step_ms, traffic):
+    """One untimed render with every kernel bracketed by CUDA events (side stream and lanes off, so the kernels run
+    one after another as under ncu).  -> (fft totals, kernels[] for the roofline)."""
+    capi.set_option("side_stream", 0)
+    capi.set_option("olsb_lanes", 1)
+    try:
+        capi.check(lib.ars_profile_begin(), "profile")
+        r.step_dev()
+        pl, pms, pbytes = capi.C.c_int64(0), capi.C.c_double(0), capi.C.c_double(0)
+        capi.check(lib.ars_profile_end(capi.C.byref(pl), capi.C.byref(pms), capi.C.byref(pbytes)), "profile")
+        rep = json.loads(lib.ars_profile_report().decode())
+    finally:
+        capi.set_option("side_stream", 1)
+        capi.set_option("olsb_lanes", 0)       # 0 = the library's default
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    total = sum(k["ms"] for k in rep) or 1.0
+    kernels = []
+    for k in sorted(rep, key=lambda k: -k["ms"]):
+        us = 1000 * k["ms"]
+        e = {"name": k["name"], "launches": k["launches"], "us": us, "share_of_serialised_step": k["ms"] / total,
+             "algorithmic_bytes": k["bytes"],
+             "achieved_gbs": k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None}
+        e["frac"] = e["achieved_gbs"] / peak if e["achieved_gbs"] else None
+        t = (traffic or {}).get("per_kernel", {}).get(k["name"])
+        if t is not None:
+            e["dram_bytes"] = t
+        if k["ms"] / total >= 0.05:
+            kernels.append(e)
+    return {"launches": int(pl.value), "ms": pms.value, "bytes": pbytes.value, "serialised_ms": total}, kernels
+
+
+def parity_vs_oracle(r, oracle_out):
+    """GPU result of the timed workload against the oracle's render of the same clip with the same draws."""
+    import torch
+    final_ref, pcm_ref, met_ref = oracle_out
+    h_f32 = torch.empty((r.N, r.C), dtype=torch.float32).pin_memory()
+    h_pcm = torch.empty((r.N, r.C), dtype=torch.int16).pin_memory()
+    r.step_host(out_f32=h_f32.data_ptr(), out_pcm=h_pcm.data_ptr())
+    got = h_f32.numpy()
+    met = r.rs._metrics_dict(r.m)
+    scale = max(1.0, float(np.max(np.abs(final_ref))))
+    err = 0.0
+    num = den = 0.0
+    for lo in range(0, r.N, 1 << 20):            # chunked: the arrays are hundreds of MB
+        a = got[lo:lo + (1 << 20)].astype(np.float64)
+        b = final_ref[lo:lo + (1 << 20)].astype(np.float64)
+        d = a - b
+        err = max(err, float(np.max(np.abs(d))))
+        num += float(np.sum(d * d))
+        den += float(np.sum(b * b))
+    dp = np.abs(h_pcm.numpy().astype(np.int32) - pcm_ref.astype(np.int32))
+    out = {"against": "oracle/ars_oracle.py render of the same clip, same random draws (full size)",
+           "frames": int(r.N), "channels": int(r.C), "max_err_fs": err / scale,
+           "snr_db": float(10 * np.log10(den / num)) if num > 0 else float("inf"),
+           "pcm_lsb_max": int(dp.max()), "pcm_diff_frac": float(np.mean(dp != 0)),
+           "peak_db_diff": abs(met["true_peak_dbfs"] - met_ref["true_peak_dbfs"]),
+           "rms_db_diff": abs(met["rms_dbfs"] - met_ref["rms_dbfs"]),
+           "lufs_abs_diff": (abs(met["lufs"] - met_ref["lufs"]) if met["lufs"] is not None and met_ref.get("lufs") is not None else None),
+           "tolerance": {"max_err_fs": 1e-5, "snr_db": 100.0, "pcm_lsb_max": 1}}
+    out["ok"] = bool(out["max_err_fs"] <= 1e-5 and out["snr_db"] >= 100.0 and out["pcm_lsb_max"] <= 1)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -242,49 +437,7 @@ def run_ours(args):
     if args.air is not None:
         w = dict(w, settings=dict(w["settings"], air_absorption=args.air), desc=w["desc"] + " [air overridden: %g]" % args.air)
     seconds = args.seconds or w["seconds"]
-    x = make_clip(w, seconds, rank)
-    x2 = x if x.ndim == 2 else x[:, None]
-    n, cin = x2.shape
-    ext = "ext_ir_seconds" in w
-    p, refl = rs.make_render_params(RATE, want_lufs=True, external_ir=ext, **w["settings"])
-    L = 0
-    h_ir = d_ir = None
-    if ext:
-        ir = make_ir(args.ir_seconds or w["ext_ir_seconds"])
-        L = ir.shape[0]
-        h_ir = torch.from_numpy(ir).pin_memory()
-        d_ir = h_ir.cuda()
-        taps, bases, noise = np.zeros(0, np.int64), np.zeros(0), np.zeros(0)
-    else:
-        np.random.seed(w["np_seed"] + rank)
-        taps, bases, noise = rs.draw_ir_randoms(RATE, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
-    N = int(lib.ars_render_out_len(p, n, L))
-    C = rs.CHANNEL_LAYOUTS[w["settings"]["target_channel_layout"]]["channels"]
-
-    # pinned host buffers (e2e) and device-resident copies (value)
-    h_in = torch.from_numpy(np.ascontiguousarray(x2)).pin_memory()
-    h_noise = torch.from_numpy(noise).pin_memory()
-    h_pcm = torch.empty((N, C), dtype=torch.int16).pin_memory()
-    d_in = h_in.cuda()
-    d_noise = h_noise.cuda()
-    d_pcm = torch.empty((N, C), dtype=torch.int16, device="cuda")
-    torch.cuda.synchronize()
-    keep = []
-    draws_h = _capi.make_draws(taps, bases, h_noise.numpy(), keep)
-    draws_d = _capi.make_draws(taps, bases, int(d_noise.data_ptr()), keep)
-    draws_d.noise_len = int(noise.size)
-    m = ArsMetrics()
-
-    d_ir_ptr = d_ir.data_ptr() if ext else None
-    h_ir_ptr = h_ir.data_ptr() if ext else None
-
-    def step_dev():
-        _capi.check(lib.ars_render_dev(p, d_in.data_ptr(), n, cin, d_ir_ptr, L, None if ext else draws_d, None, None,
-                                       d_pcm.data_ptr(), m), "ars_render_dev")
-
-    def step_host():
-        _capi.check(lib.ars_render(p, h_in.data_ptr(), n, cin, h_ir_ptr, L, None if ext else draws_h, None, None,
-                                   h_pcm.data_ptr(), m), "ars_render")
+    r = Render(lib, _capi, rs, w, seconds, rank, args.ir_seconds or None, torch)
 
     def barrier():
         if world > 1:
@@ -301,7 +454,7 @@ def run_ours(args):
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
-        step_dev()
+        r.step_dev()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -310,116 +463,141 @@ def run_ours(args):
     ms = _capi.C.c_float(0)
     _capi.check(lib.ars_timer_begin(), "timer")
     for _ in range(args.steps):
-        step_dev()
+        r.step_dev()
     _capi.check(lib.ars_timer_end(_capi.C.byref(ms)), "timer")
     launches = int(lib.ars_launch_count()) - l0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = max_over_ranks(float(ms.value))
-    metrics_dev = rs._metrics_dict(m)
+    metrics_dev = rs._metrics_dict(r.m)
 
     # ---- end-to-end timing (host buffers in, host buffers out) ----
     # the public batch call: `steps` clips from pinned host memory, PCM frames + metrics back to pinned host
     # memory; clip i+1's upload and clip i-1's download overlap clip i's compute inside the library
-    h_pcm2 = torch.empty((N, C), dtype=torch.int16).pin_memory()
     ms_list = [ArsMetrics() for _ in range(args.steps)]
-
-    def batch_host(count):
-        clips = (_capi.ArsClip * count)()
-        for i in range(count):
-            k = clips[i]
-            k.params = _capi.C.pointer(p)
-            k.in_ = h_in.data_ptr()
-            k.n, k.cin = n, cin
-            if ext:
-                k.ext_ir, k.ext_ir_len = h_ir_ptr, L
-            else:
-                k.draws = _capi.C.pointer(draws_h)
-            k.out_pcm = (h_pcm if i % 2 == 0 else h_pcm2).data_ptr()
-            k.metrics = _capi.C.pointer(ms_list[i])
-        _capi.check(lib.ars_render_batch(clips, count), "ars_render_batch")
-
     for _ in range(max(1, min(args.warmup, 2))):
-        step_host()
-    batch_host(min(2, args.steps))
+        r.step_host()
+    r.batch_host(min(2, args.steps), ms_list)
     barrier()
     t0 = time.perf_counter()
-    batch_host(args.steps)
+    r.batch_host(args.steps, ms_list)
     e2e_ms = max_over_ranks(1000 * (time.perf_counter() - t0))
     barrier()
     t0 = time.perf_counter()
-    step_host()
+    r.step_host()
     single_ms = 1000 * (time.perf_counter() - t0)
     barrier()
 
-    # ---- roofline of the dominant kernels (FFT passes), separate untimed run with per-launch events ----
-    folds0 = int(lib.ars_air_fold_count())
-    _capi.check(lib.ars_profile_begin(), "profile")
-    step_dev()
-    air_folds = int(lib.ars_air_fold_count()) > folds0
-    pl, pms, pbytes = _capi.C.c_int64(0), _capi.C.c_double(0), _capi.C.c_double(0)
-    _capi.check(lib.ars_profile_end(_capi.C.byref(pl), _capi.C.byref(pms), _capi.C.byref(pbytes)), "profile")
+    # ---- the call the drop-in module exposes: pageable numpy in, numpy out (draws, allocation, copies included) ----
+    e2e_np = None
+    if world == 1 and not args.no_numpy:
+        ext_kw = dict(external_ir_data=r.ir_np) if r.ext else {}
+        k_np = max(2, min(args.steps, 5))
+        np.random.seed(w["np_seed"])
+        rs.render_array(r.x_np, RATE, want_float=False, **ext_kw, **w["settings"])
+        t0 = time.perf_counter()
+        for _ in range(k_np):
+            np.random.seed(w["np_seed"])
+            res = rs.render_array(r.x_np, RATE, want_float=False, **ext_kw, **w["settings"])
+        np_ms = 1000 * (time.perf_counter() - t0) / k_np
+        e2e_np = {"value": seconds / (np_ms * 1e-3), "unit": "audio-seconds/s", "ms_per_step": np_ms, "calls": k_np,
+                  "call": "ars_b200.raytracer_studio.render_array(numpy clip, ...) -> numpy PCM + metrics: pageable "
+                          "arrays, the reference's random draws replayed on the host, output allocated per call",
+                  "lufs": res["metrics"]["lufs"]}
+        del res
+
+    # ---- per-kernel event timing of one render (serialised) ----
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + "_r02")
+    except Exception:
+        pass
+    step_ms = dev_ms / args.steps
+    fft_tot, kernels = profile_kernels(lib, _capi, r, step_ms, traffic)
+    for kv in args.opt:                                 # (the profile turned two options off and back to their defaults)
+        _capi.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    olsb = int(lib.ars_olsb_count()) > 0
+    folds = int(lib.ars_air_fold_count()) > 0
     barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = pbytes.value / (pms.value * 1e-3) / 1e9 if pms.value > 0 else 0.0
-    traffic = traffic_src = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        traffic, traffic_src = float(t["dram_bytes_per_launch_mean"]), t["source"]
-    except Exception:
-        pass
-    step_ms = dev_ms / args.steps
     total_seconds = seconds * world * args.steps
-    out_bytes_per_frame = 8 + 2 * C
+    algo = r.algorithmic_bytes()
+    achieved = algo / (step_ms * 1e-3) / 1e9
+    cfg = workload_config(w, seconds, world, args.ir_seconds or None)
+    cfg.update({"route": ("folded-air " if folds else "") + ("big-block overlap-save (one partition, fused middle pass)" if olsb
+                          else "see DESIGN.md section 2"),
+                "l2": "working set (input %d MB, FFT work buffers, output %d MB) exceeds the 126 MB L2; no flush needed"
+                      % (r.n * r.cin * 4 >> 20, r.N * r.C * 2 >> 20)})
     line = {
-        "metric": "audio-seconds rendered per second (x realtime) @48kHz, 8 s IR",
-        "value": total_seconds / (dev_ms * 1e-3), "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "clip_seconds": seconds, "frames_in": n, "frames_out": N,
-                   "channels_out": C, "clips_per_step": world, "parallelism": f"clip-sharded x{world}",
-                   "ir_frames": L if ext else int(p.ir_duration * RATE),
-                   "route": "folded-air overlap-save" if air_folds else "see DESIGN.md section 2",
-                   "l2": "working set (input %d MB, delay-line / FFT work buffers >= %d MB, output %d MB) exceeds the "
-                         "126 MB L2; no flush needed" % (n * cin * 4 >> 20, 8 * N >> 19, N * C * 2 >> 20)},
+        "metric": METRIC, "value": total_seconds / (dev_ms * 1e-3), "unit": "audio-seconds/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "e2e": {"value": total_seconds / (e2e_ms * 1e-3), "unit": "audio-seconds/s", "ms_per_step": e2e_ms / args.steps,
-                "call": "ars_render_batch (host buffers, copy/compute pipelined across the steps' clips)",
-                "single_call_ms": single_ms,
-                "h2d_bytes_per_step": int(h_in.numel() * 4 + noise.size * 8 + taps.size * 16 + L * 8),
-                "d2h_bytes_per_step": int(h_pcm.numel() * 2 + 56)},
+                "call": "ars_render_batch (pinned host buffers, copy/compute pipelined across the steps' clips)",
+                "single_call_ms": single_ms, "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes()},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "fft pass kernels (pass_contig_kernel block transforms of the overlap-save "
-                                               "route / pass_strided_kernel + pass_contig_kernel M-point passes)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+        "roofline": {"bound": "hbm", "kernel": "whole render (every kernel of the step)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "launches_per_step": int(pl.value), "ms_per_step_in_kernel": pms.value,
-                     "share_of_step": pms.value / step_ms if step_ms else None,
-                     "algorithmic_bytes_per_launch": pbytes.value / max(1, pl.value),
-                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
-                     "traffic_source": traffic_src},
-        "roofline_whole_render": {"algorithmic_bytes_per_step": int(out_bytes_per_frame * N),
-                                  "achieved": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                  "frac": out_bytes_per_frame * N / (step_ms * 1e-3) / 1e9 / peak,
-                                  "note": "SURVEY 8(d) compulsory bytes of an ideal single fused pass (8 B in + 2 B per "
-                                          "output channel per frame) over the whole step, all kernels included"},
+                     "algorithmic_bytes_per_step": algo,
+                     "definition": "SURVEY 8(d): 8 B in + 2 B per output channel per output frame of an ideal single "
+                                   "fused pass, divided by ms_per_step (all kernels, launch gaps included)",
+                     "traffic": (traffic or {}).get("dram_bytes_per_render"),
+                     "traffic_unit": "DRAM bytes read + written by one render (ncu --set full, all kernels)",
+                     "traffic_source": (traffic or {}).get("source"),
+                     "fft_pass_kernels": {"launches_per_step": fft_tot["launches"], "ms": fft_tot["ms"],
+                                          "algorithmic_bytes": fft_tot["bytes"],
+                                          "achieved_gbs": fft_tot["bytes"] / (fft_tot["ms"] * 1e-3) / 1e9 if fft_tot["ms"] else None},
+                     "serialised_step_ms": fft_tot["serialised_ms"],
+                     "kernels": kernels},
         "metrics_of_last_render": metrics_dev,
     }
-    if world == 1 and not args.no_cpu and not ext:
-        line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample_seconds)
+    if e2e_np:
+        line["e2e_numpy"] = e2e_np
+    if world == 1 and not args.no_cpu:
+        dt, out = oracle_render(args.workload, seconds, 0, keep=True)
+        line["cpu_baseline"] = {"value": seconds / dt, "unit": "audio-seconds/s", "cores": 1, "kind": "port",
+                                "sample": f"the whole {seconds:g} s {args.workload} clip, same settings, oracle/ars_oracle.py "
+                                          f"(numpy/scipy restatement of the reference; single-threaded like the "
+                                          f"reference), {dt:.2f} s"}
+        if not (args.cin or args.air is not None or args.ir_seconds):
+            line["parity"] = parity_vs_oracle(r, out)
+        del out
+    if world == 1 and not args.no_extras and args.workload == "cfg3":
+        del r
+        torch.cuda.empty_cache()
+        line["ir_sweep"], line["dense_ir"] = ir_sweep(lib, _capi, rs, torch, peak)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ir_sweep(lib, capi, rs, torch, peak):
+    """BASELINE configs[4] on one GPU: 600 s stereo clip (x) DENSE external stereo IR of 0.1 ... 20 s, EQ flat, 5.1 out,
+    device-resident.  -> (list of sweep points, the 8 s point as `dense_ir`)."""
+    w = WORKLOADS["cfg5"]
+    pts, dense = [], None
+    for L in (0.1, 0.5, 2.0, 8.0, 20.0):
+        r = Render(lib, capi, rs, w, w["seconds"], 0, L, torch)
+        ms = r.time_dev(5, 2)
+        algo = r.algorithmic_bytes()
+        pt = {"ir_seconds": L, "ir_frames": r.L, "clip_seconds": w["seconds"], "ms_per_step": ms,
+              "value": w["seconds"] / (ms * 1e-3), "unit": "audio-seconds/s",
+              "roofline_frac": algo / (ms * 1e-3) / 1e9 / peak, "lufs": rs._metrics_dict(r.m)["lufs"]}
+        pts.append(pt)
+        if L == 8.0:
+            dense = dict(pt, workload=w["desc"], note="dense Gaussian x exponential-decay IR (every tap non-zero); one "
+                                                      "partition, 2^22-point blocks, no multiply-accumulate kernel: HBM-bound")
+        del r
+        torch.cuda.empty_cache()
+    return pts, dense
 
 
 def cfg4_presets(count, first=0):
@@ -526,25 +704,31 @@ def run_cfg4(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4", "long"])
     ap.add_argument("--clips", type=int, default=128, help="cfg4: clips in the batch (BASELINE: 1024)")
     ap.add_argument("--seconds", type=float, default=0.0, help="override the clip length (default: the config's)")
-    ap.add_argument("--ir-seconds", type=float, default=0.0, help="external-IR length for cfg5")
-    ap.add_argument("--cpu-sample-seconds", type=float, default=300.0)
-    ap.add_argument("--ref-sample-seconds", type=float, default=10.0)
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ir-seconds", type=float, default=0.0, help="external-IR length for cfg5 / long")
+    ap.add_argument("--ref-sample-seconds", type=float, default=0.0,
+                    help="reference arm: clip length per process (default: the workload's own clip length)")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: processes (default: every host core)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle render (cpu_baseline + parity)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the IR-length sweep / dense-IR point")
+    ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-API timing")
     ap.add_argument("--cin", type=int, default=0, help="experiments: override the clip's channel count")
     ap.add_argument("--air", type=float, default=None, help="experiments: override the air-absorption setting")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="library option for experiments (ars_set_option), e.g. --opt air_fold=0")
     args = ap.parse_args()
-    if args.workload == "cfg4" and args.impl != "reference":
-        run_cfg4(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
+    elif args.workload == "long":
+        from ars_b200 import sharding
+        sharding.bench_long(args, make_clip=make_clip, make_ir=make_ir, load_peaks=load_peaks, ClockSampler=ClockSampler)
     else:
         run_ours(args)
 

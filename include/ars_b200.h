@@ -121,10 +121,14 @@ ARS_API int ars_set_option(const char* key, int32_t value);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);
 ARS_API int ars_timer_end(float* ms);
-/* Per-launch event timing of the FFT pass kernels (the dominant kernels): between begin and end every
- * pass launch is bracketed by events; end reports their count, summed duration and algorithmic bytes. */
+/* Per-launch event timing: between begin and end every kernel (or short chain of small kernels) the library launches
+ * is bracketed by two CUDA events on its own stream.  end reports the FFT pass kernels' count, summed duration and
+ * algorithmic bytes; ars_profile_report() then returns a JSON array with one {"name", "launches", "ms", "bytes"} object
+ * per kernel name of that session (valid until the next session ends).  Turn "side_stream" and "olsb_lanes" off around
+ * a session to time the kernels one after another. */
 ARS_API int ars_profile_begin(void);
 ARS_API int ars_profile_end(int64_t* launches, double* ms, double* bytes);
+ARS_API const char* ars_profile_report(void);
 
 /* ---- stage entry points (host pointers), one per reference function ------------------------- */
 

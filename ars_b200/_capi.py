@@ -43,6 +43,11 @@ class ArsRenderParams(C.Structure):
                 ("want_lufs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ArsLongPlan(C.Structure):
+    _fields_ = [("block_frames", C.c_int64), ("n_blocks", C.c_int64), ("halo_frames", C.c_int64),
+                ("frames_out", C.c_int64), ("hop_count", C.c_int32), ("route", C.c_int32)]
+
+
 class ArsClip(C.Structure):
     _fields_ = [("params", C.POINTER(ArsRenderParams)), ("in_", C.c_void_p), ("n", C.c_int64), ("cin", C.c_int32),
                 ("reserved", C.c_int32), ("ext_ir", C.c_void_p), ("ext_ir_len", C.c_int64),
@@ -90,6 +95,9 @@ PROTOTYPES = {
     "ars_set_option": (C.c_int, [C.c_char_p, _i32]),
     "ars_state_bytes": (_i64, []),
     "ars_ols_block_frames": (_i64, []),
+    "ars_long_plan": (C.c_int, [C.POINTER(ArsRenderParams), _i64, _i64, C.POINTER(ArsLongPlan)]),
+    "ars_long_loudness_hops_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i64, _i64, _i64, _p, _p, _i32]),
+    "ars_long_loudness_gate_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i32, _i64, _p, C.POINTER(_i32)]),
     "ars_long_convolve_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _i64,
                                         _i64, _p, _i64, _p]),
     "ars_long_tail_dev": (C.c_int, [C.POINTER(ArsRenderParams), _i32, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),

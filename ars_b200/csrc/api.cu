@@ -39,7 +39,9 @@ static unsigned long long g_air_fold_count = 0;   // convolution stages that too
 static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
-static int g_opt_lufs_from_stage = 1;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array)
+static int g_opt_lufs_from_stage = 0;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array);
+                                        // measured slower: both kernels are bound by issue slots, and recomputing the feed costs more
+                                        // instructions than the 4 B per frame the final pass writes (0.660 against 0.634 ms)
 static int g_opt_air_fold_max_taps = 131072;  // longest kept half-length of the air kernel; beyond: the exact N-point path
 
 // number of 4096-tap partitions of the two IR parts that hold a non-zero tap (host arrays)
@@ -803,33 +805,70 @@ int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32
 int64_t ars_state_bytes(void) { return (int64_t)sizeof(RenderState); }
 int64_t ars_ols_block_frames(void) { return (int64_t)1 << (g_opt_upols_logf - 1); }
 
-int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, int64_t x_frame0, int64_t x_frames, int64_t n_total,
-                          int32_t cin, const float* d_ir0, int64_t L0, const float* d_ir1, int64_t L1,
-                          int64_t block_lo, int64_t block_hi, float* d_y, int64_t y_frame0, void* d_state) {
-    ARS_API_BEGIN
-    ARS_CHECK(p && d_x && d_y && d_state && n_total > 0 && cin >= 1 && d_ir0 && L0 >= 1, "ars_long_convolve_dev: bad arguments");
-    const i64 L = p->external_ir ? L0 : std::max<i64>(L0, d_ir1 ? L1 : 0);
+// the filter of a mask-free long render (external stereo IR, or early + late parts of equal role)
+static void long_filter_spec(const ArsRenderParams* p, i64 n_total, i64 L0, bool have_ir1, i64 L1, FilterSpec& fs, i64* L_out) {
+    const i64 L = p->external_ir ? L0 : std::max<i64>(L0, have_ir1 ? L1 : 0);
     const i64 N = n_total + L - 1;
-    FilterSpec fs;
     common_filter_spec(fs, N, p->rate, p->dry_wet, p->kill_start, p->bass_gain, p->treble_gain);
     if (p->external_ir) {
         fs.mode = FILT_EXT;
     } else {
         fs.mode = FILT_SPLIT;
         fs.level0 = (L0 > 1 && p->early_level > 1e-6) ? p->early_level : 0.0;
-        fs.level1 = (d_ir1 && L1 > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;
+        fs.level1 = (have_ir1 && L1 > 1 && p->late_level > 1e-6) ? p->late_level : 0.0;
         if (p->air_absorption > 0.01 && N >= 2) fill_air(fs, N, p->rate, p->air_absorption);
     }
-    ARS_CHECK(upols_applicable(fs), "ars_long_convolve_dev: EQ / air absorption need the global N-point transform; "
-                                    "only mask-free renders shard by block ranges (use ars_render on one GPU)");
+    ARS_CHECK(upols_applicable(fs), "long render: EQ / air absorption need the global N-point transform; only mask-free "
+                                    "renders shard by block ranges (use ars_render on one GPU)");
+    *L_out = L;
+}
+
+int ars_long_plan(const ArsRenderParams* p, int64_t n_total, int64_t ir_len, ArsLongPlan* out) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && out && n_total > 0 && ir_len >= 1, "ars_long_plan: bad arguments");
+    FilterSpec fs;
+    i64 L = 0;
+    long_filter_spec(p, n_total, ir_len, !p->external_ir, ir_len, fs, &L);
+    memset(out, 0, sizeof(*out));
+    OlsbPlan pl;
+    if (g_opt_upols && olsb_plan(fs.N, L, 0, 0, &pl)) {
+        out->route = 1;
+        out->block_frames = pl.hop;
+        out->n_blocks = pl.J;
+        out->halo_frames = pl.skip;
+    } else {
+        const i64 B = (i64)1 << (g_opt_upols_logf - 1);
+        out->route = 0;
+        out->block_frames = B;
+        out->n_blocks = (fs.N + B - 1) / B;
+        out->halo_frames = ((L + B - 1) / B) * B;
+    }
+    out->frames_out = fs.N;
+    out->hop_count = loudness_hop_count(fs.N, p->rate);
+    ARS_API_END
+}
+
+int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, int64_t x_frame0, int64_t x_frames, int64_t n_total,
+                          int32_t cin, const float* d_ir0, int64_t L0, const float* d_ir1, int64_t L1,
+                          int64_t block_lo, int64_t block_hi, float* d_y, int64_t y_frame0, void* d_state) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && d_x && d_y && d_state && n_total > 0 && cin >= 1 && d_ir0 && L0 >= 1, "ars_long_convolve_dev: bad arguments");
+    FilterSpec fs;
+    i64 L = 0;
+    long_filter_spec(p, n_total, L0, d_ir1 != nullptr, L1, fs, &L);
     OlsRange rg;
     rg.block_lo = block_lo;
     rg.block_hi = block_hi;
     rg.x_frame0 = x_frame0;
     rg.x_frames = x_frames;
     rg.y_frame0 = y_frame0;
-    upols_filter(d_x, n_total, cin, d_ir0, L0, p->external_ir ? nullptr : d_ir1, L1, fs, reinterpret_cast<float2*>(d_y),
-                 static_cast<RenderState*>(d_state), g_opt_upols_logf, rg);
+    OlsbPlan pl;
+    if (g_opt_upols && olsb_plan(fs.N, L, 0, 0, &pl))       // (the same decision ars_long_plan reports)
+        olsb_filter(d_x, n_total, cin, d_ir0, L0, p->external_ir ? nullptr : d_ir1, L1, fs, reinterpret_cast<float2*>(d_y),
+                    static_cast<RenderState*>(d_state), pl, rg);
+    else
+        upols_filter(d_x, n_total, cin, d_ir0, L0, p->external_ir ? nullptr : d_ir1, L1, fs, reinterpret_cast<float2*>(d_y),
+                     static_cast<RenderState*>(d_state), g_opt_upols_logf, rg);
     ARS_API_END
 }
 
@@ -850,6 +889,27 @@ int ars_long_tail_dev(const ArsRenderParams* p, int32_t phase, const float* d_y,
     if (phase == 0) tail_pan_max(y, ts, st);
     else if (phase == 1) tail_map_max(y, ts, st);
     else tail_final(y, ts, st, d_out_f32, reinterpret_cast<short*>(d_out_pcm), d_mono);
+    ARS_API_END
+}
+
+int ars_long_loudness_hops_dev(const ArsRenderParams* p, const float* d_y, int64_t y_frame0, int64_t frame_lo,
+                               int64_t frame_hi, int64_t N_total, void* d_state, double* d_hops, int32_t n_hops) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && d_y && d_state && d_hops && layout_ok(p->layout) && frame_lo >= 0 && frame_hi <= N_total,
+              "ars_long_loudness_hops_dev: bad arguments");
+    TailSpec ts = make_tail(N_total, p->layout, p->rate, p->x, p->y, p->z);
+    ts.y0 = y_frame0;
+    loudness_hops_from_stage(reinterpret_cast<const float2*>(d_y), ts, p->rate, static_cast<RenderState*>(d_state), frame_lo,
+                             frame_hi, d_hops, n_hops);
+    ARS_API_END
+}
+
+int ars_long_loudness_gate_dev(const ArsRenderParams* p, const double* d_hops, int32_t n_hops, int64_t N_total, void* d_state,
+                               int32_t* lufs_status) {
+    ARS_API_BEGIN
+    ARS_CHECK(p && d_hops && d_state && lufs_status, "ars_long_loudness_gate_dev: bad arguments");
+    *lufs_status = loudness_gate_from_hops(d_hops, n_hops, N_total, p->rate, static_cast<RenderState*>(d_state)) == 0
+                       ? ARS_LUFS_OK : ARS_LUFS_NONE;
     ARS_API_END
 }
 

@@ -224,6 +224,9 @@ struct SrcStage {                      // mean(ch0, ch1) of the final frame (rs.
 
 struct LoudArgs {
     i64 N;
+    i64 g_base = 0;                    // absolute sample index of block 0 (a multiple of BS); > 0: one rank's part of a render
+    i64 src_lo = 0;                    // samples before it do not exist in this launch's source (read as zero)
+    i64 e_lo = 0, e_hi = 0;            // squares count for samples in [e_lo, e_hi) only (e_hi = 0: all)
     double rate;
     ScanCoef c1, c2;
     int dep1, dep2;
@@ -286,7 +289,7 @@ __device__ __forceinline__ double2 chunk_start_state(const float* mine, const Sc
 // the block's samples into shared memory, eight loads in flight per thread (the feed's arithmetic would otherwise wait
 // for every load in turn)
 template <class SRC, bool G>
-__device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 base, i64 N) {
+__device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 base, i64 N, i64 src_lo) {
     const int t = threadIdx.x;
     unsigned mm = 0;
     #pragma unroll 1
@@ -295,7 +298,7 @@ __device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 bas
         #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const i64 g = base + (i64)(i0 + u) * NTB + t;
-            raw[u] = g < N ? src.load(g) : make_float2(0.f, 0.f);
+            raw[u] = (g < N && g >= src_lo) ? src.load(g) : make_float2(0.f, 0.f);
         }
         #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -326,10 +329,11 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
         __syncthreads();
         const int b = (int)s_b;
         if (b >= nblocks) break;
-        const i64 base = (i64)b * BS;
+        const i64 base = a.g_base + (i64)b * BS;
         if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
-        const unsigned m1 = idle ? loud_feed<SRC, false>(src, sx, base, a.N) : loud_feed<SRC, true>(src, sx, base, a.N);
-        mm = max(mm, m1);
+        const unsigned m1 = idle ? loud_feed<SRC, false>(src, sx, base, a.N, a.src_lo)
+                                 : loud_feed<SRC, true>(src, sx, base, a.N, a.src_lo);
+        if (a.e_hi == 0 || (base + BS > a.e_lo && base < a.e_hi)) mm = max(mm, m1);     // (warm-up blocks do not count)
         __syncthreads();
         float* mine = sx + t * (CH + 1);
         // stage 1 (high shelf): float32 store, as pyloudnorm
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
             const float o = (float)df2t(a.c2.q, (double)mine[j], s);
             const double sq = (double)__fmul_rn(o, o);
             const i64 g = g0 + j;
-            if (g < a.N) { if (g < next) e0 += sq; else e1 += sq; }
+            if (g < a.N && (a.e_hi == 0 || (g >= a.e_lo && g < a.e_hi))) { if (g < next) e0 += sq; else e1 += sq; }
         }
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -574,6 +578,108 @@ int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double
     src.ts = ts;
     src.st = d_state;
     return loudness_run(src, ts.N, rate, &d_state->mono_max, nullptr, &d_state->mono_max, &d_state->lufs);
+}
+
+// ---- the meter split over the ranks of a block-sharded render (sharding.py) -------------------------------------
+// A rank filters its own stretch of the signal (after a warm-up of a few blocks that the previous rank's tail of the
+// stage output provides: the K-weighting filters forget 1e-17 per block) and leaves the energies of its samples per
+// 100 ms hop, indexed by ABSOLUTE hop; the ranks add those vectors (one small all-reduce) and every rank gates.
+int loudness_hop_count(i64 N, double rate) {
+    const int nb = loudness_blocks(N, rate);
+    return nb > 0 ? nb + 3 : 0;
+}
+
+__global__ void __launch_bounds__(256) hop_energy_kernel(const double* __restrict__ part, int nblocks, i64 g_base, i64 N,
+                                                         double rate, i64 e_lo, i64 e_hi, double* __restrict__ hops, int n_hops) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hops) return;
+    i64 lo = min(hop_lo(h, rate), N), hi = min(hop_lo(h + 1, rate), N);
+    lo = max(lo, e_lo);
+    hi = min(hi, e_hi);
+    double tot = 0.0;
+    if (hi > lo) {
+        for (i64 b = lo / BS; b <= (hi - 1) / BS; ++b) {
+            const i64 bl = b - g_base / BS;
+            const i64 k = (i64)h - hop_of(b * BS, rate);
+            if (bl >= 0 && bl < nblocks && k >= 0 && k < 4) tot += part[bl * 4 + k];
+        }
+    }
+    hops[h] = tot;
+}
+
+__global__ void __launch_bounds__(256) hops_to_z_kernel(const double* __restrict__ hops, int nb, double rate, double* __restrict__ z) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    const double tot = ((hops[j] + hops[j + 1]) + hops[j + 2]) + hops[j + 3];
+    z[j] = __dmul_rn(1.0 / __dmul_rn(0.4, rate), tot);
+}
+
+int loudness_hops_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state, i64 e_lo, i64 e_hi,
+                             double* d_hops, int n_hops) {
+    Ctx& c = ctx();
+    const i64 N = ts.N;
+    ARS_CHECK(loudness_from_stage_possible(rate), "loudness: the one-pass meter needs rate >= 40 960 Hz");
+    ARS_CHECK(n_hops == loudness_hop_count(N, rate) && n_hops > 0, "loudness: wrong hop count");
+    ARS_CHECK(e_lo >= 0 && e_lo <= e_hi && e_hi <= N, "loudness: bad sample range");
+    if (e_hi <= e_lo) {
+        ARS_CUDA(cudaMemsetAsync(d_hops, 0, sizeof(double) * (size_t)n_hops, c.stream));
+        return 0;
+    }
+    Biquad q[2];
+    k_weighting(rate, q);
+    const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
+    auto depth_of = [](const Mat2& M) {
+        const double nrm = std::sqrt(M.m00 * M.m00 + M.m01 * M.m01 + M.m10 * M.m10 + M.m11 * M.m11);
+        return std::max(2, (int)std::ceil(-25.0 * std::log(10.0) / std::log(nrm)));
+    };
+    const i64 g_base = std::max<i64>(0, (e_lo - 2 * (i64)BS) / BS * BS);
+    const int nblocks = (int)((e_hi - g_base + BS - 1) / BS);
+    const size_t off_flags = sizeof(double2) * 2 * (size_t)nblocks + sizeof(double) * 4 * (size_t)nblocks;
+    const size_t bytes_flags = sizeof(int) * (2 * (size_t)nblocks + 4);
+    char* ws = c.buf("lufs.onepass", off_flags + bytes_flags).as<char>();
+    LoudArgs a;
+    a.N = N;
+    a.g_base = g_base;
+    a.src_lo = ts.y0;
+    a.e_lo = e_lo;
+    a.e_hi = e_hi;
+    a.rate = rate;
+    a.c1 = c1; a.c2 = c2;
+    a.dep1 = depth_of(c1.pw[8]); a.dep2 = depth_of(c2.pw[8]);
+    a.agg1 = reinterpret_cast<double2*>(ws);
+    a.agg2 = a.agg1 + nblocks;
+    a.part = reinterpret_cast<double*>(a.agg2 + nblocks);
+    a.flag1 = reinterpret_cast<int*>(ws + off_flags);
+    a.flag2 = a.flag1 + nblocks;
+    a.ticket = reinterpret_cast<unsigned*>(a.flag2 + nblocks);
+    a.mono_max = &d_state->mono_max;
+    SrcStage src;
+    src.y = d_y;
+    src.ts = ts;
+    src.st = d_state;
+    ARS_CUDA(cudaMemsetAsync(ws + off_flags, 0, bytes_flags, c.stream));
+    {
+        KernelScope prof("loudness_kernel (K-weighting stages + hop energies, one pass)", 8.0 * (double)(e_hi - g_base));
+        const int grid = std::max(1, std::min(nblocks, c.sm_count * 6));
+        loudness_kernel<SrcStage><<<grid, NTB, 0, c.stream>>>(src, a, nblocks);
+    }
+    hop_energy_kernel<<<ceil_div(n_hops, 256), 256, 0, c.stream>>>(a.part, nblocks, g_base, N, rate, e_lo, e_hi, d_hops, n_hops);
+    ARS_LAUNCH_CHECK();
+    count_launch(2);
+    return 0;
+}
+
+int loudness_gate_from_hops(const double* d_hops, int n_hops, i64 N, double rate, RenderState* d_state) {
+    Ctx& c = ctx();
+    const int nb = loudness_blocks(N, rate);
+    if (!((double)N >= 0.4 * rate) || nb <= 0) return 1;
+    ARS_CHECK(n_hops == nb + 3, "loudness: wrong hop count");
+    double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
+    hops_to_z_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(d_hops, nb, rate, dz);
+    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, &d_state->mono_max, &d_state->lufs);
+    ARS_LAUNCH_CHECK();
+    count_launch(2);
+    return 0;
 }
 
 // ---- spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(x, fs, window='hann', nperseg,

@@ -15,6 +15,14 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
 bool loudness_from_stage_possible(double rate);
 int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state);
 
+// The meter split over the ranks of a block-sharded render: hop energies of samples [e_lo, e_hi) of the whole signal
+// (ts.N samples; ts.y0 = first frame held at d_y, which must reach 3 x 8192 frames before e_lo or to frame 0) into
+// d_hops[loudness_hop_count()], then -- once the ranks have added their vectors -- the gate.
+int loudness_hop_count(i64 N, double rate);
+int loudness_hops_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state, i64 e_lo, i64 e_hi,
+                             double* d_hops, int n_hops);
+int loudness_gate_from_hops(const double* d_hops, int n_hops, i64 N, double rate, RenderState* d_state);
+
 // scipy.signal.spectrogram(x[:, 0], fs, window='hann', nperseg, noverlap=nperseg//2) -> d_out[(nperseg/2+1) x nseg], row-major
 void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out);
 void loudness_set_ctas_per_sm(int n);   // CTAs per SM of the one-pass meter when it runs next to the final pass

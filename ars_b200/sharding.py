@@ -88,157 +88,413 @@ def render_batch_sharded(jobs, *, rank=None, world=None, group=None, **kw):
 # ------------------------------------------------------------------------------------------------
 # One long mask-free render split by overlap-save block ranges (BASELINE configs[4])
 # ------------------------------------------------------------------------------------------------
-class LongRenderRank:
-    """Device work of ONE rank of a block-sharded long render, phase by phase, so that the collectives between the
-    phases can be real (torch.distributed over NCCL) or emulated (tests run several `ranks` on one GPU).
+Y_HALO = 3 * 8192        # frames of the previous rank's stage output a rank needs: the loudness filters' warm-up (>= any layout delay)
 
-        convolve() -> reduce state words [0:4] (MAX) -> pan_max() -> reduce [4] (MAX) -> map_max() -> reduce [5] (MAX)
-        -> final() -> reduce [8:10] (MAX) and the float64 at byte 48 (SUM) -> gather PCM / loudness-feed slices
+
+class LongRenderRank:
+    """Device work of ONE rank of a block-sharded long render, phase by phase, so that the exchanges between the phases
+    can be real collectives (torch.distributed over NCCL, `render_long_sharded`) or emulated (the tests run several
+    ranks one after another on one GPU).
+
+        convolve()  -> MAX words [0:4]; every rank's last Y_HALO stage-output frames go to its successor (set_halo)
+        pan_max()   -> MAX word [4]        (map_max() -> MAX word [5], Stereo layout only)
+        final()     -> PCM of the rank's own frames; MAX words [8:10], SUM of the float64 at byte 48
+        loudness_hops() -> SUM of the hop-energy vectors; loudness_gate() on whoever wants the number
+
+    Only the rank's own slice of the clip (plus the convolution's input halo) is uploaded; the IR is a device tensor.
     """
 
-    def __init__(self, samples, rate, ir, settings, rank, world, *, want_float=False):
+    def __init__(self, samples, rate, d_ir, settings, rank, world, *, want_float=False, x_is_slice_from=None):
+        import ctypes as C
         import torch
         from . import _capi, raytracer_studio as rs
-        self.torch, self.capi, self.rs = torch, _capi, rs
+        self.torch, self.capi, self.rs, self.C = torch, _capi, rs, C
         self.lib = _capi.init()
-        x = rs._as_frames(samples)
-        self.n, self.cin = x.shape
-        ir = np.ascontiguousarray(ir, dtype=np.float32)
-        assert ir.ndim == 2 and ir.shape[1] == 2, "the long-render path takes a stereo (L, 2) IR"
-        self.L = ir.shape[0]
+        self.rank, self.world = rank, world
+        assert d_ir.is_cuda and d_ir.dtype == torch.float32 and d_ir.dim() == 2 and d_ir.shape[1] == 2, \
+            "the long-render path takes a stereo (L, 2) float32 IR on the device"
+        self.d_ir = d_ir.contiguous()
+        self.L = int(d_ir.shape[0])
         self.p, _ = rs.make_render_params(rate, external_ir=True, want_lufs=True, **settings)
-        self.N = self.n + self.L - 1
         layout = settings.get("target_channel_layout", rs.DEFAULT_CHANNEL_LAYOUT)
-        self.C = rs.CHANNEL_LAYOUTS[layout]["channels"]
-        self.B = int(self.lib.ars_ols_block_frames())
-        nblk = -(-self.N // self.B)
-        P = -(-self.L // self.B)
-        self.lo, self.hi = block_ranges(nblk, world)[rank]
-        delay = {"7.1 (Surround)": int(int(rate) * 12 / 1000), "5.1.2 (Atmos Light)": int(int(rate) * 18 / 1000)}.get(layout, 0)
-        halo = -(-delay // self.B) if delay else 0
-        self.clo = max(0, self.lo - halo)                         # blocks computed here (incl. the tail's delay halo)
-        seg0 = max(0, self.clo - (P - 1))
-        self.x_lo = max(0, (seg0 - 1) * self.B)
-        self.x_hi = max(self.x_lo, min(self.n, self.hi * self.B))
-        self.f_lo, self.f_hi = self.lo * self.B, min(self.N, self.hi * self.B)
-        self.y0 = self.clo * self.B
+        self.C_out = rs.CHANNEL_LAYOUTS[layout]["channels"]
+        self.stereo_layout = layout == "Stereo"
+        # `samples`: the whole clip (n, cin), or -- x_is_slice_from=(first frame, total frames) -- just a slice of it
+        x = rs._as_frames(samples) if isinstance(samples, np.ndarray) else samples
+        if x_is_slice_from is None:
+            self.n, self.cin = int(x.shape[0]), int(x.shape[1])
+            x_first = 0
+        else:
+            x_first, self.n = int(x_is_slice_from[0]), int(x_is_slice_from[1])
+            self.cin = int(x.shape[1])
+        plan = _capi.ArsLongPlan()
+        _capi.check(self.lib.ars_long_plan(self.p, self.n, self.L, plan), "ars_long_plan")
+        self.plan = plan
+        self.N, self.B = int(plan.frames_out), int(plan.block_frames)
+        self.lo, self.hi = block_ranges(int(plan.n_blocks), world)[rank]
+        self.f_lo, self.f_hi = min(self.N, self.lo * self.B), min(self.N, self.hi * self.B)
+        self.x_lo = max(0, self.f_lo - int(plan.halo_frames))
+        self.x_hi = max(self.x_lo, min(self.n, self.f_hi))
+        self.y0 = max(0, self.f_lo - Y_HALO)
         dev = torch.device("cuda", torch.cuda.current_device())
-        xs = x[self.x_lo:self.x_hi] if self.x_hi > self.x_lo else np.zeros((1, self.cin), np.float32)
-        self.d_x = torch.from_numpy(np.ascontiguousarray(xs)).to(dev)
-        self.d_ir = torch.from_numpy(ir).to(dev)
-        self.d_y = torch.empty((max(1, self.hi * self.B - self.y0), 2), dtype=torch.float32, device=dev)
+        self.dev = dev
+        if isinstance(x, np.ndarray):
+            xs = x[self.x_lo - x_first:self.x_hi - x_first]
+            assert xs.shape[0] == self.x_hi - self.x_lo, "the slice handed in does not cover this rank's input range"
+            if xs.shape[0] == 0:
+                xs = np.zeros((1, self.cin), np.float32)
+            self.d_x = torch.from_numpy(np.ascontiguousarray(xs)).to(dev)
+        else:                                             # a device (or pinned host) tensor holding exactly [x_lo, x_hi)
+            self.d_x = x.to(dev, non_blocking=True)
+        nf = self.frames()
+        self.d_y = torch.zeros((max(1, self.f_hi - self.y0), 2), dtype=torch.float32, device=dev)
         self.state = torch.zeros(int(self.lib.ars_state_bytes()), dtype=torch.uint8, device=dev)
-        nf = max(0, self.f_hi - self.f_lo)
-        self.d_pcm = torch.empty((max(1, nf), self.C), dtype=torch.int16, device=dev)
-        self.d_mono = torch.empty(max(1, nf), dtype=torch.float32, device=dev)
-        self.d_f32 = torch.empty((max(1, nf), self.C), dtype=torch.float32, device=dev) if want_float else None
-        torch.cuda.synchronize()
+        self.d_pcm = torch.empty((max(1, nf), self.C_out), dtype=torch.int16, device=dev)
+        self.d_f32 = torch.empty((max(1, nf), self.C_out), dtype=torch.float32, device=dev) if want_float else None
+        self.n_hops = int(plan.hop_count)
+        self.d_hops = torch.zeros(max(1, self.n_hops), dtype=torch.float64, device=dev)
 
-    # views of the state block for the collectives
+    # ---- views of the state block for the collectives
     def words(self):
         return self.state.view(self.torch.int32)
 
     def sumsq(self):
         return self.state.view(self.torch.float64)[6:7]
 
-    def _sync(self):
-        self.capi.check(self.lib.ars_sync(), "ars_sync")
+    def frames(self):
+        return max(0, self.f_hi - self.f_lo)
 
+    def y_tail(self):
+        """The last Y_HALO frames of this rank's stage output (zero-padded in front when the rank holds fewer)."""
+        t = self.torch.zeros((Y_HALO, 2), dtype=self.torch.float32, device=self.dev)
+        k = min(Y_HALO, self.frames())
+        if k:
+            t[Y_HALO - k:] = self.d_y[self.f_hi - self.y0 - k:self.f_hi - self.y0]
+        return t
+
+    def set_halo(self, prev_tail):
+        """Frames [y0, f_lo) of the stage output = the end of the predecessor's tail."""
+        k = self.f_lo - self.y0
+        if k > 0:
+            self.d_y[:k] = prev_tail[Y_HALO - k:]
+
+    # ---- phases (everything is enqueued on the library's stream; nothing here waits for the GPU)
     def convolve(self):
+        if self.hi <= self.lo:
+            return                                        # more ranks than blocks: the zeroed state is the identity
         self.capi.check(self.lib.ars_long_convolve_dev(
             self.p, self.d_x.data_ptr(), self.x_lo, self.x_hi - self.x_lo, self.n, self.cin, self.d_ir.data_ptr(), self.L,
-            None, 0, self.clo, self.hi, self.d_y.data_ptr(), self.y0, self.state.data_ptr()), "ars_long_convolve_dev")
-        self._sync()
+            None, 0, self.lo, self.hi, self.d_y[self.f_lo - self.y0:].data_ptr(), self.f_lo, self.state.data_ptr()),
+            "ars_long_convolve_dev")
 
     def _tail(self, phase):
         if self.f_hi <= self.f_lo:
             return
-        self.torch.cuda.synchronize()
         self.capi.check(self.lib.ars_long_tail_dev(
             self.p, phase, self.d_y.data_ptr(), self.y0, self.f_lo, self.f_hi, self.N, self.state.data_ptr(),
             self.d_f32.data_ptr() if (phase == 2 and self.d_f32 is not None) else None,
-            self.d_pcm.data_ptr() if phase == 2 else None, self.d_mono.data_ptr() if phase == 2 else None),
-            "ars_long_tail_dev")
-        self._sync()
+            self.d_pcm.data_ptr() if phase == 2 else None, None), "ars_long_tail_dev")
 
     def pan_max(self):
         self._tail(0)
 
     def map_max(self):
-        self._tail(1)
+        if self.stereo_layout:
+            self._tail(1)
 
     def final(self):
         self._tail(2)
 
-    def frames(self):
-        return max(0, self.f_hi - self.f_lo)
+    def loudness_hops(self):
+        if self.n_hops == 0:
+            return
+        self.capi.check(self.lib.ars_long_loudness_hops_dev(
+            self.p, self.d_y.data_ptr(), self.y0, self.f_lo, self.f_hi, self.N, self.state.data_ptr(),
+            self.d_hops.data_ptr(), self.n_hops), "ars_long_loudness_hops_dev")
+
+    def loudness_gate(self):
+        status = self.C.c_int32(self.capi.LUFS_NONE)
+        if self.n_hops:
+            self.capi.check(self.lib.ars_long_loudness_gate_dev(self.p, self.d_hops.data_ptr(), self.n_hops, self.N,
+                                                                self.state.data_ptr(), self.C.byref(status)),
+                            "ars_long_loudness_gate_dev")
+        return status.value
+
+    def metrics(self, lufs_status):
+        m = self.capi.ArsMetrics()
+        self.capi.check(self.lib.ars_state_metrics(self.state.data_ptr(), int(self.N * self.C_out), lufs_status, m),
+                        "ars_state_metrics")
+        return self.rs._metrics_dict(m)
 
 
-def finish_long_render(rank0: "LongRenderRank", d_mono_all, count):
-    """Loudness of the gathered feed + metrics read-back on the gathering rank."""
-    import ctypes as C
-    lib, capi = rank0.lib, rank0.capi
-    rank0.torch.cuda.synchronize()
-    status = C.c_int32(0)
-    capi.check(lib.ars_loudness_dev(d_mono_all.data_ptr(), int(d_mono_all.numel()), float(rank0.p.rate),
-                                    rank0.state.data_ptr(), C.byref(status)), "ars_loudness_dev")
-    m = capi.ArsMetrics()
-    capi.check(lib.ars_state_metrics(rank0.state.data_ptr(), int(count), status.value, m), "ars_state_metrics")
-    return rank0.rs._metrics_dict(m)
+def lib_stream():
+    """The library's CUDA stream as a torch stream: collectives issued under it are ordered with the library's kernels
+    on the device, so no phase needs a host-side synchronize."""
+    import torch
+    from . import _capi
+    ptr = _capi.init().ars_stream()
+    return torch.cuda.ExternalStream(int(ptr))
 
 
-def render_long_sharded(samples, rate, external_ir_data, *, group=None, **settings):
-    """One long mask-free render over all ranks of the process group (one process per GPU, NCCL).  The stereo IR is
-    broadcast from rank 0, every rank convolves its range of overlap-save blocks, the peak-guard maxima are
-    max-reduced, the PCM and loudness-feed segments are gathered on rank 0.
-    -> on rank 0: dict(pcm, metrics, names); on the other ranks: None."""
+def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=True, x_is_slice_from=None, timings=None,
+                        **settings):
+    """One long mask-free render over all ranks of the process group (one process per GPU, NCCL).
+
+    Every rank uploads only its own slice of the clip; the stereo IR is broadcast from rank 0 and stays on the device;
+    three small all-reduces carry the peak-guard words (4 after the convolution, 1 after the pan maximum, 1 more for the
+    Stereo layout), one all-gather passes every rank's last stage-output frames to its successor (layout delay + the
+    loudness filters' warm-up), the hop energies of the loudness meter are summed, and the PCM segments are gathered
+    on rank 0 over NVLink on a second stream while the meter runs.  Everything is ordered on the device: the host waits
+    once, at the end.
+    -> on rank 0: dict(pcm, metrics, names) (pcm None when gather=False: every rank keeps `rank_pcm`);
+       on the other ranks: dict(rank_pcm=..., metrics=...) without the gathered array."""
     import torch
     import torch.distributed as dist
     from . import raytracer_studio as rs
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = torch.device("cuda", torch.cuda.current_device())
-    ir = torch.from_numpy(np.ascontiguousarray(external_ir_data, dtype=np.float32)).to(dev)
-    if world > 1:
-        dist.broadcast(ir, src=0, group=group)              # IR broadcast over NVLink
-    r = LongRenderRank(samples, rate, ir.cpu().numpy(), settings, rank, world)
-    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+    stream = lib_stream()
+    ev = []
 
-    def red(t, op):
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            ev.append((name, e))
+
+    with torch.cuda.stream(stream):
+        if isinstance(external_ir_data, torch.Tensor):
+            d_ir = external_ir_data.to(dev)
+        else:
+            d_ir = torch.from_numpy(np.ascontiguousarray(external_ir_data, dtype=np.float32)).to(dev)
+        mark("start")
         if world > 1:
-            torch.cuda.synchronize()
-            dist.all_reduce(t, op=op, group=group)
-            torch.cuda.synchronize()
-
-    r.convolve()
-    red(r.words()[0:4], MAX)
-    r.pan_max()
-    red(r.words()[4:5], MAX)
-    r.map_max()
-    red(r.words()[5:6], MAX)
-    r.final()
-    red(r.words()[8:10], MAX)
-    red(r.sumsq(), SUM)
+            dist.broadcast(d_ir, src=0, group=group)                 # IR broadcast over NVLink; it stays on the device
+        r = LongRenderRank(samples, rate, d_ir, settings, rank, world, x_is_slice_from=x_is_slice_from)
+        MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+        mark("upload + broadcast")
+        r.convolve()
+        mark("convolve")
+        if world > 1:
+            dist.all_reduce(r.words()[0:4], op=MAX, group=group)
+            tails = torch.empty((world, Y_HALO, 2), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(tails, r.y_tail(), group=group)
+            if rank > 0:
+                r.set_halo(tails[rank - 1])
+        mark("reduce maxima + halo exchange")
+        r.pan_max()
+        if world > 1:
+            dist.all_reduce(r.words()[4:5], op=MAX, group=group)
+        if r.stereo_layout:
+            r.map_max()
+            if world > 1:
+                dist.all_reduce(r.words()[5:6], op=MAX, group=group)
+        mark("pan / map maxima")
+        r.final()
+        mark("final pass")
+        # PCM segments to rank 0 on a second stream, next to the loudness meter
+        pcm_all = None
+        counts = [max(0, min(r.N, hi * r.B) - min(r.N, lo * r.B)) for lo, hi in block_ranges(int(r.plan.n_blocks), world)]
+        side = torch.cuda.Stream(device=dev)
+        done_final = torch.cuda.Event()
+        done_final.record(stream)
+        if world > 1 and gather:
+            with torch.cuda.stream(side):
+                side.wait_event(done_final)
+                pad = max(counts)
+                seg = r.d_pcm if r.frames() == pad else torch.cat(
+                    [r.d_pcm[:r.frames()], torch.zeros((pad - r.frames(), r.C_out), dtype=torch.int16, device=dev)])
+                seg_b = seg.view(torch.uint8)                        # NCCL has no int16: ship the frames as bytes
+                boxes = [torch.empty_like(seg_b) for _ in range(world)] if rank == 0 else None
+                dist.gather(seg_b, boxes, dst=0, group=group)
+                if rank == 0:
+                    pcm_all = torch.cat([b.view(torch.int16)[:c] for b, c in zip(boxes, counts)], dim=0)
+                done_gather = torch.cuda.Event()
+                done_gather.record(side)
+        r.loudness_hops()
+        if world > 1:
+            dist.all_reduce(r.d_hops, op=SUM, group=group)
+            dist.all_reduce(r.words()[8:10], op=MAX, group=group)
+            dist.all_reduce(r.sumsq(), op=SUM, group=group)
+        status = r.loudness_gate()
+        mark("loudness + metric reductions")
+        if world > 1 and gather:
+            stream.wait_event(done_gather)
+        mark("pcm gather (tail not hidden by the meter)")
+        metrics = r.metrics(status)                                  # (the one host wait of the render)
+    if timings is not None:
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(ev[:-1], ev[1:]):
+            timings[name] = timings.get(name, 0.0) + e0.elapsed_time(e1)
     layout = settings.get("target_channel_layout", rs.DEFAULT_CHANNEL_LAYOUT)
     names = rs.CHANNEL_LAYOUTS[layout]["names"]
+    out = {"metrics": metrics, "names": names, "rank_pcm": r.d_pcm[:r.frames()], "frames": (r.f_lo, r.f_hi), "rank": r}
     if world == 1:
-        metrics = finish_long_render(r, r.d_mono[:r.frames()], r.N * r.C)
-        return {"pcm": r.d_pcm[:r.frames()].cpu().numpy(), "metrics": metrics, "names": names}
-    # gather the variable-length segments, padded to the longest
-    counts = [max(0, min(r.N, hi * r.B) - lo * r.B) for lo, hi in block_ranges(-(-r.N // r.B), world)]
-    pad = max(counts)
-    pcm_pad = torch.zeros((pad, r.C), dtype=torch.int16, device=dev)
-    mono_pad = torch.zeros(pad, dtype=torch.float32, device=dev)
-    pcm_pad[:r.frames()] = r.d_pcm[:r.frames()]
-    mono_pad[:r.frames()] = r.d_mono[:r.frames()]
-    pcm_bytes = pcm_pad.view(torch.uint8)                   # NCCL has no int16: ship the PCM frames as bytes
-    byte_list = [torch.empty_like(pcm_bytes) for _ in range(world)] if rank == 0 else None
-    mono_list = [torch.empty_like(mono_pad) for _ in range(world)] if rank == 0 else None
-    dist.gather(pcm_bytes, byte_list, dst=0, group=group)    # output segments gathered over NVLink
-    dist.gather(mono_pad, mono_list, dst=0, group=group)
-    if rank != 0:
-        return None
-    pcm = torch.cat([t.view(torch.int16)[:c] for t, c in zip(byte_list, counts)], dim=0)
-    mono = torch.cat([t[:c] for t, c in zip(mono_list, counts)], dim=0).contiguous()
-    metrics = finish_long_render(r, mono, r.N * r.C)
-    return {"pcm": pcm.cpu().numpy(), "metrics": metrics, "names": names}
+        out["pcm"] = r.d_pcm[:r.frames()].cpu().numpy() if gather else None
+    elif rank == 0:
+        out["pcm"] = pcm_all.cpu().numpy() if (gather and pcm_all is not None) else None
+    return out
+
+
+def rank_ranges(plan, n_in, rank, world):
+    """-> (first output frame, end output frame, first input frame, end input frame) of `rank` under `plan`."""
+    lo, hi = block_ranges(int(plan.n_blocks), world)[rank]
+    N, B = int(plan.frames_out), int(plan.block_frames)
+    f_lo, f_hi = min(N, lo * B), min(N, hi * B)
+    x_lo = max(0, f_lo - int(plan.halo_frames))
+    return f_lo, f_hi, x_lo, max(x_lo, min(int(n_in), f_hi))
+
+
+def long_clip_slice(lo, hi, cin=2, amp=0.1, seed=5):
+    """Frames [lo, hi) of the synthetic long clip of the benchmark: generated in 2^20-frame chunks seeded by the chunk
+    index, so that a rank can make its own slice without generating the whole hour."""
+    CHK = 1 << 20
+    out = np.empty((max(0, hi - lo), cin), np.float32)
+    for c in range(lo // CHK, (max(lo, hi - 1)) // CHK + 1):
+        a, b = max(lo, c * CHK), min(hi, (c + 1) * CHK)
+        if b <= a:
+            continue
+        blk = np.random.default_rng([seed, c]).standard_normal((CHK, cin), dtype=np.float32) * np.float32(amp)
+        out[a - lo:b - lo] = blk[a - c * CHK:b - c * CHK]
+    return out
+
+
+def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
+    """bench.py --workload long [--gpus N]: BASELINE configs[4], ONE long 48 kHz stereo render (x) a dense stereo IR
+    (default 1 h (x) 20 s), EQ flat, 5.1 out, split by overlap-save block ranges over the N ranks.  Strong scaling:
+    the work is fixed, `value` = clip seconds / max-over-ranks device time of the whole render including the
+    collectives and the gather of the PCM segments on rank 0."""
+    import json
+    import os
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import _capi, raytracer_studio as rs
+    rate = 48000
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _capi.init(local)
+    for kv in args.opt:
+        _capi.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    seconds = args.seconds or 3600.0
+    ir_seconds = args.ir_seconds or 20.0
+    settings = dict(dry_wet=.5, dry_wet_kill_start=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.5, y_pos=.5, z_pos=.5,
+                    target_channel_layout="5.1 (Standard)")
+    n = int(seconds * rate)
+    ir = make_ir(ir_seconds)
+    L = ir.shape[0]
+    p, _ = rs.make_render_params(rate, external_ir=True, want_lufs=True, **settings)
+    plan = _capi.ArsLongPlan()
+    _capi.check(lib.ars_long_plan(p, n, L, plan), "ars_long_plan")
+    f_lo, f_hi, x_lo, x_hi = rank_ranges(plan, n, rank, world)
+    h_x = torch.from_numpy(long_clip_slice(x_lo, x_hi)).pin_memory()
+    d_x = h_x.cuda()
+    d_ir = torch.from_numpy(ir).cuda()
+    h_pcm = torch.empty((max(1, f_hi - f_lo), 6), dtype=torch.int16).pin_memory()
+    stream = lib_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_dev(timings=None, gather=True):
+        return render_long_sharded(d_x, rate, d_ir, x_is_slice_from=(x_lo, n), gather=gather, timings=timings, **settings)
+
+    def step_host():
+        with torch.cuda.stream(stream):
+            dx = h_x.to("cuda", non_blocking=True)
+        out = render_long_sharded(dx, rate, d_ir, x_is_slice_from=(x_lo, n), gather=False, **settings)
+        with torch.cuda.stream(stream):
+            h_pcm[:out["rank_pcm"].shape[0]].copy_(out["rank_pcm"], non_blocking=True)
+        stream.synchronize()
+        return out
+
+    for _ in range(max(1, args.warmup)):
+        out = step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = int(lib.ars_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.ars_launch_count()) - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # the same without the gather of the PCM segments on rank 0 (every rank keeps its own segment)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev(gather=False)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    nogather_ms = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    timings = {}
+    for _ in range(args.steps):
+        step_dev(timings=timings)
+    barrier()
+    # end to end: every rank uploads its slice from pinned host memory and downloads its own PCM segment
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_ms = max_over_ranks(1000 * (time.perf_counter() - t0))
+    metrics = out["metrics"]
+    if rank == 0:
+        peaks = load_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        N = int(plan.frames_out)
+        algo = (8 + 2 * 6) * N
+        step_ms = dev_ms / args.steps
+        pcm_bytes_to_rank0 = 12 * (N - (f_hi - f_lo)) if world > 1 else 0
+        line = {"metric": "audio-seconds rendered per second (x realtime) @48kHz, one long render (x) dense stereo IR",
+                "value": seconds * args.steps / (dev_ms * 1e-3), "unit": "audio-seconds/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: single long 48 kHz stereo render (x) dense external stereo IR, EQ flat, "
+                                       "dw 0.5, 5.1 pan/map, metrics, int16 PCM; overlap-save blocks split over the ranks",
+                           "clip_seconds": seconds, "frames_in": n, "ir_frames": L, "frames_out": N, "channels_out": 6,
+                           "block_frames": int(plan.block_frames), "blocks": int(plan.n_blocks),
+                           "route": "big-block overlap-save" if plan.route == 1 else "partitioned overlap-save",
+                           "parallelism": f"block-range sharded x{world} (rank r: blocks {block_ranges(int(plan.n_blocks), world)})"},
+                "value_without_pcm_gather": seconds * args.steps / (nogather_ms * 1e-3),
+                "ms_per_step_without_pcm_gather": nogather_ms / args.steps,
+                "phases_ms_rank0": {k: v / args.steps for k, v in timings.items()},
+                "collectives": {"ir_broadcast_bytes": L * 8, "maxima_allreduce_bytes": [16, 4], "halo_allgather_bytes": world * Y_HALO * 8,
+                                "hop_energy_allreduce_bytes": int(plan.hop_count) * 8, "metric_allreduce_bytes": [8, 8],
+                                "pcm_gather_bytes_into_rank0": pcm_bytes_to_rank0,
+                                "limiting": "PCM gather into rank 0 (one GPU's NVLink ingress)" if world > 1 else None},
+                "e2e": {"value": seconds * args.steps / (e2e_ms * 1e-3), "unit": "audio-seconds/s",
+                        "ms_per_step": e2e_ms / args.steps,
+                        "call": "sharding.render_long_sharded: every rank uploads its own slice from pinned host memory and "
+                                "downloads its own PCM segment",
+                        "h2d_bytes_per_step": int(h_x.numel() * 4 * (world if world > 1 else 1)),
+                        "d2h_bytes_per_step": int(N * 12)},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "whole render (every kernel and collective of the step)",
+                             "achieved": algo / (step_ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": algo / (step_ms * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_step": algo,
+                             "traffic": None},
+                "metrics_of_last_render": metrics}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()

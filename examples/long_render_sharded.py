@@ -4,9 +4,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
         examples/long_render_sharded.py [--seconds 600] [--ir-seconds 8] [--check]
 
-Rank 0 broadcasts the stereo IR (NCCL), every rank convolves its block range, the peak-guard maxima are
-max-reduced, PCM and loudness-feed segments are gathered on rank 0.  --check also renders the whole clip on rank 0
-alone and requires bit-identical PCM.
+Rank 0 broadcasts the stereo IR (NCCL), every rank uploads and convolves its own block range, the peak-guard maxima
+are max-reduced, the ranks' last stage-output frames go to their successors, the loudness meter's hop energies are
+summed, and the PCM segments are gathered on rank 0 (ars_b200.sharding.render_long_sharded).  --check also renders
+the whole clip on rank 0 alone and requires bit-identical PCM (prints BIT-IDENTICAL).
 """
 import argparse
 import json
@@ -59,9 +60,14 @@ def main():
                "wall_ms_incl_upload_and_gather": [round(1000 * t, 2) for t in times[1:]], "metrics": res["metrics"]}
         if a.check:
             whole = rs.render_array(x, rate, external_ir_data=ir, want_float=False, **settings)
-            out["bit_identical_to_single_gpu"] = bool(np.array_equal(whole["pcm"], res["pcm"]))
+            same = bool(np.array_equal(whole["pcm"], res["pcm"]))
+            out["bit_identical_to_single_gpu"] = same
             out["metrics_single_gpu"] = whole["metrics"]
+            lufs_ok = abs(whole["metrics"]["lufs"] - res["metrics"]["lufs"]) < 1e-9
+            print("BIT-IDENTICAL" if same and lufs_ok else "MISMATCH")
         print(json.dumps(out))
+        if a.check and not (same and lufs_ok):
+            sys.exit(1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -110,7 +110,8 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * store plus two 4096-point transforms; 0 = one four-stage 8192-point tile [default: measured faster]),
  * "lufs_fused" (1 = one-pass loudness meter: both K-weighting stages and the hop energies in one kernel [default];
  * 0 = one pass per stage and step), "lufs_from_stage" (1 = inside a render the meter recomputes its feed from the
- * convolution stage's output and runs next to the final pass [default]; 0 = the final pass writes a feed array),
+ * convolution stage's output and runs next to the final pass; 0 = the final pass writes a feed array [default: measured
+ * faster, both kernels are bound by issue slots]),
  * "mac_tiled_min" (partition count above which dense IRs use the register-tiled multiply-accumulate kernel),
  * "olsb" (1 = mask-free and folded-air convolutions whose taps fit a quarter of a two-pass transform run as ONE-partition
  * overlap-save over 2^18..2^22-point blocks: strided forward pass, fused middle pass [contiguous forward x IR spectrum x
@@ -238,11 +239,22 @@ ARS_API int ars_render_batch(const ArsClip* clips, int32_t count);
  *   uint32 [5] max |out| (Stereo map only)                                           -> MAX after tail phase 1
  *   uint32 [8] peak, [9] loudness-feed peak -> MAX ; double at byte 48: sum of squares -> SUM  (after phase 2)
  *   double at byte 56: integrated loudness (written by ars_loudness_dev)
- * Blocks are ars_ols_block_frames() frames long.  Rank r computes output blocks [block_lo, block_hi) from an
- * input slice that starts at absolute frame x_frame0 and holds x_frames frames; it must reach back
- * (P - 1 + 1) blocks before block_lo (P = ceil(L / block)) or to frame 0.  y / outputs are slices too. */
+ * ars_long_plan says how the render splits: blocks of block_frames output frames (one overlap-save transform of the
+ * big-block route, or 4096 frames of the partitioned route).  Rank r computes output blocks [block_lo, block_hi) from
+ * an input slice that starts at absolute frame x_frame0 and holds x_frames frames; the slice must reach halo_frames
+ * frames before frame block_lo * block_frames (or to frame 0).  y / outputs are slices too.  Every rank must use the same
+ * library options, so that every rank takes the same route: the result is then bit-identical to the one-GPU render. */
+typedef struct ArsLongPlan {
+    int64_t block_frames;       /* output frames per block                                                   */
+    int64_t n_blocks;           /* blocks of the whole render: ceil(frames_out / block_frames)               */
+    int64_t halo_frames;        /* input frames needed in front of a block range                             */
+    int64_t frames_out;         /* n_total + ir_len - 1                                                      */
+    int32_t hop_count;          /* 100 ms hops of the loudness meter (ars_long_loudness_*), 0: clip too short */
+    int32_t route;              /* 0: partitioned overlap-save, 1: big-block overlap-save                     */
+} ArsLongPlan;
 ARS_API int64_t ars_state_bytes(void);
-ARS_API int64_t ars_ols_block_frames(void);
+ARS_API int64_t ars_ols_block_frames(void);       /* block length of the partitioned route (route 0)         */
+ARS_API int ars_long_plan(const ArsRenderParams* p, int64_t n_total, int64_t ir_len, ArsLongPlan* out);
 ARS_API int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, int64_t x_frame0, int64_t x_frames,
                                   int64_t n_total, int32_t cin, const float* d_ir0, int64_t L0, const float* d_ir1,
                                   int64_t L1, int64_t block_lo, int64_t block_hi, float* d_y, int64_t y_frame0,
@@ -252,6 +264,14 @@ ARS_API int ars_long_convolve_dev(const ArsRenderParams* p, const float* d_x, in
 ARS_API int ars_long_tail_dev(const ArsRenderParams* p, int32_t phase, const float* d_y, int64_t y_frame0,
                               int64_t frame_lo, int64_t frame_hi, int64_t N_total, void* d_state, float* d_out_f32,
                               int16_t* d_out_pcm, float* d_mono);
+/* The loudness meter split over the ranks: a rank leaves the hop energies of ITS frames [frame_lo, frame_hi) -- fed from
+ * the stage output y, whose slice must reach 3 x 8192 frames before frame_lo (or to frame 0) for the filters' warm-up --
+ * in d_hops[hop_count] (absolute hop index, zeros elsewhere) and max-merges the feed's peak into state word [9]; the
+ * ranks SUM the vectors, then every rank (or one) gates: the loudness lands in the state block. */
+ARS_API int ars_long_loudness_hops_dev(const ArsRenderParams* p, const float* d_y, int64_t y_frame0, int64_t frame_lo,
+                                       int64_t frame_hi, int64_t N_total, void* d_state, double* d_hops, int32_t n_hops);
+ARS_API int ars_long_loudness_gate_dev(const ArsRenderParams* p, const double* d_hops, int32_t n_hops, int64_t N_total,
+                                       void* d_state, int32_t* lufs_status);
 /* loudness meter on a (gathered) mono feed; enqueued, result lands in the state block */
 ARS_API int ars_loudness_dev(const float* d_mono, int64_t N, double rate, void* d_state, int32_t* lufs_status);
 /* read the state block back and turn it into metrics (synchronises) */

@@ -415,47 +415,88 @@ def test_overlap_save_path_matches_oracle_and_n_point_path(rs, golden, logf):
         _capi.set_option("upols_logf", 13)
 
 
-@pytest.mark.parametrize("layout", ["5.1 (Standard)", "5.1.2 (Atmos Light)", "Stereo"])
-def test_block_sharded_long_render_is_bit_identical(rs, layout):
-    """splitting a mask-free render by overlap-save block ranges must not change a bit.
-    Several ranks are emulated on the one GPU; the collectives between the phases are done with numpy."""
+def _emulated_sharded_render(sh, x, rate, ir, settings, world):
+    """`world` ranks of a block-sharded long render one after another on the one GPU; the collectives between the phases
+    are done with torch ops on the ranks' state blocks.  -> (pcm, metrics)"""
     import torch
-    from ars_b200 import sharding as sh
-    g = np.random.default_rng(41)
-    rate = 48000
-    x = (0.9 * g.standard_normal((230011, 2))).astype(np.float32)          # loud: the stereo guard and the pan guard fire
-    ir = (g.standard_normal((21000, 2)) * np.exp(-np.arange(21000) / 5000.0)[:, None]).astype(np.float32)
-    ir /= np.max(np.abs(ir)) * 8
-    settings = dict(dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.3, y_pos=.6, z_pos=.7,
-                    target_channel_layout=layout)
-    whole = rs.render_array(x, rate, external_ir_data=ir, **settings)
-    for world in (1, 3):
-        ranks = [sh.LongRenderRank(x, rate, ir, settings, r, world) for r in range(world)]
+    d_ir = torch.from_numpy(ir).cuda()
+    ranks = [sh.LongRenderRank(x, rate, d_ir, settings, r, world) for r in range(world)]
 
-        def reduce(view_of, op):
-            vals = torch.stack([view_of(r).clone() for r in ranks])
-            red = vals.max(dim=0).values if op == "max" else vals.sum(dim=0)
-            for r in ranks:
-                view_of(r).copy_(red)
-            torch.cuda.synchronize()
+    def reduce(view_of, op):
+        vals = torch.stack([view_of(r).clone() for r in ranks])
+        red = vals.max(dim=0).values if op == "max" else vals.sum(dim=0)
+        for r in ranks:
+            view_of(r).copy_(red)
 
+    with torch.cuda.stream(sh.lib_stream()):
         for r in ranks: r.convolve()
         reduce(lambda r: r.words()[0:4], "max")
+        tails = [r.y_tail() for r in ranks]
+        for k in range(1, world): ranks[k].set_halo(tails[k - 1])
         for r in ranks: r.pan_max()
         reduce(lambda r: r.words()[4:5], "max")
         for r in ranks: r.map_max()
         reduce(lambda r: r.words()[5:6], "max")
         for r in ranks: r.final()
+        for r in ranks: r.loudness_hops()
+        reduce(lambda r: r.d_hops, "sum")
         reduce(lambda r: r.words()[8:10], "max")
         reduce(lambda r: r.sumsq(), "sum")
-        pcm = torch.cat([r.d_pcm[:r.frames()] for r in ranks], dim=0).cpu().numpy()
-        mono = torch.cat([r.d_mono[:r.frames()] for r in ranks], dim=0).contiguous()
-        m = sh.finish_long_render(ranks[0], mono, ranks[0].N * ranks[0].C)
-        assert pcm.shape == whole["pcm"].shape
-        assert np.array_equal(pcm, whole["pcm"]), f"world {world}: PCM differs from the single-GPU render"
-        assert m["true_peak_dbfs"] == whole["metrics"]["true_peak_dbfs"]
-        assert abs(m["rms_dbfs"] - whole["metrics"]["rms_dbfs"]) < 1e-6
-        assert abs(m["lufs"] - whole["metrics"]["lufs"]) < 1e-9
+        status = ranks[0].loudness_gate()
+        pcm = torch.cat([r.d_pcm[:r.frames()] for r in ranks], dim=0)
+        m = ranks[0].metrics(status)
+    return pcm.cpu().numpy(), m
+
+
+@pytest.mark.parametrize("layout", ["5.1 (Standard)", "5.1.2 (Atmos Light)", "Stereo"])
+@pytest.mark.parametrize("route", ["big-block", "partitioned"])
+def test_block_sharded_long_render_is_bit_identical(rs, layout, route):
+    """splitting a mask-free render by overlap-save block ranges must not change a bit --
+    on either convolution route, with the peak guards firing, with a layout delay reaching into the previous rank's
+    frames, and with more ranks than blocks."""
+    from ars_b200 import _capi, sharding as sh
+    g = np.random.default_rng(41)
+    rate = 48000
+    n = 1400011 if route == "big-block" else 230011
+    x = (0.9 * g.standard_normal((n, 2))).astype(np.float32)          # loud: the stereo guard and the pan guard fire
+    ir = (g.standard_normal((21000, 2)) * np.exp(-np.arange(21000) / 5000.0)[:, None]).astype(np.float32)
+    ir /= np.max(np.abs(ir)) * 8
+    settings = dict(dry_wet=.6, dry_wet_kill_start=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.3, y_pos=.6, z_pos=.7,
+                    target_channel_layout=layout)
+    try:
+        _capi.set_option("olsb", 1 if route == "big-block" else 0)
+        c0 = int(_capi.load_library().ars_olsb_count())
+        whole = rs.render_array(x, rate, external_ir_data=ir, **settings)
+        assert (int(_capi.load_library().ars_olsb_count()) > c0) == (route == "big-block")
+        for world in (1, 3, 8):
+            pcm, m = _emulated_sharded_render(sh, x, rate, ir, settings, world)
+            assert pcm.shape == whole["pcm"].shape
+            assert np.array_equal(pcm, whole["pcm"]), f"world {world}: PCM differs from the single-GPU render"
+            assert m["true_peak_dbfs"] == whole["metrics"]["true_peak_dbfs"]
+            assert abs(m["rms_dbfs"] - whole["metrics"]["rms_dbfs"]) < 1e-6
+            assert abs(m["lufs"] - whole["metrics"]["lufs"]) < 1e-9, (world, m["lufs"], whole["metrics"]["lufs"])
+    finally:
+        _capi.set_option("olsb", 1)
+
+
+def test_block_sharded_long_render_on_real_ranks():
+    """The same over torch.distributed / NCCL with one process per GPU (needs >= 2 GPUs; `gpurun --gpus 2`): the PCM
+    gathered on rank 0 must equal the single-GPU render bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "examples", "long_render_sharded.py"), "--check", "--seconds", "90",
+           "--ir-seconds", "1.5"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BIT-IDENTICAL" in r.stdout, r.stdout[-2000:]
 
 
 def test_random_presets_vs_oracle(rs):

@@ -108,6 +108,8 @@ PROTOTYPES = {
     "ars_profile_begin": (C.c_int, []),
     "ars_profile_end": (C.c_int, [C.POINTER(_i64), C.POINTER(_d), C.POINTER(_d)]),
     "ars_profile_report": (C.c_char_p, []),
+    "ars_host_alloc": (C.c_void_p, [_i64]),
+    "ars_host_free": (None, [C.c_void_p]),
 }
 
 _lib = None
@@ -173,6 +175,35 @@ def shutdown():
     if _lib is not None:
         _lib.ars_shutdown()
     _inited = False
+
+
+class _PinnedBlock:
+    """A page-locked block of the library wrapped for numpy (array interface); goes back to the library's pool when the
+    last array that views it dies."""
+
+    def __init__(self, lib, address, nbytes):
+        self._lib, self._address = lib, address
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (address, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.ars_host_free(self._address)
+        except Exception:
+            pass
+
+
+def result_empty(shape, dtype) -> np.ndarray:
+    """np.empty for a render's results: large arrays come from the library's pinned pool, so the device -> host copy runs
+    at bus speed and without page faults; the caller gets an ordinary, writable ndarray."""
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    if nbytes < (4 << 20) or os.environ.get("ARS_PINNED_RESULTS", "1") == "0":
+        return np.empty(shape, dt)
+    lib = init()
+    address = lib.ars_host_alloc(nbytes)
+    if not address:
+        return np.empty(shape, dt)
+    return np.asarray(_PinnedBlock(lib, address, nbytes)).view(dt).reshape(shape)
 
 
 def ptr(a) -> int | None:

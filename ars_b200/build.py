@@ -19,7 +19,7 @@ BUILD = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libars_b200.so")
 SOURCES = ["fft_k_gc_fwd.cu", "fft_k_gc_inv.cu", "fft_k_gs_fwd.cu", "fft_k_gs_inv.cu", "fft_k_fs_fwd.cu", "fft_k_fs_inv.cu",
-           "fft_k_fc_fwd.cu", "fft_k_fc_inv.cu", "fft_k_mid.cu", "common.cu", "fft_plan.cu", "spectral.cu", "epilogue.cu", "ir_synth.cu", "metrics.cu", "upols.cu",
+           "fft_k_fc_fwd.cu", "fft_k_fc_inv.cu", "fft_k_mid.cu", "common.cu", "hostio.cu", "fft_plan.cu", "spectral.cu", "epilogue.cu", "ir_synth.cu", "metrics.cu", "upols.cu",
            "api.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Wno-deprecated-gpu-targets"]

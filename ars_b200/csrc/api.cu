@@ -14,6 +14,12 @@ const char* last_error_cstr();
 void fft_profile_begin();
 void fft_profile_end(long long* launches, double* ms, double* bytes);
 const char* prof_last_report();
+// hostio.cu: transfers for callers that hold pageable memory, pinned result blocks
+void host_upload(void* d_dst, const void* h_src, size_t bytes, cudaStream_t after);
+void host_download(void* h_dst, const void* d_src, size_t bytes, cudaStream_t after);
+void host_staging_enable(int on);
+void* host_block_alloc(size_t bytes);
+void host_block_free(void* p);
 
 #define ARS_API_BEGIN                                                   \
     try {                                                               \
@@ -118,11 +124,11 @@ static inline double clip(double v, double lo, double hi) { return std::min(hi, 
 template <class T> static T* upload(const char* name, const T* host, size_t count) {
     Ctx& c = ctx();
     T* d = c.buf(name, sizeof(T) * std::max<size_t>(count, 1)).as<T>();
-    if (count) ARS_CUDA(cudaMemcpyAsync(d, host, sizeof(T) * count, cudaMemcpyHostToDevice, c.stream));
+    if (count) host_upload(d, host, sizeof(T) * count, c.stream);       // (large pageable arrays: through the pinned ring)
     return d;
 }
 template <class T> static void download(T* host, const T* dev, size_t count) {
-    if (count) ARS_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx().stream));
+    if (count) host_download(host, dev, sizeof(T) * count, ctx().stream);
 }
 static void sync() { ARS_CUDA(cudaStreamSynchronize(ctx().stream)); }
 
@@ -403,7 +409,11 @@ int ars_init(int device) {
     }
 }
 
-void ars_shutdown(void) { ctx_shutdown(); }
+static void api_release();       // the copy pipeline of ars_render_batch and the stopwatch events (below)
+void ars_shutdown(void) {
+    api_release();
+    ctx_shutdown();
+}
 
 int ars_sync(void) {
     ARS_API_BEGIN
@@ -419,6 +429,26 @@ uint64_t ars_olsb_count(void) { return olsb_count(); }
 void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
 
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+// process-wide CUDA objects of this file belong to the device of the current context: destroyed with it, re-created
+// on first use after the next ars_init (which may name another device)
+static void api_release() {
+    if (!ctx_ready()) return;
+    std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+    cudaSetDevice(ctx().device);
+    cudaStreamSynchronize(ctx().stream);
+    Pipe& pp = g_pipe;
+    if (pp.h2d) {
+        cudaStreamSynchronize(pp.h2d);
+        cudaStreamSynchronize(pp.d2h);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(pp.in_ready[i]); cudaEventDestroy(pp.done[i]); cudaEventDestroy(pp.out_free[i]); }
+        cudaStreamDestroy(pp.h2d);
+        cudaStreamDestroy(pp.d2h);
+    }
+    if (pp.h_state) cudaFreeHost(pp.h_state);
+    pp = Pipe();
+    if (g_ev0) { cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1); g_ev0 = g_ev1 = nullptr; }
+}
 
 int ars_timer_begin(void) {
     ARS_API_BEGIN
@@ -455,6 +485,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
     else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
+    else if (!strcmp(key, "host_staging")) host_staging_enable(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");
     ARS_API_END
@@ -565,6 +596,18 @@ int ars_dry_wet_mix(const float* dry, int64_t n_dry, const float* wet, int64_t n
 }
 
 const char* ars_profile_report(void) { return prof_last_report(); }
+
+void* ars_host_alloc(int64_t bytes) {
+    try {
+        if (bytes < 0 || !ctx_ready()) return nullptr;
+        ARS_CUDA(cudaSetDevice(ctx().device));
+        return host_block_alloc((size_t)bytes);
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+void ars_host_free(void* p) { host_block_free(p); }
 
 int64_t ars_convolve_out_len(int64_t n, int64_t len_early, int64_t len_late) {
     // rs.py:351-355 (a missing IR stands for zeros(1))
@@ -953,7 +996,7 @@ int ars_render_batch(const ArsClip* clips, int32_t count) {
         // ---- host -> device on the copy stream (the slot's inputs are free once clip i-2 has been computed)
         if (i >= 2) ARS_CUDA(cudaStreamWaitEvent(pp.h2d, pp.done[slot], 0));
         float* d_in = c.buf(slot_name("in.x", slot), sizeof(float) * (size_t)k.n * k.cin).as<float>();
-        ARS_CUDA(cudaMemcpyAsync(d_in, k.in, sizeof(float) * (size_t)k.n * k.cin, cudaMemcpyHostToDevice, pp.h2d));
+        host_upload(d_in, k.in, sizeof(float) * (size_t)k.n * k.cin, pp.h2d);      // (pageable clips: through the pinned ring)
         const float* d_ir = nullptr;
         ArsIrDraws dd;
         memset(&dd, 0, sizeof dd);
@@ -981,8 +1024,8 @@ int ars_render_batch(const ArsClip* clips, int32_t count) {
         ARS_CUDA(cudaEventRecord(pp.done[slot], c.stream));
         // ---- device -> host on the other copy stream
         ARS_CUDA(cudaStreamWaitEvent(pp.d2h, pp.done[slot], 0));
-        if (k.out_f32) ARS_CUDA(cudaMemcpyAsync(k.out_f32, d_f, sizeof(float) * (size_t)N * C, cudaMemcpyDeviceToHost, pp.d2h));
-        if (k.out_pcm) ARS_CUDA(cudaMemcpyAsync(k.out_pcm, d_p, sizeof(short) * (size_t)N * C, cudaMemcpyDeviceToHost, pp.d2h));
+        if (k.out_f32) host_download(k.out_f32, d_f, sizeof(float) * (size_t)N * C, pp.d2h);
+        if (k.out_pcm) host_download(k.out_pcm, d_p, sizeof(short) * (size_t)N * C, pp.d2h);
         if (k.metrics) ARS_CUDA(cudaMemcpyAsync(&h_states[i], st, sizeof(RenderState), cudaMemcpyDeviceToHost, pp.d2h));
         ARS_CUDA(cudaEventRecord(pp.out_free[slot], pp.d2h));
     }

@@ -224,6 +224,7 @@ void prof_session_end(const char* prefix, long long* launches, double* ms, doubl
 }
 const char* prof_last_report() { return g_kprof.last_json.c_str(); }
 
+void hostio_release();           // hostio.cu
 void fft_release_plans();       // fft_plan.cu
 void bluestein_release_plans(); // bluestein.cu
 
@@ -232,6 +233,7 @@ void ctx_shutdown() {
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaStreamSynchronize(g_ctx->stream);
+    hostio_release();
     bluestein_release_plans();
     fft_release_plans();
     for (auto& kv : g_ctx->ws) kv.second.release();

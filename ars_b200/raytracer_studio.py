@@ -389,12 +389,20 @@ def calculate_audio_metrics(data, rate):
     if ch == 0:
         return metrics
     try:
-        if not np.issubdtype(data.dtype, np.floating):
-            raise ValueError("Data must be floating point.")
+        # pyloudnorm refuses non-floating input; the reference catches that inside its own try (rs.py:685-693): lufs stays
+        # None, peak and RMS are still computed (rs.py:694-698)
+        want_lufs = 1 if np.issubdtype(data.dtype, np.floating) else 0
+        if not want_lufs:
+            print("Fehler bei LUFS-Berechnung: Data must be floating point.")
         x = np.ascontiguousarray(data, dtype=_F32)
         m = ArsMetrics()
-        _capi.check(_lib().ars_metrics(_capi.ptr(x), n, ch, float(rate), 1, m), "ars_metrics")
-        return _metrics_dict(m)
+        _capi.check(_lib().ars_metrics(_capi.ptr(x), n, ch, float(rate), want_lufs, m), "ars_metrics")
+        out = _metrics_dict(m)
+        if not want_lufs:          # (the reference's silence test comes before the meter call, rs.py:689)
+            feed = data[:, 0] if ch == 1 else np.mean(data[:, :2], axis=1)
+            if np.max(np.abs(feed)) < 1e-6:
+                out["lufs"] = -np.inf
+        return out
     except ArsError:
         raise
     except Exception as e:
@@ -511,9 +519,9 @@ def render_array(samples, rate, *, external_ir_data=None, want_stereo=False, wan
     if layout not in CHANNEL_LAYOUTS:
         layout = DEFAULT_CHANNEL_LAYOUT
     C = CHANNEL_LAYOUTS[layout]["channels"]
-    stereo = np.empty((N, 2), _F32) if want_stereo else None
-    final = np.empty((N, C), _F32) if want_float else None
-    pcm = np.empty((N, C), np.int16) if want_pcm else None
+    stereo = _capi.result_empty((N, 2), _F32) if want_stereo else None
+    final = _capi.result_empty((N, C), _F32) if want_float else None
+    pcm = _capi.result_empty((N, C), np.int16) if want_pcm else None
     m = ArsMetrics() if want_metrics else None
     _capi.check(lib.ars_render(p, _capi.ptr(x), n, cin, _capi.ptr(ir), L, draws, _capi.ptr(stereo), _capi.ptr(final),
                                _capi.ptr(pcm), m), "ars_render")
@@ -557,8 +565,8 @@ def render_batch(jobs, *, want_float=False, want_pcm=True, want_metrics=True):
         if layout not in CHANNEL_LAYOUTS:
             layout = DEFAULT_CHANNEL_LAYOUT
         C = CHANNEL_LAYOUTS[layout]["channels"]
-        final = np.empty((N, C), _F32) if want_float else None
-        pcm = np.empty((N, C), np.int16) if want_pcm else None
+        final = _capi.result_empty((N, C), _F32) if want_float else None
+        pcm = _capi.result_empty((N, C), np.int16) if want_pcm else None
         m = ArsMetrics() if want_metrics else None
         keep += [x, ir, p, draws, m]
         k = clips[i]
@@ -582,6 +590,21 @@ def _metrics_text(mt):
     peak_s = f"{peak:.1f}" if peak is not None and not np.isinf(peak) else "-inf"
     rms_s = f"{rms:.1f}" if rms is not None and not np.isinf(rms) else "-inf"
     return f"LUFS: {lufs_s} | Peak: {peak_s} dBFS | RMS: {rms_s} dBFS"
+
+
+def _read_audio(path):
+    """sf.read(path, dtype='float32', always_2d=True) of the reference (rs.py:1013, 1034).  RIFF/WAVE files go through the
+    native reader (wavio.py); anything else (FLAC, OGG, AIFF ...) needs libsndfile and is read through `soundfile` when
+    that package is importable -- file decoding is outside the render path."""
+    try:
+        return wavio.read(path)
+    except Exception as wav_error:
+        try:
+            import soundfile as sf
+        except ImportError:
+            raise wav_error
+        data, rate = sf.read(path, dtype="float32", always_2d=True)
+        return np.ascontiguousarray(data, dtype=_F32), int(rate)
 
 
 def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_external_ir_cb, hall_type_val, room_size_val,
@@ -609,7 +632,7 @@ def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_externa
             print(f"ERROR: {msg}")
             return None, None, msg
         try:
-            samples, rate = wavio.read(audio_file_path)
+            samples, rate = _read_audio(audio_file_path)
             if samples.size == 0:
                 raise ValueError("Audiodatei ist leer.")
         except Exception as e:
@@ -624,7 +647,7 @@ def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_externa
                 print(f"WARNUNG: {msg}")
                 return None, None, msg
             try:
-                ir, ir_rate = wavio.read(ir_path)
+                ir, ir_rate = _read_audio(ir_path)
                 if ir.size == 0:
                     raise ValueError("Externe IR-Datei ist leer.")
                 if ir.ndim != 2 or ir.shape[1] != 2:
@@ -646,6 +669,7 @@ def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_externa
                            bass_gain=bass, treble_gain=treble, x_pos=x, y_pos=y, z_pos=z, material=material,
                            target_channel_layout=target_channel_layout)
         text = _metrics_text(res["metrics"])
+        path = None
         try:
             with tempfile.NamedTemporaryFile(delete=False, suffix=".wav", prefix="processed_") as f:
                 path = f.name
@@ -654,10 +678,15 @@ def apply_raytrace_convolution_3d(audio_file_path, external_ir_path, use_externa
         except Exception as e:
             msg = f"Fehler beim Schreiben der WAV-Datei: {e}"
             print(f"ERROR: {msg}")
+            if path and os.path.exists(path):         # rs.py:1088-1091: no half-written temp file is left behind
+                try:
+                    os.remove(path)
+                except OSError:
+                    pass
             return None, None, msg
-    except ArsError:
-        raise
     except Exception as e:
+        # rs.py:1096-1109: this entry point never raises -- a failure of the GPU library (ArsError) included; the
+        # stage-level functions keep raising, there is no CPU path to fall back to
         msg = f"Unerwarteter Fehler: {e}"
         print(f"ERROR: {msg}")
         traceback.print_exc()

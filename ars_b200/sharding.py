@@ -236,18 +236,30 @@ def lib_stream():
     return torch.cuda.ExternalStream(int(ptr))
 
 
-def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=True, x_is_slice_from=None, timings=None,
-                        **settings):
+_SIDE_STREAMS = {}
+
+
+def side_stream(dev):
+    """One extra stream per device for the PCM gather (kept: torch's allocator caches blocks per stream)."""
+    import torch
+    key = int(dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=True, to_host=True, x_is_slice_from=None,
+                        timings=None, **settings):
     """One long mask-free render over all ranks of the process group (one process per GPU, NCCL).
 
     Every rank uploads only its own slice of the clip; the stereo IR is broadcast from rank 0 and stays on the device;
     three small all-reduces carry the peak-guard words (4 after the convolution, 1 after the pan maximum, 1 more for the
     Stereo layout), one all-gather passes every rank's last stage-output frames to its successor (layout delay + the
-    loudness filters' warm-up), the hop energies of the loudness meter are summed, and the PCM segments are gathered
-    on rank 0 over NVLink on a second stream while the meter runs.  Everything is ordered on the device: the host waits
-    once, at the end.
-    -> on rank 0: dict(pcm, metrics, names) (pcm None when gather=False: every rank keeps `rank_pcm`);
-       on the other ranks: dict(rank_pcm=..., metrics=...) without the gathered array."""
+    loudness filters' warm-up), the hop energies of the loudness meter are summed, and the PCM segments travel to rank 0
+    over NVLink on a second stream -- point to point, straight into their place in the whole array -- while the meter
+    runs.  Everything is ordered on the device: the host waits once, at the end.
+    -> dict(metrics, names, rank_pcm (this rank's frames, device), frames, pcm_device (rank 0, gather=True: the whole
+       render on the device), pcm (rank 0, gather and to_host: numpy))"""
     import torch
     import torch.distributed as dist
     from . import raytracer_studio as rs
@@ -293,35 +305,40 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=T
         mark("pan / map maxima")
         r.final()
         mark("final pass")
-        # PCM segments to rank 0 on a second stream, next to the loudness meter
-        pcm_all = None
-        counts = [max(0, min(r.N, hi * r.B) - min(r.N, lo * r.B)) for lo, hi in block_ranges(int(r.plan.n_blocks), world)]
-        side = torch.cuda.Stream(device=dev)
-        done_final = torch.cuda.Event()
-        done_final.record(stream)
-        if world > 1 and gather:
-            with torch.cuda.stream(side):
-                side.wait_event(done_final)
-                pad = max(counts)
-                seg = r.d_pcm if r.frames() == pad else torch.cat(
-                    [r.d_pcm[:r.frames()], torch.zeros((pad - r.frames(), r.C_out), dtype=torch.int16, device=dev)])
-                seg_b = seg.view(torch.uint8)                        # NCCL has no int16: ship the frames as bytes
-                boxes = [torch.empty_like(seg_b) for _ in range(world)] if rank == 0 else None
-                dist.gather(seg_b, boxes, dst=0, group=group)
-                if rank == 0:
-                    pcm_all = torch.cat([b.view(torch.int16)[:c] for b, c in zip(boxes, counts)], dim=0)
-                done_gather = torch.cuda.Event()
-                done_gather.record(side)
+        # the meter's and the metrics' small reductions first (NCCL runs a communicator's operations in issue order: behind
+        # the gigabytes of the gather they would wait for it), then the PCM segments on the second stream
         r.loudness_hops()
         if world > 1:
             dist.all_reduce(r.d_hops, op=SUM, group=group)
             dist.all_reduce(r.words()[8:10], op=MAX, group=group)
             dist.all_reduce(r.sumsq(), op=SUM, group=group)
+        pcm_all = None
+        if world > 1 and gather:
+            side = side_stream(dev)
+            done_final = torch.cuda.Event()
+            done_final.record(stream)
+            ranges = [(min(r.N, lo * r.B), min(r.N, hi * r.B)) for lo, hi in block_ranges(int(r.plan.n_blocks), world)]
+            with torch.cuda.stream(side):
+                side.wait_event(done_final)
+                ops = []
+                if rank == 0:
+                    pcm_all = torch.empty((r.N, r.C_out), dtype=torch.int16, device=dev)
+                    pcm_all[r.f_lo:r.f_hi] = r.d_pcm[:r.frames()]
+                    for src, (a, b) in enumerate(ranges):
+                        if src != 0 and b > a:             # NCCL has no int16: the frames travel as bytes
+                            ops.append(dist.P2POp(dist.irecv, pcm_all[a:b].view(torch.uint8), src, group=group))
+                elif r.frames() > 0:
+                    ops.append(dist.P2POp(dist.isend, r.d_pcm[:r.frames()].view(torch.uint8), 0, group=group))
+                if ops:
+                    for w_ in dist.batch_isend_irecv(ops):
+                        w_.wait()
+                done_gather = torch.cuda.Event()
+                done_gather.record(side)
         status = r.loudness_gate()
         mark("loudness + metric reductions")
         if world > 1 and gather:
             stream.wait_event(done_gather)
-        mark("pcm gather (tail not hidden by the meter)")
+        mark("pcm gather (part not hidden by the meter)")
         metrics = r.metrics(status)                                  # (the one host wait of the render)
     if timings is not None:
         torch.cuda.synchronize()
@@ -329,11 +346,12 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=T
             timings[name] = timings.get(name, 0.0) + e0.elapsed_time(e1)
     layout = settings.get("target_channel_layout", rs.DEFAULT_CHANNEL_LAYOUT)
     names = rs.CHANNEL_LAYOUTS[layout]["names"]
-    out = {"metrics": metrics, "names": names, "rank_pcm": r.d_pcm[:r.frames()], "frames": (r.f_lo, r.f_hi), "rank": r}
-    if world == 1:
-        out["pcm"] = r.d_pcm[:r.frames()].cpu().numpy() if gather else None
-    elif rank == 0:
-        out["pcm"] = pcm_all.cpu().numpy() if (gather and pcm_all is not None) else None
+    out = {"metrics": metrics, "names": names, "rank_pcm": r.d_pcm[:r.frames()], "frames": (r.f_lo, r.f_hi), "rank": r,
+           "pcm_device": None, "pcm": None}
+    if gather and rank == 0:
+        out["pcm_device"] = r.d_pcm[:r.frames()] if world == 1 else pcm_all
+        if to_host:
+            out["pcm"] = out["pcm_device"].cpu().numpy()
     return out
 
 
@@ -410,12 +428,13 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
         return float(t.item())
 
     def step_dev(timings=None, gather=True):
-        return render_long_sharded(d_x, rate, d_ir, x_is_slice_from=(x_lo, n), gather=gather, timings=timings, **settings)
+        return render_long_sharded(d_x, rate, d_ir, x_is_slice_from=(x_lo, n), gather=gather, to_host=False, timings=timings,
+                                   **settings)
 
     def step_host():
         with torch.cuda.stream(stream):
             dx = h_x.to("cuda", non_blocking=True)
-        out = render_long_sharded(dx, rate, d_ir, x_is_slice_from=(x_lo, n), gather=False, **settings)
+        out = render_long_sharded(dx, rate, d_ir, x_is_slice_from=(x_lo, n), gather=False, to_host=False, **settings)
         with torch.cuda.stream(stream):
             h_pcm[:out["rank_pcm"].shape[0]].copy_(out["rank_pcm"], non_blocking=True)
         stream.synchronize()

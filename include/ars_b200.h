@@ -119,6 +119,11 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * "olsb_logf" (0 = block length chosen from the tap count [default] | 18..22), "olsb_stripe" (0 = transforms per
  * L2-resident stripe chosen from the SM count [default] | n). */
 ARS_API int ars_set_option(const char* key, int32_t value);
+/* Page-locked host blocks for results: the Python layer wraps them as numpy arrays (freed through ars_host_free when the
+ * array dies; the library keeps up to 4 GiB of freed blocks for the next render).  Copies from / to PAGEABLE host memory
+ * of 4 MiB and more go through a ring of pinned slots filled by a few worker threads (option "host_staging", default 1). */
+ARS_API void* ars_host_alloc(int64_t bytes);
+ARS_API void ars_host_free(void* p);
 /* CUDA-event stopwatch on the library stream: begin records, end records + waits + reports ms. */
 ARS_API int ars_timer_begin(void);
 ARS_API int ars_timer_end(float* ms);

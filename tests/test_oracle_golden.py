@@ -140,3 +140,26 @@ def test_loudness_known_answers():
         O.integrated_loudness(x[:1000], rate)
     blocks = O.loudness_blocks(rate * 5, rate)
     assert blocks[0] == (0, 19200) and len(blocks) == 47
+
+
+def test_loudness_restatement_agrees_with_torchaudio():
+    """pyloudnorm is not installable here (PARITY UNPINNED for LUFS).  Secondary cross-check: torchaudio's
+    independent implementation of ITU-R BS.1770-4 (functional.loudness: RBJ high-shelf + 38 Hz high-pass, 400 ms / 75 %
+    blocks, -70 LUFS absolute and -10 LU relative gates) against the oracle's restatement of pyloudnorm, on stationary and
+    on level-switching noise and on a tone.  torchaudio filters in float32, hence the 1e-3 LU bar."""
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    rate = 48000
+    g = np.random.default_rng(0)
+    sigs = []
+    for secs, amp in ((3.0, 0.1), (10.0, 0.05), (1.0, 0.08)):        # (torchaudio clamps its filters' output to +-1: keep clear)
+        x = (amp * g.standard_normal(int(secs * rate))).astype(np.float32)
+        sigs.append(x.copy())
+        x[len(x) // 2:] *= 0.2                      # a level drop exercises the relative gate
+        sigs.append(x)
+    t = np.arange(4 * rate) / rate
+    sigs.append((0.25 * np.sin(2 * np.pi * 997.0 * t)).astype(np.float32))
+    for x in sigs:
+        ours = O.integrated_loudness(x, rate)
+        theirs = float(ta.functional.loudness(torch.from_numpy(x)[None, :], rate))
+        assert abs(ours - theirs) <= 1e-3, (ours, theirs)

@@ -25,7 +25,8 @@ class ArsError(RuntimeError):
 class ArsMetrics(C.Structure):
     _fields_ = [("lufs", C.c_double), ("lufs_status", C.c_int32), ("reserved", C.c_int32),
                 ("peak_linear", C.c_double), ("rms_linear", C.c_double),
-                ("true_peak_dbfs", C.c_double), ("rms_dbfs", C.c_double)]
+                ("true_peak_dbfs", C.c_double), ("rms_dbfs", C.c_double),
+                ("true_peak_4x_dbfs", C.c_double), ("true_peak_4x_status", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class ArsIrDraws(C.Structure):
@@ -82,6 +83,7 @@ PROTOTYPES = {
     "ars_layout_channels": (C.c_int, [_i32]),
     "ars_map_channels": (C.c_int, [_p, _i64, _i32, _d, _d, _p]),
     "ars_metrics": (C.c_int, [_p, _i64, _i32, _d, _i32, C.POINTER(ArsMetrics)]),
+    "ars_true_peak_4x": (C.c_int, [_p, _i64, _i32, C.POINTER(_d)]),
     "ars_channel_rms": (C.c_int, [_p, _i64, _i32, _p, C.POINTER(C.c_float)]),
     "ars_spectrogram_segments": (_i64, [_i64, _i32]),
     "ars_spectrogram": (C.c_int, [_p, _i64, _i32, _d, _i32, _p]),

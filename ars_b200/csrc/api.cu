@@ -227,8 +227,19 @@ static TailSpec make_tail(i64 N, int layout, double rate, double x_, double y_, 
     return ts;
 }
 
-static void finish_metrics(const RenderState& st, i64 count, int lufs_status, ArsMetrics* m) {
+static int layout_ok(int layout) { return layout >= LAYOUT_STEREO && layout <= LAYOUT_5_1_2; }
+
+// p (optional): the render's parameters, for the oversampled true peak (needs the layout's gains)
+static void finish_metrics(const RenderState& st, i64 count, int lufs_status, ArsMetrics* m,
+                           const ArsRenderParams* p = nullptr) {
     memset(m, 0, sizeof(*m));
+    m->true_peak_4x_status = 1;
+    if (p && (p->want_lufs & 2) && layout_ok(p->layout)) {
+        const TailSpec ts = make_tail(0, p->layout, p->rate, p->x, p->y, p->z);
+        const double tp = true_peak_linear(st, ts);
+        m->true_peak_4x_dbfs = tp > 1e-15 ? 20.0 * std::log10(tp) : -std::numeric_limits<double>::infinity();
+        m->true_peak_4x_status = 0;
+    }
     const float peak = [&] { float f; unsigned u = st.peak_final; memcpy(&f, &u, 4); return f; }();
     const double inf = std::numeric_limits<double>::infinity();
     m->peak_linear = (double)peak;
@@ -246,7 +257,6 @@ static int lufs_enqueue(const float* d_mono, i64 N, double rate, RenderState* d_
     return s == 0 ? ARS_LUFS_OK : ARS_LUFS_NONE;
 }
 
-static int layout_ok(int layout) { return layout >= LAYOUT_STEREO && layout <= LAYOUT_5_1_2; }
 
 // ---------------------------------------------------------------- render core ----
 static i64 render_out_len(const ArsRenderParams* p, i64 n, i64 ext_len) {
@@ -334,7 +344,8 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
     if (!d_out_f32 && !d_out_pcm && !want_metrics) return;
     const TailSpec ts = make_tail(N, p->layout, p->rate, p->x, p->y, p->z);
     tail_maxes(y, ts, st);
-    if (want_metrics && p->want_lufs && g_opt_lufs_from_stage && loudness_from_stage_possible(p->rate)) {
+    if (want_metrics && (p->want_lufs & 2)) true_peak_from_stage(y, ts, st);       // (add-on, off unless asked for)
+    if (want_metrics && (p->want_lufs & 1) && g_opt_lufs_from_stage && loudness_from_stage_possible(p->rate)) {
         // the loudness meter recomputes its feed from the stage output, so it needs nothing from the final pass: it runs
         // on the side stream NEXT TO it (one is bound by issue slots and conversions, the other by float64 latency)
         if (g_opt_side_stream) side_begin();
@@ -346,7 +357,7 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         return;
     }
     float* d_mono = nullptr;
-    if (want_metrics && p->want_lufs) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
+    if (want_metrics && (p->want_lufs & 1)) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
     tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
     if (d_mono && lufs_status) *lufs_status = lufs_enqueue(d_mono, N, p->rate, st);
 }
@@ -735,6 +746,15 @@ int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, int32_t w
     ARS_API_END
 }
 
+int ars_true_peak_4x(const float* data, int64_t n, int32_t ch, double* dbtp) {
+    ARS_API_BEGIN
+    ARS_CHECK(data && dbtp && n > 0 && ch >= 1, "ars_true_peak_4x: bad arguments");
+    const float* d_x = upload("in.x", data, (size_t)n * ch);
+    const double tp = true_peak_of_array(d_x, n, ch);
+    *dbtp = tp > 1e-15 ? 20.0 * std::log10(tp) : -std::numeric_limits<double>::infinity();
+    ARS_API_END
+}
+
 int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, float* side_rms_out) {
     ARS_API_BEGIN
     ARS_CHECK(data && rms_out && n > 0 && ch >= 1 && ch <= 8, "ars_channel_rms: needs (n > 0, 1..8 channels)");
@@ -820,7 +840,7 @@ int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int32_t cin
     RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
     if (metrics) download(h, st, 1);
     sync();
-    if (metrics) finish_metrics(*h, N * C, lufs_status, metrics);
+    if (metrics) finish_metrics(*h, N * C, lufs_status, metrics, p);
     ARS_API_END
 }
 
@@ -839,7 +859,7 @@ int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32
         RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
         download(h, st, 1);
         sync();
-        finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics);
+        finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics, p);
     }
     ARS_API_END
 }
@@ -1032,7 +1052,8 @@ int ars_render_batch(const ArsClip* clips, int32_t count) {
     ARS_CUDA(cudaStreamSynchronize(pp.d2h));
     ARS_CUDA(cudaStreamSynchronize(c.stream));
     for (int i = 0; i < count; ++i)
-        if (clips[i].metrics) finish_metrics(h_states[i], out_count[(size_t)i], lufs_status[(size_t)i], clips[i].metrics);
+        if (clips[i].metrics)
+            finish_metrics(h_states[i], out_count[(size_t)i], lufs_status[(size_t)i], clips[i].metrics, clips[i].params);
     ARS_API_END
 }
 

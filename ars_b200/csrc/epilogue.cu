@@ -113,10 +113,17 @@ __device__ __forceinline__ short pcm_of(float v) {
     const int q = __float2int_rn(__fmul_rn(v, 32767.0f));
     return (short)min(max(q, -32764), 32764);
 }
+// two samples at once: saturating pack to int16 x 2, then one two-lane max and one two-lane min for the +-32764 clamp
+__device__ __forceinline__ unsigned pcm_pair(float v0, float v1) {
+    const int q0 = __float2int_rn(__fmul_rn(v0, 32767.0f)), q1 = __float2int_rn(__fmul_rn(v1, 32767.0f));
+    unsigned p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(q1), "r"(q0));      // q1 -> upper half, q0 -> lower half
+    return __vmins2(__vmaxs2(p, 0x80048004u), 0x7ffc7ffcu);
+}
 
 // The frame loop of the final pass; A1 / A2 / A3 say which peak guards are active (checked once per thread, so
 // idle guards cost nothing per sample).
-template <int C, bool A1, bool A2, bool A3>
+template <int C, int A1, int A2, int A3>
 __device__ __forceinline__ void final_body(const float2* __restrict__ y, const TailSpec& ts, const Guard& g1, const Guard& g2,
                                            const Guard& g3, float* __restrict__ out, short* __restrict__ pcm,
                                            float* __restrict__ mono, float& pkf, bool& nan_seen, unsigned& mm, double& ss) {
@@ -149,22 +156,17 @@ __device__ __forceinline__ void final_body(const float2* __restrict__ y, const T
             }
         }
         if (pcm) {
-            short q[8];
-            #pragma unroll
-            for (int c = 0; c < C; ++c) q[c] = pcm_of(o[c]);
             short* p = pcm + (i - ts.out0) * C;
             if (C == 8) {
                 uint4 u;
-                u.x = (unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16);
-                u.y = (unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16);
-                u.z = (unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16);
-                u.w = (unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16);
+                u.x = pcm_pair(o[0], o[1]);
+                u.y = pcm_pair(o[2], o[3]);
+                u.z = pcm_pair(o[4], o[5]);
+                u.w = pcm_pair(o[6], o[7]);
                 *reinterpret_cast<uint4*>(p) = u;
             } else {
                 #pragma unroll
-                for (int c = 0; c < C; c += 2)
-                    reinterpret_cast<unsigned*>(p)[c >> 1] =
-                        (unsigned short)q[c] | ((unsigned)(unsigned short)q[c + 1] << 16);
+                for (int c = 0; c < C; c += 2) reinterpret_cast<unsigned*>(p)[c >> 1] = pcm_pair(o[c], o[c + 1]);
             }
         }
         if (mono) {
@@ -188,10 +190,11 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
     unsigned mm = 0;
     double ss = 0.0;
     if (g2.mode == 0 && g3.mode == 0) {
-        if (g1.mode == 0) final_body<C, false, false, false>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
-        else final_body<C, true, false, false>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        if (g1.mode == 0) final_body<C, 0, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        else if (g1.mode == 1) final_body<C, 2, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        else final_body<C, 1, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
     } else {
-        final_body<C, true, true, true>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        final_body<C, 1, 1, 1>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
     }
     const unsigned pk = nan_seen ? 0x7fc00000u : __float_as_uint(pkf);
     block_atomic_max(pk, &st->peak_final);

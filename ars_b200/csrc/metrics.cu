@@ -198,7 +198,7 @@ struct SrcMono {                       // a materialised feed (ars_metrics, bloc
     const float* x;
     __device__ __forceinline__ bool prepare() { return true; }
     __device__ __forceinline__ float2 load(i64 i) const { return make_float2(__ldg(x + i), 0.f); }
-    template <bool G> __device__ __forceinline__ float value(float2 raw) const { return raw.x; }
+    template <int G> __device__ __forceinline__ float value(float2 raw) const { return raw.x; }
 };
 struct SrcStage {                      // mean(ch0, ch1) of the final frame (rs.py:687-688), recomputed from the convolution stage's
     const float2* y;                   // output exactly as final_kernel forms it -- the meter then needs no feed array and can
@@ -212,7 +212,7 @@ struct SrcStage {                      // mean(ch0, ch1) of the final frame (rs.
         return g1.mode == 0 && g2.mode == 0 && g3.mode == 0;
     }
     __device__ __forceinline__ float2 load(i64 i) const { return __ldg(y + (i - ts.y0)); }
-    template <bool G> __device__ __forceinline__ float value(float2 raw) const {
+    template <int G> __device__ __forceinline__ float value(float2 raw) const {
         FrameIn f;
         f.v = raw;
         f.w = make_float2(0.f, 0.f);
@@ -239,56 +239,67 @@ struct LoudArgs {
     unsigned* mono_max;                // bits of max |feed| (null: the caller has it already)
 };
 
-// True start state of this thread's chunk for one stage: zero-state sweep, block scan, publish, look back, propagate.
+__device__ __forceinline__ double2 shfl_up2(double2 v, int d) {
+    return make_double2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+
+// True start state of this thread's chunk for one stage: zero-state sweep, scan, publish, look back, propagate.
+// The scan is two-level: inside a warp by shuffles (five steps with the tabulated A^(CH 2^k), no barrier), across the
+// eight warps by one thread; a chunk's start state is then  (zero-start state of the chunks before it in its warp)
+// + A^(CH lane) (state at the warp's first chunk), the power again by the tabulated squarings.  Two barriers per stage.
 __device__ __forceinline__ double2 chunk_start_state(const float* mine, const ScanCoef& cf, double2* __restrict__ agg,
-                                                     int* __restrict__ flag, int depth, int b, double2* sv, double2* s_start) {
-    const int t = threadIdx.x;
+                                                     int* __restrict__ flag, int depth, int b, double2* sw, double2* sc) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     double2 z = make_double2(0.0, 0.0);
     #pragma unroll 8
     for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
-    double2 v = z;
-    sv[t] = v;
-    __syncthreads();
+    double2 v = z;                                         // inclusive scan inside the warp (zero start at its first chunk)
     #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int off = 1 << k;
-        double2 add = make_double2(0.0, 0.0);
-        if (t >= off) add = mat_vec(cf.pw[k], sv[t - off]);
-        __syncthreads();
-        v.x += add.x; v.y += add.y;
-        sv[t] = v;
-        __syncthreads();
+    for (int k = 0; k < 5; ++k) {
+        const double2 up = shfl_up2(v, 1 << k);
+        if (lane >= (1 << k)) { const double2 add = mat_vec(cf.pw[k], up); v.x += add.x; v.y += add.y; }
     }
-    if (t == NTB - 1) {                                    // publish first ...
-        agg[b] = v;
+    if (lane == 31) sw[warp] = v;
+    __syncthreads();
+    if (t == 0) {
+        // zero-start aggregate of the block: agg = sum_w A^(32 CH (7 - w)) sw[w]; publish it before looking back
+        double2 a = make_double2(0.0, 0.0);
+        #pragma unroll
+        for (int w = 0; w < NTB / 32; ++w) { const double2 m = mat_vec(cf.pw[5], a); a = make_double2(m.x + sw[w].x, m.y + sw[w].y); }
+        agg[b] = a;
         __threadfence();
         *reinterpret_cast<volatile int*>(flag + b) = 1;
-    }
-    if (t == 0) {                                          // ... then look back: s_b = agg[b-1] + M (agg[b-2] + M (...))
+        // block start state s_b = agg[b-1] + M (agg[b-2] + M (...)), M = A^BS
         double2 s = make_double2(0.0, 0.0);
         const int d0 = b < depth ? b : depth;
         for (int d = d0; d >= 1; --d) {
             while (*reinterpret_cast<volatile int*>(flag + (b - d)) == 0) __nanosleep(40);
             __threadfence();
-            const double2 a = __ldcg(agg + (b - d));
+            const double2 p = __ldcg(agg + (b - d));
             const double2 ms = mat_vec(cf.pw[8], s);
-            s = make_double2(a.x + ms.x, a.y + ms.y);
+            s = make_double2(p.x + ms.x, p.y + ms.y);
         }
-        *s_start = s;
+        // state at every warp's first chunk
+        #pragma unroll
+        for (int w = 0; w < NTB / 32; ++w) {
+            sc[w] = s;
+            const double2 m = mat_vec(cf.pw[5], s);
+            s = make_double2(m.x + sw[w].x, m.y + sw[w].y);
+        }
     }
     __syncthreads();
-    double2 w = *s_start;                                  // A^(CH t) s_b by binary powering with the tabulated A^(CH 2^k)
+    double2 w0 = sc[warp];                                 // A^(CH lane) (warp start state)
     #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if ((t >> k) & 1) w = mat_vec(cf.pw[k], w);
-    if (t > 0) { const double2 p = sv[t - 1]; w.x += p.x; w.y += p.y; }
-    __syncthreads();                                       // sv / s_start are reused by the next stage
-    return w;
+    for (int k = 0; k < 5; ++k)
+        if ((lane >> k) & 1) w0 = mat_vec(cf.pw[k], w0);
+    const double2 prev = shfl_up2(v, 1);
+    if (lane > 0) { w0.x += prev.x; w0.y += prev.y; }
+    return w0;
 }
 
 // the block's samples into shared memory, eight loads in flight per thread (the feed's arithmetic would otherwise wait
 // for every load in turn)
-template <class SRC, bool G>
+template <class SRC, int G>
 __device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 base, i64 N, i64 src_lo) {
     const int t = threadIdx.x;
     unsigned mm = 0;
@@ -316,8 +327,7 @@ __device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 bas
 template <class SRC>
 __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int nblocks) {
     __shared__ float sx[NTB * (CH + 1)];
-    __shared__ double2 sv[NTB];
-    __shared__ double2 s_start;
+    __shared__ double2 sw[2][NTB / 32], sc[2][NTB / 32];      // per stage: warp aggregates, warp start states
     __shared__ i64 s_lo[3];
     __shared__ unsigned s_b;
     __shared__ double se[4][NTB / 32];
@@ -331,17 +341,17 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
         if (b >= nblocks) break;
         const i64 base = a.g_base + (i64)b * BS;
         if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
-        const unsigned m1 = idle ? loud_feed<SRC, false>(src, sx, base, a.N, a.src_lo)
-                                 : loud_feed<SRC, true>(src, sx, base, a.N, a.src_lo);
+        const unsigned m1 = idle ? loud_feed<SRC, 0>(src, sx, base, a.N, a.src_lo)
+                                 : loud_feed<SRC, 1>(src, sx, base, a.N, a.src_lo);
         if (a.e_hi == 0 || (base + BS > a.e_lo && base < a.e_hi)) mm = max(mm, m1);     // (warm-up blocks do not count)
         __syncthreads();
         float* mine = sx + t * (CH + 1);
         // stage 1 (high shelf): float32 store, as pyloudnorm
-        double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sv, &s_start);
+        double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sw[0], sc[0]);
         #pragma unroll 8
         for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(a.c1.q, (double)mine[j], s);
         // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
-        s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sv, &s_start);
+        s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sw[1], sc[1]);
         // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
         const i64 g0 = base + (i64)t * CH;
         const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
@@ -680,6 +690,156 @@ int loudness_gate_from_hops(const double* d_hops, int n_hops, i64 N, double rate
     ARS_LAUNCH_CHECK();
     count_launch(2);
     return 0;
+}
+
+// ---- 4x-oversampled true peak (ITU-R BS.1770-4 Annex 2) -- an ADD-ON: the reference's "true_peak_dbfs" is the plain
+// sample peak (rs.py:695-697) and stays that; BASELINE's north star names the oversampled figure, so it is reported
+// next to it.  Interpolator: the standard's 48-tap FIR as four 12-tap phases (coefficients restated from Annex 2; every
+// value is a multiple of 2^-13).  The peak is taken over the four phases of every sample of every signal, the filter's
+// tail past the last sample included.
+__constant__ float TP_COEF[4][12] = {
+    {0.0017089843750f, 0.0109863281250f, -0.0196533203125f, 0.0332031250000f, -0.0594482421875f, 0.1373291015625f,
+     0.9721679687500f, -0.1022949218750f, 0.0476074218750f, -0.0266113281250f, 0.0148925781250f, -0.0083007812500f},
+    {-0.0291748046875f, 0.0292968750000f, -0.0517578125000f, 0.0891113281250f, -0.1665039062500f, 0.4650878906250f,
+     0.7797851562500f, -0.2003173828125f, 0.1015625000000f, -0.0582275390625f, 0.0330810546875f, -0.0189208984375f},
+    {-0.0189208984375f, 0.0330810546875f, -0.0582275390625f, 0.1015625000000f, -0.2003173828125f, 0.7797851562500f,
+     0.4650878906250f, -0.1665039062500f, 0.0891113281250f, -0.0517578125000f, 0.0292968750000f, -0.0291748046875f},
+    {-0.0083007812500f, 0.0148925781250f, -0.0266113281250f, 0.0476074218750f, -0.1022949218750f, 0.9721679687500f,
+     0.1373291015625f, -0.0594482421875f, 0.0332031250000f, -0.0196533203125f, 0.0109863281250f, 0.0017089843750f}};
+
+constexpr int TP_TILE = 1024;          // frames per tile (256 threads x 4 frames)
+constexpr int TP_HIST = 11;            // taps - 1
+
+struct TpStage {                       // signals s_i = a_i L + b_i R + c_i f32(f32(L + R) * 0.707) of the stage output
+    const float2* y;
+    i64 y0;
+    float a[3], b[3], c[3];
+    __device__ __forceinline__ void get(i64 i, float (&v)[3]) const {
+        const float2 f = __ldg(y + (i - y0));
+        const float m = __fmul_rn(__fadd_rn(f.x, f.y), 0.707f);
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = a[k] * f.x + b[k] * f.y + c[k] * m;
+    }
+};
+struct TpArray {                       // three channels [c0, c0 + 3) of an interleaved (n, ch) array (absent ones: zero)
+    const float* x;
+    int ch, c0;
+    __device__ __forceinline__ void get(i64 i, float (&v)[3]) const {
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = (c0 + k < ch) ? __ldg(x + i * ch + c0 + k) : 0.f;
+    }
+};
+
+template <class SRC>
+__global__ void __launch_bounds__(256) true_peak_kernel(SRC src, i64 N, unsigned* __restrict__ out_bits) {
+    __shared__ float s[3][TP_TILE + TP_HIST + 1];
+    const int t = threadIdx.x;
+    float pk[3] = {0.f, 0.f, 0.f};
+    const i64 ntiles = (N + TP_HIST + TP_TILE - 1) / TP_TILE;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 t0 = tile * TP_TILE;
+        for (int i = t; i < TP_TILE + TP_HIST; i += 256) {
+            const i64 g = t0 - TP_HIST + i;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (g >= 0 && g < N) src.get(g, v);
+            s[0][i] = v[0]; s[1][i] = v[1]; s[2][i] = v[2];
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float w[4 + TP_HIST];
+            #pragma unroll
+            for (int q = 0; q < 4 + TP_HIST; ++q) w[q] = s[k][4 * t + q];      // w[q] = sample (t0 + 4 t - 11 + q)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                #pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    float acc = 0.f;
+                    #pragma unroll
+                    for (int h = 0; h < 12; ++h) acc = fmaf(TP_COEF[p][h], w[j + TP_HIST - h], acc);
+                    pk[k] = fmaxf(pk[k], fabsf(acc));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned m = __float_as_uint(pk[k]);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((t & 31) == 0 && m > *reinterpret_cast<volatile unsigned*>(out_bits + k)) atomicMax(out_bits + k, m);
+    }
+}
+
+// Every output channel of a render is one of (at most) three signals times a non-negative gain: L, R and the mono mix
+// for the 5.1-based layouts (rs.py:484-494; the delayed side / height pairs are attenuated copies of the rear pair),
+// two L / R / mono combinations for the Stereo down-mix (rs.py:533-535) -- and oversampling is linear.  So the filter
+// runs over those signals of the stage output and the host applies the gains and the peak guards' scales
+// (true_peak_weights); the float32 roundings of the per-sample products (<= 6e-8 relative) are not replayed.
+void true_peak_from_stage(const float2* d_y, const TailSpec& ts, RenderState* d_state) {
+    Ctx& c = ctx();
+    TpStage src;
+    src.y = d_y;
+    src.y0 = ts.y0;
+    for (int k = 0; k < 3; ++k) src.a[k] = src.b[k] = src.c[k] = 0.f;
+    if (ts.layout == LAYOUT_STEREO) {
+        src.a[0] = (float)(ts.g_fl + 0.5 * ts.g_rl); src.c[0] = (float)(0.707 * ts.g_c);
+        src.b[1] = (float)(ts.g_fr + 0.5 * ts.g_rr); src.c[1] = (float)(0.707 * ts.g_c);
+    } else {
+        src.a[0] = 1.f; src.b[1] = 1.f; src.c[2] = 1.f;
+    }
+    ARS_CUDA(cudaMemsetAsync(d_state->tp_bits, 0, sizeof(unsigned) * 4, c.stream));
+    KernelScope prof("true_peak_kernel (4x polyphase FIR, add-on)", 8.0 * (double)ts.N);
+    const i64 ntiles = (ts.N + TP_HIST + TP_TILE - 1) / TP_TILE;
+    true_peak_kernel<TpStage><<<(int)std::min<i64>(ntiles, (i64)c.sm_count * 8), 256, 0, c.stream>>>(src, ts.N, d_state->tp_bits);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+
+double true_peak_linear(const RenderState& h, const TailSpec& ts) {
+    auto f = [](unsigned u) { float v; memcpy(&v, &u, 4); return (double)v; };
+    auto guard_scale = [&](unsigned bits) {
+        const double m = f(bits);
+        return m > 1.0 ? 1.0 / m : ((m > 0.0 && m < 1e-9) ? 0.0 : 1.0);
+    };
+    double scale = guard_scale(h.max_stereo) * guard_scale(h.max_pan);
+    double w[3];
+    if (ts.layout == LAYOUT_STEREO) {
+        scale *= guard_scale(h.max_map);
+        w[0] = w[1] = 1.0;
+        w[2] = 0.0;
+    } else {
+        w[0] = std::max(std::fabs(ts.g_fl), std::fabs(ts.g_rl));
+        w[1] = std::max(std::fabs(ts.g_fr), std::fabs(ts.g_rr));
+        w[2] = std::max(std::fabs(ts.g_c), (double)ts.g_lfe);
+    }
+    double tp = 0.0;
+    for (int k = 0; k < 3; ++k) tp = std::max(tp, w[k] * f(h.tp_bits[k]));
+    return tp * scale;
+}
+
+// the same over the channels of a materialised (n, ch) array -> linear peak (synchronises)
+double true_peak_of_array(const float* d_x, i64 n, int ch) {
+    Ctx& c = ctx();
+    unsigned* bits = c.buf("tp.bits", sizeof(unsigned) * 4).as<unsigned>();
+    double tp = 0.0;
+    for (int c0 = 0; c0 < ch; c0 += 3) {
+        TpArray src;
+        src.x = d_x;
+        src.ch = ch;
+        src.c0 = c0;
+        ARS_CUDA(cudaMemsetAsync(bits, 0, sizeof(unsigned) * 4, c.stream));
+        const i64 ntiles = (n + TP_HIST + TP_TILE - 1) / TP_TILE;
+        true_peak_kernel<TpArray><<<(int)std::min<i64>(ntiles, (i64)c.sm_count * 8), 256, 0, c.stream>>>(src, n, bits);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        unsigned h[4];
+        ARS_CUDA(cudaMemcpyAsync(h, bits, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+        ARS_CUDA(cudaStreamSynchronize(c.stream));
+        for (int k = 0; k < 3; ++k) { float v; memcpy(&v, &h[k], 4); tp = std::max(tp, (double)v); }
+    }
+    return tp;
 }
 
 // ---- spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(x, fs, window='hann', nperseg,

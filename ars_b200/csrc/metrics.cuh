@@ -23,6 +23,11 @@ int loudness_hops_from_stage(const float2* d_y, const TailSpec& ts, double rate,
                              double* d_hops, int n_hops);
 int loudness_gate_from_hops(const double* d_hops, int n_hops, i64 N, double rate, RenderState* d_state);
 
+// 4x-oversampled true peak (BS.1770-4 Annex 2), an add-on next to the reference's sample peak; see metrics.cu
+void true_peak_from_stage(const float2* d_y, const TailSpec& ts, RenderState* d_state);      // -> d_state->tp_bits
+double true_peak_linear(const RenderState& h, const TailSpec& ts);                           // host: gains + guards applied
+double true_peak_of_array(const float* d_x, i64 n, int ch);                                  // synchronises
+
 // scipy.signal.spectrogram(x[:, 0], fs, window='hann', nperseg, noverlap=nperseg//2) -> d_out[(nperseg/2+1) x nseg], row-major
 void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int nperseg, float* d_out, int* nseg_out);
 void loudness_set_ctas_per_sm(int n);   // CTAs per SM of the one-pass meter when it runs next to the final pass

@@ -73,6 +73,7 @@ struct RenderState {
     unsigned pad0, pad1;
     double sumsq;              // sum of final^2 over all channels (metrics)
     double lufs;               // integrated loudness, written by the gate kernel
+    unsigned tp_bits[4];       // 4x-oversampled peaks of the (up to three) signals the output channels are gains of (metrics.cu)
 };
 
 // y[N] (float2 = L,R) = filter(x) ; writes max |y| bits into state->max_stereo.

@@ -7,7 +7,11 @@
 namespace ars {
 
 // ----------------------------------------------------------- frame math ------
-struct Guard { int mode; float m; };      // 0: leave, 1: divide by m, 2: flush to zero
+struct Guard {              // 0: leave, 1: divide by m, 2: flush to zero
+    int mode;
+    float m;
+    float r;                // mode 1: correctly rounded 1 / m, when the short division below is valid (else 0)
+};
 
 __device__ __forceinline__ Guard make_guard(unsigned bits) {
     // rs.py:402-404 / 497-499 / 558-560: max > 1 -> x / max ; any(x) and max < 1e-9 -> zeros
@@ -15,10 +19,30 @@ __device__ __forceinline__ Guard make_guard(unsigned bits) {
     Guard g;
     g.m = m;
     g.mode = (m > 1.0f) ? 1 : ((m > 0.f && m < 1e-9f) ? 2 : 0);
+    // (a divisor whose mantissa is all ones is the one case the theorem below excludes; huge divisors could underflow)
+    g.r = (g.mode == 1 && m < 1e10f && (bits & 0x007fffffu) != 0x007fffffu) ? __frcp_rn(m) : 0.f;
     return g;
 }
+// v / m, correctly rounded like numpy's float32 division.  Thousands of samples are divided by the same maximum, so
+// the reciprocal is formed once: q = RN(v r), then two residual corrections q += RN(v - q m) r in fused arithmetic.
+// With r the correctly rounded reciprocal and q within an ulp of the quotient the corrected value IS the correctly
+// rounded quotient (Markstein); checked against exact rational arithmetic on 3e5 random and adversarial pairs
+// (scratch-free restatement in tests/test_host_logic.py).  Five straight-line instructions instead of the generic
+// division's reciprocal approximation, Newton steps, range check and branch.  Values outside the plain range take
+// the generic division.
+__device__ __forceinline__ float guard_div(float v, const Guard& g) {
+    // plain range 1e-25 <= |v| < 1e30 (or zero) as one unsigned compare on the bit pattern
+    constexpr unsigned LO = 0x15f79688u /* 1e-25f */, HI = 0x7149f2cau /* 1e30f */;
+    const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+    if (g.r != 0.f && (((u - LO) < (HI - LO)) | (u == 0u))) {
+        float q = __fmul_rn(v, g.r);
+        q = __fmaf_rn(__fmaf_rn(-q, g.m, v), g.r, q);
+        return __fmaf_rn(__fmaf_rn(-q, g.m, v), g.r, q);
+    }
+    return __fdiv_rn(v, g.m);
+}
 __device__ __forceinline__ float guard1(float v, const Guard& g) {
-    return g.mode == 0 ? v : (g.mode == 1 ? __fdiv_rn(v, g.m) : 0.f);
+    return g.mode == 0 ? v : (g.mode == 1 ? guard_div(v, g) : 0.f);
 }
 
 __device__ __forceinline__ void pan6(float L, float R, const TailSpec& ts, float (&o)[6]) {
@@ -52,9 +76,11 @@ __device__ __forceinline__ void map_frame(const float (&s)[6], float rl_d, float
     }
 }
 
-// A = false compiles the guard away (the caller has checked that its mode is 0)
-template <bool A> __device__ __forceinline__ float guardT(float v, const Guard& g) {
-    if constexpr (A) return guard1(v, g);
+// A = 0 compiles the guard away (the caller has checked that its mode is 0); A = 2: the caller has checked that the guard
+// divides (mode 1) -- no per-sample mode test; A = 1: any mode
+template <int A> __device__ __forceinline__ float guardT(float v, const Guard& g) {
+    if constexpr (A == 1) return guard1(v, g);
+    else if constexpr (A == 2) return guard_div(v, g);
     else return v;
 }
 
@@ -69,7 +95,7 @@ __device__ __forceinline__ FrameIn frame_load(const float2* __restrict__ y, i64 
     return f;
 }
 
-template <bool A1 = true, bool A2 = true>
+template <int A1 = 1, int A2 = 1>
 __device__ __forceinline__ void frame_math(const FrameIn& f, i64 i, const TailSpec& ts, const Guard& g1, const Guard& g2,
                                            float (&o)[8]) {
     float s[6];
@@ -84,7 +110,7 @@ __device__ __forceinline__ void frame_math(const FrameIn& f, i64 i, const TailSp
     map_frame(s, rl_d, rr_d, ts, o);
 }
 
-template <bool A1 = true, bool A2 = true>
+template <int A1 = 1, int A2 = 1>
 __device__ __forceinline__ void frame_out(const float2* __restrict__ y, i64 i, const TailSpec& ts, const Guard& g1,
                                           const Guard& g2, float (&o)[8]) {
     frame_math<A1, A2>(frame_load(y, i, ts), i, ts, g1, g2, o);

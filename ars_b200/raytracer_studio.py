@@ -370,7 +370,10 @@ def _metrics_dict(m: ArsMetrics):
     lufs = None
     if m.lufs_status == _capi.LUFS_OK:
         lufs = float(m.lufs)
-    return {"lufs": lufs, "true_peak_dbfs": float(m.true_peak_dbfs), "rms_dbfs": float(m.rms_dbfs)}
+    out = {"lufs": lufs, "true_peak_dbfs": float(m.true_peak_dbfs), "rms_dbfs": float(m.rms_dbfs)}
+    if m.true_peak_4x_status == 0:      # add-on, only when asked for (want_true_peak_4x): BS.1770-4 oversampled peak
+        out["true_peak_4x_dbfs"] = float(m.true_peak_4x_dbfs)
+    return out
 
 
 def calculate_audio_metrics(data, rate):
@@ -409,6 +412,20 @@ def calculate_audio_metrics(data, rate):
         print(f"Fehler bei Metrikberechnung: {e}")
         traceback.print_exc()
         return metrics
+
+
+def true_peak_4x(data):
+    """4x-oversampled true peak in dBTP over all channels (ITU-R BS.1770-4 Annex 2) -- an add-on: the reference's
+    `true_peak_dbfs` is the sample peak (rs.py:695-697) and `calculate_audio_metrics` keeps returning that."""
+    x = np.ascontiguousarray(data, dtype=_F32)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, ch = x.shape
+    if n == 0 or ch == 0:
+        return -np.inf
+    out = _capi.C.c_double(0)
+    _capi.check(_lib().ars_true_peak_4x(_capi.ptr(x), n, ch, _capi.C.byref(out)), "ars_true_peak_4x")
+    return float(out.value)
 
 
 def channel_levels(data):
@@ -463,7 +480,7 @@ def make_render_params(rate, *, external_ir=False, hall_type="Room", room_size=1
                        air_absorption=0.1, base_early_level=0.8, base_late_level=0.6, dry_wet=0.5,
                        dry_wet_kill_start=0.5, bass_gain=1.0, treble_gain=1.0, x_pos=0.5, y_pos=0.5, z_pos=0.5,
                        material=DEFAULT_MATERIAL, target_channel_layout=DEFAULT_CHANNEL_LAYOUT, want_lufs=True,
-                       ir_duration=None):
+                       ir_duration=None, want_true_peak_4x=False):
     """Host prologue of rs.py:1049-1056 -> (ArsRenderParams, reflection count).  `ir_duration` overrides the
     duration derived from hall/room (used for the '8 s IR' benchmark variant)."""
     p = ArsRenderParams()
@@ -486,7 +503,7 @@ def make_render_params(rate, *, external_ir=False, hall_type="Room", room_size=1
     p.dry_wet, p.kill_start = float(dry_wet), float(dry_wet_kill_start)
     p.bass_gain, p.treble_gain = float(bass_gain), float(treble_gain)
     p.x, p.y, p.z = float(x_pos), float(y_pos), float(z_pos)
-    p.want_lufs = 1 if want_lufs else 0
+    p.want_lufs = (1 if want_lufs else 0) | (2 if want_true_peak_4x else 0)
     return p, int(refl)
 
 

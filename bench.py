@@ -264,14 +264,15 @@ def run_reference(args):
 class Render:
     """One workload set up for repeated rendering: device-resident and pinned-host copies of the inputs."""
 
-    def __init__(self, lib, capi, rs, w, seconds, rank, ir_seconds=None, torch=None):
+    def __init__(self, lib, capi, rs, w, seconds, rank, ir_seconds=None, torch=None, true_peak=False):
         self.lib, self.capi, self.rs, self.w, self.seconds, self.torch = lib, capi, rs, w, seconds, torch
         x = make_clip(w, seconds, rank)
         self.x_np = x
         x2 = x if x.ndim == 2 else x[:, None]
         self.n, self.cin = x2.shape
         self.ext = "ext_ir_seconds" in w
-        self.p, refl = rs.make_render_params(RATE, want_lufs=True, external_ir=self.ext, **w["settings"])
+        self.p, refl = rs.make_render_params(RATE, want_lufs=True, external_ir=self.ext, want_true_peak_4x=true_peak,
+                                             **w["settings"])
         self.L = 0
         self.h_ir = self.d_ir = None
         self.ir_np = None
@@ -437,7 +438,7 @@ def run_ours(args):
     if args.air is not None:
         w = dict(w, settings=dict(w["settings"], air_absorption=args.air), desc=w["desc"] + " [air overridden: %g]" % args.air)
     seconds = args.seconds or w["seconds"]
-    r = Render(lib, _capi, rs, w, seconds, rank, args.ir_seconds or None, torch)
+    r = Render(lib, _capi, rs, w, seconds, rank, args.ir_seconds or None, torch, true_peak=args.true_peak)
 
     def barrier():
         if world > 1:
@@ -493,8 +494,14 @@ def run_ours(args):
     if world == 1 and not args.no_numpy:
         ext_kw = dict(external_ir_data=r.ir_np) if r.ext else {}
         k_np = max(2, min(args.steps, 5))
-        np.random.seed(w["np_seed"])
-        rs.render_array(r.x_np, RATE, want_float=False, **ext_kw, **w["settings"])
+        # steady state of a caller that keeps the previous result while asking for the next one: two result blocks of the
+        # library's pinned pool exist before the clock starts (page-locking a fresh 236 MB block costs ~0.2 s, once)
+        warm = []
+        for _ in range(2):
+            np.random.seed(w["np_seed"])
+            warm.append(rs.render_array(r.x_np, RATE, want_float=False, **ext_kw, **w["settings"]))
+        res = warm[-1]
+        del warm
         t0 = time.perf_counter()
         for _ in range(k_np):
             np.random.seed(w["np_seed"])
@@ -502,7 +509,8 @@ def run_ours(args):
         np_ms = 1000 * (time.perf_counter() - t0) / k_np
         e2e_np = {"value": seconds / (np_ms * 1e-3), "unit": "audio-seconds/s", "ms_per_step": np_ms, "calls": k_np,
                   "call": "ars_b200.raytracer_studio.render_array(numpy clip, ...) -> numpy PCM + metrics: pageable "
-                          "arrays, the reference's random draws replayed on the host, output allocated per call",
+                          "input array (staged through the library's pinned ring), the reference's random draws replayed on the "
+                          "host, results returned as numpy arrays over the library's pinned result pool",
                   "lufs": res["metrics"]["lufs"]}
         del res
 
@@ -719,6 +727,7 @@ def main():
     ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-API timing")
     ap.add_argument("--cin", type=int, default=0, help="experiments: override the clip's channel count")
     ap.add_argument("--air", type=float, default=None, help="experiments: override the air-absorption setting")
+    ap.add_argument("--true-peak", action="store_true", help="also compute the 4x-oversampled true peak (add-on metric)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="library option for experiments (ars_set_option), e.g. --opt air_fold=0")
     args = ap.parse_args()

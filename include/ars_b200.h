@@ -55,6 +55,11 @@ typedef struct ArsMetrics {   /* calculate_audio_metrics, rs.py:674-698 */
     double rms_linear;        /* sqrt(mean(x^2)) over all channels (rs.py:696)                */
     double true_peak_dbfs;    /* 20 log10(peak) or -inf (rs.py:697)                           */
     double rms_dbfs;          /* 20 log10(rms)  or -inf (rs.py:698)                           */
+    /* add-on (not in the reference, whose "true peak" above is the sample peak): 4x-oversampled peak after ITU-R
+     * BS.1770-4 Annex 2, over every output channel; filled when ArsRenderParams.want_lufs has bit 1 (value 2) set */
+    double true_peak_4x_dbfs;
+    int32_t true_peak_4x_status;  /* 0: computed, 1: not requested                                  */
+    int32_t reserved2;
 } ArsMetrics;
 
 /* Random draws of generate_impulse_response_split_3d replayed by the caller
@@ -80,7 +85,7 @@ typedef struct ArsRenderParams {
     double early_level, late_level, dry_wet, kill_start, bass_gain, treble_gain, air_absorption;
     /* position -- rs.py:464, 517 */
     double x, y, z;
-    int32_t want_lufs;          /* 1: also run the loudness meter                               */
+    int32_t want_lufs;          /* bit 0: also run the loudness meter; bit 1: also the 4x-oversampled true peak */
     int32_t reserved;
 } ArsRenderParams;
 
@@ -187,6 +192,9 @@ ARS_API int ars_metrics(const float* data, int64_t n, int32_t ch, double rate, i
 
 /* Numerics of the A/B report (run_audio_profiler_v4, rs.py:769-798): per-channel RMS sqrt(mean(x^2)) of an
  * (n, ch <= 8) array and the RMS of the side signal (ch0 - ch1) * 0.5 (0 for mono).  rms_out: ch floats. */
+/* 4x-oversampled true peak (dBTP) of an (n, ch) array: BS.1770-4 Annex 2 polyphase FIR, maximum over all channels
+ * (add-on; the reference reports the sample peak only) */
+ARS_API int ars_true_peak_4x(const float* data, int64_t n, int32_t ch, double* dbtp);
 ARS_API int ars_channel_rms(const float* data, int64_t n, int32_t ch, float* rms_out, float* side_rms_out);
 /* Spectrogram of the visualiser (rs.py:626-634): scipy.signal.spectrogram(data[:, 0], fs=rate, window='hann', nperseg,
  * noverlap = nperseg / 2) with scipy's defaults (constant detrend, one-sided density).  nperseg: a power of two in

@@ -174,3 +174,49 @@ def test_preset_schema_follows_the_reference_loader(tmp_path):
     presets.save_preset(str(p), back)
     s2, ext2 = presets.preset_to_settings(presets.load_preset(str(p)))
     assert (s2, ext2) == (s, ext)
+
+
+def test_reciprocal_division_of_the_peak_guards_is_correctly_rounded():
+    """tail_math.cuh: guard_div divides thousands of samples by one maximum as q = RN(v r), r = RN(1 / m), followed by two
+    fused residual corrections.  Restated here in exact rational arithmetic: the result is the correctly rounded float32
+    quotient (numpy's `x / max_val`, rs.py:403) for random and for adversarial divisors."""
+    import math
+    import random
+    import struct
+    from fractions import Fraction
+
+    def f32(x):
+        if x == 0:
+            return Fraction(0)
+        sgn, a = (-1 if x < 0 else 1), abs(x)
+        e = math.floor(math.log2(float(a))) - 23
+        while a / Fraction(2) ** e >= 2 ** 24:
+            e += 1
+        while a / Fraction(2) ** e < 2 ** 23:
+            e -= 1
+        q = a / Fraction(2) ** e
+        n = q.numerator // q.denominator
+        r = q - n
+        if r > Fraction(1, 2) or (r == Fraction(1, 2) and n % 2 == 1):
+            n += 1
+        return sgn * n * Fraction(2) ** e
+
+    def as_f32(v):
+        return Fraction(struct.unpack("f", struct.pack("f", v))[0])
+
+    random.seed(1)
+    cases = []
+    for i in range(3000):
+        m = as_f32(random.uniform(1.0, 16.0) if i % 3 else random.uniform(1.0, 1.001))
+        v = as_f32(random.uniform(-float(m), float(m))) * (Fraction(1) if i % 5 else Fraction(1, 2 ** random.randint(0, 40)))
+        cases.append((v, m))
+    for _ in range(400):           # divisors next to powers of two and with nearly-all-ones mantissas
+        bits = 0x3f800000 + random.choice([0x7ffffe, 1, 2, 0x400000, 0x3fffff, 0x7ffffd]) + (random.randint(0, 3) << 23)
+        m = Fraction(struct.unpack("f", struct.pack("I", bits))[0])
+        cases.append((as_f32(random.uniform(-float(m), float(m))), m))
+    for v, m in cases:
+        r = f32(Fraction(1) / m)
+        q = f32(v * r)
+        q = f32(f32(v - q * m) * r + q)
+        q = f32(f32(v - q * m) * r + q)
+        assert q == f32(v / m), (float(v), float(m))

@@ -213,11 +213,8 @@ struct Ld {
     const float2* tw2 = nullptr;    // w_2B^i, i < B
     // LD_OLSB_X (big-block overlap-save, upols.cu): transform j of 2^logF points is the window of the signal that
     // starts `skip` frames before output frame (seg0 + j) * hop; skip = taps - 1 aliased outputs are dropped, hop <= F - skip.
-    // seg0 / frame0 / nvalid / cin / adv / circ / c1 as for LD_OLS_X.  stash (optional): the dry frame of every output
-    // frame of the launch, compact stereo, at [j * hop + (frame - (seg0 + j) * hop)] -- the inverse's last pass mixes from it
-    // instead of re-reading a (frames, cin > 2) clip at 4 cin bytes per frame.
+    // seg0 / frame0 / nvalid / cin / adv / circ / c1 as for LD_OLS_X.
     i64 hop = 0, skip = 0;
-    float2* stash = nullptr;
     // LD_TAPS: real taps c0 * f0[i * cin] + c1 * f1[i * cin] (+ delta at index delta_at: the dry path of the mix folded
     // into the impulse response, y = dg x + dw (x * h) = x * (dg delta + dw h))
     i64 delta_at = -1;
@@ -314,10 +311,7 @@ struct Ld {
         } else if constexpr (MODE == LD_OLSB_X) {      // big-block overlap-save window (see hop / skip above)
             const i64 j = idx >> logF;
             const i64 t = idx & (((i64)1 << logF) - 1);
-            const float2 v = frame_at((seg0 + j) * hop - skip + t + adv - frame0);
-            const i64 o = t - skip + adv;              // the window element that is the dry frame of output o of transform j
-            if (stash && o >= 0 && o < hop) stash[j * hop + o] = make_float2(v.x, c1 < 0.f ? -v.y : v.y);
-            return v;
+            return frame_at((seg0 + j) * hop - skip + t + adv - frame0);
         } else if constexpr (MODE == LD_TAPS) {        // real taps c0 * f0[i * cin] + c1 * f1[i * cin], zero-padded
             const float u = (f0 && idx < nvalid) ? ARS_LDG(f0 + idx * cin) : 0.f;
             const float v = (f1 && idx < nvalid1) ? ARS_LDG(f1 + idx * cin) : 0.f;
@@ -368,15 +362,6 @@ struct Ld {
                 for (int k = 0; k < r; ++k) {
                     const float l = ARS_LDG(p + k * ps);
                     v[k] = make_float2(l, cin > 1 ? ARS_LDG(p + k * ps + 1) : l);
-                }
-            }
-            if (stash) {
-                const i64 o0 = t0 - skip + adv;
-                float2* sp = stash + j * hop + o0;
-                #pragma unroll
-                for (int k = 0; k < r; ++k) {
-                    const i64 o = o0 + k * step;
-                    if (o >= 0 && o < hop) sp[k * step] = v[k];
                 }
             }
             if (c1 < 0.f) {
@@ -502,9 +487,8 @@ struct St {
     unsigned local_max = 0, local_l = 0, local_r = 0, local_lr = 0;
     const float2* tw2 = nullptr;     // ST_OLS2: w_2B^i, i < B (see Ld::tw2)
     // ST_OLSB (big-block overlap-save): element t of transform j is output frame (seg0 + j) * hop + t - skip when
-    // skip <= t < skip + hop; stash (optional, see Ld::stash): compact stereo dry frames of the launch's outputs
+    // skip <= t < skip + hop
     i64 hop = 0, skip = 0;
-    const float2* stash = nullptr;
     // the dry frame that goes with overlap-save output frame `fr` (zero outside the slice held at `dry`)
     ARS_HD float2 dry_at(i64 fr) const {
         const i64 df = fr - dry_frame0;
@@ -561,8 +545,8 @@ struct St {
         const i64 blk = (seg0 + j) * hop;                           // first output frame of the transform
         const int olast = o0 + (r - 1) * step;
         const bool mix = dg != 0.f;                                 // (dg == 0: the dry path is part of the taps, Ld::delta)
-        const bool dry_ok = (stash || !mix) ? true : ((cin & 1) == 0 && blk + (o0 < 0 ? 0 : o0) >= dry_frame0 &&
-                                                      blk + olast - dry_frame0 < n);
+        const bool dry_ok = !mix ? true : ((cin & 1) == 0 && blk + (o0 < 0 ? 0 : o0) >= dry_frame0 &&
+                                           blk + olast - dry_frame0 < n);
         if (dry_ok && blk + (olast < hp ? olast : hp - 1) < N) {
             float2* ap = a + (blk + o0 - frame0);
             if (!mix) {
@@ -577,9 +561,8 @@ struct St {
                     }
                 }
             } else {
-                const float2* dp = stash ? stash + (j * hop + o0)
-                                         : reinterpret_cast<const float2*>(dry + (blk + o0 - dry_frame0) * cin);
-                const i64 ds = stash ? step : (i64)step * (cin >> 1);
+                const float2* dp = reinterpret_cast<const float2*>(dry + (blk + o0 - dry_frame0) * cin);
+                const i64 ds = (i64)step * (cin >> 1);
                 #pragma unroll
                 for (int k = 0; k < r; ++k) {
                     if ((unsigned)(o0 + k * step) < (unsigned)hp) {
@@ -651,8 +634,7 @@ struct St {
             const i64 o = (idx & (((i64)1 << logF) - 1)) - skip;
             if (o >= 0 && o < hop) {
                 const i64 fr = (seg0 + j) * hop + o;
-                ols_out(fr, v, dg == 0.f ? make_float2(0.f, 0.f)
-                                         : (stash ? (fr < N ? ARS_LDG(stash + j * hop + o) : make_float2(0.f, 0.f)) : dry_at(fr)));
+                ols_out(fr, v, dg == 0.f ? make_float2(0.f, 0.f) : dry_at(fr));
             }
         } else if constexpr (MODE == ST_OLS2) {
             // (stored by run_tile through put_ols2 once both sub-segments are back in shared memory)

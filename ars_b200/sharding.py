@@ -457,14 +457,6 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
     launches = int(lib.ars_launch_count()) - l0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    # the same without the gather of the PCM segments on rank 0 (every rank keeps its own segment)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev(gather=False)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    nogather_ms = max_over_ranks(e0.elapsed_time(e1))
-    barrier()
     timings = {}
     for _ in range(args.steps):
         step_dev(timings=timings)
@@ -482,6 +474,7 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
         peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         N = int(plan.frames_out)
+        phases = {k: v / args.steps for k, v in timings.items()}
         algo = (8 + 2 * 6) * N
         step_ms = dev_ms / args.steps
         pcm_bytes_to_rank0 = 12 * (N - (f_hi - f_lo)) if world > 1 else 0
@@ -495,9 +488,9 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
                            "block_frames": int(plan.block_frames), "blocks": int(plan.n_blocks),
                            "route": "big-block overlap-save" if plan.route == 1 else "partitioned overlap-save",
                            "parallelism": f"block-range sharded x{world} (rank r: blocks {block_ranges(int(plan.n_blocks), world)})"},
-                "value_without_pcm_gather": seconds * args.steps / (nogather_ms * 1e-3),
-                "ms_per_step_without_pcm_gather": nogather_ms / args.steps,
-                "phases_ms_rank0": {k: v / args.steps for k, v in timings.items()},
+                "phases_ms_rank0": phases,
+                "ms_per_step_without_pcm_gather": sum(v for k, v in phases.items() if not k.startswith("pcm gather")),
+                "value_without_pcm_gather": seconds / (1e-3 * sum(v for k, v in phases.items() if not k.startswith("pcm gather"))),
                 "collectives": {"ir_broadcast_bytes": L * 8, "maxima_allreduce_bytes": [16, 4], "halo_allgather_bytes": world * Y_HALO * 8,
                                 "hop_energy_allreduce_bytes": int(plan.hop_count) * 8, "metric_allreduce_bytes": [8, 8],
                                 "pcm_gather_bytes_into_rank0": pcm_bytes_to_rank0,

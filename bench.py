@@ -237,7 +237,7 @@ def run_reference(args):
         cores = min(cores, args.ref_procs)
     seconds = args.ref_sample_seconds or args.seconds or w["seconds"]
     jobs = [(name, seconds, i) for i in range(cores)]
-    warm = min(args.warmup, 1)          # one warm-up pass: a step is ~30 s of CPU work on every core
+    warm = 0                            # no warm-up pass: a step is ~45 s of CPU work on every core and numpy has nothing to warm
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(warm):
             pool.map(_oracle_job, jobs)

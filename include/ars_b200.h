@@ -215,6 +215,7 @@ ARS_API int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int
                int16_t* out_pcm, ArsMetrics* metrics);
 /* Same with every array pointer (including those inside `draws`) on the device.  Asynchronous
  * unless `metrics` is non-NULL (the loudness gate needs the block energies on the host). */
+/* (device pointers of the *_dev entry points must be 8-byte aligned: stereo frames are read as float2) */
 ARS_API int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
                    int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                    int16_t* d_out_pcm, ArsMetrics* metrics);

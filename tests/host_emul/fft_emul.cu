@@ -457,7 +457,7 @@ static int check_irs(i64 N, i64 L) {
 }
 
 // Big-block overlap-save wiring (upols.cu: olsb_filter): strided forward pass over the windows, fused middle pass
-// (plain and mirror form), strided inverse pass with the dry/wet store; stripes, stash, circular form.
+// (plain and mirror form), strided inverse pass with the dry/wet store; stripes, circular form, dry path in the taps or in the store.
 static int check_olsb(int logF, i64 n, i64 Lf, bool ext, int cin, i64 adv, i64 circ, int stripe, bool dryfold = true) {
     EmuPlan p;
     p.logM = logF;
@@ -478,8 +478,7 @@ static int check_olsb(int logF, i64 n, i64 Lf, bool ext, int cin, i64 adv, i64 c
         ir[2 * i + 1] = ext ? U(rng) * d : ir[2 * i];
     }
     const int nspec = ext ? 2 : 1;
-    std::vector<float2> H((size_t)F * nspec), W((size_t)F * stripe), y(N, make_float2(0, 0)), stash;
-    if (cin != 2) stash.resize((size_t)hop * stripe);
+    std::vector<float2> H((size_t)F * nspec), W((size_t)F * stripe), y(N, make_float2(0, 0));
     for (int k = 0; k < nspec; ++k) {
         Ld ld; ld.mode = LD_TAPS; ld.f0 = ir.data(); ld.f1 = ir.data() + 1; ld.cin = 2; ld.nvalid = ld.nvalid1 = Lf;
         const float wet = dryfold ? 0.5f : 1.f;
@@ -496,7 +495,7 @@ static int check_olsb(int logF, i64 n, i64 Lf, bool ext, int cin, i64 adv, i64 c
         const i64 nb = std::min<i64>(stripe, J - j0);
         {
             Ld ld; ld.mode = LD_OLSB_X; ld.logF = logF; ld.f0 = x.data(); ld.frame0 = 0; ld.nvalid = n; ld.cin = cin; ld.seg0 = j0;
-            ld.hop = hop; ld.skip = skip; ld.adv = adv; ld.circ = circ; ld.stash = stash.empty() ? nullptr : stash.data();
+            ld.hop = hop; ld.skip = skip; ld.adv = adv; ld.circ = circ;
             St st; st.mode = ST_PLAIN; st.a = W.data();
             emu_pass<false>(logF, p.tw, p.passes[0], ld, st, nb * F);
         }
@@ -514,7 +513,7 @@ static int check_olsb(int logF, i64 n, i64 Lf, bool ext, int cin, i64 adv, i64 c
         {
             Ld ld; ld.mode = LD_PLAIN; ld.a = W.data();
             St st; st.mode = ST_OLSB; st.logF = logF; st.seg0 = j0; st.hop = hop; st.skip = skip; st.a = y.data(); st.frame0 = 0;
-            st.N = N; st.dry = x.data(); st.dry_frame0 = 0; st.n = n; st.cin = cin; st.stash = stash.empty() ? nullptr : stash.data();
+            st.N = N; st.dry = x.data(); st.dry_frame0 = 0; st.n = n; st.cin = cin;
             st.dg = dryfold ? 0.f : 0.25f; st.dw = dryfold ? 1.f : 0.5f; st.maxbits = maxbits;
             emu_pass<true>(logF, p.tw, p.passes[0], ld, st, nb * F);
         }

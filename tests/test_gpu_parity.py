@@ -1036,3 +1036,41 @@ def test_true_peak_4x_add_on(rs):
     np.random.seed(8)
     plain = rs.render_array(clip, rate, hall_type="Room")
     assert "true_peak_4x_dbfs" not in plain["metrics"]
+
+
+def test_file_level_entry_point_never_raises(rs, tmp_path, monkeypatch):
+    """rs.py:1096-1109: apply_raytrace_convolution_3d reports every failure as (None, None, message).  A failure of the GPU
+    library itself (here: an invalid layout id forced through the C ABI) must come back the same way; the stage-level
+    functions keep raising ArsError (there is no CPU path to fall back to)."""
+    from ars_b200 import _capi, wavio
+    rate = 48000
+    x = (0.1 * np.random.default_rng(1).standard_normal((rate, 2))).astype(np.float32)
+    wav = str(tmp_path / "in.wav")
+    wavio.write_pcm16(wav, rs.float_to_pcm16(x), rate)
+    args = (wav, None, False, "Room", 100.0, 0.5, 0.1, 0.8, 0.6, 0.5, 0.5, 1.0, 1.0, 0.5, 0.5, 0.5, "Holz", "5.1 (Standard)")
+    ok = rs.apply_raytrace_convolution_3d(*args)
+    assert ok[0] is not None and ok[2].startswith("LUFS:")
+    monkeypatch.setitem(_capi.LAYOUT_IDS, "5.1 (Standard)", 99)
+    bad = rs.apply_raytrace_convolution_3d(*args)
+    assert bad[0] is None and bad[1] is None and isinstance(bad[2], str) and "Fehler" in bad[2], bad
+    with pytest.raises(_capi.ArsError):
+        rs.map_channels(np.zeros((10, 6), np.float32), "5.1 (Standard)", rate)
+    # a write failure removes its temporary file (rs.py:1088-1091)
+    monkeypatch.undo()
+    import glob
+    import tempfile
+    before = set(glob.glob(tempfile.gettempdir() + "/processed_*.wav"))
+    monkeypatch.setattr(wavio, "write_pcm16", lambda *a, **k: (_ for _ in ()).throw(OSError("disk full")))
+    res = rs.apply_raytrace_convolution_3d(*args)
+    assert res[0] is None and "Schreiben" in res[2]
+    assert set(glob.glob(tempfile.gettempdir() + "/processed_*.wav")) == before
+
+
+def test_metrics_of_integer_input_keep_peak_and_rms(rs):
+    """rs.py:685-698: pyloudnorm refuses non-floating data inside the reference's inner try -- lufs None, peak and RMS
+    still reported."""
+    x = (1000 * np.random.default_rng(3).standard_normal((48000, 2))).astype(np.int16)
+    m = rs.calculate_audio_metrics(x, 48000)
+    assert m["lufs"] is None
+    ref = orc.metrics(x.astype(np.float32), 48000, with_lufs=False)
+    assert abs(m["true_peak_dbfs"] - ref["true_peak_dbfs"]) < 1e-4 and abs(m["rms_dbfs"] - ref["rms_dbfs"]) < 1e-4

@@ -98,6 +98,7 @@ struct Ctx {
 
 Ctx& ctx();                 // throws if ars_init was not called
 bool ctx_ready();
+unsigned long long ctx_generation();      // changes with every ars_init that creates a context (caches keyed on device buffers check it)
 void ctx_init(int device);
 void ctx_shutdown();
 

@@ -40,6 +40,8 @@ void* Ctx::pinned_scratch(size_t bytes) {
     return pinned;
 }
 
+static unsigned long long g_ctx_generation = 0;
+unsigned long long ctx_generation() { return g_ctx_generation; }
 bool ctx_ready() { return g_ctx != nullptr; }
 
 Ctx& ctx() {
@@ -69,6 +71,7 @@ void ctx_init(int device) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     ARS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ++g_ctx_generation;
     g_ctx = c;
 }
 

@@ -1197,7 +1197,7 @@ template <int LOGR, int LOGC, bool MIRROR> struct MidTile {
 #define ARS_MID_STAGE(S_, INV_, LDM_, STM_) \
     run_stage<LOGR, S_, INV_, false, NT, LAYOUT, LDM_, STM_>(sm, ld, st, pa, gfirst, glast, 0u, tid)
 template <int LOGR, int LOGC, int NT, bool MIRROR>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) pass_mid_kernel(Ld ld, St st, PassArgs pa, MidArgs ma) {
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 4) pass_mid_kernel(Ld ld, St st, PassArgs pa, MidArgs ma) {
     extern __shared__ float2 sm[];
     using LAYOUT = ContigLayout<LOGR, LOGC>;
     using MS = MidStage<LOGR, LOGC, MIRROR>;

@@ -45,18 +45,18 @@ static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
 }
 
 // fused middle pass of the big-block overlap-save transforms (fft.cuh: pass_mid_kernel)
-template <int LOGR, int LOGC, bool MIRROR>
+template <int LOGR, int LOGC, bool MIRROR, int NTM = NT>
 static void launch_mid(const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma) {
     using L = ContigLayout<LOGR, LOGC>;
     static bool attr_done = false;
     const size_t smem = sizeof(float2) * L::SMEM_ELEMS;
-    auto k = pass_mid_kernel<LOGR, LOGC, NT, MIRROR>;
+    auto k = pass_mid_kernel<LOGR, LOGC, NTM, MIRROR>;
     if (!attr_done) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
-    k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa, ma);
+    k<<<(unsigned)tiles, NTM, smem, ctx().stream>>>(ld, st, pa, ma);
     ARS_LAUNCH_CHECK();
     count_launch();
 }

@@ -653,9 +653,20 @@ void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early
     std::unique_ptr<KernelScope> prof(new KernelScope("air fold chain (air kernel table, far taps, fold)", 4.0 * (double)(L0 + L1)));
     double* g = c.buf("fold.g", sizeof(double) * (size_t)(K + 1)).as<double>();
     float* taps = c.buf("fold.taps", sizeof(float) * (size_t)Lf).as<float>();
-    air_kernel_table_kernel<<<ceil_div(K + 1, 256), 256, 0, c.stream>>>(g, K, fs.N, fs.ka, fs.val, fs.ftop, fs.depth);
-    ARS_LAUNCH_CHECK();
-    count_launch();
+    // the air kernel depends on the render length and the air setting only (like the chirp of the exact-N route): its
+    // table and the far-tap table below are kept from one render to the next while those -- and the buffers -- stay the same
+    static struct { const void* g = nullptr; const void* G2 = nullptr; i64 K = 0, N = 0, ka = 0, half = 0; double val = 0, ftop = 0, depth = 0;
+                    unsigned long long gen = 0; } kept;
+    if (kept.gen != ctx_generation()) { kept.g = kept.G2 = nullptr; kept.gen = ctx_generation(); }
+    const bool same_air = kept.g == g && kept.K == K && kept.N == fs.N && kept.ka == fs.ka && kept.val == fs.val &&
+                          kept.ftop == fs.ftop && kept.depth == fs.depth;
+    if (!same_air) {
+        air_kernel_table_kernel<<<ceil_div(K + 1, 256), 256, 0, c.stream>>>(g, K, fs.N, fs.ka, fs.val, fs.ftop, fs.depth);
+        ARS_LAUNCH_CHECK();
+        count_launch();
+        kept.g = g; kept.K = K; kept.N = fs.N; kept.ka = fs.ka; kept.val = fs.val; kept.ftop = fs.ftop; kept.depth = fs.depth;
+        kept.G2 = nullptr;
+    }
     const i64 S = late_hi - late_lo;
     float* part = nullptr;
     int nsplit = 0;
@@ -663,19 +674,24 @@ void upols_filter_airfold(const float* d_x, i64 n, int cin, const float* d_early
     if (K > AIR_NEAR && S > 0 && fs.level1 != 0.0) {
         const int nx = ceil_div(S + 2 * K, FAR_OUT);
         nout = (i64)nx * FAR_OUT;
-        nsplit = std::max(1, std::min(32, ceil_div(2 * c.sm_count, nx)));
+        nsplit = std::max(1, std::min(32, ceil_div(6 * c.sm_count, nx)));      // ~6 CTAs of 4 warps per SM: the product is latency-bound
         const i64 step = 32 * FAR_R;                                         // a stretch of j is whole unrolled sweeps
         const i64 chunk = ((ceil_div(S, nsplit) + step - 1) / step) * step;
         nsplit = ceil_div(S, chunk);
         const i64 half = K + (i64)nsplit * chunk + nout + 64;                // |q - j| never leaves the table
         float* G2 = c.buf("fold.G2", sizeof(float) * (size_t)(2 * half + 1)).as<float>();
         part = c.buf("fold.part", sizeof(float) * (size_t)(nsplit * nout)).as<float>();
-        air_far_table_kernel<<<ceil_div(2 * half + 1, 256), 256, 0, c.stream>>>(g, K, half, G2);
-        ARS_LAUNCH_CHECK();
+        if (!(kept.G2 == G2 && kept.half == half)) {
+            air_far_table_kernel<<<ceil_div(2 * half + 1, 256), 256, 0, c.stream>>>(g, K, half, G2);
+            ARS_LAUNCH_CHECK();
+            count_launch();
+            kept.G2 = G2;
+            kept.half = half;
+        }
         air_far_kernel<<<dim3((unsigned)nx, (unsigned)nsplit), 32 * FAR_WARPS, 0, c.stream>>>(d_late, late_lo, S, G2 + half, K,
                                                                                            chunk, nout, part);
         ARS_LAUNCH_CHECK();
-        count_launch(2);
+        count_launch();
     }
     air_fold_kernel<<<ceil_div(Lf, 128), 128, 0, c.stream>>>(d_early, L0, d_late, late_lo, late_hi, g, K, part, nsplit, nout,
                                                               fs.level0, S > 0 ? fs.level1 : 0.0, adv, Lf, taps);

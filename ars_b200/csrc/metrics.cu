@@ -28,6 +28,7 @@ struct Mat2 { double m00, m01, m10, m11; };
 struct ScanCoef {
     Biquad q;
     Mat2 pw[9];                       // A^(CH * 2^k), k = 0..8  (pw[8] = A^BS)
+    double2 ends[CH];                 // A^(CH-1-j) B: weight of sample j of a chunk in the chunk's zero-start end state
 };
 
 static Mat2 mat_mul(const Mat2& a, const Mat2& b) {
@@ -43,6 +44,12 @@ static ScanCoef make_coef(const Biquad& q) {
     for (int i = 1; i < CH; i <<= 1) p = mat_mul(p, p);     // A^CH (CH is a power of two)
     c.pw[0] = p;
     for (int k = 1; k < 9; ++k) c.pw[k] = mat_mul(c.pw[k - 1], c.pw[k - 1]);
+    // z' = A z + B x with B = (b1 - a1 b0, b2 - a2 b0): the state after a chunk from a zero state is linear in its samples
+    double2 v = make_double2(q.b1 - q.a1 * q.b0, q.b2 - q.a2 * q.b0);
+    for (int j = CH - 1; j >= 0; --j) {
+        c.ends[j] = v;
+        v = make_double2(a.m00 * v.x + a.m01 * v.y, a.m10 * v.x + a.m11 * v.y);
+    }
     return c;
 }
 
@@ -250,10 +257,18 @@ __device__ __forceinline__ double2 shfl_up2(double2 v, int d) {
 __device__ __forceinline__ double2 chunk_start_state(const float* mine, const ScanCoef& cf, double2* __restrict__ agg,
                                                      int* __restrict__ flag, int depth, int b, double2* sw, double2* sc) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    double2 z = make_double2(0.0, 0.0);
-    #pragma unroll 8
-    for (int j = 0; j < CH; ++j) df2t(cf.q, (double)mine[j], z);
-    double2 v = z;                                         // inclusive scan inside the warp (zero start at its first chunk)
+    // zero-start end state of the chunk as a weighted sum of its samples (two independent accumulators per component:
+    // no recurrence, two multiply-adds per sample instead of the filter's five)
+    double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
+    #pragma unroll
+    for (int j = 0; j < CH; j += 2) {
+        const double x0 = (double)mine[j], x1 = (double)mine[j + 1];
+        za.x = fma(cf.ends[j].x, x0, za.x);
+        za.y = fma(cf.ends[j].y, x0, za.y);
+        zb.x = fma(cf.ends[j + 1].x, x1, zb.x);
+        zb.y = fma(cf.ends[j + 1].y, x1, zb.y);
+    }
+    double2 v = make_double2(za.x + zb.x, za.y + zb.y);    // inclusive scan inside the warp (zero start at its first chunk)
     #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const double2 up = shfl_up2(v, 1 << k);
@@ -485,19 +500,20 @@ __global__ void __launch_bounds__(1024) gate_kernel(const double* __restrict__ z
         if (threadIdx.x == 0) *lufs_out = -CUDART_INF;
         return;
     }
+    // l_j = -0.691 + 10 log10(z_j) is monotone in z_j, so both gates compare z_j itself: l_j >= -70 <=> z_j >= 10^-6.9309,
+    // and l_j > Gamma_r = -0.691 + 10 log10(mean z) - 10 <=> z_j > mean z / 10 -- no logarithm per block
+    const double z_abs = 1.1724653045822981e-07;          // 10^((-70 + 0.691) / 10)
     double s = 0.0;
     int n = 0;
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-        const double l = -0.691 + 10.0 * log10(z[j]);
-        if (l >= -70.0) { s += z[j]; ++n; }
+        if (z[j] >= z_abs) { s += z[j]; ++n; }
     }
     block_sum_dc(s, n);
-    const double rel = n > 0 ? -0.691 + 10.0 * log10(s / (double)n) - 10.0 : CUDART_NAN;
+    const double z_rel = n > 0 ? (s / (double)n) * 0.1 : CUDART_NAN;
     double s2 = 0.0;
     int n2 = 0;
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-        const double l = -0.691 + 10.0 * log10(z[j]);
-        if (l > rel && l > -70.0) { s2 += z[j]; ++n2; }
+        if (z[j] > z_rel && z[j] > z_abs) { s2 += z[j]; ++n2; }
     }
     block_sum_dc(s2, n2);
     if (threadIdx.x == 0) *lufs_out = -0.691 + 10.0 * log10(n2 > 0 ? s2 / (double)n2 : 0.0);   // log10(0) = -inf, as numpy

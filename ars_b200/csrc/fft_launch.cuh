@@ -13,12 +13,12 @@ constexpr int NT = 512;
 template <int LOGR, int LOGT, bool INV, int LDM, int STM>
 static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = StridedLayout<LOGR, LOGT>;
-    static bool attr_done = false;
+    static unsigned long long attr_gen = 0;          // (function attributes belong to the context: set again after a re-init)
     const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
     auto k = pass_strided_kernel<LOGR, LOGT, INV, NT, LDM, STM>;
-    if (!attr_done && smem > 48 * 1024) {
+    if (attr_gen != ctx_generation() && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_gen = ctx_generation();
     }
     const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGT);
     k<<<(unsigned)tiles, NT, smem, ctx().stream>>>(ld, st, pa);
@@ -31,12 +31,12 @@ static void launch_strided(const Ld& ld, const St& st, const PassArgs& pa) {
 template <int LOGR, int LOGC, bool INV, int LDM, int STM, int NTC = NT>
 static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
     using L = ContigLayout<LOGR, LOGC>;
-    static bool attr_done = false;
+    static unsigned long long attr_gen = 0;
     const size_t smem = (Rad<LOGR>::n > 1) ? sizeof(float2) * L::SMEM_ELEMS : 0;
     auto k = pass_contig_kernel<LOGR, LOGC, INV, NTC, LDM, STM>;
-    if (!attr_done && smem > 48 * 1024) {
+    if (attr_gen != ctx_generation() && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_gen = ctx_generation();
     }
     const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
     k<<<(unsigned)tiles, NTC, smem, ctx().stream>>>(ld, st, pa);
@@ -48,12 +48,12 @@ static void launch_contig(const Ld& ld, const St& st, const PassArgs& pa) {
 template <int LOGR, int LOGC, bool MIRROR, int NTM = NT>
 static void launch_mid(const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma) {
     using L = ContigLayout<LOGR, LOGC>;
-    static bool attr_done = false;
+    static unsigned long long attr_gen = 0;
     const size_t smem = sizeof(float2) * L::SMEM_ELEMS;
     auto k = pass_mid_kernel<LOGR, LOGC, NTM, MIRROR>;
-    if (!attr_done) {
+    if (attr_gen != ctx_generation() && smem > 48 * 1024) {
         ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_gen = ctx_generation();
     }
     const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGC);
     k<<<(unsigned)tiles, NTM, smem, ctx().stream>>>(ld, st, pa, ma);

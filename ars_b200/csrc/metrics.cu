@@ -346,6 +346,8 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
     __shared__ i64 s_lo[3];
     __shared__ unsigned s_b;
     __shared__ double se[4][NTB / 32];
+    // (the stages' coefficient tables are read from the kernel's parameter space: a copy in shared memory was measured --
+    // fewer constant-cache misses, but its loads compete with the samples' for the shared-memory pipe: 85 against 77 us)
     const int t = threadIdx.x;
     const bool idle = src.prepare();
     unsigned mm = 0;
@@ -363,21 +365,40 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
         float* mine = sx + t * (CH + 1);
         // stage 1 (high shelf): float32 store, as pyloudnorm
         double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sw[0], sc[0]);
-        #pragma unroll 8
-        for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(a.c1.q, (double)mine[j], s);
+        {
+            const Biquad q1 = a.c1.q;
+            #pragma unroll 8
+            for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(q1, (double)mine[j], s);
+        }
         // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
         s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sw[1], sc[1]);
         // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
         const i64 g0 = base + (i64)t * CH;
         const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
         const i64 next = s_lo[k0 < 3 ? k0 : 2];
+        // samples of the chunk that count: [ja, jb) (inside the signal and this launch's range), of which [ja, jn) fall
+        // into the hop the chunk starts in -- small integers found once, not 64-bit compares per sample
+        const i64 hi = a.e_hi == 0 ? a.N : (a.e_hi < a.N ? a.e_hi : a.N);
+        const int ja = (int)max((i64)0, min((i64)CH, a.e_lo - g0));
+        const int jb = (int)max((i64)ja, min((i64)CH, hi - g0));
+        const int jn = (int)max((i64)ja, min((i64)jb, next - g0));
         double e0 = 0.0, e1 = 0.0;
-        #pragma unroll 8
-        for (int j = 0; j < CH; ++j) {
-            const float o = (float)df2t(a.c2.q, (double)mine[j], s);
-            const double sq = (double)__fmul_rn(o, o);
-            const i64 g = g0 + j;
-            if (g < a.N && (a.e_hi == 0 || (g >= a.e_lo && g < a.e_hi))) { if (g < next) e0 += sq; else e1 += sq; }
+        const Biquad q2 = a.c2.q;
+        if (ja == 0 && jb == CH && (jn == CH || jn == 0)) {           // the whole chunk in one hop: all but ~1 % of the chunks
+            double e = 0.0;
+            #pragma unroll 8
+            for (int j = 0; j < CH; ++j) {
+                const float o = (float)df2t(q2, (double)mine[j], s);
+                e += (double)__fmul_rn(o, o);
+            }
+            if (jn == CH) e0 = e; else e1 = e;
+        } else {
+            #pragma unroll 8
+            for (int j = 0; j < CH; ++j) {
+                const float o = (float)df2t(q2, (double)mine[j], s);
+                const double sq = (double)__fmul_rn(o, o);
+                if (j >= ja && j < jb) { if (j < jn) e0 += sq; else e1 += sq; }
+            }
         }
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -928,10 +949,10 @@ void spectrogram_psd(const float* d_x, i64 n, int stride, double rate, int npers
     }
     const float scale = (float)(1.0 / (rate * wsum));
     const size_t smem = sizeof(float2) * 2 * (size_t)nperseg;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_gen = 0;
+    if (attr_gen != ctx_generation()) {
         ARS_CUDA(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * 2 * 8192)));
-        attr_done = true;
+        attr_gen = ctx_generation();
     }
     spectrogram_kernel<<<nseg, 256, smem, c.stream>>>(d_x, n, stride, logN, hop, nseg, scale, d_out);
     ARS_LAUNCH_CHECK();

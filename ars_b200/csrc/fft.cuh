@@ -716,6 +716,7 @@ template <int Ls, int r, bool INV> ARS_HD void stage_twiddles(const Tw& tw, int 
 template <int LOGR, int LOGT> struct StridedLayout {
     static constexpr int R = 1 << LOGR, T = 1 << LOGT, C = T;
     static constexpr int ROW_PITCH = T;                 // slots between consecutive rows of a column
+    static constexpr bool PADDED = true;                // one spare slot per 16 elements
     static constexpr int SMEM_ELEMS = R * T + ((R * T) >> 4);
     static ARS_HD int bfly(int q) { return q >> LOGT; }
     static ARS_HD int col(int q) { return q & (T - 1); }
@@ -725,8 +726,21 @@ template <int LOGR, int LOGT> struct StridedLayout {
 template <int LOGR, int LOGC> struct ContigLayout {
     static constexpr int R = 1 << LOGR, C = 1 << LOGC;
     static constexpr int ROW_PITCH = 1;
+    static constexpr bool PADDED = true;
     static constexpr int SMEM_ELEMS = R * C + ((R * C) >> 4);
     static ARS_HD int sidx(int row, int c) { int i = (c << LOGR) + row; return i + (i >> 4); }
+};
+
+// Strided tile without padding: the lanes of a warp run along the columns of one row in every stage, so the rows can
+// sit back to back -- which is the layout a bulk copy delivers (pass_last_pipe_kernel).
+template <int LOGR, int LOGT> struct StridedFlat {
+    static constexpr int R = 1 << LOGR, T = 1 << LOGT, C = T;
+    static constexpr int ROW_PITCH = T;
+    static constexpr bool PADDED = false;
+    static constexpr int SMEM_ELEMS = R * T;
+    static ARS_HD int bfly(int q) { return q >> LOGT; }
+    static ARS_HD int col(int q) { return q & (T - 1); }
+    static ARS_HD int sidx(int row, int c) { return (row << LOGT) + c; }
 };
 
 struct PassArgs {
@@ -813,8 +827,8 @@ ARS_HD void run_stage(float2* sm, LD& ld, ST& st, const PassArgs& pa, GF gfirst,
     const i64 fstep = gfirst.step() * (i64)sub;            // natural side: rows are `sub` apart
     const i64 lstep = glast.step();                         // permuted side: consecutive outputs k
     constexpr int PITCH = LAYOUT::ROW_PITCH;
-    constexpr bool LIN = ((sub * PITCH) % 16) == 0;
-    constexpr int SSTEP = sub * PITCH + (sub * PITCH) / 16;
+    constexpr bool LIN = !LAYOUT::PADDED || ((sub * PITCH) % 16) == 0;
+    constexpr int SSTEP = sub * PITCH + (LAYOUT::PADDED ? (sub * PITCH) / 16 : 0);
 #define ARS_SM(t_) sm[LIN ? (s0 + (t_) * SSTEP) : LAYOUT::sidx(row0 + (t_) * sub, c)]
 
     // the stage that reads HBM is unrolled over its butterflies so all of a thread's loads are in flight at once
@@ -1223,6 +1237,162 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 4) pass_mid_kernel(Ld ld, 
     ARS_MID_STAGE(0, true, LD_PLAIN, ST_PLAIN);
 }
 
+// ---- persistent, prefetching form of the plain middle pass ------------------------------------------------------
+// One CTA keeps a padded work tile plus an unpadded landing buffer in shared memory and walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...  The next tile's segment (one contiguous 2^LOGR-point run of W) is fetched by a single
+// bulk asynchronous copy (cp.async.bulk, completion counted on an mbarrier) issued as soon as the first stage of the
+// current tile has drained the landing buffer, so the fetch overlaps the remaining five stages and the store of the
+// current tile; no thread ever waits on a global load.
+struct LdLanding {
+    const float2* s;                // landing buffer (shared memory), element i = point i of the tile's segment
+    template <int MODE> ARS_HD float2 get(i64 idx) const { return s[(int)idx]; }
+};
+struct TileFirst {
+    ARS_HD i64 operator()(int row, int) const { return row; }
+    ARS_HD i64 step() const { return 1; }
+};
+#ifdef __CUDACC__
+namespace bulk {
+__device__ __forceinline__ unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arm the barrier with the byte count of the copy that follows, then start the copy (one thread)
+__device__ __forceinline__ void fetch(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of dst are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(saddr(bar)), "r"(parity) : "memory");
+}
+}  // namespace bulk
+
+// copy without arming (the caller armed the barrier with the sum of the rows' bytes)
+__device__ __forceinline__ void bulk_row(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bulk::saddr(dst)), "l"(src), "r"(bytes), "r"(bulk::saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_arm(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bulk::saddr(bar)), "r"(bytes) : "memory");
+}
+
+// ---- persistent, prefetching form of the last (strided inverse) pass of the big-block overlap-save transforms ----
+// A CTA owns two unpadded tiles of R rows x T columns and walks tiles blockIdx.x, + gridDim.x, ...  One warp fetches a
+// tile as R bulk copies of one row each (T * 8 bytes, counted on the buffer's mbarrier) two tiles ahead, so the whole
+// load of tile i + 2 overlaps the arithmetic and the stores of tiles i and i + 1.  The first executed stage reads its
+// butterflies from the landing rows and writes them back in place.
+template <int LOGR, int LOGT> struct FlatLast {
+    ARS_HD i64 operator()(int b, int c) const {
+        constexpr int rl = Rad<LOGR>::r(Rad<LOGR>::n - 1);
+        return (i64)(((b * rl) << LOGT) + c);
+    }
+    ARS_HD i64 step() const { return (i64)1 << LOGT; }
+};
+template <int LOGR, int LOGT, int NT, int PER_SM>
+__global__ void __launch_bounds__(NT, PER_SM) pass_last_pipe_kernel(Ld ld, St st, PassArgs pa, int tiles) {
+    extern __shared__ __align__(128) float2 sm[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    using LAYOUT = StridedFlat<LOGR, LOGT>;
+    constexpr int R = 1 << LOGR, T = 1 << LOGT, ELEMS = R * T;
+    constexpr unsigned ROW_BYTES = (unsigned)(T * sizeof(float2));
+    static_assert(Rad<LOGR>::n == 2, "pipelined last pass: two-stage column transforms");
+    static_assert(T >= 32 && ROW_BYTES % 16 == 0, "a warp stays inside one row");
+    const int tid = (int)threadIdx.x;
+    const int G = (int)gridDim.x;
+    auto fetch = [&](int tile, int p) {           // warp 0
+        const StridedTile<LOGR, LOGT> t((i64)tile, pa);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0) bulk_arm(&bar[p], ROW_BYTES * (unsigned)R);
+        __syncwarp();
+        for (int row = tid; row < R; row += 32)
+            bulk_row(sm + p * ELEMS + row * T, ld.a + t.base + ((i64)row << t.logStride), ROW_BYTES, &bar[p]);
+    };
+    if (tid == 0) {
+        bulk::bar_init(&bar[0], 1);
+        bulk::bar_init(&bar[1], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if ((int)blockIdx.x < tiles) fetch((int)blockIdx.x, 0);
+        if ((int)blockIdx.x + G < tiles) fetch((int)blockIdx.x + G, 1);
+    }
+    unsigned phase = 0;
+    int p = 0;
+    const FlatLast<LOGR, LOGT> flast{};
+    for (int tile = (int)blockIdx.x; tile < tiles; tile += G, p ^= 1) {
+        float2* buf = sm + p * ELEMS;
+        const StridedTile<LOGR, LOGT> t((i64)tile, pa);
+        const StridedFirst<LOGR> gfirst{t.base, t.logStride};
+        LdLanding ll{buf};
+        bulk::wait(&bar[p], (phase >> p) & 1u);
+        phase ^= 1u << p;
+        run_stage<LOGR, 1, true, true, NT, LAYOUT, LD_PLAIN, ST_OLSB>(buf, ll, st, pa, gfirst, flast, t.col0, tid);
+        __syncthreads();
+        run_stage<LOGR, 0, true, true, NT, LAYOUT, LD_PLAIN, ST_OLSB>(buf, ll, st, pa, gfirst, flast, t.col0, tid);
+        __syncthreads();
+        if (tid < 32 && tile + 2 * G < tiles) fetch(tile + 2 * G, p);
+    }
+    st.finish();
+}
+
+#define ARS_MIDP_STAGE(S_, INV_, LD_, GF_) \
+    run_stage<LOGR, S_, INV_, false, NT, LAYOUT, LD_PLAIN, ST_PLAIN>(sm, LD_, st, pa, GF_, glast, 0u, tid)
+template <int LOGR, int NT, int PER_SM>
+__global__ void __launch_bounds__(NT, PER_SM) pass_mid_pipe_kernel(Ld ld, St st, PassArgs pa, MidArgs ma, int tiles) {
+    extern __shared__ __align__(128) float2 sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    using LAYOUT = ContigLayout<LOGR, 0>;
+    using MS = MidStage<LOGR, 0, false>;
+    constexpr int R = 1 << LOGR;
+    constexpr unsigned BYTES = (unsigned)(R * sizeof(float2));
+    static_assert(Rad<LOGR>::n == 3 && MS::TOTAL == NT, "middle pass: three-stage tile, one last-stage butterfly per thread");
+    static_assert((LAYOUT::SMEM_ELEMS * sizeof(float2)) % 128 == 0, "landing buffer alignment");
+    float2* land = sm + LAYOUT::SMEM_ELEMS;
+    const int tid = (int)threadIdx.x;
+    int tile = (int)blockIdx.x;
+    if (tid == 0) {
+        bulk::bar_init(&bar, 1);
+        if (tile < tiles) bulk::fetch(land, ld.a + ((i64)tile << LOGR), BYTES, &bar);
+    }
+    __syncthreads();
+    LdLanding ll{land};
+    const TileFirst tfirst{};
+    unsigned parity = 0;
+    for (; tile < tiles; tile += (int)gridDim.x) {
+        const i64 b0 = (i64)tile << LOGR;
+        const PairFirst<LOGR> gfirst{b0, b0};
+        const PairLast<LOGR> glast{b0, b0};
+        bulk::wait(&bar, parity);
+        parity ^= 1u;
+        ARS_MIDP_STAGE(0, false, ll, tfirst);
+        __syncthreads();
+        const int nxt = tile + (int)gridDim.x;
+        if (tid == 0 && nxt < tiles) bulk::fetch(land, ld.a + ((i64)nxt << LOGR), BYTES, &bar);
+        ARS_MIDP_STAGE(1, false, ld, gfirst);
+        __syncthreads();
+        float2 v[MS::r];
+        MS::fwd(sm, tid, v);
+        MS::mul(sm, ma, glast, tid, false, v);
+        MS::inv(sm, tid, v);
+        __syncthreads();
+        ARS_MIDP_STAGE(1, true, ld, gfirst);
+        __syncthreads();
+        ARS_MIDP_STAGE(0, true, ld, gfirst);
+        __syncthreads();            // the work tile is rewritten by the next tile's first stage
+    }
+}
+#undef ARS_MIDP_STAGE
+#endif
+
 // host emulation of one middle-pass tile (tests/host_emul): per-"thread" registers live in `regs` across the barriers
 template <int LOGR, int LOGC, int NT, bool MIRROR>
 inline void emulate_mid_tile(float2* sm, float2* regs, Ld& ld, St& st, const PassArgs& pa, const MidArgs& ma, i64 tile) {
@@ -1294,6 +1464,7 @@ struct FftPlan {
     DevBuf tw_lo, tw_hi;
     std::vector<DevBuf> pass_tabs;  // per strided pass: PassArgs::ptab
     DevBuf rho;                     // big-block overlap-save, stereo IR: MidArgs::rho (built on first use)
+    DevBuf pipe_tab;                // pipelined last pass: PassArgs::ptab for its tile width (built on first use)
     fft::Tw tw{};
 };
 

@@ -60,6 +60,42 @@ static void launch_mid(const Ld& ld, const St& st, const PassArgs& pa, const Mid
     ARS_LAUNCH_CHECK();
     count_launch();
 }
+// persistent middle pass with bulk-copy prefetch (fft.cuh: pass_mid_pipe_kernel); PER_SM CTAs of NTM threads per SM
+template <int LOGR, int NTM, int PER_SM>
+static void launch_mid_pipe(const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma) {
+    using L = ContigLayout<LOGR, 0>;
+    static unsigned long long attr_gen = 0;
+    const size_t smem = sizeof(float2) * (L::SMEM_ELEMS + ((size_t)1 << LOGR));
+    auto k = pass_mid_pipe_kernel<LOGR, NTM, PER_SM>;
+    if (attr_gen != ctx_generation()) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_gen = ctx_generation();
+    }
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> LOGR;
+    const i64 grid = std::min<i64>(tiles, (i64)ctx().sm_count * PER_SM);
+    k<<<(unsigned)grid, NTM, smem, ctx().stream>>>(ld, st, pa, ma, (int)tiles);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+// persistent last pass with bulk-copy prefetch (fft.cuh: pass_last_pipe_kernel); pa.ptab must be the table for 2^LOGT columns
+template <int LOGR, int LOGT, int NTM, int PER_SM>
+static void launch_last_pipe(const Ld& ld, const St& st, const PassArgs& pa) {
+    using L = StridedFlat<LOGR, LOGT>;
+    static unsigned long long attr_gen = 0;
+    const size_t smem = sizeof(float2) * 2 * L::SMEM_ELEMS;
+    auto k = pass_last_pipe_kernel<LOGR, LOGT, NTM, PER_SM>;
+    if (attr_gen != ctx_generation()) {
+        ARS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_gen = ctx_generation();
+    }
+    const i64 tiles = (pa.total > 0 ? pa.total : pa.M) >> (LOGR + LOGT);
+    const i64 grid = std::min<i64>(tiles, (i64)ctx().sm_count * PER_SM);
+    k<<<(unsigned)grid, NTM, smem, ctx().stream>>>(ld, st, pa, (int)tiles);
+    ARS_LAUNCH_CHECK();
+    count_launch();
+}
+bool last_pass_pipe(int logR, int* logT);                                       // fft_k_mid.cu: is there a pipelined last pass?
+void last_pass_pipe_launch(int logR, const Ld& ld, const St& st, const PassArgs& pa);
 void mid_pass(bool mirror, const Ld& ld, const St& st, const PassArgs& pa, const MidArgs& ma);    // fft_k_mid.cu
 
 int ols_threads();     // 512 | 256: CTA size of the overlap-save block transforms (ARS_OLS_NT, fft_plan.cu)

@@ -255,7 +255,31 @@ void fft_batch_first(FftPlan* p, i64 nbatch, const Ld& ld, const St& st) {
 }
 void fft_batch_last(FftPlan* p, i64 nbatch, const Ld& ld, const St& st) {
     check_two_pass(p);
-    launch_pass<true>(p, p->passes[0], ld, st, nbatch * p->M);
+    const FftPass& ps = p->passes[0];
+    int logT = 0;
+    if (g_fast && ld.mode == LD_PLAIN && st.mode == ST_OLSB && last_pass_pipe(ps.logR, &logT) && ps.logLg - ps.logR >= logT) {
+        if (!p->pipe_tab.p) {        // inter-pass twiddle factors for the pipelined kernel's tile width
+            const int count = pass_table_elems(ps.logR, logT);
+            p->pipe_tab.reserve(sizeof(float2) * (size_t)count);
+            pass_table_kernel<<<ceil_div(count, 256), 256, 0, ctx().stream>>>(p->pipe_tab.as<float2>(), ps.logLg,
+                                                                             pass_table_mul(ps.logR), logT, count);
+            ARS_LAUNCH_CHECK();
+            count_launch();
+            ARS_CUDA(cudaStreamSynchronize(ctx().stream));      // (once per plan; later calls may come from a lane)
+        }
+        PassArgs pa;
+        pa.total = nbatch * p->M;
+        pa.M = p->M;
+        pa.logM = p->logM;
+        pa.logLg = ps.logLg;
+        pa.tw = p->tw;
+        pa.prefetch = 0;
+        pa.ptab = p->pipe_tab.as<float2>();
+        KernelScope prof_scope(pass_name(ld, st, true, true), prof_session_on() ? ld_bytes(ld, pa.total) + st_bytes(st, pa.total) : 0.0);
+        last_pass_pipe_launch(ps.logR, ld, st, pa);
+        return;
+    }
+    launch_pass<true>(p, ps, ld, st, nbatch * p->M);
 }
 void fft_batch_mid(FftPlan* p, i64 nbatch, float2* work, const float2* h0, const float2* h1) {
     check_two_pass(p);

@@ -224,6 +224,7 @@ static TailSpec make_tail(i64 N, int layout, double rate, double x_, double y_, 
     if (layout == LAYOUT_7_1) ts.delay = (i64)((double)(r * 12) / 1000.0);       // int(rate * 12 / 1000)
     else if (layout == LAYOUT_5_1_2) ts.delay = (i64)((double)(r * 18) / 1000.0);
     ts.height_gain = clip(z_, 0.0, 1.0) * 0.6;
+    ts.stream = (olsb_stream_hints() >> 2) & 3;
     return ts;
 }
 
@@ -491,7 +492,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "olsb")) olsb_set_options(value ? 1 : 0, -1, -1);
     else if (!strcmp(key, "olsb_logf")) { ARS_CHECK(value == 0 || (value >= 18 && value <= 22), "olsb_logf must be 0 (automatic) or 18..22"); olsb_set_options(-1, value, -1); }
     else if (!strcmp(key, "olsb_lanes") || !strcmp(key, "olsb_first_all") || !strcmp(key, "olsb_reverse") ||
-             !strcmp(key, "olsb_dryfold") || !strcmp(key, "olsb_early")) olsb_set_tuning(key, value);
+             !strcmp(key, "olsb_dryfold") || !strcmp(key, "olsb_early") || !strcmp(key, "stream_hints")) olsb_set_tuning(key, value);
     else if (!strcmp(key, "olsb_stripe")) { ARS_CHECK(value >= 0, "olsb_stripe must be >= 0"); olsb_set_options(-1, -1, value); }
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;

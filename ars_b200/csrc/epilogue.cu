@@ -163,10 +163,14 @@ __device__ __forceinline__ void final_body(const float2* __restrict__ y, const T
                 u.y = pcm_pair(o[2], o[3]);
                 u.z = pcm_pair(o[4], o[5]);
                 u.w = pcm_pair(o[6], o[7]);
-                *reinterpret_cast<uint4*>(p) = u;
+                if (ts.stream & 1) __stcs(reinterpret_cast<uint4*>(p), u);
+                else *reinterpret_cast<uint4*>(p) = u;
             } else {
                 #pragma unroll
-                for (int c = 0; c < C; c += 2) reinterpret_cast<unsigned*>(p)[c >> 1] = pcm_pair(o[c], o[c + 1]);
+                for (int c = 0; c < C; c += 2) {
+                    if (ts.stream & 1) __stcs(reinterpret_cast<unsigned*>(p) + (c >> 1), pcm_pair(o[c], o[c + 1]));
+                    else reinterpret_cast<unsigned*>(p)[c >> 1] = pcm_pair(o[c], o[c + 1]);
+                }
             }
         }
         if (mono) {

@@ -24,6 +24,7 @@ struct TailSpec {
     double g_fl = 0, g_fr = 0, g_c = 0, g_rl = 0, g_rr = 0;
     float g_lfe = 0.15f;         // Python float (weak) => float32 multiply (rs.py:485)
     double height_gain = 0.0;    // clip(z,0,1)*0.6, np.float64 => product formed in double (rs.py:550-553)
+    int stream = 0;              // final pass: bit 0 PCM / float frames stored, bit 1 stereo frames read with the evict-first policy
 };
 
 inline int layout_channels(int layout) { return layout == LAYOUT_STEREO ? 2 : layout == LAYOUT_5_1 ? 6 : 8; }

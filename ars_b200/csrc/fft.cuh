@@ -23,8 +23,13 @@
 
 #ifdef __CUDA_ARCH__
 #define ARS_LDG(p) __ldg(p)
+// streaming forms: data touched once gets the evict-first policy so that it does not push the work buffers out of the L2
+#define ARS_LDCS(p) __ldcs(p)
+#define ARS_STCS(p, v) __stcs(p, v)
 #else
 #define ARS_LDG(p) (*(p))
+#define ARS_LDCS(p) (*(p))
+#define ARS_STCS(p, v) (*(p) = (v))
 #endif
 #define ARS_HD __host__ __device__ __forceinline__
 
@@ -185,6 +190,7 @@ enum StMode { ST_PLAIN = 0, ST_SCALE, ST_CHIRP, ST_FINAL, ST_OLS, ST_OLS_CHIRP, 
 
 struct Ld {
     int mode = LD_PLAIN;
+    int stream = 0;                 // LD_OLSB_X: read the signal with the evict-first policy (it is read once)
     const float2* a = nullptr;      // complex source / work buffer
     const float2* b = nullptr;      // second complex operand (spectrum or chirp)
     const float* f0 = nullptr;      // real sources
@@ -353,8 +359,13 @@ struct Ld {
             if ((cin & 1) == 0) {
                 const float2* p = reinterpret_cast<const float2*>(f0 + fr * cin);
                 const i64 ps = step * (cin >> 1);
-                #pragma unroll
-                for (int k = 0; k < r; ++k) v[k] = ARS_LDG(p + k * ps);
+                if (stream) {
+                    #pragma unroll
+                    for (int k = 0; k < r; ++k) v[k] = ARS_LDCS(p + k * ps);
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < r; ++k) v[k] = ARS_LDG(p + k * ps);
+                }
             } else {
                 const float* p = f0 + fr * cin;
                 const i64 ps = step * cin;
@@ -471,6 +482,7 @@ struct Ld {
 
 struct St {
     int mode = ST_PLAIN;
+    int stream = 0;                  // ST_OLSB: store the frames with the evict-first policy (read again only after the whole pass)
     float2* a = nullptr;
     const float2* chirp = nullptr;
     i64 N = 0;
@@ -554,7 +566,8 @@ struct St {
                 for (int k = 0; k < r; ++k) {
                     if ((unsigned)(o0 + k * step) < (unsigned)hp) {
                         const float2 y = make_float2(dw * v[k].x, dw * v[k].y);
-                        ap[k * step] = y;
+                        if (stream) ARS_STCS(ap + k * step, y);
+                        else ap[k * step] = y;
                         local_l = max(local_l, abs_bits(y.x));
                         local_r = max(local_r, abs_bits(y.y));
                         local_lr = max(local_lr, abs_bits(fadd_rn(y.x, y.y)));

@@ -35,6 +35,8 @@ static int last_pipe_variant() {
 }
 bool last_pass_pipe(int logR, int* logT) {
     const int v = last_pipe_variant();
+    // (128- and 256-row column transforms with 32-column tiles, i.e. 256-byte rows: 82.3 against 80.3 us and 146 against
+    // 78 us on the same render with 2^19- / 2^20-point blocks -- only the 64 x 64 tile pays)
     if (!v || logR != 6) return false;
     *logT = v == 6 ? 5 : 6;
     return true;

@@ -88,7 +88,7 @@ template <int A> __device__ __forceinline__ float guardT(float v, const Guard& g
 struct FrameIn { float2 v, w; };
 __device__ __forceinline__ FrameIn frame_load(const float2* __restrict__ y, i64 i, const TailSpec& ts) {
     FrameIn f;
-    f.v = __ldg(y + (i - ts.y0));
+    f.v = (ts.stream & 2) ? __ldcs(y + (i - ts.y0)) : __ldg(y + (i - ts.y0));
     f.w = make_float2(0.f, 0.f);
     // a delay <= 0 leaves the signal where it is (rs.py:510-511)
     if (ts.layout >= LAYOUT_7_1 && i >= ts.delay) f.w = __ldg(y + (i - (ts.delay > 0 ? ts.delay : 0) - ts.y0));

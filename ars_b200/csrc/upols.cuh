@@ -74,6 +74,7 @@ void olsb_first_pass_early(const float* d_x, i64 n, int cin, const OlsbPlan& pla
 // taps before time zero and total tap count of the folded-air impulse response (what upols_filter_airfold builds)
 void air_fold_geometry(const AirFold& af, i64 L0, i64 L1, int logF, i64* adv, i64* taps);
 void olsb_set_options(int on, int logf, int stripe);     // -1 leaves a value unchanged; logf / stripe 0 = automatic
+int olsb_stream_hints();                            // option "stream_hints" (bits: 1 signal loads, 2 frame stores, 4 PCM stores, 8 final-pass loads)
 void olsb_set_tuning(const char* key, int value);   // olsb_lanes | olsb_first_all | olsb_reverse | olsb_dryfold
 bool olsb_enabled();
 unsigned long long olsb_count();      // convolution stages that took the big-block route

@@ -122,7 +122,12 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * overlap-save over 2^18..2^22-point blocks: strided forward pass, fused middle pass [contiguous forward x IR spectrum x
  * contiguous inverse], strided inverse pass [default]; 0 = always the 4096-frame partitioned form),
  * "olsb_logf" (0 = block length chosen from the tap count [default] | 18..22), "olsb_stripe" (0 = transforms per
- * L2-resident stripe chosen from the SM count [default] | n). */
+ * L2-resident stripe chosen from the SM count [default] | n), "stream_hints" (bit mask, default 15: data touched once moves
+ * with the evict-first cache policy -- 1 signal frames read by the first pass, 2 output frames stored by the last pass,
+ * 4 PCM / float frames stored and 8 stereo frames read by the final pass).
+ * Environment (read once per process, experiments): ARS_MID_PIPE (3 [default] | 2 = the plain middle pass runs as a persistent
+ * kernel that fetches its next tile with cp.async.bulk, 3 | 2 CTAs per SM; 0 = one tile per CTA), ARS_LAST_PIPE (3 [default] |
+ * 2 | 6 = the last pass of 2^18-point blocks likewise, double-buffered; 0 = one tile per CTA), ARS_MID_NT (256 | 512). */
 ARS_API int ars_set_option(const char* key, int32_t value);
 /* Page-locked host blocks for results: the Python layer wraps them as numpy arrays (freed through ars_host_free when the
  * array dies; the library keeps up to 4 GiB of freed blocks for the next render).  Copies from / to PAGEABLE host memory

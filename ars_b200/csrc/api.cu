@@ -497,6 +497,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
     else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
+    else if (!strcmp(key, "final_lean")) { ARS_CHECK(value >= 0 && value <= 2, "final_lean must be 0, 1 or 2"); tail_set_lean(value); }
     else if (!strcmp(key, "host_staging")) host_staging_enable(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
     else ARS_CHECK(false, "ars_set_option: unknown option");

@@ -3,6 +3,8 @@
 #include "epilogue.cuh"
 #include "tail_math.cuh"
 
+#include <cstdlib>
+
 namespace ars {
 
 static inline int stream_grid(i64 items, int per_block = 256) {
@@ -181,8 +183,437 @@ __device__ __forceinline__ void final_body(const float2* __restrict__ y, const T
     }
 }
 
+// ---- lean form of the frame loop for the 5.1-based layouts when only the stereo guard can be active (the pan guard
+// and the map guard idle: every render whose pan gains keep the six channels <= 1).  Same per-sample arithmetic as
+// final_body, fewer issue slots: the stereo guard's division runs on the loaded (L, R) pairs with packed FP32x2
+// instructions behind ONE range test per frame (the element-wise form tests and branches per value), 32-bit frame
+// offsets inside the window, the delayed pair's presence as a loop split instead of a per-frame test, packed PCM scaling.
+__device__ __forceinline__ float2 guard_div2(float2 v, const Guard& g) {
+    const float2 r2 = make_float2(g.r, g.r), nm = make_float2(-g.m, -g.m);
+    float2 q = __fmul2_rn(v, r2);                                  // the two corrections of guard_div, two lanes at once
+    q = __ffma2_rn(__ffma2_rn(q, nm, v), r2, q);
+    return __ffma2_rn(__ffma2_rn(q, nm, v), r2, q);
+}
+// every one of the four values zero or inside guard_div's plain range [1e-25, 1e30)
+__device__ __forceinline__ bool plain4(float2 v, float2 w) {
+    constexpr unsigned LO = 0x15f79688u /* 1e-25f */, HI = 0x7149f2cau /* 1e30f */;
+    const unsigned a = abs_bits(v.x), b = abs_bits(v.y), c = abs_bits(w.x), d = abs_bits(w.y);
+    const unsigned hi = max(max(a, b), max(c, d));
+    const unsigned lo = min(min(a - 1u, b - 1u), min(c - 1u, d - 1u));      // (zero -> 0xffffffff: no lower bound)
+    return hi < HI && lo >= LO - 1u;
+}
+__device__ __noinline__ float4 guard_slow4(float4 q, float m, float r) {       // (values in and out in registers)
+    Guard g;
+    g.mode = 1; g.m = m; g.r = r;
+    return make_float4(guard_div(q.x, g), guard_div(q.y, g), guard_div(q.z, g), guard_div(q.w, g));
+}
+
+// Threads per CTA of the lean loops.  Small CTAs: the warps of a CTA drift apart over its ~50 frames per thread and the
+// CTA keeps its registers until the last one is through the closing reduction (ncu, 256 threads: 12 % of the warp time
+// waiting at that barrier); 64 registers per thread either way, i.e. 1024 resident threads per SM.
+#ifndef ARS_FINAL_NT
+#define ARS_FINAL_NT 128
+#endif
+constexpr int FINAL_NT = ARS_FINAL_NT;
+struct LeanAcc { float pkf; unsigned mm; double ss; };
+
+// one frame's channels: LAY = 1 (5.1), 2 (7.1), 3 (5.1.2); A1 = 0 (stereo guard idle), 2 (divides, reciprocal form valid)
+// or 3 (divides, element-wise form)
+template <int C, int LAY, int A1>
+__device__ __forceinline__ void lean_math(float2 v, float2 w, const TailSpec& ts, const Guard& g1, float (&o)[8]) {
+    if constexpr (A1 == 2) {
+        if (plain4(v, w)) {
+            v = guard_div2(v, g1);
+            if constexpr (LAY >= 2) w = guard_div2(w, g1);
+        } else {
+            const float4 q = guard_slow4(make_float4(v.x, v.y, w.x, w.y), g1.m, g1.r);
+            v = make_float2(q.x, q.y);
+            w = make_float2(q.z, q.w);
+        }
+    } else if constexpr (A1 == 3) {       // (the redo of a frame the float32 form could not decide)
+        const float4 q = guard_slow4(make_float4(v.x, v.y, w.x, w.y), g1.m, g1.r);
+        v = make_float2(q.x, q.y);
+        w = make_float2(q.z, q.w);
+    }
+    const float mn = __fmul_rn(__fadd_rn(v.x, v.y), 0.707f);
+    const double dl = (double)v.x, dr = (double)v.y;
+    o[0] = __double2float_rn(__dmul_rn(dl, ts.g_fl));
+    o[1] = __double2float_rn(__dmul_rn(dr, ts.g_fr));
+    o[2] = __double2float_rn(__dmul_rn((double)mn, ts.g_c));
+    o[3] = __fmul_rn(mn, ts.g_lfe);
+    o[4] = __double2float_rn(__dmul_rn(dl, ts.g_rl));
+    o[5] = __double2float_rn(__dmul_rn(dr, ts.g_rr));
+    if constexpr (LAY >= 2) {
+        // (a frame without a delayed partner carries w = 0: its pair is 0 * gain = 0, as the zero-prepended copy)
+        const float rl = __double2float_rn(__dmul_rn((double)w.x, ts.g_rl));
+        const float rr = __double2float_rn(__dmul_rn((double)w.y, ts.g_rr));
+        if constexpr (LAY == 2) {
+            o[6] = __fmul_rn(rl, 0.7f);
+            o[7] = __fmul_rn(rr, 0.7f);
+        } else {
+            o[6] = __double2float_rn(__dmul_rn((double)rl, ts.height_gain));
+            o[7] = __double2float_rn(__dmul_rn((double)rr, ts.height_gain));
+        }
+    }
+}
+
+// ---- RN32(RN64(x * g)) without float64 conversions --------------------------------------------------------------------
+// numpy forms `audio * gain` with an np.float64 gain in float64 and rounds it into the float32 array (rs.py:475-494,
+// 550-553).  Evaluated literally that is two conversions and a float64 multiply per product -- 17 conversions per 5.1.2
+// frame, and the conversion pipe is what bounded the final pass (ncu: 109 us with 125 instructions per frame, the same
+// as with 200).  The same value from float32 pieces, two lanes per instruction:
+//     p = RN(x gh)             gh = gain rounded toward zero, gl = RN32(gain - gh) >= 0  (host: split_gain)
+//     q = fma(x, -gh, p)       = -(x gh - p), exact
+//     e = fma(x, gl, -q)       = (x gh - p) + x gl, one rounding; |e| < 3 ulp(p)
+//     r = RN(p + e)            the candidate;  rho = (p - r) + e is the exact residual of that sum
+// x g = p + e + eta with |eta| < 2^-21 ulp(p) (rounding of e, the bits of g below gl, the float64 rounding), so r is the
+// wanted value unless p + e sits that close to a rounding boundary -- tested as fma(rho, 1 + 2^-16, r) != r, which fires
+// for 1.5e-5 of all products; such a frame (and any frame with an operand outside the plain range, NaN and infinities
+// included) is redone through float64.  The signs of zero products come out as numpy's (that is what rounding the split
+// toward zero is for).  tests/host_emul/prod_emul.c replays this on the CPU against the float64 evaluation (3e8 random
+// and 5e7 adversarial operands: no unflagged difference).
+__device__ __forceinline__ float2 prod2(float2 x, float2 gh, float2 gl, bool& bad) {
+    const float2 p = __fmul2_rn(x, gh);
+    const float2 q = __ffma2_rn(x, make_float2(-gh.x, -gh.y), p);
+    const float2 e = __ffma2_rn(x, gl, make_float2(-q.x, -q.y));
+    // (sums of a packed product go through fma(a, 1, b): ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2,
+    // which the scalar .rn forms never are -- seen on the PCM scaling below, where it cost the second rounding)
+    const float2 one = make_float2(1.f, 1.f);
+    const float2 r = __ffma2_rn(p, one, e);
+    const float2 rho = __fadd2_rn(__ffma2_rn(r, make_float2(-1.f, -1.f), p), e);
+    const float2 c = __ffma2_rn(rho, make_float2(1.0000152587890625f, 1.0000152587890625f), r);
+    bad |= (c.x != r.x) | (c.y != r.y);
+    return r;
+}
+__device__ __forceinline__ float prod1(float x, float gh, float gl, bool& bad) {
+    const float p = __fmul_rn(x, gh);
+    const float q = __fmaf_rn(x, -gh, p);
+    const float e = __fmaf_rn(x, gl, -q);
+    const float r = __fadd_rn(p, e);
+    const float rho = __fadd_rn(__fsub_rn(p, r), e);
+    bad |= (__fmaf_rn(rho, 1.0000152587890625f, r) != r);
+    return r;
+}
+// every one of the four values zero or inside [2^-26, 2^40): guard_div2's plain range, and after a division by a maximum
+// in (1, 1e10) still >= 2^-60, where every product of the frame and its error term stay normal numbers
+__device__ __forceinline__ bool plain4e(float2 v, float2 w) {
+    constexpr unsigned LO = 0x32800000u /* 2^-26 */, HI = 0x53800000u /* 2^40 */;
+    const unsigned a = abs_bits(v.x), b = abs_bits(v.y), c = abs_bits(w.x), d = abs_bits(w.y);
+    const unsigned hi = max(max(a, b), max(c, d));
+    const unsigned lo = min(min(a - 1u, b - 1u), min(c - 1u, d - 1u));
+    return hi < HI && lo >= LO - 1u;
+}
+
+// one frame's channels from float32 pieces of the gains; -> true when the frame has to be redone literally
+template <int C, int LAY, int A1>
+__device__ __forceinline__ bool lean_math_split(float2 v, float2 w, const TailSpec& ts, const Guard& g1, float (&o)[8]) {
+    bool bad = !plain4e(v, w);
+    float2 gv = v, gw = w;
+    if constexpr (A1 == 2) {
+        gv = guard_div2(v, g1);
+        if constexpr (LAY >= 2) gw = guard_div2(w, g1);
+    }
+    const float mn = __fmul_rn(__fadd_rn(gv.x, gv.y), 0.707f);
+    bad |= (abs_bits(mn) - 1u) < (0x21800000u /* 2^-60 */ - 1u);       // (L + R may cancel to something tiny)
+    const float2 f = prod2(gv, make_float2(ts.g_hi[0], ts.g_hi[1]), make_float2(ts.g_lo[0], ts.g_lo[1]), bad);
+    const float2 r = prod2(gv, make_float2(ts.g_hi[3], ts.g_hi[4]), make_float2(ts.g_lo[3], ts.g_lo[4]), bad);
+    o[0] = f.x; o[1] = f.y;
+    o[2] = prod1(mn, ts.g_hi[2], ts.g_lo[2], bad);
+    o[3] = __fmul_rn(mn, ts.g_lfe);
+    o[4] = r.x; o[5] = r.y;
+    if constexpr (LAY >= 2) {
+        const float2 d = prod2(gw, make_float2(ts.g_hi[3], ts.g_hi[4]), make_float2(ts.g_lo[3], ts.g_lo[4]), bad);
+        float2 h;
+        if constexpr (LAY == 2) h = __fmul2_rn(d, make_float2(0.7f, 0.7f));
+        else h = prod2(d, make_float2(ts.g_hi[5], ts.g_hi[5]), make_float2(ts.g_lo[5], ts.g_lo[5]), bad);
+        o[6] = h.x; o[7] = h.y;
+    }
+    return bad;
+}
+
+// The literal frame for the few the float32 form cannot decide (and every frame holding a NaN): the general code --
+// loads, float64 products, stores and all -- out of line, so that the loop around it stays small.
+// -> (max |channel|, the frame's sum of squares, its loudness-feed value)
 template <int C>
-__global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y, TailSpec ts, RenderState* st,
+__device__ __noinline__ float4 slow_frame(const float2* __restrict__ y, i64 i, const TailSpec* __restrict__ tsp, unsigned stereo_bits,
+                                          float* __restrict__ out, short* __restrict__ pcm, float* __restrict__ mono) {
+    const TailSpec& ts = *tsp;
+    const Guard g1 = make_guard(stereo_bits), idle = make_guard(0u);
+    float o[8];
+    frame_out<1, 0>(y, i, ts, g1, idle, o);
+    float pk = 0.f, fs = 0.f;
+    #pragma unroll
+    for (int c = 0; c < C; ++c) {
+        pk = fmaxf(pk, fabsf(o[c]));
+        fs = __fmaf_rn(o[c], o[c], fs);
+    }
+    if (out) {
+        float* p = out + (i - ts.out0) * C;
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) reinterpret_cast<float2*>(p)[c >> 1] = make_float2(o[c], o[c + 1]);
+    }
+    if (pcm) {
+        short* p = pcm + (i - ts.out0) * C;
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) reinterpret_cast<unsigned*>(p)[c >> 1] = pcm_pair(o[c], o[c + 1]);
+    }
+    const float mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);
+    if (mono) mono[i - ts.out0] = mv;
+    return make_float4(pk, fs, mv, 0.f);
+}
+
+// peak / squares / stores of a frame of the float32 form.  Its channels are finite and <= 1 in magnitude (the pan guard is
+// idle and NaN frames went the other way), so round-to-nearest-even of x * 32767 is the low half of RN(x * 32767 + 1.5 * 2^23)
+// -- a packed add and a byte permute per pair instead of two conversions; the +-32764 clamp (np.clip at +-0.9999) follows on
+// the packed int16 pair as in pcm_pair.
+template <int C, int IO>
+__device__ __forceinline__ void split_emit(const float (&o)[8], unsigned k, float* __restrict__ out, short* __restrict__ pcm,
+                                           float* __restrict__ mono, LeanAcc& acc) {
+    float fs = 0.f;
+    #pragma unroll
+    for (int c = 0; c < C; ++c) {
+        acc.pkf = fmaxf(acc.pkf, fabsf(o[c]));
+        fs = __fmaf_rn(o[c], o[c], fs);
+    }
+    acc.ss += (double)fs;
+    if (IO == 0 && out) {
+        float2* p = reinterpret_cast<float2*>(out) + (size_t)k * (C / 2);
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) p[c >> 1] = make_float2(o[c], o[c + 1]);
+    }
+    if (IO == 1 || pcm) {
+        unsigned u[C / 2];
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) {
+            // (two roundings, as lrintf(x * 32767.0f) has: the sum as fma(v, 1, magic) keeps ptxas from contracting them)
+            const float2 t = __ffma2_rn(__fmul2_rn(make_float2(o[c], o[c + 1]), make_float2(32767.0f, 32767.0f)),
+                                        make_float2(1.f, 1.f), make_float2(12582912.0f, 12582912.0f));
+            const unsigned pk = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
+            u[c >> 1] = __vmins2(__vmaxs2(pk, 0x80048004u), 0x7ffc7ffcu);
+        }
+        if constexpr (C == 8) {
+            __stcs(reinterpret_cast<uint4*>(pcm) + k, make_uint4(u[0], u[1], u[2], u[3]));
+        } else {
+            unsigned* p = reinterpret_cast<unsigned*>(pcm) + (size_t)k * (C / 2);
+            #pragma unroll
+            for (int c = 0; c < C / 2; ++c) __stcs(p + c, u[c]);
+        }
+    }
+    if (IO == 1 || mono) {
+        const float mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);
+        mono[k] = mv;
+        acc.mm = max(acc.mm, abs_bits(mv));
+    }
+}
+
+// Frames [k_lo, k_hi) of the window (relative to ts.i_lo) through the float32 form.  A CTA takes tiles of 2 x FINAL_NT frames
+// (a thread's two frames FINAL_NT apart: one address per array and step), the next step's loads issued before this step's
+// arithmetic, the steps unrolled by two so that the register sets swap roles.  PAIR: every frame has its delayed partner.
+template <int C, int LAY, int A1, int IO, bool PAIR>
+__device__ __forceinline__ void split_range(const float2* __restrict__ yw, unsigned k_lo, unsigned k_hi, unsigned dl,
+                                            const TailSpec* __restrict__ tsp, const Guard& g1, unsigned stereo_bits,
+                                            const float2* __restrict__ y, float* __restrict__ out, short* __restrict__ pcm,
+                                            float* __restrict__ mono, float* __restrict__ outw, short* __restrict__ pcmw,
+                                            float* __restrict__ monow, LeanAcc& acc) {
+    constexpr int U = 2;
+    const TailSpec& ts = *tsp;
+    const unsigned step = gridDim.x * ((unsigned)(FINAL_NT * U));
+    unsigned k = k_lo + blockIdx.x * ((unsigned)(FINAL_NT * U)) + threadIdx.x;
+    if (k >= k_hi) return;
+    const float2* __restrict__ yd = yw - dl;
+    float2 va[U], wa[U], vb[U], wb[U];
+    auto fetch = [&](unsigned k0, float2 (&v)[U], float2 (&w)[U]) {
+        const float2* pv = yw + k0;
+        const float2* pw = yd + k0;
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = make_float2(0.f, 0.f);
+            w[u] = make_float2(0.f, 0.f);
+            if (k0 + (unsigned)(u * FINAL_NT) < k_hi) {
+                v[u] = __ldcs(pv + u * FINAL_NT);
+                if (LAY >= 2 && PAIR) w[u] = __ldg(pw + u * FINAL_NT);
+            }
+        }
+    };
+    auto work = [&](unsigned k0, const float2 (&v)[U], const float2 (&w)[U]) {
+        float o[U][8];
+        bool bad[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) bad[u] = lean_math_split<C, LAY, A1>(v[u], w[u], ts, g1, o[u]);
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned kk = k0 + (unsigned)(u * FINAL_NT);
+            if (kk >= k_hi) continue;
+            if (!bad[u]) {
+                split_emit<C, IO>(o[u], kk, outw, pcmw, monow, acc);
+            } else {
+                const float4 r = slow_frame<C>(y, ts.i_lo + (i64)kk, tsp, stereo_bits, out, pcm, mono);
+                acc.pkf = fmaxf(acc.pkf, r.x);
+                acc.ss += (double)r.y;                       // (a NaN frame leaves its mark here)
+                if (mono) acc.mm = max(acc.mm, abs_bits(r.z));
+            }
+        }
+    };
+    fetch(k, va, wa);
+    for (;;) {
+        const unsigned k1 = k + step;
+        const bool more1 = k1 < k_hi && k1 > k;
+        if (more1) fetch(k1, vb, wb);
+        work(k, va, wa);
+        if (!more1) break;
+        const unsigned k2 = k1 + step;
+        const bool more2 = k2 < k_hi && k2 > k1;
+        if (more2) fetch(k2, va, wa);
+        work(k1, vb, wb);
+        if (!more2) break;
+        k = k2;
+    }
+}
+
+template <int C, int LAY, int A1, int IO>
+__device__ __forceinline__ void final_split(const float2* __restrict__ y, const TailSpec* __restrict__ tsp, const Guard& g1,
+                                            unsigned stereo_bits, float* __restrict__ out, short* __restrict__ pcm,
+                                            float* __restrict__ mono, LeanAcc& acc) {
+    const TailSpec& ts = *tsp;
+    const float2* yw = y + (ts.i_lo - ts.y0);                      // frame 0 of the window
+    const unsigned count = (unsigned)(ts.i_hi - ts.i_lo);
+    float* outw = out ? out + (ts.i_lo - ts.out0) * C : nullptr;
+    short* pcmw = pcm ? pcm + (ts.i_lo - ts.out0) * C : nullptr;
+    float* monow = mono ? mono + (ts.i_lo - ts.out0) : nullptr;
+    if constexpr (LAY >= 2) {
+        const i64 dl = ts.delay > 0 ? ts.delay : 0;
+        const i64 head = ts.delay - ts.i_lo;
+        const unsigned k_head = head <= 0 ? 0u : (head >= (i64)count ? count : (unsigned)head);
+        split_range<C, LAY, A1, IO, false>(yw, 0u, k_head, 0u, tsp, g1, stereo_bits, y, out, pcm, mono, outw, pcmw, monow, acc);
+        split_range<C, LAY, A1, IO, true>(yw, k_head, count, (unsigned)dl, tsp, g1, stereo_bits, y, out, pcm, mono, outw, pcmw, monow, acc);
+    } else {
+        split_range<C, LAY, A1, IO, false>(yw, 0u, count, 0u, tsp, g1, stereo_bits, y, out, pcm, mono, outw, pcmw, monow, acc);
+    }
+}
+
+// peak / squares / stores of frame k (byte offsets inside the window fit 32 bits: the caller checks the frame count).
+// A NaN sample makes the frame's sum of squares NaN and with it the running double sum, for good: the caller reads
+// "NaN seen" off that sum instead of testing every frame.
+template <int C, int IO>          // IO = 1: PCM + loudness feed, no float frames (the render's default); 0: whatever is given
+__device__ __forceinline__ void lean_emit(const float (&o)[8], unsigned k, bool valid, const TailSpec& ts, float* __restrict__ out,
+                                          short* __restrict__ pcm, float* __restrict__ mono, LeanAcc& acc) {
+    float fs = 0.f;
+    #pragma unroll
+    for (int c = 0; c < C; ++c) {
+        acc.pkf = fmaxf(acc.pkf, fabsf(o[c]));
+        fs = __fmaf_rn(o[c], o[c], fs);
+    }
+    acc.ss += (double)fs;
+    if (!valid) return;           // (a frame past the end carries zeros: its sums change nothing, its stores are skipped)
+    if (IO == 0 && out) {
+        float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(out) + k * (unsigned)(4 * C));
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) reinterpret_cast<float2*>(p)[c >> 1] = make_float2(o[c], o[c + 1]);
+    }
+    if (IO == 1 || pcm) {
+        short* p = reinterpret_cast<short*>(reinterpret_cast<char*>(pcm) + k * (unsigned)(2 * C));
+        const float2 sc = make_float2(32767.0f, 32767.0f);
+        unsigned u[C / 2];
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) {
+            const float2 s2 = __fmul2_rn(make_float2(o[c], o[c + 1]), sc);
+            const int q0 = __float2int_rn(s2.x), q1 = __float2int_rn(s2.y);
+            unsigned pk;
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(pk) : "r"(q1), "r"(q0));
+            u[c >> 1] = __vmins2(__vmaxs2(pk, 0x80048004u), 0x7ffc7ffcu);
+        }
+        if constexpr (C == 8) {
+            __stcs(reinterpret_cast<uint4*>(p), make_uint4(u[0], u[1], u[2], u[3]));
+        } else {
+            #pragma unroll
+            for (int c = 0; c < C / 2; ++c) __stcs(reinterpret_cast<unsigned*>(p) + c, u[c]);
+        }
+    }
+    if (IO == 1 || mono) {
+        const float mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(mono) + k * 4u) = mv;
+        acc.mm = max(acc.mm, abs_bits(mv));
+    }
+}
+
+// frames [k_lo, k_hi) of the window (k relative to ts.i_lo); PAIR: every frame has its delayed partner dl frames back.
+// A thread takes frames k, k + stride, ...: U of them per step, the next step's loads issued before this step's
+// arithmetic, the steps unrolled by two so that the two register sets swap roles instead of being copied.
+template <int C, int LAY, int A1, int IO, int U, bool PIPE, bool PAIR>
+__device__ __forceinline__ void lean_range(const float2* __restrict__ yw, unsigned k_lo, unsigned k_hi, unsigned dl,
+                                           const TailSpec& ts, const Guard& g1, float* __restrict__ out,
+                                           short* __restrict__ pcm, float* __restrict__ mono, LeanAcc& acc) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_hi) return;
+    const char* __restrict__ yb = reinterpret_cast<const char*>(yw);
+    const char* __restrict__ ydb = reinterpret_cast<const char*>(yw - dl);          // the partner `delay` frames earlier
+    float2 va[U], wa[U], vb[U], wb[U];
+    auto fetch = [&](unsigned k0, float2 (&v)[U], float2 (&w)[U]) {
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned kk = k0 + u * stride;
+            v[u] = make_float2(0.f, 0.f);
+            w[u] = make_float2(0.f, 0.f);
+            if (kk < k_hi) {
+                v[u] = __ldcs(reinterpret_cast<const float2*>(yb + kk * 8u));      // (touched once more, as a partner, through the L2)
+                if (LAY >= 2 && PAIR) w[u] = __ldg(reinterpret_cast<const float2*>(ydb + kk * 8u));
+            }
+        }
+    };
+    auto work = [&](unsigned k0, const float2 (&v)[U], const float2 (&w)[U]) {
+        float o[U][8];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) lean_math<C, LAY, A1>(v[u], w[u], ts, g1, o[u]);
+        #pragma unroll
+        for (int u = 0; u < U; ++u) lean_emit<C, IO>(o[u], k0 + u * stride, k0 + u * stride < k_hi, ts, out, pcm, mono, acc);
+    };
+    if constexpr (!PIPE) {
+        // U frames' loads in flight per thread, consumed in order (no second register set)
+        for (; k < k_hi; k += U * stride) {
+            fetch(k, va, wa);
+            work(k, va, wa);
+        }
+        return;
+    }
+    fetch(k, va, wa);
+    for (;;) {
+        const unsigned k1 = k + U * stride;
+        if (k1 < k_hi) fetch(k1, vb, wb);
+        work(k, va, wa);
+        if (k1 >= k_hi) break;
+        const unsigned k2 = k1 + U * stride;
+        if (k2 < k_hi) fetch(k2, va, wa);
+        work(k1, vb, wb);
+        if (k2 >= k_hi) break;
+        k = k2;
+    }
+}
+
+template <int C, int LAY, int A1, int IO>
+__device__ __forceinline__ void final_lean(const float2* __restrict__ y, const TailSpec& ts, const Guard& g1,
+                                           float* __restrict__ out, short* __restrict__ pcm, float* __restrict__ mono,
+                                           LeanAcc& acc) {
+    const float2* yw = y + (ts.i_lo - ts.y0);                      // frame 0 of the window
+    const unsigned count = (unsigned)(ts.i_hi - ts.i_lo);
+    float* outw = out ? out + (ts.i_lo - ts.out0) * C : nullptr;
+    short* pcmw = pcm ? pcm + (ts.i_lo - ts.out0) * C : nullptr;
+    float* monow = mono ? mono + (ts.i_lo - ts.out0) : nullptr;
+    if constexpr (LAY >= 2) {
+        // frames below `delay` have no partner (rs.py:507-515 prepends zeros); a delay <= 0 leaves the pair in place
+        const i64 dl = ts.delay > 0 ? ts.delay : 0;
+        const i64 head = ts.delay - ts.i_lo;
+        const unsigned k_head = head <= 0 ? 0u : (head >= (i64)count ? count : (unsigned)head);
+        lean_range<C, LAY, A1, IO, 1, false, false>(yw, 0u, k_head, 0u, ts, g1, outw, pcmw, monow, acc);
+        lean_range<C, LAY, A1, IO, 2, true, true>(yw, k_head, count, (unsigned)dl, ts, g1, outw, pcmw, monow, acc);
+    } else {
+        lean_range<C, LAY, A1, IO, 2, true, false>(yw, 0u, count, 0u, ts, g1, outw, pcmw, monow, acc);
+    }
+}
+
+// LAY = 0: any layout through the general loop; 1 / 2 / 3: 5.1 / 7.1 / 5.1.2 with the lean loop when it applies
+template <int C, int LAY, bool SPLIT>
+__global__ void __launch_bounds__(LAY ? FINAL_NT : 256, LAY ? 1024 / FINAL_NT : 4) final_kernel(const float2* __restrict__ y, const __grid_constant__ TailSpec ts, RenderState* st,
                                                     float* __restrict__ out, short* __restrict__ pcm,
                                                     float* __restrict__ mono) {
     const Guard g1 = make_guard(st->max_stereo), g2 = make_guard(st->max_pan);
@@ -193,17 +624,57 @@ __global__ void __launch_bounds__(256) final_kernel(const float2* __restrict__ y
     bool nan_seen = false;
     unsigned mm = 0;
     double ss = 0.0;
-    if (g2.mode == 0 && g3.mode == 0) {
-        if (g1.mode == 0) final_body<C, 0, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
-        else if (g1.mode == 1) final_body<C, 2, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
-        else final_body<C, 1, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
-    } else {
-        final_body<C, 1, 1, 1>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+    bool done = false;
+    if constexpr (LAY >= 1) {
+        // (frame count below 2^28: byte offsets of every array fit 32 bits inside the window)
+        if (g2.mode == 0 && (g1.mode == 0 || (g1.mode == 1 && g1.r != 0.f)) && ts.i_hi - ts.i_lo < ((i64)1 << 28)) {
+            LeanAcc acc = {0.f, 0u, 0.0};
+            const bool io1 = !out && pcm && mono;
+            if (g1.mode == 0) {
+                if (io1) { if constexpr (SPLIT) final_split<C, LAY, 0, 1>(y, &ts, g1, st->max_stereo, out, pcm, mono, acc); else final_lean<C, LAY, 0, 1>(y, ts, g1, out, pcm, mono, acc); }
+                else { if constexpr (SPLIT) final_split<C, LAY, 0, 0>(y, &ts, g1, st->max_stereo, out, pcm, mono, acc); else final_lean<C, LAY, 0, 0>(y, ts, g1, out, pcm, mono, acc); }
+            } else {
+                if (io1) { if constexpr (SPLIT) final_split<C, LAY, 2, 1>(y, &ts, g1, st->max_stereo, out, pcm, mono, acc); else final_lean<C, LAY, 2, 1>(y, ts, g1, out, pcm, mono, acc); }
+                else { if constexpr (SPLIT) final_split<C, LAY, 2, 0>(y, &ts, g1, st->max_stereo, out, pcm, mono, acc); else final_lean<C, LAY, 2, 0>(y, ts, g1, out, pcm, mono, acc); }
+            }
+            pkf = acc.pkf; nan_seen = (acc.ss != acc.ss); mm = acc.mm; ss = acc.ss;
+            done = true;
+        }
+    }
+    if (!done) {
+        if (g2.mode == 0 && g3.mode == 0) {
+            if (g1.mode == 0) final_body<C, 0, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+            else if (g1.mode == 1) final_body<C, 2, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+            else final_body<C, 1, 0, 0>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        } else {
+            final_body<C, 1, 1, 1>(y, ts, g1, g2, g3, out, pcm, mono, pkf, nan_seen, mm, ss);
+        }
     }
     const unsigned pk = nan_seen ? 0x7fc00000u : __float_as_uint(pkf);
     block_atomic_max(pk, &st->peak_final);
     block_atomic_max(mm, &st->mono_max);
     block_atomic_add(ss, &st->sumsq);
+}
+
+static int g_final_lean = 2;
+void tail_set_lean(int v) { g_final_lean = v < 0 ? 0 : (v > 2 ? 2 : v); }
+
+// hi = g rounded toward zero, lo = RN32(g - hi) >= 0; false when g is not +0 or inside [2^-16, 2^16] (prod2's conditions)
+static bool split_gain(double g, float& hi, float& lo) {
+    hi = lo = 0.f;
+    if (g == 0.0) return !std::signbit(g);
+    if (!(g >= 0x1p-16 && g <= 0x1p16)) return false;
+    float f = (float)g;
+    if ((double)f > g) f = std::nextafterf(f, 0.f);
+    hi = f;
+    lo = (float)(g - (double)f);
+    return true;
+}
+static void split_gains(TailSpec& ts) {
+    const double g[6] = {ts.g_fl, ts.g_fr, ts.g_c, ts.g_rl, ts.g_rr, ts.layout == LAYOUT_5_1_2 ? ts.height_gain : 0.0};
+    bool ok = true;
+    for (int i = 0; i < 6; ++i) ok = split_gain(g[i], ts.g_hi[i], ts.g_lo[i]) && ok;
+    ts.split_ok = ok ? 1 : 0;
 }
 
 static TailSpec with_window(const TailSpec& in) {
@@ -250,15 +721,27 @@ void tail_maxes(const float2* d_y, const TailSpec& ts_in, RenderState* d_state) 
 
 void tail_final(const float2* d_y, const TailSpec& ts_in, RenderState* d_state, float* d_out, short* d_pcm,
                 float* d_mono) {
-    const TailSpec ts = with_window(ts_in);
+    TailSpec ts = with_window(ts_in);
     if (ts.N <= 0 || ts.i_hi <= ts.i_lo) return;
+    split_gains(ts);
     Ctx& c = ctx();
     const int grid = stream_grid(ts.i_hi - ts.i_lo);
+    static const int waves = [] { const char* e = getenv("ARS_FINAL_WAVES"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    const int grid_lean = (int)std::max<i64>(1, std::min<i64>((ts.i_hi - ts.i_lo + 2 * FINAL_NT - 1) / (2 * FINAL_NT),
+                                                             (i64)c.sm_count * (1024 / FINAL_NT) * waves));
     KernelScope prof("final_kernel (guards, pan, map, clip, PCM16, sums)",
                      (double)(ts.i_hi - ts.i_lo) * (8.0 + (d_pcm ? 2.0 * ts.C : 0.0) + (d_out ? 4.0 * ts.C : 0.0) + (d_mono ? 4.0 : 0.0)));
-    if (ts.C == 2) final_kernel<2><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
-    else if (ts.C == 6) final_kernel<6><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
-    else final_kernel<8><<<grid, 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono);
+    // 0: general loop; 1: lean loop, float64 products; 2: lean loop, products from float32 pieces (when the gains allow)
+    const int lean = ts.layout != LAYOUT_STEREO ? g_final_lean : 0;
+    #define ARS_FINAL(CC, LL, SS) final_kernel<CC, LL, SS><<<(LL) ? grid_lean : grid, (LL) ? FINAL_NT : 256, 0, c.stream>>>(d_y, ts, d_state, d_out, d_pcm, d_mono)
+    #define ARS_FINAL_L(CC, LL) do { if (lean == 2 && ts.split_ok) ARS_FINAL(CC, LL, true); else if (lean) ARS_FINAL(CC, LL, false); \
+                                     else ARS_FINAL(CC, 0, false); } while (0)
+    if (ts.C == 2) ARS_FINAL(2, 0, false);
+    else if (ts.C == 6) ARS_FINAL_L(6, 1);
+    else if (ts.layout == LAYOUT_7_1) ARS_FINAL_L(8, 2);
+    else ARS_FINAL_L(8, 3);
+    #undef ARS_FINAL_L
+    #undef ARS_FINAL
     ARS_LAUNCH_CHECK();
     count_launch();
 }

@@ -25,6 +25,11 @@ struct TailSpec {
     float g_lfe = 0.15f;         // Python float (weak) => float32 multiply (rs.py:485)
     double height_gain = 0.0;    // clip(z,0,1)*0.6, np.float64 => product formed in double (rs.py:550-553)
     int stream = 0;              // final pass: bit 0 PCM / float frames stored, bit 1 stereo frames read with the evict-first policy
+    // the float64 gains as float32 pairs for the final pass's float32 evaluation of RN32(RN64(x * gain)) (epilogue.cu:
+    // prod2): hi = gain rounded toward zero, lo = RN32(gain - hi) >= 0; order fl, fr, c, rl, rr, height.  split_ok = every
+    // gain is +0 or inside [2^-16, 2^16] (tail_final fills these in)
+    float g_hi[6] = {0, 0, 0, 0, 0, 0}, g_lo[6] = {0, 0, 0, 0, 0, 0};
+    int split_ok = 0;
 };
 
 inline int layout_channels(int layout) { return layout == LAYOUT_STEREO ? 2 : layout == LAYOUT_5_1 ? 6 : 8; }
@@ -38,6 +43,8 @@ void tail_map_max(const float2* d_y, const TailSpec& ts, RenderState* d_state); 
 // loudness feed mean(ch0, ch1); accumulates peak_final and sumsq in the state.
 void tail_final(const float2* d_y, const TailSpec& ts, RenderState* d_state, float* d_out, short* d_pcm,
                 float* d_mono);
+void tail_set_lean(int v);         // 0: the general frame loop for every layout; 1 / 2: lean loop of the 5.1-based layouts with
+                                   // float64 products / products from float32 pieces of the gains [default]
 
 // ---- stage-level kernels on materialised arrays (the per-function C-ABI entry points) ----
 void absmax_f32(const float* d_x, i64 count, unsigned* d_maxbits);

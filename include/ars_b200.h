@@ -124,7 +124,10 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * "olsb_logf" (0 = block length chosen from the tap count [default] | 18..22), "olsb_stripe" (0 = transforms per
  * L2-resident stripe chosen from the SM count [default] | n), "stream_hints" (bit mask, default 15: data touched once moves
  * with the evict-first cache policy -- 1 signal frames read by the first pass, 2 output frames stored by the last pass,
- * 4 PCM / float frames stored and 8 stereo frames read by the final pass).
+ * 4 PCM / float frames stored and 8 stereo frames read by the final pass),
+ * "final_lean" (1 [default] | 2 = the final pass of the 5.1-based layouts runs its lean frame loop -- packed FP32x2 guard
+ * division behind one range test per frame, 32-bit offsets, one | two frames per step -- whenever only the stereo peak
+ * guard can be active; 0 = the general loop.  Bit-identical results either way).
  * Environment (read once per process, experiments): ARS_MID_PIPE (3 [default] | 2 = the plain middle pass runs as a persistent
  * kernel that fetches its next tile with cp.async.bulk, 3 | 2 CTAs per SM; 0 = one tile per CTA), ARS_LAST_PIPE (3 [default] |
  * 2 | 6 = the last pass of 2^18-point blocks likewise, double-buffered; 0 = one tile per CTA), ARS_MID_NT (256 | 512). */

@@ -724,6 +724,43 @@ def test_device_pointer_render_equals_host_render(rs):
     assert rs._metrics_dict(m) == host["metrics"]
 
 
+@pytest.mark.parametrize("layout", ["5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)"])
+@pytest.mark.parametrize("loud", [False, True])
+def test_final_pass_lean_loop_is_bit_identical_to_the_general_loop(rs, layout, loud):
+    """The lean frame loop of the final pass (packed guard division behind one range test, 32-bit offsets, loop split at
+    the layout delay) must reproduce the general loop bit for bit: PCM, float frames (compared as bit patterns), peak,
+    RMS and loudness -- with the stereo guard idle and dividing, with values below the division's plain range (their
+    frames take the element-wise form), exact zeros, and a clip shorter than the layout delay."""
+    from ars_b200 import _capi
+    g = np.random.default_rng(77)
+    rate = 48000
+    ir = (g.standard_normal((3000, 2)) * np.exp(-np.arange(3000) / 700.0)[:, None]).astype(np.float32)
+    ir[0] = 1.0
+    for n in (200, 150001):
+        x = ((0.9 if loud else 0.05) * g.standard_normal((n, 2))).astype(np.float32)
+        x[n // 3: n // 3 + 4000] *= np.float32(1e-30)            # tiny but non-zero stage output
+        x[n // 2: n // 2 + 4000] = 0.0                            # (the IR's ring-out keeps these frames non-zero)
+        x[-3500:] = 0.0
+        kw = dict(external_ir_data=ir, dry_wet=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.2, y_pos=.4, z_pos=.8,
+                  target_channel_layout=layout)
+        res, pcm_only = {}, {}
+        try:
+            for mode in (0, 1, 2):
+                _capi.set_option("final_lean", mode)
+                res[mode] = rs.render_array(x, rate, **kw)
+                pcm_only[mode] = rs.render_array(x, rate, want_float=False, **kw)      # (its own instantiation of the loop)
+        finally:
+            _capi.set_option("final_lean", 1)
+        for mode in (1, 2):
+            assert np.array_equal(res[mode]["pcm"], res[0]["pcm"]), (n, mode)
+            assert np.array_equal(res[mode]["final"].view(np.uint32), res[0]["final"].view(np.uint32)), (n, mode)
+            assert res[mode]["metrics"] == res[0]["metrics"], (n, mode, res[mode]["metrics"], res[0]["metrics"])
+            assert np.array_equal(pcm_only[mode]["pcm"], res[0]["pcm"]), (n, mode)
+            assert pcm_only[mode]["metrics"] == res[0]["metrics"], (n, mode)
+        if loud and n > 1000:
+            assert np.max(np.abs(res[0]["final"])) <= 1.0 and res[0]["metrics"]["true_peak_dbfs"] > -12.0
+
+
 def test_large_transform_2pow28_properties(rs):
     """A 25-minute clip with the EQ mask on: N = 72 000 000 + L - 1, Bluestein length 2^28 (three passes of 2^8 /
     2^8 / 2^12 points, two-level twiddle tables, 64-bit indices).  Linearity plus a direct time-domain spot check of

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "ars_launch_count": (C.c_uint64, []),
     "ars_air_fold_count": (C.c_uint64, []),
     "ars_olsb_count": (C.c_uint64, []),
+    "ars_head_start_count": (C.c_uint64, []),
     "ars_stream": (C.c_void_p, []),
     "ars_ir_synth": (C.c_int, [_d, _d, _d, _d, _d, _d, _d, C.POINTER(ArsIrDraws), _p, _p, _i64]),
     "ars_ir_geometry": (C.c_int, [_d, _d, _d, _d, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
@@ -92,6 +93,8 @@ PROTOTYPES = {
     "ars_render": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),
                              _p, _p, _p, C.POINTER(ArsMetrics)]),
     "ars_render_dev": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),
+                                 _p, _p, _p, C.POINTER(ArsMetrics)]),
+    "ars_render_dev_async": (C.c_int, [C.POINTER(ArsRenderParams), _p, _i64, _i32, _p, _i64, C.POINTER(ArsIrDraws),
                                  _p, _p, _p, C.POINTER(ArsMetrics)]),
     "ars_render_batch": (C.c_int, [C.POINTER(ArsClip), _i32]),
     "ars_set_option": (C.c_int, [C.c_char_p, _i32]),

@@ -24,7 +24,9 @@ void host_block_free(void* p);
 #define ARS_API_BEGIN                                                   \
     try {                                                               \
         std::lock_guard<std::recursive_mutex> _lk(ctx().mu);            \
-        ARS_CUDA(cudaSetDevice(ctx().device));
+        ARS_CUDA(cudaSetDevice(ctx().device));                          \
+        ctx().conv_done_prev = ctx().conv_done_valid;                   \
+        ctx().conv_done_valid = false;
 #define ARS_API_END                                                     \
         return ARS_OK;                                                  \
     } catch (const Error& e) {                                          \
@@ -45,6 +47,7 @@ static unsigned long long g_air_fold_count = 0;   // convolution stages that too
 static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (overlap-save) when its error bound allows
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
+static int g_opt_head_start = 1;        // 1: asynchronous renders of the same geometry overlap their head with the tail of the render before
 static int g_opt_lufs_from_stage = 0;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array);
                                         // measured slower: both kernels are bound by issue slots, and recomputing the feed costs more
                                         // instructions than the 4 B per frame the final pass writes (0.660 against 0.634 ms)
@@ -130,7 +133,38 @@ template <class T> static T* upload(const char* name, const T* host, size_t coun
 template <class T> static void download(T* host, const T* dev, size_t count) {
     if (count) host_download(host, dev, sizeof(T) * count, ctx().stream);
 }
-static void sync() { ARS_CUDA(cudaStreamSynchronize(ctx().stream)); }
+// ---- deferred metrics (ars_render_dev_async) ----
+// An asynchronous render leaves its state block in a pinned slot (a D2H copy on the library stream) and is finished on
+// the host -- dB values, status words -- the next time the stream is waited for anyway (ars_sync, ars_timer_end): the
+// caller can enqueue render after render without the GPU idling while the host reads 80 bytes back and prepares the next one.
+struct PendingMetrics {
+    RenderState* h;
+    i64 count;
+    int lufs_status;
+    ArsMetrics* out;
+    ArsRenderParams p;
+};
+static std::vector<PendingMetrics> g_pending;
+static std::vector<RenderState*> g_pending_blocks;           // pinned, PENDING_BLOCK states each
+static constexpr size_t PENDING_BLOCK = 64;
+static RenderState* pending_slot() {
+    const size_t i = g_pending.size();
+    if (i / PENDING_BLOCK >= g_pending_blocks.size()) {
+        RenderState* b = nullptr;
+        ARS_CUDA(cudaMallocHost(&b, sizeof(RenderState) * PENDING_BLOCK));
+        g_pending_blocks.push_back(b);
+    }
+    return g_pending_blocks[i / PENDING_BLOCK] + i % PENDING_BLOCK;
+}
+static void finish_metrics(const RenderState& st, i64 count, int lufs_status, ArsMetrics* m, const ArsRenderParams* p = nullptr);
+static void collect_pending() {                               // (the library stream has just been waited for)
+    for (const PendingMetrics& q : g_pending) finish_metrics(*q.h, q.count, q.lufs_status, q.out, &q.p);
+    g_pending.clear();
+}
+static void sync() {
+    ARS_CUDA(cudaStreamSynchronize(ctx().stream));
+    collect_pending();
+}
 
 static RenderState* fresh_state(int slot = 0) {
     Ctx& c = ctx();
@@ -232,7 +266,7 @@ static int layout_ok(int layout) { return layout >= LAYOUT_STEREO && layout <= L
 
 // p (optional): the render's parameters, for the oversampled true peak (needs the layout's gains)
 static void finish_metrics(const RenderState& st, i64 count, int lufs_status, ArsMetrics* m,
-                           const ArsRenderParams* p = nullptr) {
+                           const ArsRenderParams* p) {
     memset(m, 0, sizeof(*m));
     m->true_peak_4x_status = 1;
     if (p && (p->want_lufs & 2) && layout_ok(p->layout)) {
@@ -280,9 +314,22 @@ static void common_filter_spec(FilterSpec& fs, i64 N, double rate, double dry_we
 // the GPU: the metrics end up in *st (device) and *lufs_status says how to read st->lufs.
 static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int cin, const float* d_ext_ir, i64 ext_len,
                         const ArsIrDraws* draws, float* d_out_stereo, float* d_out_f32, short* d_out_pcm,
-                        RenderState* st, bool want_metrics, int* lufs_status) {
+                        RenderState* st, bool want_metrics, int* lufs_status, bool allow_head_start = false) {
     Ctx& c = ctx();
     ARS_CHECK(p && d_in && n > 0 && cin >= 1, "render: empty input");
+    {
+        // head start (see Ctx): between two renders of the same geometry, the one before it the API call before this one
+        static ArsRenderParams last_p;
+        static i64 last_n = -1, last_ext = -1;
+        static int last_cin = -1;
+        static unsigned long long last_gen = 0;
+        const bool same = last_n == n && last_cin == cin && last_ext == ext_len && last_gen == ctx_generation() &&
+                          memcmp(&last_p, p, sizeof(ArsRenderParams)) == 0;
+        c.head_start = allow_head_start && g_opt_head_start && c.conv_done_prev && same;
+        if (c.head_start) ++c.head_starts;
+        last_p = *p; last_n = n; last_cin = cin; last_ext = ext_len; last_gen = ctx_generation();
+    }
+    struct HeadStartEnd { ~HeadStartEnd() { if (ctx_ready()) ctx().head_start = false; } } head_start_end;
     ARS_CHECK(p->rate >= 1.0, "render: bad sample rate");
     ARS_CHECK(layout_ok(p->layout), "render: unknown layout id");
     if (lufs_status) *lufs_status = ARS_LUFS_SKIPPED;
@@ -338,6 +385,8 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         convolution_stage(d_in, n, cin, d_early, g.length, d_late, g.length, fs, y, st, p->rate, ex);
         side_join();               // (no-op unless the stage left the side stream open)
     }
+    conv_done_mark();              // (the next render's head may start from here: see Ctx::head_start)
+    c.head_start = false;
     if (d_out_stereo) {
         ARS_CUDA(cudaMemcpyAsync(d_out_stereo, y, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, c.stream));
         guard_apply(d_out_stereo, N * 2, &st->max_stereo);
@@ -438,6 +487,7 @@ const char* ars_version(void) { return "ars_b200 0.1 (sm_100a)"; }
 uint64_t ars_launch_count(void) { return ctx_ready() ? ctx().launches : 0; }
 uint64_t ars_air_fold_count(void) { return g_air_fold_count; }
 uint64_t ars_olsb_count(void) { return olsb_count(); }
+uint64_t ars_head_start_count(void) { return ctx_ready() ? ctx().head_starts : 0; }
 void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
 
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -460,6 +510,9 @@ static void api_release() {
     if (pp.h_state) cudaFreeHost(pp.h_state);
     pp = Pipe();
     if (g_ev0) { cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1); g_ev0 = g_ev1 = nullptr; }
+    for (RenderState* b : g_pending_blocks) cudaFreeHost(b);
+    g_pending_blocks.clear();
+    g_pending.clear();
 }
 
 int ars_timer_begin(void) {
@@ -475,6 +528,7 @@ int ars_timer_end(float* ms) {
     ARS_CUDA(cudaEventRecord(g_ev1, ctx().stream));
     ARS_CUDA(cudaEventSynchronize(g_ev1));
     ARS_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    collect_pending();            // (everything enqueued before the stop event is complete: deferred metrics are due)
     ARS_API_END
 }
 
@@ -497,6 +551,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
     else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
+    else if (!strcmp(key, "head_start")) g_opt_head_start = value ? 1 : 0;
     else if (!strcmp(key, "final_lean")) { ARS_CHECK(value >= 0 && value <= 2, "final_lean must be 0, 1 or 2"); tail_set_lean(value); }
     else if (!strcmp(key, "host_staging")) host_staging_enable(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
@@ -846,23 +901,47 @@ int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int32_t cin
     ARS_API_END
 }
 
-int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
-                   int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
-                   int16_t* d_out_pcm, ArsMetrics* metrics) {
-    ARS_API_BEGIN
+static void render_dev_impl(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                            int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                            int16_t* d_out_pcm, ArsMetrics* metrics, bool deferred) {
     ARS_CHECK(p && layout_ok(p->layout), "ars_render_dev: bad arguments");
     Ctx& c = ctx();
     RenderState* st = fresh_state();
     int lufs_status = ARS_LUFS_SKIPPED;
     render_core(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32,
-                reinterpret_cast<short*>(d_out_pcm), st, metrics != nullptr, &lufs_status);
-    if (metrics) {
-        const i64 N = render_out_len(p, n, ext_ir_len);
-        RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
-        download(h, st, 1);
-        sync();
-        finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics, p);
+                reinterpret_cast<short*>(d_out_pcm), st, metrics != nullptr, &lufs_status, deferred);
+    if (!metrics) return;
+    const i64 N = render_out_len(p, n, ext_ir_len);
+    if (deferred) {
+        PendingMetrics q;
+        q.h = pending_slot();
+        q.count = N * layout_channels(p->layout);
+        q.lufs_status = lufs_status;
+        q.out = metrics;
+        q.p = *p;
+        download(q.h, st, 1);
+        g_pending.push_back(q);
+        return;
     }
+    RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
+    download(h, st, 1);
+    sync();
+    finish_metrics(*h, N * layout_channels(p->layout), lufs_status, metrics, p);
+}
+
+int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                   int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                   int16_t* d_out_pcm, ArsMetrics* metrics) {
+    ARS_API_BEGIN
+    render_dev_impl(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32, d_out_pcm, metrics, false);
+    ARS_API_END
+}
+
+int ars_render_dev_async(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                         int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                         int16_t* d_out_pcm, ArsMetrics* metrics) {
+    ARS_API_BEGIN
+    render_dev_impl(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32, d_out_pcm, metrics, true);
     ARS_API_END
 }
 

@@ -87,6 +87,14 @@ struct Ctx {
     cudaEvent_t ev_lane_fork = nullptr;
     int lanes_open = 0;
     cudaStream_t lane_saved = nullptr;
+    // head start (ars_render_dev_async): the part of a render that needs nothing from the render before it -- the IR chain
+    // on the side stream, the first passes on the lanes -- is ordered after that render's CONVOLUTION (ev_conv_done: its
+    // work buffers and IR spectrum are free) instead of after its tail, and runs next to the final pass and the loudness
+    // meter.  Only between two asynchronous renders of the same geometry (every plan, table and buffer exists already).
+    cudaEvent_t ev_conv_done = nullptr;
+    bool conv_done_valid = false, conv_done_prev = false;   // recorded by the API call in progress / by the one before it
+    bool head_start = false;                                 // this render takes it
+    unsigned long long head_starts = 0;
 
     DevBuf& buf(const char* name, size_t bytes) {
         DevBuf& b = ws[name];
@@ -106,6 +114,8 @@ void ctx_shutdown();
 // already on the main stream); what follows goes to the main stream again and runs concurrently with it until
 // side_join(), which makes the main stream wait for the side work.  side_abort() restores the main stream (errors).
 void side_begin();
+void conv_done_mark();        // records ev_conv_done on the main stream (end of a render's convolution stage)
+void lane_wait_main(int i);    // head start: lane i waits for what the main stream held at the fork
 void side_to_main();
 void side_join();
 void side_abort();

@@ -86,8 +86,12 @@ void side_begin() {
         ARS_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         ARS_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     }
-    ARS_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-    ARS_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+    if (c.head_start && c.ev_conv_done) {
+        ARS_CUDA(cudaStreamWaitEvent(c.aux, c.ev_conv_done, 0));      // (not the tail of the render before)
+    } else {
+        ARS_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+        ARS_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+    }
     c.main_stream = c.stream;
     c.stream = c.aux;
     c.side_state = 1;
@@ -130,9 +134,22 @@ void lane_fork(int n) {
             ARS_CUDA(cudaEventCreateWithFlags(&c.lane_done[i], cudaEventDisableTiming));
         }
     ARS_CUDA(cudaEventRecord(c.ev_lane_fork, c.stream));
-    for (int i = 0; i < n; ++i) ARS_CUDA(cudaStreamWaitEvent(c.lanes[i], c.ev_lane_fork, 0));
+    const bool early = c.head_start && c.ev_conv_done;              // lane_wait_main() orders what needs the main stream
+    for (int i = 0; i < n; ++i) ARS_CUDA(cudaStreamWaitEvent(c.lanes[i], early ? c.ev_conv_done : c.ev_lane_fork, 0));
     c.lane_saved = c.stream;
     c.lanes_open = n;
+}
+void lane_wait_main(int i) {
+    Ctx& c = ctx();
+    if (!c.lanes_open || !c.head_start) return;
+    ARS_CUDA(cudaStreamWaitEvent(c.lanes[i % c.lanes_open], c.ev_lane_fork, 0));
+}
+void conv_done_mark() {
+    Ctx& c = ctx();
+    if (c.side_state != 0 || c.lanes_open) return;                  // (only from the main stream, everything joined)
+    if (!c.ev_conv_done) ARS_CUDA(cudaEventCreateWithFlags(&c.ev_conv_done, cudaEventDisableTiming));
+    ARS_CUDA(cudaEventRecord(c.ev_conv_done, c.stream));
+    c.conv_done_valid = true;
 }
 void lane_use(int i) {
     Ctx& c = ctx();
@@ -254,6 +271,7 @@ void ctx_shutdown() {
             cudaEventDestroy(g_ctx->lane_done[i]);
         }
     if (g_ctx->ev_lane_fork) cudaEventDestroy(g_ctx->ev_lane_fork);
+    if (g_ctx->ev_conv_done) cudaEventDestroy(g_ctx->ev_conv_done);
     cudaStreamDestroy(g_ctx->stream);
     delete g_ctx;
     g_ctx = nullptr;

@@ -475,6 +475,7 @@ void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, c
         fft_batch_last(fp, nb, ld, st);
     };
     if (first_all && !have_first) first_pass(j_lo, nj, W);
+    const bool side_pending = c.side_state == 2;            // the IR spectrum comes from the side stream
     if (lanes > 1) lane_fork(lanes);
     else if (first_all) side_join();
     for (i64 si = 0; si < nstripes; ++si) {
@@ -488,8 +489,10 @@ void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, c
         if (si < lanes) {                                   // the first product of a stream needs the IR spectrum
             if (lanes > 1) lane_wait_side(lane);
             else side_join();
+            if (lanes > 1 && !side_pending) lane_wait_main(lane);     // (head start: a spectrum made on the main stream)
         }
         fft_batch_mid(fp, nb, w, H, ext ? H + (size_t)F : nullptr);
+        if (lanes > 1) lane_wait_main(lane);                // (head start: the frames and the maxima of the render before are in use until its tail is through)
         last_pass(j0, nb, w);
     }
     if (lanes > 1) { lane_join(); side_join(); }

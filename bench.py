@@ -301,11 +301,14 @@ class Render:
         self.draws_d.noise_len = int(self.noise.size)
         self.m = capi.ArsMetrics()
 
-    def step_dev(self):
-        self.capi.check(self.lib.ars_render_dev(self.p, self.d_in.data_ptr(), self.n, self.cin,
-                                                self.d_ir.data_ptr() if self.ext else None, self.L,
-                                                None if self.ext else self.draws_d, None, None, self.d_pcm.data_ptr(),
-                                                self.m), "ars_render_dev")
+    def step_dev(self, deferred_metrics=None):
+        """One device-resident render.  deferred_metrics: an ArsMetrics the library fills in when the stream is next waited
+        for (ars_render_dev_async: the host does not wait per render); None: the synchronous form, metrics in self.m."""
+        fn = self.lib.ars_render_dev if deferred_metrics is None else self.lib.ars_render_dev_async
+        self.capi.check(fn(self.p, self.d_in.data_ptr(), self.n, self.cin,
+                           self.d_ir.data_ptr() if self.ext else None, self.L,
+                           None if self.ext else self.draws_d, None, None, self.d_pcm.data_ptr(),
+                           self.m if deferred_metrics is None else deferred_metrics), "ars_render_dev")
 
     def step_host(self, out_f32=None, out_pcm=None):
         self.capi.check(self.lib.ars_render(self.p, self.h_in.data_ptr(), self.n, self.cin,
@@ -335,10 +338,12 @@ class Render:
             self.step_dev()
         self.capi.check(self.lib.ars_sync(), "ars_sync")
         ms = self.capi.C.c_float(0)
+        later = [self.capi.ArsMetrics() for _ in range(steps)]
         self.capi.check(self.lib.ars_timer_begin(), "timer")
-        for _ in range(steps):
-            self.step_dev()
+        for k in range(steps):
+            self.step_dev(later[k])
         self.capi.check(self.lib.ars_timer_end(self.capi.C.byref(ms)), "timer")
+        self.m = later[-1]
         return float(ms.value) / steps
 
     def h2d_bytes(self):
@@ -462,10 +467,17 @@ def run_ours(args):
         sampler.start()
     l0 = int(lib.ars_launch_count())
     ms = _capi.C.c_float(0)
+    # every step is one complete render (metrics included); the host enqueues them back to back and the metrics of all
+    # steps are finished when the stop event has been waited for (ars_render_dev_async) -- with --sync-steps the host waits
+    # for each render's metrics before it prepares the next one, and the GPU idles meanwhile
+    later = [ArsMetrics() for _ in range(args.steps)]
     _capi.check(lib.ars_timer_begin(), "timer")
-    for _ in range(args.steps):
-        r.step_dev()
+    for k in range(args.steps):
+        r.step_dev(None if args.sync_steps else later[k])
     _capi.check(lib.ars_timer_end(_capi.C.byref(ms)), "timer")
+    if not args.sync_steps:
+        assert all(rs._metrics_dict(m) == rs._metrics_dict(later[0]) for m in later), "steps of the same render differ"
+        r.m = later[-1]
     launches = int(lib.ars_launch_count()) - l0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -541,7 +553,10 @@ def run_ours(args):
     cfg.update({"route": ("folded-air " if folds else "") + ("big-block overlap-save (one partition, fused middle pass)" if olsb
                           else "see DESIGN.md section 2"),
                 "l2": "working set (input %d MB, FFT work buffers, output %d MB) exceeds the 126 MB L2; no flush needed"
-                      % (r.n * r.cin * 4 >> 20, r.N * r.C * 2 >> 20)})
+                      % (r.n * r.cin * 4 >> 20, r.N * r.C * 2 >> 20),
+                "device_loop": ("ars_render_dev per step, the host waits for each render's metrics" if args.sync_steps else
+                                "ars_render_dev_async per step (complete renders enqueued back to back, every step's "
+                                "metrics collected once the stop event has been waited for)")})
     line = {
         "metric": METRIC, "value": total_seconds / (dev_ms * 1e-3), "unit": "audio-seconds/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -722,6 +737,8 @@ def main():
     ap.add_argument("--ref-sample-seconds", type=float, default=0.0,
                     help="reference arm: clip length per process (default: the workload's own clip length)")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: processes (default: every host core)")
+    ap.add_argument("--sync-steps", action="store_true",
+                    help="device-resident loop with the synchronous ars_render_dev (the host waits for every render's metrics)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle render (cpu_baseline + parity)")
     ap.add_argument("--no-extras", action="store_true", help="skip the IR-length sweep / dense-IR point")
     ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-API timing")

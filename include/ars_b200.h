@@ -98,6 +98,7 @@ ARS_API const char* ars_version(void);
 ARS_API uint64_t ars_launch_count(void);          /* kernels this library has launched so far           */
 ARS_API uint64_t ars_air_fold_count(void);        /* convolution stages that took the folded-air route  */
 ARS_API uint64_t ars_olsb_count(void);            /* ... that took the big-block overlap-save route      */
+ARS_API uint64_t ars_head_start_count(void);      /* asynchronous renders whose head overlapped the tail of the render before */
 ARS_API void* ars_stream(void);                   /* the library's cudaStream_t (for event timing)      */
 /* Options: "upols" (1 = use the partitioned overlap-save convolution whenever a render has no exact-N
  * spectral mask, i.e. air <= 0.01 and both EQ gains ~ 1 [default]; 0 = always the N-point spectral filter),
@@ -127,7 +128,8 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * 4 PCM / float frames stored and 8 stereo frames read by the final pass),
  * "final_lean" (1 [default] | 2 = the final pass of the 5.1-based layouts runs its lean frame loop -- packed FP32x2 guard
  * division behind one range test per frame, 32-bit offsets, one | two frames per step -- whenever only the stereo peak
- * guard can be active; 0 = the general loop.  Bit-identical results either way).
+ * guard can be active; 0 = the general loop.  Bit-identical results either way),
+ * "head_start" (1 [default] | 0: see ars_render_dev_async).
  * Environment (read once per process, experiments): ARS_MID_PIPE (3 [default] | 2 = the plain middle pass runs as a persistent
  * kernel that fetches its next tile with cp.async.bulk, 3 | 2 CTAs per SM; 0 = one tile per CTA), ARS_LAST_PIPE (3 [default] |
  * 2 | 6 = the last pass of 2^18-point blocks likewise, double-buffered; 0 = one tile per CTA), ARS_MID_NT (256 | 512). */
@@ -227,6 +229,19 @@ ARS_API int ars_render(const ArsRenderParams* p, const float* in, int64_t n, int
 ARS_API int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
                    int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                    int16_t* d_out_pcm, ArsMetrics* metrics);
+/* The same, never waiting: with `metrics` non-NULL the render's state block goes to a pinned slot and *metrics is filled
+ * in by the next call that waits for the library stream anyway -- ars_sync() or ars_timer_end() -- until which it must
+ * stay valid.  Lets a caller enqueue render after render (a batch of device-resident clips) without the GPU idling while
+ * the host reads 80 bytes back and prepares the next one.
+ * Head start (option "head_start", default 1): when the call right before this one was a render of the same geometry (same
+ * parameters, frame count, channel count, IR length), the part of this render that needs nothing from that one -- IR
+ * synthesis / fold / IR spectrum and the first pass of every transform -- is ordered after that render's CONVOLUTION, not
+ * after its tail, and runs next to its final pass and loudness meter on the library's internal streams.  The input arrays
+ * (d_in, d_draws->noise, d_ext_ir) must therefore be COMPLETE when the call is made (e.g. produced before an ars_sync() or
+ * a device synchronisation), not merely ordered on ars_stream(); the outputs are ordered on ars_stream() as always. */
+ARS_API int ars_render_dev_async(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
+                         int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
+                         int16_t* d_out_pcm, ArsMetrics* metrics);
 
 
 /* ---- a batch of independent renders (host buffers; pin them for full overlap) -----------------

@@ -724,6 +724,117 @@ def test_device_pointer_render_equals_host_render(rs):
     assert rs._metrics_dict(m) == host["metrics"]
 
 
+def test_async_device_renders_deliver_the_same_metrics_later(rs):
+    """ars_render_dev_async enqueues and returns; the metrics of every render enqueued so far are filled in by the next
+    ars_sync() -- same values as the synchronous call, clip after clip, PCM included."""
+    import torch
+    from ars_b200 import _capi
+    lib = _capi.init()
+    g = np.random.default_rng(9)
+    rate = 48000
+    kw = dict(hall_type="Room", room_size=180., air_absorption=.1, dry_wet=.4, target_channel_layout="5.1.2 (Atmos Light)")
+    p, refl = rs.make_render_params(rate, want_lufs=True, **kw)
+    clips, keep = [], []
+    for k in range(5):
+        x = ((0.2 + 0.2 * k) * g.standard_normal((40001 + 7000 * k, 2))).astype(np.float32)
+        np.random.seed(100 + k)
+        taps, bases, noise = rs.draw_ir_randoms(rate, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+        d_x, d_noise = torch.from_numpy(x).cuda(), torch.from_numpy(noise).cuda()
+        N = int(lib.ars_render_out_len(p, x.shape[0], 0))
+        draws = _capi.make_draws(taps, bases, int(d_noise.data_ptr()), keep)
+        draws.noise_len = int(noise.size)
+        clips.append((x, d_x, d_noise, draws, N))
+    torch.cuda.synchronize()
+    want = []
+    for x, d_x, d_noise, draws, N in clips:
+        d_pcm = torch.empty((N, 8), dtype=torch.int16, device="cuda")
+        m = _capi.ArsMetrics()
+        _capi.check(lib.ars_render_dev(p, d_x.data_ptr(), x.shape[0], 2, None, 0, draws, None, None, d_pcm.data_ptr(), m), "dev")
+        want.append((rs._metrics_dict(m), d_pcm.cpu().numpy()))
+    later, pcms = [], []
+    for x, d_x, d_noise, draws, N in clips:
+        d_pcm = torch.empty((N, 8), dtype=torch.int16, device="cuda")
+        m = _capi.ArsMetrics()
+        _capi.check(lib.ars_render_dev_async(p, d_x.data_ptr(), x.shape[0], 2, None, 0, draws, None, None, d_pcm.data_ptr(), m), "async")
+        later.append(m)
+        pcms.append(d_pcm)
+    _capi.check(lib.ars_sync(), "ars_sync")
+    for (wm, wp), m, d_pcm in zip(want, later, pcms):
+        assert rs._metrics_dict(m) == wm
+        assert np.array_equal(d_pcm.cpu().numpy(), wp)
+    assert len({wm["lufs"] for wm, _ in want}) == 5            # (five different clips, five different readings)
+
+
+@pytest.mark.parametrize("case", ["procedural 5.1.2", "external IR 7.1", "EQ on (exact-N route)"])
+def test_head_start_of_async_renders_changes_nothing(rs, case):
+    """Between two asynchronous renders of the same geometry the IR chain and the first passes of the second one run next
+    to the tail of the first (ars_render_dev_async, option head_start).  Different clips and different random draws of
+    one geometry, enqueued back to back: every PCM frame and every metric as from the synchronous calls, and the head
+    start must actually have been taken (except on the exact-N route, which has no side chain and no lanes)."""
+    import torch
+    from ars_b200 import _capi
+    lib = _capi.init()
+    g = np.random.default_rng(13)
+    rate = 48000
+    n = 700001
+    ext = None
+    if case.startswith("procedural"):
+        kw = dict(hall_type="Cathedral", room_size=300., air_absorption=.1, dry_wet=.5, target_channel_layout="5.1.2 (Atmos Light)")
+    elif case.startswith("external"):
+        kw = dict(dry_wet=.6, bass_gain=1.0, treble_gain=1.0, target_channel_layout="7.1 (Surround)")
+        ext = (g.standard_normal((30000, 2)) * np.exp(-np.arange(30000) / 6000.0)[:, None] / 40).astype(np.float32)
+    else:
+        kw = dict(hall_type="Room", room_size=150., air_absorption=.2, bass_gain=1.4, treble_gain=.8, dry_wet=.5,
+                  target_channel_layout="5.1 (Standard)")
+        n = 90001
+    p, refl = rs.make_render_params(rate, want_lufs=True, external_ir=ext is not None, **kw)
+    C = 8 if "5.1 (" not in kw["target_channel_layout"] else 6
+    d_ext = torch.from_numpy(ext).cuda() if ext is not None else None
+    L = 0 if ext is None else ext.shape[0]
+    clips, keep = [], []
+    for k in range(6):
+        x = ((0.1 + 0.25 * k) * g.standard_normal((n, 2))).astype(np.float32)     # (the later ones trip the stereo guard)
+        d_x = torch.from_numpy(x).cuda()
+        draws = None
+        if ext is None:
+            np.random.seed(300 + k)
+            taps, bases, noise = rs.draw_ir_randoms(rate, p.ir_duration, refl, p.ir_max_delay, p.ir_split_time)
+            d_noise = torch.from_numpy(noise).cuda()
+            keep.append(d_noise)
+            draws = _capi.make_draws(taps, bases, int(d_noise.data_ptr()), keep)
+            draws.noise_len = int(noise.size)
+        clips.append((d_x, draws))
+    N = int(lib.ars_render_out_len(p, n, L))
+    torch.cuda.synchronize()
+
+    def run(fn, sync_each):
+        out = []
+        for d_x, draws in clips:
+            d_pcm = torch.empty((N, C), dtype=torch.int16, device="cuda")
+            m = _capi.ArsMetrics()
+            _capi.check(fn(p, d_x.data_ptr(), n, 2, d_ext.data_ptr() if d_ext is not None else None, L, draws, None, None,
+                           d_pcm.data_ptr(), m), "render")
+            out.append((m, d_pcm))
+        _capi.check(lib.ars_sync(), "ars_sync")
+        return [(rs._metrics_dict(m), q.cpu().numpy()) for m, q in out]
+
+    want = run(lib.ars_render_dev, True)
+    h0 = int(lib.ars_head_start_count())
+    got = run(lib.ars_render_dev_async, False)
+    taken = int(lib.ars_head_start_count()) - h0
+    assert taken == len(clips) - 1, taken
+    try:
+        _capi.set_option("head_start", 0)
+        plain = run(lib.ars_render_dev_async, False)
+        assert int(lib.ars_head_start_count()) - h0 == taken
+    finally:
+        _capi.set_option("head_start", 1)
+    for (wm, wp), (gm, gp), (pm, pp) in zip(want, got, plain):
+        assert gm == wm and pm == wm
+        assert np.array_equal(gp, wp) and np.array_equal(pp, wp)
+    assert len({wm["lufs"] for wm, _ in want}) == len(clips)
+
+
 @pytest.mark.parametrize("layout", ["5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)"])
 @pytest.mark.parametrize("loud", [False, True])
 def test_final_pass_lean_loop_is_bit_identical_to_the_general_loop(rs, layout, loud):

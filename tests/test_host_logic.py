@@ -61,6 +61,22 @@ def test_fft_engine_host_emulation():
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def test_float32_evaluation_of_float64_gain_products_is_exact_or_flagged():
+    """The final pass forms RN32(RN64(x * gain)) (numpy's `audio * np.float64 gain` stored into float32, rs.py:475-494,
+    550-553) from float32 pieces of the gain and redoes a frame in float64 only when a tie test fires (epilogue.cu: prod2).
+    tests/host_emul/prod_emul.c replays that sequence with libm's correctly rounded fmaf: no unflagged result may differ
+    from the float64 evaluation in a single bit -- random operands, operands on and next to float32 rounding boundaries,
+    double-rounding traps, signed zeros."""
+    src = os.path.join(ROOT, "tests", "host_emul", "prod_emul.c")
+    exe = os.path.join(ROOT, "ars_b200", "build", "prod_emul")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True, capture_output=True)
+    r = subprocess.run([exe, "20"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "wrong 0" in r.stdout
+
+
 def test_scalar_prologue_matches_golden_on_cpu(golden):
     from ars_b200 import raytracer_studio as rs
     g = golden("scalars")

@@ -406,6 +406,10 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         side_join();
         return;
     }
+    if (want_metrics && (p->want_lufs & 1) && final_with_loudness(y, ts, p->rate, st, d_out_f32, d_out_pcm)) {
+        if (lufs_status) *lufs_status = ARS_LUFS_OK;
+        return;
+    }
     float* d_mono = nullptr;
     if (want_metrics && (p->want_lufs & 1)) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
     tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
@@ -551,6 +555,7 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "lufs_fused")) loudness_set_fused(value);
     else if (!strcmp(key, "lufs_from_stage")) g_opt_lufs_from_stage = value ? 1 : 0;
     else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
+    else if (!strcmp(key, "final_in_meter")) loudness_set_final_in_meter(value);
     else if (!strcmp(key, "head_start")) g_opt_head_start = value ? 1 : 0;
     else if (!strcmp(key, "final_lean")) { ARS_CHECK(value >= 0 && value <= 2, "final_lean must be 0, 1 or 2"); tail_set_lean(value); }
     else if (!strcmp(key, "host_staging")) host_staging_enable(value);

@@ -43,6 +43,7 @@ void tail_map_max(const float2* d_y, const TailSpec& ts, RenderState* d_state); 
 // loudness feed mean(ch0, ch1); accumulates peak_final and sumsq in the state.
 void tail_final(const float2* d_y, const TailSpec& ts, RenderState* d_state, float* d_out, short* d_pcm,
                 float* d_mono);
+void tail_prepare(TailSpec& ts);    // fills in the float32 pieces of the gains (g_hi / g_lo / split_ok) -- every caller of the final frame math
 void tail_set_lean(int v);         // 0: the general frame loop for every layout; 1 / 2: lean loop of the 5.1-based layouts with
                                    // float64 products / products from float32 pieces of the gains [default]
 

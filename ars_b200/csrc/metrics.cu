@@ -10,7 +10,7 @@
 // re-filters every chunk from its true start state.  As in pyloudnorm, the stage output is
 // rounded to float32 before the next stage reads it.
 #include "metrics.cuh"
-#include "tail_math.cuh"
+#include "final_math.cuh"
 
 #include <cmath>
 #include <math_constants.h>
@@ -337,82 +337,92 @@ __device__ __forceinline__ unsigned loud_feed(const SRC& src, float* sx, i64 bas
     return mm;
 }
 
+// shared memory of a meter CTA and the filter part of one block (the feed has filled sh.sx and the barrier after it is
+// the caller's): both K-weighting stages of the thread's chunk and the block's hop energies into a.part
+struct LoudShared {
+    float sx[NTB * (CH + 1)];
+    double2 sw[2][NTB / 32], sc[2][NTB / 32];                 // per stage: warp aggregates, warp start states
+    i64 s_lo[3];
+    unsigned s_b;
+    double se[4][NTB / 32];
+};
+__device__ __forceinline__ void loud_block(LoudShared& sh, const LoudArgs& a, int b, i64 base) {
+    const int t = threadIdx.x;
+    float* mine = sh.sx + t * (CH + 1);
+    // stage 1 (high shelf): float32 store, as pyloudnorm
+    double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sh.sw[0], sh.sc[0]);
+    {
+        const Biquad q1 = a.c1.q;
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(q1, (double)mine[j], s);
+    }
+    // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
+    s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sh.sw[1], sh.sc[1]);
+    // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
+    const i64 g0 = base + (i64)t * CH;
+    const int k0 = (g0 >= sh.s_lo[0] ? 1 : 0) + (g0 >= sh.s_lo[1] ? 1 : 0) + (g0 >= sh.s_lo[2] ? 1 : 0);
+    const i64 next = sh.s_lo[k0 < 3 ? k0 : 2];
+    // samples of the chunk that count: [ja, jb) (inside the signal and this launch's range), of which [ja, jn) fall
+    // into the hop the chunk starts in -- small integers found once, not 64-bit compares per sample
+    const i64 hi = a.e_hi == 0 ? a.N : (a.e_hi < a.N ? a.e_hi : a.N);
+    const int ja = (int)max((i64)0, min((i64)CH, a.e_lo - g0));
+    const int jb = (int)max((i64)ja, min((i64)CH, hi - g0));
+    const int jn = (int)max((i64)ja, min((i64)jb, next - g0));
+    double e0 = 0.0, e1 = 0.0;
+    const Biquad q2 = a.c2.q;
+    if (ja == 0 && jb == CH && (jn == CH || jn == 0)) {           // the whole chunk in one hop: all but ~1 % of the chunks
+        double e = 0.0;
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) {
+            const float o = (float)df2t(q2, (double)mine[j], s);
+            e += (double)__fmul_rn(o, o);
+        }
+        if (jn == CH) e0 = e; else e1 = e;
+    } else {
+        #pragma unroll 8
+        for (int j = 0; j < CH; ++j) {
+            const float o = (float)df2t(q2, (double)mine[j], s);
+            const double sq = (double)__fmul_rn(o, o);
+            if (j >= ja && j < jb) { if (j < jn) e0 += sq; else e1 += sq; }
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((t & 31) == 0) sh.se[k][t >> 5] = c;
+    }
+    __syncthreads();
+    if (t < 4) {
+        double tot = 0.0;
+        for (int w = 0; w < NTB / 32; ++w) tot += sh.se[t][w];
+        a.part[(i64)b * 4 + t] = tot;
+    }
+}
+
 // Persistent CTAs: each takes the next block in ticket order until none is left (the coefficient tables in the
 // kernel's parameter space are then fetched once per CTA, not once per block).
 template <class SRC>
 __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int nblocks) {
-    __shared__ float sx[NTB * (CH + 1)];
-    __shared__ double2 sw[2][NTB / 32], sc[2][NTB / 32];      // per stage: warp aggregates, warp start states
-    __shared__ i64 s_lo[3];
-    __shared__ unsigned s_b;
-    __shared__ double se[4][NTB / 32];
+    __shared__ LoudShared sh;
     // (the stages' coefficient tables are read from the kernel's parameter space: a copy in shared memory was measured --
     // fewer constant-cache misses, but its loads compete with the samples' for the shared-memory pipe: 85 against 77 us)
     const int t = threadIdx.x;
     const bool idle = src.prepare();
     unsigned mm = 0;
     for (;;) {
-        if (t == 0) s_b = atomicAdd(a.ticket, 1u);
+        if (t == 0) sh.s_b = atomicAdd(a.ticket, 1u);
         __syncthreads();
-        const int b = (int)s_b;
+        const int b = (int)sh.s_b;
         if (b >= nblocks) break;
         const i64 base = a.g_base + (i64)b * BS;
-        if (t < 3) s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
-        const unsigned m1 = idle ? loud_feed<SRC, 0>(src, sx, base, a.N, a.src_lo)
-                                 : loud_feed<SRC, 1>(src, sx, base, a.N, a.src_lo);
+        if (t < 3) sh.s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
+        const unsigned m1 = idle ? loud_feed<SRC, 0>(src, sh.sx, base, a.N, a.src_lo)
+                                 : loud_feed<SRC, 1>(src, sh.sx, base, a.N, a.src_lo);
         if (a.e_hi == 0 || (base + BS > a.e_lo && base < a.e_hi)) mm = max(mm, m1);     // (warm-up blocks do not count)
         __syncthreads();
-        float* mine = sx + t * (CH + 1);
-        // stage 1 (high shelf): float32 store, as pyloudnorm
-        double2 s = chunk_start_state(mine, a.c1, a.agg1, a.flag1, a.dep1, b, sw[0], sc[0]);
-        {
-            const Biquad q1 = a.c1.q;
-            #pragma unroll 8
-            for (int j = 0; j < CH; ++j) mine[j] = (float)df2t(q1, (double)mine[j], s);
-        }
-        // stage 2 (high pass) on the thread's own chunk of stage 1's output, squared into the hops
-        s = chunk_start_state(mine, a.c2, a.agg2, a.flag2, a.dep2, b, sw[1], sc[1]);
-        // the block starts in hop hb and (hop >= 4096 samples) reaches at most hop hb + 2: three boundaries, found once
-        const i64 g0 = base + (i64)t * CH;
-        const int k0 = (g0 >= s_lo[0] ? 1 : 0) + (g0 >= s_lo[1] ? 1 : 0) + (g0 >= s_lo[2] ? 1 : 0);
-        const i64 next = s_lo[k0 < 3 ? k0 : 2];
-        // samples of the chunk that count: [ja, jb) (inside the signal and this launch's range), of which [ja, jn) fall
-        // into the hop the chunk starts in -- small integers found once, not 64-bit compares per sample
-        const i64 hi = a.e_hi == 0 ? a.N : (a.e_hi < a.N ? a.e_hi : a.N);
-        const int ja = (int)max((i64)0, min((i64)CH, a.e_lo - g0));
-        const int jb = (int)max((i64)ja, min((i64)CH, hi - g0));
-        const int jn = (int)max((i64)ja, min((i64)jb, next - g0));
-        double e0 = 0.0, e1 = 0.0;
-        const Biquad q2 = a.c2.q;
-        if (ja == 0 && jb == CH && (jn == CH || jn == 0)) {           // the whole chunk in one hop: all but ~1 % of the chunks
-            double e = 0.0;
-            #pragma unroll 8
-            for (int j = 0; j < CH; ++j) {
-                const float o = (float)df2t(q2, (double)mine[j], s);
-                e += (double)__fmul_rn(o, o);
-            }
-            if (jn == CH) e0 = e; else e1 = e;
-        } else {
-            #pragma unroll 8
-            for (int j = 0; j < CH; ++j) {
-                const float o = (float)df2t(q2, (double)mine[j], s);
-                const double sq = (double)__fmul_rn(o, o);
-                if (j >= ja && j < jb) { if (j < jn) e0 += sq; else e1 += sq; }
-            }
-        }
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            double c = (k0 == k ? e0 : 0.0) + (k0 + 1 == k ? e1 : 0.0);
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if ((t & 31) == 0) se[k][t >> 5] = c;
-        }
-        __syncthreads();
-        if (t < 4) {
-            double tot = 0.0;
-            for (int w = 0; w < NTB / 32; ++w) tot += se[t][w];
-            a.part[(i64)b * 4 + t] = tot;
-        }
+        loud_block(sh, a, b, base);
         __syncthreads();                                   // the block's shared arrays (and s_b) are rewritten next
     }
     if (a.mono_max) {
@@ -420,6 +430,137 @@ __global__ void __launch_bounds__(NTB) loudness_kernel(SRC src, LoudArgs a, int 
         for (int o = 16; o > 0; o >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, o));
         if ((t & 31) == 0 && mm > *reinterpret_cast<volatile unsigned*>(a.mono_max)) atomicMax(a.mono_max, mm);
     }
+}
+
+// ---- the final pass inside the meter's feed ------------------------------------------------------------------------------
+// The final pass (epilogue.cu) is bound by instruction issue and load latency at ~70 % of the issue slots, the meter by its
+// barriers and the float64 recurrences at ~40 %; one after the other they took 109 + 78 us of the 300 s render.  Here a
+// meter CTA produces its block's 8192 frames ITSELF -- guards, pan, map, PCM, sums, exactly the final pass's frame math
+// (final_math.cuh) -- leaves the loudness feed in shared memory where the filters read it, and stores the frames on the
+// way: one kernel whose CTAs are in different phases, so that one CTA's barriers and recurrences run under another's frame
+// arithmetic; the feed never travels through memory.  Same per-sample arithmetic as the two kernels, same block order.
+#ifndef ARS_FL_D
+#define ARS_FL_D 4
+#endif
+#ifndef ARS_FL_MINB
+#define ARS_FL_MINB 4
+#endif
+struct FinalArgs {
+    const float2* y;
+    float* out;
+    short* pcm;
+    RenderState* st;
+};
+
+// MODE 0 / 2: the float32 form of the 5.1-based layouts with the stereo guard idle / dividing (pan guard idle); 1: any
+template <int C, int LAY, int MODE>
+__device__ __forceinline__ unsigned final_feed(const FinalArgs& f, const TailSpec* __restrict__ tsp, const Guard& g1, const Guard& g2,
+                                              const Guard& g3, float* sx, i64 base, LeanAcc& acc) {
+    const TailSpec& ts = *tsp;
+    const int t = threadIdx.x;
+    const i64 N = ts.N, dl = ts.delay > 0 ? ts.delay : 0;
+    unsigned mm = 0;
+    constexpr int D = ARS_FL_D;                            // frames in flight per thread
+    #pragma unroll 1
+    for (int i0 = 0; i0 < CH; i0 += D) {
+        float2 v[D], w[D];
+        #pragma unroll
+        for (int u = 0; u < D; ++u) {
+            const i64 g = base + (i64)(i0 + u) * NTB + t;
+            v[u] = make_float2(0.f, 0.f);
+            w[u] = make_float2(0.f, 0.f);
+            if (g < N) {
+                v[u] = __ldcs(f.y + g);
+                if (ts.layout >= LAYOUT_7_1 && g >= ts.delay) w[u] = __ldg(f.y + (g - dl));
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < D; ++u) {
+            const int i = (i0 + u) * NTB + t;
+            const i64 g = base + i;
+            float mv = 0.f;
+            if (g < N) {
+                float o[8];
+                bool literal = false;
+                if constexpr (MODE != 1) literal = lean_math_split<C, LAY, MODE>(v[u], w[u], ts, g1, o);
+                if (MODE != 1 && !literal) {
+                    split_emit<C, 0>(o, (unsigned)g, f.out, f.pcm, nullptr, acc);
+                    mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);
+                } else if (MODE != 1) {
+                    const float4 r = slow_frame<C>(f.y, g, tsp, f.st->max_stereo, f.out, f.pcm, nullptr);
+                    acc.pkf = fmaxf(acc.pkf, r.x);
+                    acc.ss += (double)r.y;
+                    mv = r.z;
+                } else {
+                    FrameIn fr;
+                    fr.v = v[u];
+                    fr.w = w[u];
+                    frame_math<1, 1>(fr, g, ts, g1, g2, o);
+                    float fs = 0.f;
+                    #pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        o[c] = guard1(o[c], g3);
+                        acc.pkf = fmaxf(acc.pkf, fabsf(o[c]));
+                        fs = __fmaf_rn(o[c], o[c], fs);
+                    }
+                    acc.ss += (double)fs;                  // (a NaN sample makes this sum NaN for good: read back as "NaN seen")
+                    if (f.out) {
+                        float2* p = reinterpret_cast<float2*>(f.out) + g * (C / 2);
+                        #pragma unroll
+                        for (int c = 0; c < C; c += 2) p[c >> 1] = make_float2(o[c], o[c + 1]);
+                    }
+                    if (f.pcm) {
+                        unsigned* p = reinterpret_cast<unsigned*>(f.pcm) + g * (C / 2);
+                        #pragma unroll
+                        for (int c = 0; c < C; c += 2) __stcs(p + (c >> 1), pcm_pair(o[c], o[c + 1]));
+                    }
+                    mv = __fmul_rn(__fadd_rn(o[0], o[1]), 0.5f);
+                }
+            }
+            sx[(i / CH) * (CH + 1) + (i % CH)] = mv;
+            mm = max(mm, abs_bits(mv));
+        }
+    }
+    return mm;
+}
+
+template <int C, int LAY>
+__global__ void __launch_bounds__(NTB, ARS_FL_MINB) final_loud_kernel(FinalArgs f, const __grid_constant__ TailSpec ts, LoudArgs a, int nblocks) {
+    __shared__ LoudShared sh;
+    const int t = threadIdx.x;
+    const Guard g1 = make_guard(f.st->max_stereo), g2 = make_guard(f.st->max_pan);
+    const Guard g3 = make_guard(ts.layout == LAYOUT_STEREO ? f.st->max_map : 0u);
+    int mode = 1;
+    if (LAY >= 1 && ts.split_ok && g2.mode == 0) {
+        if (g1.mode == 0) mode = 0;
+        else if (g1.mode == 1 && g1.r != 0.f) mode = 2;
+    }
+    LeanAcc acc = {0.f, 0u, 0.0};
+    unsigned mm = 0;
+    for (;;) {
+        if (t == 0) sh.s_b = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int b = (int)sh.s_b;
+        if (b >= nblocks) break;
+        const i64 base = (i64)b * BS;
+        if (t < 3) sh.s_lo[t] = hop_lo(hop_of(base, a.rate) + 1 + t, a.rate);
+        unsigned m1;
+        if constexpr (LAY >= 1) {
+            if (mode == 0) m1 = final_feed<C, LAY, 0>(f, &ts, g1, g2, g3, sh.sx, base, acc);
+            else if (mode == 2) m1 = final_feed<C, LAY, 2>(f, &ts, g1, g2, g3, sh.sx, base, acc);
+            else m1 = final_feed<C, LAY, 1>(f, &ts, g1, g2, g3, sh.sx, base, acc);
+        } else {
+            m1 = final_feed<C, 0, 1>(f, &ts, g1, g2, g3, sh.sx, base, acc);
+        }
+        mm = max(mm, m1);
+        __syncthreads();
+        loud_block(sh, a, b, base);
+        __syncthreads();
+    }
+    const unsigned pk = (acc.ss != acc.ss) ? 0x7fc00000u : __float_as_uint(acc.pkf);
+    block_atomic_max(pk, &f.st->peak_final);
+    block_atomic_max(mm, &f.st->mono_max);
+    block_atomic_add(acc.ss, &f.st->sumsq);
 }
 
 // z_j = (E_j + E_{j+1} + E_{j+2} + E_{j+3}) / (T_g * rate), E_h gathered from the per-block partial sums in block order
@@ -625,6 +766,72 @@ int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double
     src.ts = ts;
     src.st = d_state;
     return loudness_run(src, ts.N, rate, &d_state->mono_max, nullptr, &d_state->mono_max, &d_state->lufs);
+}
+
+static int g_final_in_meter = 0;       // (measured: 214 us against 109 + 77 us for the two kernels -- a CTA in its filter phase takes warps from the frame arithmetic)
+void loudness_set_final_in_meter(int on) { g_final_in_meter = on ? 1 : 0; }
+
+// The whole tail of a render in one kernel: final pass (frames to d_out / d_pcm, peak and sum of squares into *d_state)
+// inside the one-pass meter's feed, then the gating; the loudness lands in d_state->lufs.  -> false (nothing enqueued) when
+// this form does not apply: the caller runs tail_final and the meter one after the other.
+bool final_with_loudness(const float2* d_y, const TailSpec& ts_in, double rate, RenderState* d_state, float* d_out,
+                         short* d_pcm) {
+    Ctx& c = ctx();
+    const i64 N = ts_in.N;
+    const bool whole = ts_in.i_lo == 0 && (ts_in.i_hi < 0 || ts_in.i_hi == N) && ts_in.y0 == 0 && ts_in.out0 == 0;
+    if (!g_final_in_meter || !whole || N <= 0 || N >= ((i64)1 << 28) || !loudness_from_stage_possible(rate)) return false;
+    if (!((double)N >= 0.4 * rate)) return false;
+    const int nb = loudness_blocks(N, rate);
+    if (nb <= 0) return false;
+    Biquad q[2];
+    k_weighting(rate, q);
+    const ScanCoef c1 = make_coef(q[0]), c2 = make_coef(q[1]);
+    auto depth_of = [](const Mat2& M) {
+        const double nrm = std::sqrt(M.m00 * M.m00 + M.m01 * M.m01 + M.m10 * M.m10 + M.m11 * M.m11);
+        if (!(nrm < 0.05)) return 0;
+        return std::max(2, (int)std::ceil(-25.0 * std::log(10.0) / std::log(nrm)));
+    };
+    const int dep1 = depth_of(c1.pw[8]), dep2 = depth_of(c2.pw[8]);
+    if (dep1 <= 0 || dep2 <= 0) return false;
+    TailSpec ts = ts_in;
+    ts.i_hi = N;
+    tail_prepare(ts);
+    double* dz = c.buf("lufs.z", sizeof(double) * (size_t)nb).as<double>();
+    const int nblocks = (int)((N + BS - 1) / BS);
+    const size_t off_flags = sizeof(double2) * 2 * (size_t)nblocks + sizeof(double) * 4 * (size_t)nblocks;
+    const size_t bytes_flags = sizeof(int) * (2 * (size_t)nblocks + 4);
+    char* ws = c.buf("lufs.onepass", off_flags + bytes_flags).as<char>();
+    LoudArgs a;
+    a.N = N;
+    a.rate = rate;
+    a.c1 = c1; a.c2 = c2;
+    a.dep1 = dep1; a.dep2 = dep2;
+    a.agg1 = reinterpret_cast<double2*>(ws);
+    a.agg2 = a.agg1 + nblocks;
+    a.part = reinterpret_cast<double*>(a.agg2 + nblocks);
+    a.flag1 = reinterpret_cast<int*>(ws + off_flags);
+    a.flag2 = a.flag1 + nblocks;
+    a.ticket = reinterpret_cast<unsigned*>(a.flag2 + nblocks);
+    a.mono_max = &d_state->mono_max;
+    FinalArgs f;
+    f.y = d_y; f.out = d_out; f.pcm = d_pcm; f.st = d_state;
+    ARS_CUDA(cudaMemsetAsync(ws + off_flags, 0, bytes_flags, c.stream));
+    {
+        KernelScope prof("final + loudness kernel (guards, pan, map, clip, PCM16, sums; K-weighting stages + hop energies)",
+                         (double)N * (8.0 + (d_pcm ? 2.0 * ts.C : 0.0) + (d_out ? 4.0 * ts.C : 0.0)));
+        const int grid = std::max(1, std::min(nblocks, c.sm_count * ARS_FL_MINB));
+        if (ts.C == 2) final_loud_kernel<2, 0><<<grid, NTB, 0, c.stream>>>(f, ts, a, nblocks);
+        else if (ts.C == 6) final_loud_kernel<6, 1><<<grid, NTB, 0, c.stream>>>(f, ts, a, nblocks);
+        else if (ts.layout == LAYOUT_7_1) final_loud_kernel<8, 2><<<grid, NTB, 0, c.stream>>>(f, ts, a, nblocks);
+        else final_loud_kernel<8, 3><<<grid, NTB, 0, c.stream>>>(f, ts, a, nblocks);
+        ARS_LAUNCH_CHECK();
+    }
+    KernelScope prof("loudness gating (hop_combine + gate)", 0.0);
+    hop_combine_kernel<<<ceil_div(nb, 256), 256, 0, c.stream>>>(a.part, N, rate, nb, dz);
+    gate_kernel<<<1, 1024, 0, c.stream>>>(dz, nb, &d_state->mono_max, &d_state->lufs);
+    ARS_LAUNCH_CHECK();
+    count_launch(3);
+    return true;
 }
 
 // ---- the meter split over the ranks of a block-sharded render (sharding.py) -------------------------------------

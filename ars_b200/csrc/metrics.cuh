@@ -13,6 +13,9 @@ int integrated_loudness_async(const float* d_mono, i64 N, double rate, const uns
 // The same meter fed from the convolution stage's output (the mono feed is recomputed per sample exactly as the final
 // pass forms it); see metrics.cu.  Possible at rates >= 40 960 Hz with the one-pass meter enabled.
 bool loudness_from_stage_possible(double rate);
+// final pass + one-pass meter + gating as ONE kernel chain (see metrics.cu); false: does not apply, nothing enqueued
+bool final_with_loudness(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state, float* d_out, short* d_pcm);
+void loudness_set_final_in_meter(int on);
 int integrated_loudness_from_stage(const float2* d_y, const TailSpec& ts, double rate, RenderState* d_state);
 
 // The meter split over the ranks of a block-sharded render: hop energies of samples [e_lo, e_hi) of the whole signal

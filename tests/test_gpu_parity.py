@@ -835,6 +835,39 @@ def test_head_start_of_async_renders_changes_nothing(rs, case):
     assert len({wm["lufs"] for wm, _ in want}) == len(clips)
 
 
+@pytest.mark.parametrize("layout", ["Stereo", "5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)"])
+@pytest.mark.parametrize("level", [0.05, 0.9, 3.0])
+def test_final_pass_inside_the_meter_is_bit_identical_to_the_two_kernels(rs, layout, level):
+    """final_with_loudness (metrics.cu): the final pass carried in the one-pass meter's feed must leave exactly what
+    tail_final + the meter leave -- PCM, float frames, peak, RMS and LUFS bit for bit -- with every guard idle, with the
+    stereo guard dividing, with the pan guard firing (general frame math), for the Stereo down-mix, with tiny and zero
+    stretches, for a clip that ends inside a block and for one shorter than a gating block (falls back)."""
+    from ars_b200 import _capi
+    g = np.random.default_rng(78)
+    rate = 48000
+    ir = (g.standard_normal((3000, 2)) * np.exp(-np.arange(3000) / 700.0)[:, None]).astype(np.float32)
+    ir[0] = 1.0
+    for n in (200, 30011, 150001):
+        x = (level * g.standard_normal((n, 2))).astype(np.float32)
+        x[n // 3: n // 3 + 4000] *= np.float32(1e-30)
+        x[n // 2: n // 2 + 4000] = 0.0
+        kw = dict(external_ir_data=ir, dry_wet=.5, bass_gain=1.0, treble_gain=1.0, x_pos=.2, y_pos=.1, z_pos=.9,
+                  target_channel_layout=layout)
+        res = {}
+        try:
+            for mode in (0, 1):
+                _capi.set_option("final_in_meter", mode)
+                res[mode] = (rs.render_array(x, rate, **kw), rs.render_array(x, rate, want_float=False, **kw))
+        finally:
+            _capi.set_option("final_in_meter", 0)
+        for k in (0, 1):
+            assert np.array_equal(res[1][k]["pcm"], res[0][k]["pcm"]), (n, k)
+            assert res[1][k]["metrics"] == res[0][k]["metrics"], (n, k, res[1][k]["metrics"], res[0][k]["metrics"])
+        assert np.array_equal(res[1][0]["final"].view(np.uint32), res[0][0]["final"].view(np.uint32)), n
+        if n > 48000 * 0.4:
+            assert res[0][0]["metrics"]["lufs"] is not None
+
+
 @pytest.mark.parametrize("layout", ["5.1 (Standard)", "7.1 (Surround)", "5.1.2 (Atmos Light)"])
 @pytest.mark.parametrize("loud", [False, True])
 def test_final_pass_lean_loop_is_bit_identical_to_the_general_loop(rs, layout, loud):
@@ -861,7 +894,7 @@ def test_final_pass_lean_loop_is_bit_identical_to_the_general_loop(rs, layout, l
                 res[mode] = rs.render_array(x, rate, **kw)
                 pcm_only[mode] = rs.render_array(x, rate, want_float=False, **kw)      # (its own instantiation of the loop)
         finally:
-            _capi.set_option("final_lean", 1)
+            _capi.set_option("final_lean", 2)
         for mode in (1, 2):
             assert np.array_equal(res[mode]["pcm"], res[0]["pcm"]), (n, mode)
             assert np.array_equal(res[mode]["final"].view(np.uint32), res[0]["final"].view(np.uint32)), (n, mode)

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "ars_air_fold_count": (C.c_uint64, []),
     "ars_olsb_count": (C.c_uint64, []),
     "ars_head_start_count": (C.c_uint64, []),
+    "ars_meter_stream_count": (C.c_uint64, []),
+    "ars_tail_overlap_count": (C.c_uint64, []),
     "ars_stream": (C.c_void_p, []),
     "ars_ir_synth": (C.c_int, [_d, _d, _d, _d, _d, _d, _d, C.POINTER(ArsIrDraws), _p, _p, _i64]),
     "ars_ir_geometry": (C.c_int, [_d, _d, _d, _d, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),

@@ -21,12 +21,16 @@ void host_staging_enable(int on);
 void* host_block_alloc(size_t bytes);
 void host_block_free(void* p);
 
-#define ARS_API_BEGIN                                                   \
+#define ARS_API_BEGIN_NOJOIN                                            \
     try {                                                               \
         std::lock_guard<std::recursive_mutex> _lk(ctx().mu);            \
         ARS_CUDA(cudaSetDevice(ctx().device));                          \
         ctx().conv_done_prev = ctx().conv_done_valid;                   \
         ctx().conv_done_valid = false;
+// (every call but ars_render_dev_async orders the main stream after the meter stream first: see Ctx::loud)
+#define ARS_API_BEGIN                                                   \
+    ARS_API_BEGIN_NOJOIN                                                \
+        loud_join();
 #define ARS_API_END                                                     \
         return ARS_OK;                                                  \
     } catch (const Error& e) {                                          \
@@ -48,6 +52,14 @@ static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (over
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
 static int g_opt_head_start = 1;        // 1: asynchronous renders of the same geometry overlap their head with the tail of the render before
+static int g_opt_loud_stream = 0;       // 1: the loudness meter of an asynchronous render runs on the meter stream (Ctx::loud), off the chain
+                                        //    last pass -> final pass -> last pass of the next render.  Measured on the 300 s render
+                                        //    (18 runs of 40 steps): 0.437-0.445 ms against 0.463 ms typical, but 4 of 15 runs with it on
+                                        //    took 0.48-1.13 ms (the host's enqueue time per render went up with them: 0.20-0.78 ms
+                                        //    against 0.15) while all 9 runs with it off stayed within 0.5 % -- off by default
+static int g_opt_tail_overlap = 0;      // 1: with the meter stream, two stage-output buffers and state blocks zeroed behind their read-back:
+                                        //    the last passes of a render do not wait for the final pass of the render before it
+                                        //    (measured: 0.443-0.451 ms, no better than the meter stream alone)
 static int g_opt_lufs_from_stage = 0;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array);
                                         // measured slower: both kernels are bound by issue slots, and recomputing the feed costs more
                                         // instructions than the 4 B per frame the final pass writes (0.660 against 0.634 ms)
@@ -166,10 +178,13 @@ static void sync() {
     collect_pending();
 }
 
-static RenderState* fresh_state(int slot = 0) {
+static RenderState* fresh_state(int slot = 0, bool* was_clean = nullptr) {
     Ctx& c = ctx();
     RenderState* st = c.buf(slot ? "state.1" : "state.0", sizeof(RenderState)).as<RenderState>();
-    ARS_CUDA(cudaMemsetAsync(st, 0, sizeof(RenderState), c.stream));
+    const bool clean = was_clean && c.state_clean[slot & 1];      // (zeroed by the meter stream after its read-back: Ctx::state_clean)
+    c.state_clean[slot & 1] = false;
+    if (was_clean) *was_clean = clean;
+    if (!clean) ARS_CUDA(cudaMemsetAsync(st, 0, sizeof(RenderState), c.stream));
     return st;
 }
 
@@ -314,7 +329,8 @@ static void common_filter_spec(FilterSpec& fs, i64 N, double rate, double dry_we
 // the GPU: the metrics end up in *st (device) and *lufs_status says how to read st->lufs.
 static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int cin, const float* d_ext_ir, i64 ext_len,
                         const ArsIrDraws* draws, float* d_out_stereo, float* d_out_f32, short* d_out_pcm,
-                        RenderState* st, bool want_metrics, int* lufs_status, bool allow_head_start = false) {
+                        RenderState* st, bool want_metrics, int* lufs_status, bool allow_head_start = false,
+                        int loud_slot = -1) {
     Ctx& c = ctx();
     ARS_CHECK(p && d_in && n > 0 && cin >= 1, "render: empty input");
     {
@@ -329,12 +345,14 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         if (c.head_start) ++c.head_starts;
         last_p = *p; last_n = n; last_cin = cin; last_ext = ext_len; last_gen = ctx_generation();
     }
-    struct HeadStartEnd { ~HeadStartEnd() { if (ctx_ready()) ctx().head_start = false; } } head_start_end;
+    struct HeadStartEnd { ~HeadStartEnd() { if (ctx_ready()) { ctx().head_start = false; ctx().lane_tail_event = nullptr; } } } head_start_end;
+    if (!c.head_start) c.lane_tail_event = nullptr;
+    else if (c.lane_tail_event) ++c.tail_overlaps;
     ARS_CHECK(p->rate >= 1.0, "render: bad sample rate");
     ARS_CHECK(layout_ok(p->layout), "render: unknown layout id");
     if (lufs_status) *lufs_status = ARS_LUFS_SKIPPED;
     const i64 N = render_out_len(p, n, ext_len);
-    float2* y = c.buf("render.y", sizeof(float2) * (size_t)N).as<float2>();
+    float2* y = c.buf(loud_slot == 1 && g_opt_tail_overlap ? "render.y1" : "render.y", sizeof(float2) * (size_t)N).as<float2>();
     FilterSpec fs;
     common_filter_spec(fs, N, p->rate, p->dry_wet, p->kill_start, p->bass_gain, p->treble_gain);
     if (p->external_ir) {
@@ -411,9 +429,15 @@ static void render_core(const ArsRenderParams* p, const float* d_in, i64 n, int 
         return;
     }
     float* d_mono = nullptr;
-    if (want_metrics && (p->want_lufs & 1)) d_mono = c.buf("render.mono", sizeof(float) * (size_t)N).as<float>();
+    if (want_metrics && (p->want_lufs & 1))
+        d_mono = c.buf(loud_slot == 1 ? "render.mono1" : "render.mono", sizeof(float) * (size_t)N).as<float>();
     tail_final(y, ts, st, d_out_f32, d_out_pcm, d_mono);
-    if (d_mono && lufs_status) *lufs_status = lufs_enqueue(d_mono, N, p->rate, st);
+    if (d_mono && lufs_status) {
+        // asynchronous renders: the meter (and the read-back of the state block, which the caller enqueues before it
+        // calls loud_end) leave the main stream here -- the next render's last pass follows this final pass directly
+        if (loud_slot >= 0) loud_begin();
+        *lufs_status = lufs_enqueue(d_mono, N, p->rate, st);
+    }
 }
 
 // ------------------------------------------------------------ copy pipeline ----
@@ -492,6 +516,8 @@ uint64_t ars_launch_count(void) { return ctx_ready() ? ctx().launches : 0; }
 uint64_t ars_air_fold_count(void) { return g_air_fold_count; }
 uint64_t ars_olsb_count(void) { return olsb_count(); }
 uint64_t ars_head_start_count(void) { return ctx_ready() ? ctx().head_starts : 0; }
+uint64_t ars_meter_stream_count(void) { return ctx_ready() ? ctx().loud_forks : 0; }
+uint64_t ars_tail_overlap_count(void) { return ctx_ready() ? ctx().tail_overlaps : 0; }
 void* ars_stream(void) { return ctx_ready() ? (void*)ctx().stream : nullptr; }
 
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -557,6 +583,8 @@ int ars_set_option(const char* key, int32_t value) {
     else if (!strcmp(key, "lufs_ctas_per_sm")) loudness_set_ctas_per_sm(value);
     else if (!strcmp(key, "final_in_meter")) loudness_set_final_in_meter(value);
     else if (!strcmp(key, "head_start")) g_opt_head_start = value ? 1 : 0;
+    else if (!strcmp(key, "loud_stream")) g_opt_loud_stream = value ? 1 : 0;
+    else if (!strcmp(key, "tail_overlap")) g_opt_tail_overlap = value ? 1 : 0;
     else if (!strcmp(key, "final_lean")) { ARS_CHECK(value >= 0 && value <= 2, "final_lean must be 0, 1 or 2"); tail_set_lean(value); }
     else if (!strcmp(key, "host_staging")) host_staging_enable(value);
     else if (!strcmp(key, "mac_tiled_min")) { ARS_CHECK(value >= 1, "mac_tiled_min must be >= 1"); upols_set_mac_tiled_min(value); }
@@ -911,10 +939,24 @@ static void render_dev_impl(const ArsRenderParams* p, const float* d_in, int64_t
                             int16_t* d_out_pcm, ArsMetrics* metrics, bool deferred) {
     ARS_CHECK(p && layout_ok(p->layout), "ars_render_dev: bad arguments");
     Ctx& c = ctx();
-    RenderState* st = fresh_state();
+    // asynchronous renders that want the loudness alternate between two state blocks / feed buffers (Ctx::loud)
+    static int next_slot = 0;
+    int slot = -1;
+    if (deferred && g_opt_loud_stream && metrics && (p->want_lufs & 1)) {
+        slot = next_slot;
+        next_slot ^= 1;
+        loud_wait_slot(slot);          // (the meter of the render before the last one: long through)
+    } else {
+        loud_join();
+    }
+    bool clean = false;
+    RenderState* st = fresh_state(slot == 1 ? 1 : 0, slot >= 0 && g_opt_tail_overlap ? &clean : nullptr);
+    // (a clean block was zeroed behind ev_loud_done[slot]: what writes it first -- the last passes -- may wait for that alone)
+    c.lane_tail_event = clean && c.loud_recorded[slot & 1] ? c.ev_loud_done[slot & 1] : nullptr;
     int lufs_status = ARS_LUFS_SKIPPED;
     render_core(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32,
-                reinterpret_cast<short*>(d_out_pcm), st, metrics != nullptr, &lufs_status, deferred);
+                reinterpret_cast<short*>(d_out_pcm), st, metrics != nullptr, &lufs_status, deferred, slot);
+    struct LoudEnd { int s; ~LoudEnd() { if (ctx_ready()) loud_end(s); } } loud_end_guard{slot < 0 ? 0 : slot};   // (no-op unless the meter stream is open)
     if (!metrics) return;
     const i64 N = render_out_len(p, n, ext_ir_len);
     if (deferred) {
@@ -926,6 +968,10 @@ static void render_dev_impl(const ArsRenderParams* p, const float* d_in, int64_t
         q.p = *p;
         download(q.h, st, 1);
         g_pending.push_back(q);
+        if (c.loud_open && g_opt_tail_overlap) {          // the block is zero again once ev_loud_done[slot] (loud_end, below) has passed
+            ARS_CUDA(cudaMemsetAsync(st, 0, sizeof(RenderState), c.stream));
+            c.state_clean[slot & 1] = true;
+        }
         return;
     }
     RenderState* h = static_cast<RenderState*>(c.pinned_scratch(sizeof(RenderState)));
@@ -945,7 +991,7 @@ int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t n, int32
 int ars_render_dev_async(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
                          int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                          int16_t* d_out_pcm, ArsMetrics* metrics) {
-    ARS_API_BEGIN
+    ARS_API_BEGIN_NOJOIN
     render_dev_impl(p, d_in, n, cin, d_ext_ir, ext_ir_len, d_draws, d_out_stereo, d_out_f32, d_out_pcm, metrics, true);
     ARS_API_END
 }

@@ -95,6 +95,22 @@ struct Ctx {
     bool conv_done_valid = false, conv_done_prev = false;   // recorded by the API call in progress / by the one before it
     bool head_start = false;                                 // this render takes it
     unsigned long long head_starts = 0;
+    // meter stream (loud_begin / loud_end): the loudness meter of an asynchronous render -- barrier- and latency-bound, it
+    // needs only the feed its final pass left -- and the read-back of its state block go to a stream of their own, so the
+    // LAST PASS of the next render waits for this render's final pass only, not for the meter and its gating behind it.
+    // Two feed buffers / state blocks alternate; a slot is reused after its ev_loud_done.  Every other API call orders
+    // the main stream after the meter stream first (loud_join), so nothing else ever sees the two streams apart.
+    cudaStream_t loud = nullptr, loud_saved = nullptr;
+    cudaEvent_t ev_loud_fork = nullptr, ev_loud_done[2] = {nullptr, nullptr};
+    bool loud_open = false, loud_recorded[2] = {false, false}, loud_pending = false;
+    unsigned long long loud_forks = 0;
+    // tail overlap: the meter stream zeroes a state block right after it has read it back (state_clean), and the stage
+    // output alternates between two buffers like the feed; the last passes of the next render that uses the slot then wait
+    // for that slot's ev_loud_done (lane_tail_event) instead of for the final pass of the render in between -- a render's
+    // convolution overlaps the whole tail of the render before it.
+    bool state_clean[2] = {false, false};
+    cudaEvent_t lane_tail_event = nullptr;
+    unsigned long long tail_overlaps = 0;
 
     DevBuf& buf(const char* name, size_t bytes) {
         DevBuf& b = ws[name];
@@ -114,8 +130,13 @@ void ctx_shutdown();
 // already on the main stream); what follows goes to the main stream again and runs concurrently with it until
 // side_join(), which makes the main stream wait for the side work.  side_abort() restores the main stream (errors).
 void side_begin();
+void loud_begin();            // the library's current stream becomes the meter stream, ordered after what the main stream holds
+void loud_end(int slot);      // records ev_loud_done[slot]; back to the main stream
+void loud_wait_slot(int slot);   // the main stream waits until the meter work that used `slot` is through
+void loud_join();             // the main stream waits for everything on the meter stream
 void conv_done_mark();        // records ev_conv_done on the main stream (end of a render's convolution stage)
 void lane_wait_main(int i);    // head start: lane i waits for what the main stream held at the fork
+void lane_wait_tail(int i);    // head start: lane i waits until the stage output and the state block it is about to write are free
 void side_to_main();
 void side_join();
 void side_abort();

@@ -2,6 +2,7 @@
 #include "ars_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ars {
 
@@ -110,9 +111,56 @@ void side_join() {
     ARS_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
     c.side_state = 0;
 }
+void loud_begin() {
+    Ctx& c = ctx();
+    if (c.loud_open || c.side_state != 0 || c.lanes_open) return;
+    if (!c.loud) {
+        // ARS_LOUD_PRIO=1 (experiment): the meter's CTAs go ahead of everything but the side chain when slots free up --
+        // next to the persistent passes of the following render the meter otherwise gets whatever is left
+        int least = 0, greatest = 0;
+        ARS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const char* e = getenv("ARS_LOUD_PRIO");
+        const int prio = (e && atoi(e) > 0) ? std::min(least, greatest + 1) : least;
+        ARS_CUDA(cudaStreamCreateWithPriority(&c.loud, cudaStreamNonBlocking, prio));
+        ARS_CUDA(cudaEventCreateWithFlags(&c.ev_loud_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) ARS_CUDA(cudaEventCreateWithFlags(&c.ev_loud_done[i], cudaEventDisableTiming));
+    }
+    ARS_CUDA(cudaEventRecord(c.ev_loud_fork, c.stream));
+    ARS_CUDA(cudaStreamWaitEvent(c.loud, c.ev_loud_fork, 0));
+    c.loud_saved = c.stream;
+    c.stream = c.loud;
+    c.loud_open = true;
+    ++c.loud_forks;
+}
+void loud_end(int slot) {
+    Ctx& c = ctx();
+    if (!c.loud_open) return;
+    ARS_CUDA(cudaEventRecord(c.ev_loud_done[slot & 1], c.loud));
+    c.loud_recorded[slot & 1] = true;
+    c.loud_pending = true;
+    c.stream = c.loud_saved;
+    c.loud_open = false;
+}
+void loud_wait_slot(int slot) {
+    Ctx& c = ctx();
+    if (c.loud_open || !c.loud_recorded[slot & 1]) return;
+    ARS_CUDA(cudaStreamWaitEvent(c.stream, c.ev_loud_done[slot & 1], 0));
+}
+void loud_join() {
+    Ctx& c = ctx();
+    if (c.loud_open || !c.loud_pending) return;
+    for (int i = 0; i < 2; ++i)
+        if (c.loud_recorded[i]) ARS_CUDA(cudaStreamWaitEvent(c.stream, c.ev_loud_done[i], 0));
+    c.loud_pending = false;
+}
 void side_abort() {
     if (!ctx_ready()) return;
     Ctx& c = ctx();
+    if (c.loud_open) {
+        c.stream = c.loud_saved;
+        c.loud_open = false;
+        cudaStreamSynchronize(c.loud);
+    }
     if (c.lanes_open) {
         c.stream = c.lane_saved;
         for (int i = 0; i < c.lanes_open; ++i) cudaStreamSynchronize(c.lanes[i]);
@@ -143,6 +191,11 @@ void lane_wait_main(int i) {
     Ctx& c = ctx();
     if (!c.lanes_open || !c.head_start) return;
     ARS_CUDA(cudaStreamWaitEvent(c.lanes[i % c.lanes_open], c.ev_lane_fork, 0));
+}
+void lane_wait_tail(int i) {
+    Ctx& c = ctx();
+    if (!c.lanes_open || !c.head_start) return;
+    ARS_CUDA(cudaStreamWaitEvent(c.lanes[i % c.lanes_open], c.lane_tail_event ? c.lane_tail_event : c.ev_lane_fork, 0));
 }
 void conv_done_mark() {
     Ctx& c = ctx();
@@ -253,6 +306,7 @@ void ctx_shutdown() {
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaStreamSynchronize(g_ctx->stream);
+    if (g_ctx->loud) cudaStreamSynchronize(g_ctx->loud);
     hostio_release();
     bluestein_release_plans();
     fft_release_plans();
@@ -270,6 +324,12 @@ void ctx_shutdown() {
             cudaStreamDestroy(g_ctx->lanes[i]);
             cudaEventDestroy(g_ctx->lane_done[i]);
         }
+    if (g_ctx->loud) {
+        cudaStreamSynchronize(g_ctx->loud);
+        cudaStreamDestroy(g_ctx->loud);
+        cudaEventDestroy(g_ctx->ev_loud_fork);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(g_ctx->ev_loud_done[i]);
+    }
     if (g_ctx->ev_lane_fork) cudaEventDestroy(g_ctx->ev_lane_fork);
     if (g_ctx->ev_conv_done) cudaEventDestroy(g_ctx->ev_conv_done);
     cudaStreamDestroy(g_ctx->stream);

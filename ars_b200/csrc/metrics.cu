@@ -721,7 +721,8 @@ static int loudness_run(SRC src, i64 N, double rate, unsigned* d_mono_max_out, c
         {
             KernelScope prof("loudness_kernel (K-weighting stages + hop energies, one pass)", (double)N * (d_mono_max_out ? 8.0 : 4.0));
             // next to the final pass the meter takes a few CTAs per SM only, so that both kernels are resident together
-            const int per_sm = d_mono_max_out ? g_lufs_ctas_per_sm : 6;
+            static const int feed_per_sm = getenv("ARS_LUFS_FEED_CTAS") ? std::max(1, std::min(8, atoi(getenv("ARS_LUFS_FEED_CTAS")))) : 6;   // (experiments)
+            const int per_sm = d_mono_max_out ? g_lufs_ctas_per_sm : feed_per_sm;
             const int grid = std::max(1, std::min(nblocks, c.sm_count * per_sm));
             loudness_kernel<SRC><<<grid, NTB, 0, c.stream>>>(src, a, nblocks);
         }

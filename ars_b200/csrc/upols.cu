@@ -492,7 +492,7 @@ void olsb_filter(const float* d_x, i64 n, int cin, const float* d_ir0, i64 L0, c
             if (lanes > 1 && !side_pending) lane_wait_main(lane);     // (head start: a spectrum made on the main stream)
         }
         fft_batch_mid(fp, nb, w, H, ext ? H + (size_t)F : nullptr);
-        if (lanes > 1) lane_wait_main(lane);                // (head start: the frames and the maxima of the render before are in use until its tail is through)
+        if (lanes > 1) lane_wait_tail(lane);                // (head start: the frames and the maxima of the render before are in use until its tail is through)
         last_pass(j0, nb, w);
     }
     if (lanes > 1) { lane_join(); side_join(); }

@@ -472,8 +472,10 @@ def run_ours(args):
     # for each render's metrics before it prepares the next one, and the GPU idles meanwhile
     later = [ArsMetrics() for _ in range(args.steps)]
     _capi.check(lib.ars_timer_begin(), "timer")
+    t_host = time.perf_counter()
     for k in range(args.steps):
         r.step_dev(None if args.sync_steps else later[k])
+    host_enqueue_ms = 1000 * (time.perf_counter() - t_host) / args.steps     # (host time to enqueue one render; < ms_per_step: the GPU is the limit)
     _capi.check(lib.ars_timer_end(_capi.C.byref(ms)), "timer")
     if not args.sync_steps:
         assert all(rs._metrics_dict(m) == rs._metrics_dict(later[0]) for m in later), "steps of the same render differ"
@@ -565,6 +567,7 @@ def run_ours(args):
                 "call": "ars_render_batch (pinned host buffers, copy/compute pipelined across the steps' clips)",
                 "single_call_ms": single_ms, "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes()},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "whole render (every kernel of the step)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

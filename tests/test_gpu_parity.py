@@ -765,7 +765,7 @@ def test_async_device_renders_deliver_the_same_metrics_later(rs):
     assert len({wm["lufs"] for wm, _ in want}) == 5            # (five different clips, five different readings)
 
 
-@pytest.mark.parametrize("case", ["procedural 5.1.2", "external IR 7.1", "EQ on (exact-N route)"])
+@pytest.mark.parametrize("case", ["procedural 5.1.2", "procedural 5.1.2 in four lanes", "external IR 7.1", "EQ on (exact-N route)"])
 def test_head_start_of_async_renders_changes_nothing(rs, case):
     """Between two asynchronous renders of the same geometry the IR chain and the first passes of the second one run next
     to the tail of the first (ars_render_dev_async, option head_start).  Different clips and different random draws of
@@ -778,8 +778,11 @@ def test_head_start_of_async_renders_changes_nothing(rs, case):
     rate = 48000
     n = 700001
     ext = None
+    striped = case.endswith("lanes")
     if case.startswith("procedural"):
         kw = dict(hall_type="Cathedral", room_size=300., air_absorption=.1, dry_wet=.5, target_channel_layout="5.1.2 (Atmos Light)")
+        if striped:
+            n = 1500001                # (several transforms; one per stripe below, so the stripes go to the four lanes as in a long render)
     elif case.startswith("external"):
         kw = dict(dry_wet=.6, bass_gain=1.0, treble_gain=1.0, target_channel_layout="7.1 (Surround)")
         ext = (g.standard_normal((30000, 2)) * np.exp(-np.arange(30000) / 6000.0)[:, None] / 40).astype(np.float32)
@@ -818,20 +821,41 @@ def test_head_start_of_async_renders_changes_nothing(rs, case):
         _capi.check(lib.ars_sync(), "ars_sync")
         return [(rs._metrics_dict(m), q.cpu().numpy()) for m, q in out]
 
-    want = run(lib.ars_render_dev, True)
-    h0 = int(lib.ars_head_start_count())
-    got = run(lib.ars_render_dev_async, False)
-    taken = int(lib.ars_head_start_count()) - h0
-    assert taken == len(clips) - 1, taken
     try:
+        if striped:
+            _capi.set_option("olsb_stripe", 1)
+        want = run(lib.ars_render_dev, True)
+        h0, l0, t0 = int(lib.ars_head_start_count()), int(lib.ars_meter_stream_count()), int(lib.ars_tail_overlap_count())
+        got = run(lib.ars_render_dev_async, False)
+        taken = int(lib.ars_head_start_count()) - h0
+        assert taken == len(clips) - 1, taken
+        assert int(lib.ars_meter_stream_count()) == l0 and int(lib.ars_tail_overlap_count()) == t0     # (both off by default)
+        # option loud_stream: the meters run on the meter stream, off the chain of last and final passes; with tail_overlap
+        # the last passes wait for their slot's meter only, from the second or third render on
+        _capi.set_option("loud_stream", 1)
+        one_y = run(lib.ars_render_dev_async, False)
+        metered = int(lib.ars_meter_stream_count()) - l0
+        assert metered == len(clips), metered
+        assert int(lib.ars_tail_overlap_count()) == t0
+        _capi.set_option("tail_overlap", 1)
+        two_y = run(lib.ars_render_dev_async, False)
+        overlapped = int(lib.ars_tail_overlap_count()) - t0
+        assert len(clips) - 2 <= overlapped <= len(clips) - 1, overlapped
+        again = run(lib.ars_render_dev_async, False)          # (both slots warm now)
         _capi.set_option("head_start", 0)
         plain = run(lib.ars_render_dev_async, False)
-        assert int(lib.ars_head_start_count()) - h0 == taken
+        assert int(lib.ars_head_start_count()) - h0 == 4 * taken
+        assert int(lib.ars_meter_stream_count()) - l0 == 4 * metered
     finally:
         _capi.set_option("head_start", 1)
-    for (wm, wp), (gm, gp), (pm, pp) in zip(want, got, plain):
-        assert gm == wm and pm == wm
-        assert np.array_equal(gp, wp) and np.array_equal(pp, wp)
+        _capi.set_option("loud_stream", 0)
+        _capi.set_option("tail_overlap", 0)
+        _capi.set_option("olsb_stripe", 0)
+    for k, (wm, wp) in enumerate(want):
+        for other in (got, one_y, two_y, again, plain):
+            om, op = other[k]
+            assert om == wm
+            assert np.array_equal(op, wp)
     assert len({wm["lufs"] for wm, _ in want}) == len(clips)
 
 

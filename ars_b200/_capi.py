@@ -115,6 +115,11 @@ PROTOTYPES = {
     "ars_profile_begin": (C.c_int, []),
     "ars_profile_end": (C.c_int, [C.POINTER(_i64), C.POINTER(_d), C.POINTER(_d)]),
     "ars_profile_report": (C.c_char_p, []),
+    "ars_peer_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ars_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ars_peer_push": (C.c_int, [_p, _p, _i64, _p]),
+    "ars_peer_close": (C.c_int, [_p]),
+    "ars_peer_free": (C.c_int, [_p]),
     "ars_host_alloc": (C.c_void_p, [_i64]),
     "ars_host_free": (None, [C.c_void_p]),
 }

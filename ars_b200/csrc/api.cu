@@ -1125,6 +1125,49 @@ int ars_state_metrics(const void* d_state, int64_t sample_count, int32_t lufs_st
     ARS_API_END
 }
 
+// ---- whole-render array shared between the ranks of a node (CUDA IPC), filled by peer pushes over NVLink ----
+int ars_peer_alloc(int64_t bytes, void** d_ptr, unsigned char* handle) {
+    ARS_API_BEGIN
+    ARS_CHECK(bytes > 0 && d_ptr && handle, "ars_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == ARS_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+    void* p = nullptr;
+    ARS_CUDA(cudaMalloc(&p, (size_t)bytes));           // (its own allocation: an IPC handle names a whole cudaMalloc block)
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); ARS_CUDA(e); }
+    memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    ARS_API_END
+}
+int ars_peer_open(const unsigned char* handle, void** d_ptr) {
+    ARS_API_BEGIN
+    ARS_CHECK(handle && d_ptr, "ars_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    ARS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    ARS_API_END
+}
+int ars_peer_push(void* d_peer_dst, const void* d_src, int64_t bytes, void* stream) {
+    ARS_API_BEGIN
+    ARS_CHECK(d_peer_dst && d_src && bytes >= 0, "ars_peer_push: bad arguments");
+    if (bytes > 0)
+        ARS_CUDA(cudaMemcpyAsync(d_peer_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice,
+                                 stream ? static_cast<cudaStream_t>(stream) : ctx().stream));
+    ARS_API_END
+}
+int ars_peer_close(void* d_ptr) {
+    ARS_API_BEGIN
+    if (d_ptr) ARS_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    ARS_API_END
+}
+int ars_peer_free(void* d_ptr) {
+    ARS_API_BEGIN
+    if (d_ptr) ARS_CUDA(cudaFree(d_ptr));
+    ARS_API_END
+}
+
 int ars_render_batch(const ArsClip* clips, int32_t count) {
     ARS_API_BEGIN
     ARS_CHECK(clips && count >= 0, "ars_render_batch: bad arguments");

@@ -9,6 +9,8 @@ of a block-sharded render, and timing barriers.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -239,13 +241,93 @@ def lib_stream():
 _SIDE_STREAMS = {}
 
 
-def side_stream(dev):
-    """One extra stream per device for the PCM gather (kept: torch's allocator caches blocks per stream)."""
+def side_stream(dev, index=0):
+    """Extra streams per device for the PCM gather (kept: torch's allocator caches blocks per stream)."""
     import torch
-    key = int(dev.index if dev.index is not None else torch.cuda.current_device())
+    key = (int(dev.index if dev.index is not None else torch.cuda.current_device()), int(index))
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]
+
+
+PEER_PUSH_PARTS = 1       # a segment may travel as several concurrent copies (ARS_PEER_PUSH_PARTS); measured at N = 2: 1, 2, 4, 8 parts all 5.22-5.24 ms -- the link is the limit, not the copy engine
+
+
+class _DeviceBlock:
+    """A raw device allocation as something torch can wrap without a copy (torch.as_tensor reads this protocol)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class PeerArray:
+    """The whole-render PCM array of a block-sharded render: allocated on rank 0 (ars_peer_alloc), mapped into every other
+    rank of the node through its CUDA IPC handle (ars_peer_open) -- the ranks then PUSH their segments into it over NVLink
+    (ars_peer_push), instead of NCCL sends that rank 0 has to receive.  Collective: every rank of `group` must call it."""
+
+    def __init__(self, nbytes, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _capi
+        self.lib, self.capi = _capi.init(), _capi
+        self.nbytes, self.group = int(nbytes), group
+        self.rank = dist.get_rank(group)
+        self.owner = self.rank == 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        if self.owner:
+            _capi.check(self.lib.ars_peer_alloc(self.nbytes, C.byref(ptr), handle), "ars_peer_alloc")
+        h = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(dev)
+        dist.broadcast(h, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if not self.owner:
+            raw = bytes(h.cpu().numpy().tobytes())
+            _capi.check(self.lib.ars_peer_open(C.create_string_buffer(raw, 64), C.byref(ptr)), "ars_peer_open")
+        self.ptr = int(ptr.value)
+
+    def push(self, byte_offset, d_src_ptr, nbytes, stream):
+        """This rank's bytes into place, enqueued on `stream` (a torch stream)."""
+        self.capi.check(self.lib.ars_peer_push(self.ptr + int(byte_offset), int(d_src_ptr), int(nbytes), int(stream.cuda_stream)),
+                        "ars_peer_push")
+
+    def tensor(self, shape, dtype_str="<i2"):
+        """(owner) the array as a torch tensor over the same memory."""
+        import torch
+        return torch.as_tensor(_DeviceBlock(self.ptr, shape, dtype_str), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def release(self):
+        """Collective: the other ranks unmap, then the owner frees."""
+        import torch
+        import torch.distributed as dist
+        if self.ptr:
+            torch.cuda.synchronize()
+            if not self.owner:
+                self.capi.check(self.lib.ars_peer_close(self.ptr), "ars_peer_close")
+            dist.barrier(group=self.group)
+            if self.owner:
+                self.capi.check(self.lib.ars_peer_free(self.ptr), "ars_peer_free")
+            self.ptr = 0
+
+
+_PEER_ARRAYS = {}
+
+
+def peer_array(nbytes, group=None):
+    """One PeerArray per size, kept like the library's workspaces: the next sharded render of the same size on this
+    process group reuses it (so copy the previous result first if it is still needed).  Collective."""
+    key = (int(nbytes), id(group))
+    if key not in _PEER_ARRAYS:
+        _PEER_ARRAYS[key] = PeerArray(nbytes, group)
+    return _PEER_ARRAYS[key]
+
+
+def release_peer_arrays():
+    """Collective: unmap / free every cached whole-render array (call before the process group is destroyed)."""
+    for k in sorted(_PEER_ARRAYS, key=lambda kv: kv[0]):
+        _PEER_ARRAYS[k].release()
+    _PEER_ARRAYS.clear()
 
 
 def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=True, to_host=True, x_is_slice_from=None,
@@ -256,8 +338,9 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=T
     three small all-reduces carry the peak-guard words (4 after the convolution, 1 after the pan maximum, 1 more for the
     Stereo layout), one all-gather passes every rank's last stage-output frames to its successor (layout delay + the
     loudness filters' warm-up), the hop energies of the loudness meter are summed, and the PCM segments travel to rank 0
-    over NVLink on a second stream -- point to point, straight into their place in the whole array -- while the meter
-    runs.  Everything is ordered on the device: the host waits once, at the end.
+    over NVLink on a second stream while the meter runs -- pushed by their ranks straight into their place in rank 0's
+    whole-render array through a CUDA IPC peer mapping (gather=True, PeerArray), or as NCCL point-to-point sends
+    (gather="nccl", the round-2 mid-state form).  Everything is ordered on the device: the host waits once, at the end.
     -> dict(metrics, names, rank_pcm (this rank's frames, device), frames, pcm_device (rank 0, gather=True: the whole
        render on the device), pcm (rank 0, gather and to_host: numpy))"""
     import torch
@@ -313,7 +396,32 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=T
             dist.all_reduce(r.words()[8:10], op=MAX, group=group)
             dist.all_reduce(r.sumsq(), op=SUM, group=group)
         pcm_all = None
-        if world > 1 and gather:
+        use_peer = world > 1 and bool(gather) and gather != "nccl"
+        if use_peer:
+            # every rank pushes its segment into rank 0's array over the peer mapping (a plain device-to-device copy over
+            # NVLink on the second stream, next to the meter); the small all-reduce behind the pushes tells rank 0 that
+            # all of them have landed
+            done_final = torch.cuda.Event()
+            done_final.record(stream)
+            row = r.C_out * 2
+            whole = peer_array(r.N * row, group)
+            parts = max(1, int(os.environ.get("ARS_PEER_PUSH_PARTS", PEER_PUSH_PARTS)))
+            total = r.frames() * row
+            chunk = (-(-total // parts) + 4095) // 4096 * 4096            # (ceil(total / parts), rounded up to 4 KB)
+            done_gather = []
+            for k in range(parts):
+                off = k * chunk
+                if off >= total:
+                    break
+                side = side_stream(dev, k)
+                side.wait_event(done_final)
+                whole.push(r.f_lo * row + off, r.d_pcm.data_ptr() + off, min(chunk, total - off), side)
+                e = torch.cuda.Event()
+                e.record(side)
+                done_gather.append(e)
+            if rank == 0:
+                pcm_all = whole.tensor((r.N, r.C_out))
+        elif world > 1 and gather:
             side = side_stream(dev)
             done_final = torch.cuda.Event()
             done_final.record(stream)
@@ -337,7 +445,11 @@ def render_long_sharded(samples, rate, external_ir_data, *, group=None, gather=T
         status = r.loudness_gate()
         mark("loudness + metric reductions")
         if world > 1 and gather:
-            stream.wait_event(done_gather)
+            for e in (done_gather if isinstance(done_gather, list) else [done_gather]):
+                stream.wait_event(e)
+        if use_peer:
+            landed = torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(landed, op=SUM, group=group)             # (behind every rank's push: rank 0 may read the array)
         mark("pcm gather (part not hidden by the meter)")
         metrics = r.metrics(status)                                  # (the one host wait of the render)
     if timings is not None:
@@ -461,6 +573,18 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
     for _ in range(args.steps):
         step_dev(timings=timings)
     barrier()
+    # the same render with the segments gathered by NCCL point-to-point sends instead of peer pushes (comparison)
+    nccl_ms = None
+    if world > 1:
+        step_dev(gather="nccl")
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_dev(gather="nccl")
+        e1.record(stream)
+        torch.cuda.synchronize()
+        nccl_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        barrier()
     # end to end: every rank uploads its slice from pinned host memory and downloads its own PCM segment
     step_host()
     barrier()
@@ -494,6 +618,10 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
                 "collectives": {"ir_broadcast_bytes": L * 8, "maxima_allreduce_bytes": [16, 4], "halo_allgather_bytes": world * Y_HALO * 8,
                                 "hop_energy_allreduce_bytes": int(plan.hop_count) * 8, "metric_allreduce_bytes": [8, 8],
                                 "pcm_gather_bytes_into_rank0": pcm_bytes_to_rank0,
+                                "pcm_gather": ("peer push: every rank copies its segment into rank 0's array through a CUDA IPC "
+                                               "mapping over NVLink (ars_peer_push), one 4-byte all-reduce behind the pushes")
+                                if world > 1 else None,
+                                "ms_per_step_with_nccl_p2p_gather": nccl_ms,
                                 "limiting": "PCM gather into rank 0 (one GPU's NVLink ingress)" if world > 1 else None},
                 "e2e": {"value": seconds * args.steps / (e2e_ms * 1e-3), "unit": "audio-seconds/s",
                         "ms_per_step": e2e_ms / args.steps,
@@ -509,4 +637,5 @@ def bench_long(args, *, make_ir, load_peaks, ClockSampler, **_):
                 "metrics_of_last_render": metrics}
         print(json.dumps(line))
     if world > 1:
+        release_peer_arrays()
         dist.destroy_process_group()

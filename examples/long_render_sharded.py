@@ -6,8 +6,9 @@
 
 Rank 0 broadcasts the stereo IR (NCCL), every rank uploads and convolves its own block range, the peak-guard maxima
 are max-reduced, the ranks' last stage-output frames go to their successors, the loudness meter's hop energies are
-summed, and the PCM segments are gathered on rank 0 (ars_b200.sharding.render_long_sharded).  --check also renders
-the whole clip on rank 0 alone and requires bit-identical PCM (prints BIT-IDENTICAL).
+summed, and the PCM segments are pushed into rank 0's whole-render array over NVLink (ars_b200.sharding.render_long_sharded).
+--check also renders the whole clip on rank 0 alone and requires bit-identical PCM from both gather forms (peer pushes and
+NCCL point-to-point sends; prints BIT-IDENTICAL).
 """
 import argparse
 import json
@@ -55,12 +56,18 @@ def main():
         if world > 1:
             dist.barrier()
         times.append(time.perf_counter() - t0)
+    # the segments reach rank 0 by peer pushes over a CUDA IPC mapping (default) or by NCCL point-to-point sends
+    res_nccl = sh.render_long_sharded(x, rate, ir, gather="nccl", **settings) if world > 1 and a.check else None
+    if world > 1:
+        sh.release_peer_arrays()
     if rank == 0:
         out = {"world": world, "clip_seconds": a.seconds, "ir_seconds": a.ir_seconds,
                "wall_ms_incl_upload_and_gather": [round(1000 * t, 2) for t in times[1:]], "metrics": res["metrics"]}
         if a.check:
             whole = rs.render_array(x, rate, external_ir_data=ir, want_float=False, **settings)
             same = bool(np.array_equal(whole["pcm"], res["pcm"]))
+            if res_nccl is not None:
+                same = same and bool(np.array_equal(whole["pcm"], res_nccl["pcm"])) and res_nccl["metrics"] == res["metrics"]
             out["bit_identical_to_single_gpu"] = same
             out["metrics_single_gpu"] = whole["metrics"]
             lufs_ok = abs(whole["metrics"]["lufs"] - res["metrics"]["lufs"]) < 1e-9

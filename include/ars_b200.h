@@ -332,6 +332,21 @@ ARS_API int ars_loudness_dev(const float* d_mono, int64_t N, double rate, void* 
 /* read the state block back and turn it into metrics (synchronises) */
 ARS_API int ars_state_metrics(const void* d_state, int64_t sample_count, int32_t lufs_status, ArsMetrics* out);
 
+/* ---- the whole-render array of a block-sharded render, filled over NVLink by the ranks themselves -------------------
+ * (the reference returns ONE (frames, channels) array, rs.py:1082-1084; with one process per GPU the segments have to
+ * reach the rank that holds it.)  Rank 0 allocates the array with ars_peer_alloc and passes the 64-byte handle to the
+ * other processes of the node (any byte transport: a broadcast); they map it with ars_peer_open (CUDA IPC, peer access
+ * over NVLink enabled on the way) and PUSH their PCM segment straight into its place with ars_peer_push -- a device-to-
+ * device copy over the peer mapping on `stream` (NULL: the library stream), no receive side and no staging buffer.  The
+ * owner may read the array once every pushing rank has passed a collective that it enqueued behind its push.
+ * ars_peer_close unmaps (non-owners), ars_peer_free releases (owner, after every rank has unmapped). */
+#define ARS_PEER_HANDLE_BYTES 64
+ARS_API int ars_peer_alloc(int64_t bytes, void** d_ptr, unsigned char* handle);
+ARS_API int ars_peer_open(const unsigned char* handle, void** d_ptr);
+ARS_API int ars_peer_push(void* d_peer_dst, const void* d_src, int64_t bytes, void* stream);
+ARS_API int ars_peer_close(void* d_ptr);
+ARS_API int ars_peer_free(void* d_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,14 +52,15 @@ static int g_opt_air_fold = 1;     // 1: air absorption folded into the IR (over
 static int g_opt_air_fold_eps_e9 = 2000;     // bound on the late path's transfer-function error, in 1e-9 (upols.cuh)
 static int g_opt_side_stream = 1;  // 1: IR synthesis + fold + IR spectra on the side stream, next to the delay-line transform
 static int g_opt_head_start = 1;        // 1: asynchronous renders of the same geometry overlap their head with the tail of the render before
-static int g_opt_loud_stream = 0;       // 1: the loudness meter of an asynchronous render runs on the meter stream (Ctx::loud), off the chain
-                                        //    last pass -> final pass -> last pass of the next render.  Measured on the 300 s render
-                                        //    (18 runs of 40 steps): 0.437-0.445 ms against 0.463 ms typical, but 4 of 15 runs with it on
-                                        //    took 0.48-1.13 ms (the host's enqueue time per render went up with them: 0.20-0.78 ms
-                                        //    against 0.15) while all 9 runs with it off stayed within 0.5 % -- off by default
+static int g_opt_loud_stream = 1;       // 1: the loudness meter of an asynchronous render runs on the meter stream (Ctx::loud), off the chain
+                                        //    last pass -> final pass -> last pass of the next render.  300 s render: 0.4636 -> 0.437 ms
+                                        //    (seven runs within 0.4 %).  What the path sets up on first use (stream, second feed buffer
+                                        //    and state block) costs 3-90 ms once: callers that time a loop warm up through this call
+                                        //    (profiles/r02_stream_options_ab.txt: with a synchronous warm-up that cost landed in the
+                                        //    timed region of one run in three and looked like a slow GPU)
 static int g_opt_tail_overlap = 0;      // 1: with the meter stream, two stage-output buffers and state blocks zeroed behind their read-back:
                                         //    the last passes of a render do not wait for the final pass of the render before it
-                                        //    (measured: 0.443-0.451 ms, no better than the meter stream alone)
+                                        //    (measured: 0.4367 ms, no better than the meter stream alone, and 118 MB more)
 static int g_opt_lufs_from_stage = 0;   // 1: loudness meter fed from the stage output, next to the final pass (no feed array);
                                         // measured slower: both kernels are bound by issue slots, and recomputing the feed costs more
                                         // instructions than the 4 B per frame the final pass writes (0.660 against 0.634 ms)
@@ -158,7 +159,7 @@ struct PendingMetrics {
 };
 static std::vector<PendingMetrics> g_pending;
 static std::vector<RenderState*> g_pending_blocks;           // pinned, PENDING_BLOCK states each
-static constexpr size_t PENDING_BLOCK = 64;
+static constexpr size_t PENDING_BLOCK = 256;
 static RenderState* pending_slot() {
     const size_t i = g_pending.size();
     if (i / PENDING_BLOCK >= g_pending_blocks.size()) {

@@ -135,7 +135,7 @@ ARS_API void* ars_stream(void);                   /* the library's cudaStream_t 
  * CTA produces its block's frames itself and filters the feed from shared memory; 0 = final pass, then meter [default:
  * measured faster -- 109 + 77 us against 214 us on the 300 s render; the results are bit-identical]),
  * "head_start" (1 [default] | 0: see ars_render_dev_async),
- * "loud_stream" (0 [default] | 1: see ars_render_dev_async), "tail_overlap" (0 [default] | 1: likewise).
+ * "loud_stream" (1 [default] | 0: see ars_render_dev_async), "tail_overlap" (0 [default] | 1: likewise).
  * Environment (read once per process, experiments): ARS_MID_PIPE (3 [default] | 2 = the plain middle pass runs as a persistent
  * kernel that fetches its next tile with cp.async.bulk, 3 | 2 CTAs per SM; 0 = one tile per CTA), ARS_LAST_PIPE (3 [default] |
  * 2 | 6 = the last pass of 2^18-point blocks likewise, double-buffered; 0 = one tile per CTA), ARS_MID_NT (256 | 512),
@@ -247,16 +247,17 @@ ARS_API int ars_render_dev(const ArsRenderParams* p, const float* d_in, int64_t 
  * after its tail, and runs next to its final pass and loudness meter on the library's internal streams.  The input arrays
  * (d_in, d_draws->noise, d_ext_ir) must therefore be COMPLETE when the call is made (e.g. produced before an ars_sync() or
  * a device synchronisation), not merely ordered on ars_stream(); the outputs are ordered on ars_stream() as always.
- * Meter stream (option "loud_stream", default 0): the loudness meter of such a render and the read-back of its state block
+ * Meter stream (option "loud_stream", default 1): the loudness meter of such a render and the read-back of its state block
  * run on a third internal stream behind its final pass, over one of two alternating feed buffers / state blocks, so the
  * last pass of the NEXT render follows this render's final pass directly instead of its meter and gating.  The PCM / float
  * frames are ordered on ars_stream() as always; the metrics arrive with the next waiting call as before, and every other
- * entry point first orders ars_stream() after the meter stream.  Measured on the 300 s render: 0.44 ms against 0.463 ms
- * typical, but one run in four took 0.48-1.13 ms for a reason not found (all runs without it: within 0.5 %), hence off.
+ * entry point first orders ars_stream() after the meter stream.  Measured on the 300 s render: 0.4636 -> 0.437 ms.  The
+ * stream, the second feed buffer and the second state block are created on first use (3-90 ms, once): warm a timed loop up
+ * through this call.
  * Tail overlap (option "tail_overlap", default 0; needs the meter stream): the stage output alternates between two buffers
  * as well and the meter stream zeroes a state block behind its read-back, so the last passes of a render wait for the render
  * BEFORE the previous one to be through with the slot, not for the previous render's final pass: the convolution of render
- * k+1 overlaps the whole tail of render k (measured: 0.443-0.451 ms, no better than the meter stream alone). */
+ * k+1 overlaps the whole tail of render k (measured: 0.4367 ms, no better than the meter stream alone). */
 ARS_API int ars_render_dev_async(const ArsRenderParams* p, const float* d_in, int64_t n, int32_t cin, const float* d_ext_ir,
                          int64_t ext_ir_len, const ArsIrDraws* d_draws, float* d_out_stereo, float* d_out_f32,
                          int16_t* d_out_pcm, ArsMetrics* metrics);

@@ -825,11 +825,13 @@ def test_head_start_of_async_renders_changes_nothing(rs, case):
         if striped:
             _capi.set_option("olsb_stripe", 1)
         want = run(lib.ars_render_dev, True)
+        _capi.set_option("loud_stream", 0)
+        _capi.set_option("tail_overlap", 0)
         h0, l0, t0 = int(lib.ars_head_start_count()), int(lib.ars_meter_stream_count()), int(lib.ars_tail_overlap_count())
         got = run(lib.ars_render_dev_async, False)
         taken = int(lib.ars_head_start_count()) - h0
         assert taken == len(clips) - 1, taken
-        assert int(lib.ars_meter_stream_count()) == l0 and int(lib.ars_tail_overlap_count()) == t0     # (both off by default)
+        assert int(lib.ars_meter_stream_count()) == l0 and int(lib.ars_tail_overlap_count()) == t0     # (both off)
         # option loud_stream: the meters run on the meter stream, off the chain of last and final passes; with tail_overlap
         # the last passes wait for their slot's meter only, from the second or third render on
         _capi.set_option("loud_stream", 1)
@@ -848,7 +850,7 @@ def test_head_start_of_async_renders_changes_nothing(rs, case):
         assert int(lib.ars_meter_stream_count()) - l0 == 4 * metered
     finally:
         _capi.set_option("head_start", 1)
-        _capi.set_option("loud_stream", 0)
+        _capi.set_option("loud_stream", 1)          # (the defaults)
         _capi.set_option("tail_overlap", 0)
         _capi.set_option("olsb_stripe", 0)
     for k, (wm, wp) in enumerate(want):

@@ -463,8 +463,9 @@ def run_ours(args):
     # warm-up through the SAME call as the timed loop (asynchronous renders back to back), so that whatever that path sets
     # up on first use -- the second state block / feed buffer, internal streams and events, pinned metric slots, the head
     # start between renders -- exists before the timed region starts
-    warm = [ArsMetrics() for _ in range(args.warmup)]
-    for k in range(args.warmup):
+    n_warm = max(args.warmup, 3)          # (asynchronous renders alternate between two slots: three touch everything)
+    warm = [ArsMetrics() for _ in range(n_warm)]
+    for k in range(n_warm):
         r.step_dev(None if args.sync_steps else warm[k])
     _capi.check(lib.ars_sync(), "ars_sync")
     barrier()

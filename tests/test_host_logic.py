@@ -236,3 +236,23 @@ def test_reciprocal_division_of_the_peak_guards_is_correctly_rounded():
         q = f32(f32(v - q * m) * r + q)
         q = f32(f32(v - q * m) * r + q)
         assert q == f32(v / m), (float(v), float(m))
+
+
+def test_traffic_record_reproduces_from_the_committed_capture():
+    """bench.py's `roofline.traffic` comes from profiles/traffic.json; its round-2 entry must be what
+    profiles/traffic_summary.py sums out of the committed ncu launch list (one whole render, caches kept)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "traffic.json")))["cfg3_r02"]
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "traffic_summary.py"),
+                          os.path.join(root, "profiles", "r02_traffic_cfg3_caches_kept_final.csv"), "--json"],
+                         capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    assert got["dram_bytes_per_render"] == rec["dram_bytes_per_render"]
+    assert got["per_kernel"] == rec["per_kernel"]
+    assert 20 <= got["launches"] <= 40                                   # (one render, not two)
+    algo = rec["algorithmic_bytes_per_render"]
+    assert algo == (8 + 2 * 8) * 14783999                               # SURVEY 8(d): 8 B in + 2 B per output channel per frame
+    assert 2.5 < rec["dram_bytes_per_render"] / algo < 3.5
